@@ -1,0 +1,24 @@
+"""Case definitions shared by make_golden.py (which runs the real reference) and the tests
+(which regenerate the same weights/inputs from seeds and compare with the stored outputs)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from conformer_b200.synth import CONFORMER_L, CONFORMER_M, CONFORMER_S, EncoderConfig  # noqa: E402
+
+TINY = EncoderConfig(n_mel_channels=80, n_blocks=2, d_model=32, n_heads=2, kernel_size=7)
+
+# name, cfg, B, Tin, seed, with_lengths
+ENCODER_CASES = [
+    dict(name="tiny", cfg=TINY, B=3, Tin=83, seed=11, with_lengths=True),
+    dict(name="tiny_nolen", cfg=TINY, B=2, Tin=64, seed=12, with_lengths=False),
+    dict(name="S", cfg=CONFORMER_S, B=2, Tin=201, seed=21, with_lengths=True),       # T'=49
+    dict(name="M", cfg=CONFORMER_M, B=3, Tin=301, seed=22, with_lengths=True),       # T'=74
+    dict(name="M_T150", cfg=CONFORMER_M, B=2, Tin=605, seed=23, with_lengths=True),  # T'=150 (>1 key tile)
+    dict(name="L", cfg=CONFORMER_L, B=2, Tin=201, seed=24, with_lengths=True),       # T'=49
+]
+
+SUBMODULE_CFG = dict(cfg=EncoderConfig(80, 1, 64, 4, 31), B=3, T=41, seed=5, x_seed=6,
+                     lengths=[41, 30, 1], Tin=171, mel_lengths=[171, 100, 9])
+
+TOKEN_CASE = dict(cfg=EncoderConfig(80, 4, 144, 4, 31), B=4, Tin=401, seed=31, vocab=370, peaky=8.0)

@@ -1,0 +1,165 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in this directory by running the REAL reference.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU
+box):  ``PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py``
+
+For every case it builds the reference module from /root/reference, loads the seeded
+weights of ``conformer_b200.synth`` with a strict ``load_state_dict`` (so the key/shape
+contract is checked against the real thing), runs it on CPU in fp32 (and fp64 for a
+noise floor), and stores the outputs as .npz.  Weights and inputs are NOT stored: they are
+regenerated from (config, seed) by ``conformer_b200.synth``.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+from conformer_b200.synth import (EncoderConfig, synth_decoder_state_dict,   # noqa: E402
+                                  synth_encoder_state_dict, synth_lengths, synth_logmel)
+from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE                  # noqa: E402
+
+from model.conformer import Conformer                                        # noqa: E402
+from model.modules.encoder import Encoder                                    # noqa: E402
+from model.utils.attention import MultiHeadSelfAttentionModule              # noqa: E402
+from model.utils.block import ConformerBlock                                 # noqa: E402
+from model.utils.convolution import ConvolutionModule, ConvolutionSubsampling  # noqa: E402
+from model.utils.ffn import FeedForwardModule                                # noqa: E402
+from model.utils.masking import generate_padding_mask                        # noqa: E402
+from model.utils.position import RelativePositionalEncoding                  # noqa: E402
+
+torch.set_grad_enabled(False)
+torch.set_num_threads(8)
+
+
+def sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def reset_mask_value(m):
+    for mod in m.modules():
+        if hasattr(mod, "mask_value"):
+            mod.mask_value = None
+
+
+def run_encoder_case(name, cfg: EncoderConfig, B, Tin, seed, with_lengths):
+    sd = synth_encoder_state_dict(cfg, seed)
+    x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=1000 + seed)
+    lengths = synth_lengths(B, Tin) if with_lengths else None
+    enc = Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size).eval()
+    enc.load_state_dict(sd, strict=True)
+    y32, l32 = enc(x, lengths)
+    out = {"y": y32.numpy()}
+    if with_lengths:
+        out["out_lengths"] = l32.numpy()
+    if cfg.d_model <= 256:                       # fp64 truth for the noise floor (skip the 460 MB L model)
+        enc64 = enc.double()
+        reset_mask_value(enc64)
+        y64, _ = enc64(x.double(), lengths)
+        out["y64"] = y64.numpy()
+    np.savez_compressed(os.path.join(HERE, f"encoder_{name}.npz"), **out)
+    print(f"encoder_{name}: y {tuple(y32.shape)} mean|y|={y32.abs().mean():.4f}")
+
+
+def run_submodules():
+    cfg, B, T, seed = SUBMODULE_CFG["cfg"], SUBMODULE_CFG["B"], SUBMODULE_CFG["T"], SUBMODULE_CFG["seed"]
+    d, H, k = cfg.d_model, cfg.n_heads, cfg.kernel_size
+    sd = synth_encoder_state_dict(cfg, seed)
+    g = torch.Generator().manual_seed(SUBMODULE_CFG["x_seed"])
+    x = torch.randn(B, T, d, generator=g)
+    lengths = torch.tensor(SUBMODULE_CFG["lengths"], dtype=torch.long)
+    out = {}
+
+    ffn = FeedForwardModule(d).eval()
+    ffn.load_state_dict(sub(sd, "layers.0.ffn_1."), strict=True)
+    out["ffn"] = ffn(x).numpy()
+
+    pe = RelativePositionalEncoding(d)
+    pe.load_state_dict(sub(sd, "rel_pe."), strict=True)
+    pos = pe(x)                                         # [B, 2T-1, d]
+    out["rel_pe"] = pos[0].numpy()
+    assert torch.equal(pos[0], pos[-1])
+
+    valid = generate_padding_mask(lengths)              # [B, T] True = valid
+    out["padding_mask"] = valid.numpy()
+    mask = (~valid)[:, None, None, :]
+
+    att = MultiHeadSelfAttentionModule(d, H).eval()
+    att.load_state_dict(sub(sd, "layers.0.attention."), strict=True)
+    out["mhsa_nomask"] = att(x, pos, None).numpy()
+    reset_mask_value(att)
+    out["mhsa_mask"] = att(x, pos, mask).numpy()
+    # raw relative shift on a random score tensor
+    ps = torch.randn(2, H, T, 2 * T - 1, generator=g)
+    out["shift_in"] = ps.numpy()
+    out["shift_out"] = att.attention._relative_shift(ps).numpy()
+
+    conv = ConvolutionModule(d, k).eval()
+    conv.load_state_dict(sub(sd, "layers.0.conv."), strict=True)
+    out["conv"] = conv(x).numpy()
+
+    blk = ConformerBlock(d, H, k).eval()
+    blk.load_state_dict(sub(sd, "layers.0."), strict=True)
+    out["block_nomask"] = blk(x, pos, None).numpy()
+    reset_mask_value(blk)
+    out["block_mask"] = blk(x, pos, mask).numpy()
+
+    subs = ConvolutionSubsampling(d).eval()
+    subs.load_state_dict(sub(sd, "downsampling_conv."), strict=True)
+    mel = synth_logmel(B, cfg.n_mel_channels, SUBMODULE_CFG["Tin"], seed=77)
+    mel_len = torch.tensor(SUBMODULE_CFG["mel_lengths"], dtype=torch.long)
+    ys, ls = subs(mel, mel_len)
+    out["subsampling"] = ys.numpy()
+    out["subsampling_lengths"] = ls.numpy()
+    np.savez_compressed(os.path.join(HERE, "submodules.npz"), **out)
+    print("submodules:", {k_: v.shape for k_, v in out.items()})
+
+
+def run_tokens():
+    cfg, B, Tin, seed, vocab = (TOKEN_CASE[k] for k in ("cfg", "B", "Tin", "seed", "vocab"))
+    sd = synth_encoder_state_dict(cfg, seed, prefix="encoder.")
+    sd.update(synth_decoder_state_dict(cfg.d_model, vocab, seed=seed + 1, peaky=TOKEN_CASE["peaky"]))
+    model = Conformer(vocab, cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size).eval()
+    model.load_state_dict(sd, strict=True)
+    x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=2000 + seed)
+    lengths = synth_lengths(B, Tin)
+    logits, out_len = model(x, lengths)
+    ids = logits.argmax(-1)
+    # greedy decode, processing/processor.py:301-319 (processor.py itself needs librosa, absent here):
+    pad_id, unk_id = 0, vocab - 1
+    toks = []
+    for row in ids:
+        items, prev = [], None
+        for t in row.tolist():
+            if t == pad_id or t == unk_id:
+                continue
+            if prev is None:
+                prev = t
+                items.append(t)
+            elif prev != t:
+                prev = t
+                items.append(t)
+        toks.append(items)
+    top2 = logits.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])
+    flat = np.full((B, max(len(t) for t in toks)), -1, dtype=np.int64)
+    for i, t in enumerate(toks):
+        flat[i, :len(t)] = t
+    np.savez_compressed(os.path.join(HERE, "tokens.npz"), logits=logits.numpy(), ids=ids.numpy(),
+                        tokens=flat, out_lengths=out_len.numpy(), margin=margin.numpy())
+    print(f"tokens: logits {tuple(logits.shape)} median margin {margin.median():.4f} "
+          f"min margin {margin.min():.5f} tokens/utt {[len(t) for t in toks]}")
+
+
+if __name__ == "__main__":
+    run_submodules()
+    for c in ENCODER_CASES:
+        run_encoder_case(**c)
+    run_tokens()

@@ -1,0 +1,48 @@
+"""Shared helpers for the tests: golden loading, tolerances, weight/input regeneration."""
+import os
+
+import numpy as np
+import torch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden(name):
+    with np.load(os.path.join(GOLDEN_DIR, name + ".npz")) as z:
+        return {k: torch.from_numpy(z[k]) for k in z.files}
+
+
+def sub(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+# fp32 gate: |a-b| <= 1e-5 + 1e-4*|b|
+FP32_ATOL, FP32_RTOL = 1e-5, 1e-4
+# bf16 gate: north_star rtol 2e-2 with the explicit absolute floor BASELINE.md section 5 calls for
+BF16_ATOL, BF16_RTOL = 2e-2, 2e-2
+
+
+def assert_close_fp32(a, b, what="", scale=1.0):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = (a - b).abs()
+    tol = scale * (FP32_ATOL + FP32_RTOL * b.abs())
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} outside fp32 gate; "
+                           f"max abs err {err.max():.3e}, max |b| {b.abs().max():.3e}")
+
+
+def bf16_report(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    err = (a - b).abs()
+    return dict(rel_fro=float((a - b).norm() / b.norm()),
+                frac_in_gate=float((err <= BF16_ATOL + BF16_RTOL * b.abs()).double().mean()),
+                max_abs=float(err.max()), mean_abs=float(err.mean()))
+
+
+def assert_close_bf16(a, b, what=""):
+    """rtol 2e-2 made explicit: norm-wise relative error <= 2e-2 AND >= 99% of elements within
+    |a-b| <= 2e-2 + 2e-2*|b| AND max abs error <= 0.15 (the reference's OWN autocast-bf16 run
+    scores 1.1e-2 / 99.1% / 8.6e-2 against its fp32 run - BASELINE.md section 5)."""
+    r = bf16_report(a, b)
+    assert r["rel_fro"] <= 2e-2 and r["frac_in_gate"] >= 0.99 and r["max_abs"] <= 0.15, f"{what}: {r}"
+    return r
