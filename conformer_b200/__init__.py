@@ -1,0 +1,15 @@
+"""conformer_b200 - B200 (sm_100a) native Conformer encoder forward path.
+
+Drop-in mirrors of Alan-404/Conformer's encoder-path nn.Modules over a C-ABI library of
+hand-written CUDA kernels.  Importing the package does not need a GPU; calling
+any forward does.
+"""
+from .modules import (GLU, Conformer, ConformerBlock, ConvolutionModule, ConvolutionSubsampling, Decoder, Encoder,
+                      FeedForwardModule, MultiHeadSelfAttentionModule, RelativeMultiHeadAttention,
+                      RelativePositionalEncoding, Swish, generate_padding_mask)
+from .synth import CONFORMER_L, CONFORMER_M, CONFORMER_S, EncoderConfig
+
+__all__ = ["GLU", "Conformer", "ConformerBlock", "ConvolutionModule", "ConvolutionSubsampling", "Decoder", "Encoder",
+           "FeedForwardModule", "MultiHeadSelfAttentionModule", "RelativeMultiHeadAttention",
+           "RelativePositionalEncoding", "Swish", "generate_padding_mask", "EncoderConfig", "CONFORMER_S",
+           "CONFORMER_M", "CONFORMER_L"]

@@ -1,0 +1,186 @@
+// extern "C" surface of libconformer_b200.so (declared in include/conformer_b200.h).
+#include <cstring>
+#include <new>
+
+#include "module.h"
+
+namespace cfm {
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+}  // namespace cfm
+
+using namespace cfm;
+
+namespace {
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int run(cfm_module_t m, int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in,
+        float* y, int64_t* len_out, int B, int frames, void* ws, int64_t ws_bytes, void* stream) {
+  if (m == nullptr) { set_error("null module handle"); return 1; }
+  if (x == nullptr || y == nullptr) { set_error("null input/output pointer"); return 1; }
+  return m->forward(op, x, pos, key_pad, len_in, y, len_out, B, frames, ws, ws_bytes, S(stream), nullptr);
+}
+}  // namespace
+
+extern "C" {
+
+int cfm_abi_version(void) { return CFM_ABI_VERSION; }
+const char* cfm_last_error(void) { return g_error.c_str(); }
+
+int cfm_device_check(void) {
+  int dev = 0;
+  CFM_CUDA_OK(cudaGetDevice(&dev));
+  int major = 0;
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  CFM_REQUIRE(major == 10, "this library only carries sm_100a code (Blackwell B200)");
+  return tc_init();
+}
+
+int cfm_module_create(int kind, const cfm_config_t* cfg, cfm_module_t* out) {
+  CFM_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
+  CFM_REQUIRE(kind >= CFM_KIND_ENCODER && kind <= CFM_KIND_SUBSAMPLING, "unknown module kind");
+  cfm_module* m = new (std::nothrow) cfm_module();
+  CFM_REQUIRE(m != nullptr, "out of host memory");
+  m->kind = kind;
+  m->cfg = *cfg;
+  *out = m;
+  return 0;
+}
+
+int cfm_module_set_param(cfm_module_t m, const char* name, const float* data, int64_t numel) {
+  CFM_REQUIRE(m != nullptr && name != nullptr && data != nullptr && numel > 0, "bad parameter registration");
+  m->params[name] = ParamRef{data, numel, false};
+  m->finalized = false;
+  return 0;
+}
+
+int cfm_module_finalize(cfm_module_t m, int compute, void* stream) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  return m->finalize(compute, S(stream));
+}
+
+int cfm_module_destroy(cfm_module_t m) {
+  delete m;
+  return 0;
+}
+
+int cfm_padding_mask(const int64_t* lengths, int32_t batch, int32_t max_len, uint8_t* valid, void* stream) {
+  CFM_REQUIRE(lengths != nullptr && valid != nullptr && batch > 0 && max_len > 0, "bad padding-mask arguments");
+  return lengths_and_mask(lengths, nullptr, valid, batch, max_len, false, true, S(stream));
+}
+
+int cfm_rel_pos_encoding(const float* div_term, int32_t batch, int32_t T, int32_t d_model, float* out, void* stream) {
+  CFM_REQUIRE(div_term != nullptr && out != nullptr && batch > 0, "bad positional-encoding arguments");
+  CFM_TRY(rel_pos_table<float>(div_term, out, T, d_model, S(stream)));
+  const size_t bytes = static_cast<size_t>(2 * T - 1) * d_model * sizeof(float);
+  for (int b = 1; b < batch; ++b)                      // position.py:26 repeats the table over the batch
+    CFM_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<char*>(out) + b * bytes, out, bytes, cudaMemcpyDeviceToDevice, S(stream)));
+  return 0;
+}
+
+int cfm_swish(const float* x, float* y, int64_t numel, void* stream) {
+  CFM_REQUIRE(x != nullptr && y != nullptr && numel > 0, "bad swish arguments");
+  return swish_f32(x, y, numel, S(stream));
+}
+int cfm_glu(const float* x, float* y, int64_t rows, int32_t d_out, void* stream) {
+  CFM_REQUIRE(x != nullptr && y != nullptr && rows > 0 && d_out > 0, "bad glu arguments");
+  return glu_lastdim_f32(x, y, rows, d_out, S(stream));
+}
+int cfm_subsampled_lengths(const int64_t* lengths, int64_t* out, int32_t batch, void* stream) {
+  CFM_REQUIRE(lengths != nullptr && out != nullptr && batch > 0, "bad lengths arguments");
+  return lengths_and_mask(lengths, out, nullptr, batch, 0, true, false, S(stream));
+}
+
+int64_t cfm_workspace_bytes(cfm_module_t m, int32_t batch, int32_t frames) {
+  if (m == nullptr) { set_error("null module handle"); return -1; }
+  int64_t need = 0;
+  int s = m->forward(m->kind, nullptr, nullptr, nullptr, reinterpret_cast<const int64_t*>(8), nullptr, nullptr, batch,
+                     frames, nullptr, 0, nullptr, &need);
+  return s == 0 ? need + 256 : -1;
+}
+
+int cfm_ffn_forward(cfm_module_t m, const float* x, float* y, int32_t batch, int32_t T, void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_FFN, x, nullptr, nullptr, nullptr, y, nullptr, batch, T, ws, wsb, stream);
+}
+int cfm_mhsa_forward(cfm_module_t m, const float* x, const float* pos, const uint8_t* key_pad, float* y, int32_t batch,
+                     int32_t T, void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_MHSA, x, pos, key_pad, nullptr, y, nullptr, batch, T, ws, wsb, stream);
+}
+int cfm_conv_module_forward(cfm_module_t m, const float* x, float* y, int32_t batch, int32_t T, void* ws, int64_t wsb,
+                            void* stream) {
+  return run(m, CFM_KIND_CONV_MODULE, x, nullptr, nullptr, nullptr, y, nullptr, batch, T, ws, wsb, stream);
+}
+int cfm_block_forward(cfm_module_t m, const float* x, const float* pos, const uint8_t* key_pad, float* y, int32_t batch,
+                      int32_t T, void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_BLOCK, x, pos, key_pad, nullptr, y, nullptr, batch, T, ws, wsb, stream);
+}
+int cfm_subsampling_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y, int64_t* lengths_out,
+                            int32_t batch, int32_t Tin, void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_SUBSAMPLING, mel, nullptr, nullptr, lengths_in, y, lengths_out, batch, Tin, ws, wsb, stream);
+}
+int cfm_encoder_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y, int64_t* lengths_out,
+                        int32_t batch, int32_t Tin, void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_ENCODER, mel, nullptr, nullptr, lengths_in, y, lengths_out, batch, Tin, ws, wsb, stream);
+}
+
+int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin) {
+  const int64_t inner = cfm_workspace_bytes(m, batch, Tin);
+  if (inner < 0) return -1;
+  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
+  const int64_t mel = static_cast<int64_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
+  const int64_t y = static_cast<int64_t>(batch) * T2 * m->cfg.d_model * 4;
+  return inner + mel + y + 2 * (static_cast<int64_t>(batch) * 8 + 256) + 1024;
+}
+
+int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host, float* y_host,
+                             int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  CFM_REQUIRE(m != nullptr && mel_host != nullptr && y_host != nullptr && workspace != nullptr, "null argument");
+  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
+  const size_t mel_b = static_cast<size_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
+  const size_t y_b = static_cast<size_t>(batch) * T2 * m->cfg.d_model * 4;
+  const size_t len_b = static_cast<size_t>(batch) * 8;
+  Workspace w;
+  w.init(workspace, static_cast<size_t>(workspace_bytes), false);
+  float* mel_d = static_cast<float*>(w.take(mel_b));
+  float* y_d = static_cast<float*>(w.take(y_b));
+  int64_t* li_d = static_cast<int64_t*>(w.take(len_b));
+  int64_t* lo_d = static_cast<int64_t*>(w.take(len_b));
+  char* rest = static_cast<char*>(w.take(256));
+  CFM_REQUIRE(mel_d && y_d && li_d && lo_d && rest, "workspace too small; query cfm_encoder_host_workspace_bytes");
+  const int64_t rest_bytes = workspace_bytes - (rest - static_cast<char*>(workspace));
+  CFM_CUDA_OK(cudaMemcpyAsync(mel_d, mel_host, mel_b, cudaMemcpyHostToDevice, S(stream)));
+  if (lengths_in_host) CFM_CUDA_OK(cudaMemcpyAsync(li_d, lengths_in_host, len_b, cudaMemcpyHostToDevice, S(stream)));
+  CFM_TRY(run(m, CFM_KIND_ENCODER, mel_d, nullptr, nullptr, lengths_in_host ? li_d : nullptr, y_d,
+              lengths_in_host ? lo_d : nullptr, batch, Tin, rest, rest_bytes, stream));
+  CFM_CUDA_OK(cudaMemcpyAsync(y_host, y_d, y_b, cudaMemcpyDeviceToHost, S(stream)));
+  if (lengths_in_host && lengths_out_host)
+    CFM_CUDA_OK(cudaMemcpyAsync(lengths_out_host, lo_d, len_b, cudaMemcpyDeviceToHost, S(stream)));
+  return 0;
+}
+
+int64_t cfm_last_launch_count(cfm_module_t m) { return m ? m->last_launches : -1; }
+
+int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K, int32_t epi,
+                  const float* res, float res_scale, void* stream) {
+  CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 4, "bad GEMM arguments");
+  int dev = 0, sms = 0;
+  CFM_CUDA_OK(cudaGetDevice(&dev));
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C, N, M, N, K,
+                      static_cast<Epilogue>(epi), res, res_scale, nullptr, sms, S(stream));
+}
+int cfm_gemm_f32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t epi,
+                 const float* res, float res_scale, void* stream) {
+  CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 4, "bad GEMM arguments");
+  return gemm_f32(A, K, W, bias, C, N, M, N, K, static_cast<Epilogue>(epi), res, res_scale, nullptr, S(stream));
+}
+int cfm_dwconv_glu_bn_swish(const void* u, const float* w, const float* bias, void* y, int32_t batch, int32_t T, int32_t d,
+                            int32_t ksize, int32_t dtype, void* stream) {
+  CFM_REQUIRE(u && w && bias && y && batch > 0 && T > 0 && d > 0, "bad depthwise-conv arguments");
+  if (dtype == 0)
+    return dwconv_glu_bn_swish<float>(static_cast<const float*>(u), w, bias, static_cast<float*>(y), batch, T, d, ksize, S(stream));
+  return dwconv_glu_bn_swish<bf16>(static_cast<const bf16*>(u), w, bias, static_cast<bf16*>(y), batch, T, d, ksize, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// LayerNorm, positional table, length/mask arithmetic, casts and weight packing kernels.
+#include "ops.h"
+
+namespace cfm {
+namespace {
+
+// One warp per row; two-pass mean/variance in fp32 (rows are <= 4 KB and stay in L1).
+template <typename TOut>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x,
+                                                         const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, TOut* __restrict__ y,
+                                                         int64_t rows, int d) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * d;
+  float s = 0.f;
+  for (int c = lane; c < d; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / static_cast<float>(d);
+  float v = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float t = xr[c] - mean;
+    v = fmaf(t, t, v);
+  }
+  const float rstd = rsqrtf(warp_sum(v) / static_cast<float>(d) + 1e-5f);
+  TOut* yr = y + row * d;
+  for (int c = lane; c < d; c += 32) yr[c] = from_f32<TOut>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
+}
+
+template <typename T>
+__global__ void rel_pos_table_kernel(const float* __restrict__ div_term, T* __restrict__ pe, int Tn, int d) {
+  const int half = d >> 1;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(2 * Tn - 1) * half;
+  if (idx >= total) return;
+  const int p = static_cast<int>(idx / half), k = static_cast<int>(idx - static_cast<int64_t>(p) * half);
+  // reference: angles = position * div_term in fp32, sin/cos of +-angle (position.py:15-21)
+  const float pos = static_cast<float>(Tn - 1 - p);
+  const float ang = pos * div_term[k];
+  pe[static_cast<int64_t>(p) * d + 2 * k] = from_f32<T>(sinf(ang));
+  pe[static_cast<int64_t>(p) * d + 2 * k + 1] = from_f32<T>(cosf(ang));
+}
+
+__global__ void lengths_mask_kernel(const int64_t* __restrict__ len_in, int64_t* __restrict__ len_out,
+                                    uint8_t* __restrict__ key_pad, int B, int Tn, bool subsample,
+                                    bool mark_valid) {
+  const int b = blockIdx.x;
+  int64_t L = len_in[b];
+  if (subsample) {
+    // floor division like torch's // on int64 (convolution.py:55)
+    auto fdiv2 = [](int64_t v) { return (v >= 0) ? (v >> 1) : -((-v + 1) >> 1); };
+    L = fdiv2(fdiv2(L - 1) - 1);
+  }
+  if (threadIdx.x == 0 && len_out) len_out[b] = L;
+  if (key_pad)
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) key_pad[static_cast<int64_t>(b) * Tn + t] = ((t >= L) != mark_valid) ? 1 : 0;
+}
+
+__global__ void swish_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = swish_f(x[i]);
+}
+__global__ void glu_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t rows, int d) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = static_cast<int>(i - r * d);
+  y[i] = x[r * 2 * d + c] * sigmoid_f(x[r * 2 * d + d + c]);
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __float2bfloat16_rn(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = __bfloat162float(x[i]);
+}
+__global__ void pack_conv2_kernel(const float* __restrict__ w, float* __restrict__ out, int C) {
+  // w[n][c][kh][kw] -> out[n][(kw*3+kh)*C + c]
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(C) * C * 9;
+  if (i >= total) return;
+  const int kw = static_cast<int>(i % 3), kh = static_cast<int>((i / 3) % 3);
+  const int c = static_cast<int>((i / 9) % C), n = static_cast<int>(i / (9 * static_cast<int64_t>(C)));
+  out[static_cast<int64_t>(n) * 9 * C + static_cast<int64_t>(kw * 3 + kh) * C + c] = w[i];
+}
+__global__ void pack_linear_kernel(const float* __restrict__ w, float* __restrict__ out, int d, int C, int F2) {
+  // w[n][c*F2+f] -> out[n][f*C+c]   (flatten order of convolution.py:51-52)
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t K = static_cast<int64_t>(C) * F2;
+  if (i >= K * d) return;
+  const int64_t n = i / K, r = i - n * K;
+  const int c = static_cast<int>(r / F2), f = static_cast<int>(r - static_cast<int64_t>(c) * F2);
+  out[n * K + static_cast<int64_t>(f) * C + c] = w[i];
+}
+__global__ void fold_dwconv_bn_kernel(const float* __restrict__ w, const float* __restrict__ b,
+                                      const float* __restrict__ bn_w, const float* __restrict__ bn_b,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ w_out, float* __restrict__ b_out, int d, int k) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  // BatchNorm1d in eval mode is an affine map per channel (convolution.py:27)
+  const float s = bn_w[c] / sqrtf(rv[c] + eps);
+  for (int j = 0; j < k; ++j) w_out[static_cast<int64_t>(j) * d + c] = w[static_cast<int64_t>(c) * k + j] * s;
+  b_out[c] = (b[c] - rm[c]) * s + bn_b[c];
+}
+
+inline unsigned blocks_for(int64_t n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+}  // namespace
+
+template <typename TOut>
+int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,
+               cudaStream_t stream) {
+  CFM_REQUIRE(rows > 0 && d > 0, "empty layer_norm");
+  layer_norm_kernel<TOut><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int layer_norm<float>(const float*, const float*, const float*, float*, int64_t, int, cudaStream_t);
+template int layer_norm<bf16>(const float*, const float*, const float*, bf16*, int64_t, int, cudaStream_t);
+
+template <typename T>
+int rel_pos_table(const float* div_term, T* pe, int Tn, int d, cudaStream_t stream) {
+  CFM_REQUIRE(Tn > 0 && d > 0 && d % 2 == 0, "bad positional table shape");
+  const int64_t total = static_cast<int64_t>(2 * Tn - 1) * (d / 2);
+  rel_pos_table_kernel<T><<<blocks_for(total, 256), 256, 0, stream>>>(div_term, pe, Tn, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int rel_pos_table<float>(const float*, float*, int, int, cudaStream_t);
+template int rel_pos_table<bf16>(const float*, bf16*, int, int, cudaStream_t);
+
+int lengths_and_mask(const int64_t* lengths_in, int64_t* lengths_out, uint8_t* key_pad, int B, int Tn,
+                     bool subsample, bool mark_valid, cudaStream_t stream) {
+  CFM_REQUIRE(B > 0 && lengths_in != nullptr, "lengths_and_mask needs lengths");
+  lengths_mask_kernel<<<B, 128, 0, stream>>>(lengths_in, lengths_out, key_pad, B, Tn, subsample, mark_valid);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int swish_f32(const float* x, float* y, int64_t n, cudaStream_t stream) {
+  swish_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, y, n);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int glu_lastdim_f32(const float* x, float* y, int64_t rows, int d, cudaStream_t stream) {
+  glu_kernel<<<blocks_for(rows * d, 256), 256, 0, stream>>>(x, y, rows, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream) {
+  f32_to_bf16_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, y, n);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int cast_bf16_to_f32(const bf16* x, float* y, int64_t n, cudaStream_t stream) {
+  bf16_to_f32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, y, n);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int pack_conv2_weight(const float* w, float* out, int C, cudaStream_t stream) {
+  pack_conv2_kernel<<<blocks_for(static_cast<int64_t>(C) * C * 9, 256), 256, 0, stream>>>(w, out, C);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int pack_linear_weight(const float* w, float* out, int d, int C, int F2, cudaStream_t stream) {
+  pack_linear_kernel<<<blocks_for(static_cast<int64_t>(d) * C * F2, 256), 256, 0, stream>>>(w, out, d, C, F2);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int fold_dwconv_bn(const float* w, const float* b, const float* bn_w, const float* bn_b, const float* rm,
+                   const float* rv, float eps, float* w_out, float* b_out, int d, int k, cudaStream_t stream) {
+  fold_dwconv_bn_kernel<<<blocks_for(d, 128), 128, 0, stream>>>(w, b, bn_w, bn_b, rm, rv, eps, w_out, b_out, d, k);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cfm

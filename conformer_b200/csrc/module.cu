@@ -1,0 +1,503 @@
+// Module handles: weight registration/packing and the forward orchestration of every reference
+// module on the encoder path (Encoder, ConformerBlock, FeedForwardModule, MultiHeadSelfAttentionModule,
+// RelativeMultiHeadAttention, ConvolutionModule, ConvolutionSubsampling).
+#include "module.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace cfm {
+
+// =================================================================================== arena
+int Arena::reserve(size_t bytes) {
+  release();
+  CFM_CUDA_OK(cudaMalloc(&base_, bytes));
+  cap_ = bytes;
+  used_ = 0;
+  return 0;
+}
+void Arena::release() {
+  if (base_) cudaFree(base_);
+  base_ = nullptr;
+  cap_ = used_ = 0;
+}
+void* Arena::take(size_t bytes) {
+  const size_t a = (used_ + 255) & ~static_cast<size_t>(255);
+  if (a + bytes > cap_) return nullptr;
+  used_ = a + bytes;
+  return static_cast<char*>(base_) + a;
+}
+
+// =================================================================================== packing
+namespace {
+
+struct Packer {
+  Module& m;
+  cudaStream_t stream;
+  bool bf16_mode;
+  int status = 0;
+
+  const float* param(const std::string& name, int64_t numel) {
+    auto it = m.params.find(name);
+    if (it == m.params.end()) {
+      if (!status) set_error("missing parameter '" + name + "' (expected " + std::to_string(numel) + " elements)");
+      status = 1;
+      return nullptr;
+    }
+    if (it->second.numel != numel) {
+      if (!status)
+        set_error("parameter '" + name + "' has " + std::to_string(it->second.numel) + " elements, expected " +
+                  std::to_string(numel));
+      status = 1;
+      return nullptr;
+    }
+    it->second.used = true;
+    return it->second.data;
+  }
+  float* alloc_f32(int64_t n) {
+    float* p = static_cast<float*>(m.arena.take(static_cast<size_t>(n) * 4));
+    if (!p && !status) { set_error("weight arena exhausted"); status = 4; }
+    return p;
+  }
+  bf16* alloc_bf16(int64_t n) {
+    bf16* p = static_cast<bf16*>(m.arena.take(static_cast<size_t>(n) * 2));
+    if (!p && !status) { set_error("weight arena exhausted"); status = 4; }
+    return p;
+  }
+  // copy a vector parameter
+  const float* vec(const std::string& name, int64_t n) {
+    const float* src = param(name, n);
+    float* dst = alloc_f32(n);
+    if (status) return nullptr;
+    if (cudaMemcpyAsync(dst, src, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess) {
+      set_error("cudaMemcpyAsync failed while packing " + name);
+      status = 2;
+    }
+    return dst;
+  }
+  void finish_linear(Linear& L, float* w32, float* b, int N, int K) {
+    L.w32 = w32; L.b = b; L.N = N; L.K = K; L.w16 = nullptr;
+    if (bf16_mode && !status) {
+      L.w16 = alloc_bf16(static_cast<int64_t>(N) * K);
+      if (!status && cast_f32_to_bf16(w32, L.w16, static_cast<int64_t>(N) * K, stream)) status = 2;
+    }
+  }
+  // nn.Linear / 1x1 Conv1d: weight [N,K(,1)], bias [N]
+  void linear(Linear& L, const std::string& pre, int N, int K) {
+    float* w = const_cast<float*>(vec(pre + ".weight", static_cast<int64_t>(N) * K));
+    float* b = const_cast<float*>(vec(pre + ".bias", N));
+    finish_linear(L, w, b, N, K);
+  }
+  void ffn(FfnW& w, const std::string& pre, int d) {
+    w.ln_g = vec(pre + "layer_norm.weight", d);
+    w.ln_b = vec(pre + "layer_norm.bias", d);
+    linear(w.hidden, pre + "hidden_linear", 4 * d, d);
+    linear(w.out, pre + "out_linear", d, 4 * d);
+  }
+  void rel_attn(AttnW& w, const std::string& pre, int d, int H) {
+    w.u = vec(pre + "content_bias", d);
+    w.v = vec(pre + "position_bias", d);
+    // fused q|k|v projection: rows [0,d) query, [d,2d) key, [2d,3d) value (attention.py:78-80)
+    float* wq = alloc_f32(3LL * d * d);
+    float* bq = alloc_f32(3LL * d);
+    const char* names[3] = {"query_proj", "key_proj", "value_proj"};
+    for (int i = 0; i < 3 && !status; ++i) {
+      const float* sw = param(pre + names[i] + ".weight", static_cast<int64_t>(d) * d);
+      const float* sb = param(pre + names[i] + ".bias", d);
+      if (status) break;
+      cudaMemcpyAsync(wq + static_cast<int64_t>(i) * d * d, sw, static_cast<size_t>(d) * d * 4, cudaMemcpyDeviceToDevice, stream);
+      cudaMemcpyAsync(bq + static_cast<int64_t>(i) * d, sb, static_cast<size_t>(d) * 4, cudaMemcpyDeviceToDevice, stream);
+    }
+    finish_linear(w.qkv, wq, bq, 3 * d, d);
+    linear(w.pos, pre + "pos_proj", d, d);
+    linear(w.out, pre + "out_proj", d, d);
+  }
+  void mhsa(AttnW& w, const std::string& pre, int d, int H) {
+    w.ln_g = vec(pre + "layer_norm.weight", d);
+    w.ln_b = vec(pre + "layer_norm.bias", d);
+    rel_attn(w, pre + "attention.", d, H);
+  }
+  void conv(ConvW& w, const std::string& pre, int d, int k) {
+    w.ln_g = vec(pre + "layer_norm.weight", d);
+    w.ln_b = vec(pre + "layer_norm.bias", d);
+    linear(w.pw1, pre + "pointwise_conv_1", 2 * d, d);
+    linear(w.pw2, pre + "pointwise_conv_2", d, d);
+    const float* dw = param(pre + "deepwise_conv.weight", static_cast<int64_t>(d) * k);
+    const float* db = param(pre + "deepwise_conv.bias", d);
+    const float* bw = param(pre + "batch_norm.weight", d);
+    const float* bb = param(pre + "batch_norm.bias", d);
+    const float* rm = param(pre + "batch_norm.running_mean", d);
+    const float* rv = param(pre + "batch_norm.running_var", d);
+    float* wo = alloc_f32(static_cast<int64_t>(d) * k);
+    float* bo = alloc_f32(d);
+    if (!status && fold_dwconv_bn(dw, db, bw, bb, rm, rv, 1e-5f, wo, bo, d, k, stream)) status = 2;
+    w.dw_w = wo; w.dw_b = bo; w.ksize = k;
+  }
+  void block(BlockW& w, const std::string& pre, int d, int H, int k) {
+    ffn(w.ffn1, pre + "ffn_1.", d);
+    mhsa(w.attn, pre + "attention.", d, H);
+    conv(w.conv, pre + "conv.", d, k);
+    ffn(w.ffn2, pre + "ffn_2.", d);
+    w.ln_g = vec(pre + "layer_norm.weight", d);
+    w.ln_b = vec(pre + "layer_norm.bias", d);
+  }
+  void front(FrontW& w, const std::string& pre, int d) {
+    w.c1_w = vec(pre + "conv_1.weight", static_cast<int64_t>(d) * 9);
+    w.c1_b = vec(pre + "conv_1.bias", d);
+    const float* w2 = param(pre + "conv_2.weight", static_cast<int64_t>(d) * d * 9);
+    float* w2p = alloc_f32(static_cast<int64_t>(d) * d * 9);
+    float* b2 = const_cast<float*>(vec(pre + "conv_2.bias", d));
+    if (!status && pack_conv2_weight(w2, w2p, d, stream)) status = 2;
+    finish_linear(w.conv2, w2p, b2, d, 9 * d);
+  }
+};
+
+size_t arena_bytes_for(const Module& m) {
+  size_t total = 0;
+  for (const auto& kv : m.params) total += static_cast<size_t>(kv.second.numel);
+  // fp32 copy + bf16 copy + per-tensor 256-byte alignment slack + the fused pos_proj copy
+  const size_t d = m.cfg.d_model;
+  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 6 + (1 << 16);
+}
+
+}  // namespace
+
+int Module::finalize(int compute_mode, cudaStream_t stream) {
+  CFM_REQUIRE(compute_mode == 0 || compute_mode == 1, "compute must be CFM_COMPUTE_F32 or CFM_COMPUTE_BF16");
+  const int d = cfg.d_model, H = cfg.n_heads, k = cfg.kernel_size;
+  CFM_REQUIRE(d > 0 && d % 4 == 0, "d_model must be a positive multiple of 4");
+  CFM_REQUIRE(kind == CFM_KIND_FFN || kind == CFM_KIND_CONV_MODULE || kind == CFM_KIND_SUBSAMPLING ||
+                  (H > 0 && d % H == 0),
+              "d_model must be divisible by n_heads");
+  int dev = 0;
+  CFM_CUDA_OK(cudaGetDevice(&dev));
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  bf16_mode = compute_mode == 1;
+  if (bf16_mode) {
+    CFM_TRY(tc_init());
+    CFM_REQUIRE(d % 8 == 0, "bf16 mode needs d_model to be a multiple of 8");
+    if (kind == CFM_KIND_ENCODER || kind == CFM_KIND_SUBSAMPLING)
+      CFM_REQUIRE(d % 64 == 0, "bf16 mode needs d_model to be a multiple of 64 for the implicit-GEMM front-end; use fp32");
+  }
+  for (auto& kv : params) kv.second.used = false;
+  CFM_TRY(arena.reserve(arena_bytes_for(*this)));
+  Packer P{*this, stream, bf16_mode};
+  blocks.clear();
+  switch (kind) {
+    case CFM_KIND_FFN: P.ffn(ffn, "", d); break;
+    case CFM_KIND_MHSA: P.mhsa(attn, "", d, H); break;
+    case CFM_KIND_REL_ATTENTION: P.rel_attn(attn, "", d, H); break;
+    case CFM_KIND_CONV_MODULE: P.conv(conv, "", d, k); break;
+    case CFM_KIND_BLOCK: blocks.resize(1); P.block(blocks[0], "", d, H, k); break;
+    case CFM_KIND_SUBSAMPLING: P.front(front, "", d); break;
+    case CFM_KIND_ENCODER: {
+      P.front(front, "downsampling_conv.", d);
+      const int F2 = freq_bins();
+      const float* lw = P.param("linear.weight", static_cast<int64_t>(d) * d * F2);
+      float* lwp = P.alloc_f32(static_cast<int64_t>(d) * d * F2);
+      float* lb = const_cast<float*>(P.vec("linear.bias", d));
+      if (!P.status && pack_linear_weight(lw, lwp, d, d, F2, stream)) P.status = 2;
+      P.finish_linear(lin, lwp, lb, d, d * F2);
+      div_term = P.vec("rel_pe.div_term", d / 2);
+      blocks.resize(cfg.n_blocks);
+      for (int i = 0; i < cfg.n_blocks && !P.status; ++i)
+        P.block(blocks[i], "layers." + std::to_string(i) + ".", d, H, k);
+      // all layers' pos_proj fused into one [L*d, d] projection of the shared sinusoid table
+      if (!P.status) {
+        const int L = cfg.n_blocks;
+        float* w = P.alloc_f32(static_cast<int64_t>(L) * d * d);
+        float* b = P.alloc_f32(static_cast<int64_t>(L) * d);
+        for (int i = 0; i < L && !P.status; ++i) {
+          cudaMemcpyAsync(w + static_cast<int64_t>(i) * d * d, blocks[i].attn.pos.w32, static_cast<size_t>(d) * d * 4,
+                          cudaMemcpyDeviceToDevice, stream);
+          cudaMemcpyAsync(b + static_cast<int64_t>(i) * d, blocks[i].attn.pos.b, static_cast<size_t>(d) * 4,
+                          cudaMemcpyDeviceToDevice, stream);
+        }
+        P.finish_linear(pos_all, w, b, L * d, d);
+      }
+      break;
+    }
+    default: set_error("unknown module kind"); return 1;
+  }
+  if (P.status) return P.status;
+  if (kind != CFM_KIND_ENCODER && kind != CFM_KIND_FFN && kind != CFM_KIND_CONV_MODULE && kind != CFM_KIND_SUBSAMPLING) {
+    // default sinusoid frequencies for a stand-alone attention/block handle called without `pos`
+    std::vector<float> dt(d / 2);
+    const float c = static_cast<float>(-(std::log(10000.0) / d));
+    for (int i = 0; i < d / 2; ++i) dt[i] = std::exp(static_cast<float>(2 * i) * c);
+    float* p = P.alloc_f32(d / 2);
+    if (!p) return 4;
+    CFM_CUDA_OK(cudaMemcpyAsync(p, dt.data(), dt.size() * 4, cudaMemcpyHostToDevice, stream));
+    CFM_CUDA_OK(cudaStreamSynchronize(stream));       // dt is a host temporary
+    div_term = p;
+  }
+  for (const auto& kv : params)
+    if (!kv.second.used) {
+      set_error("unexpected parameter '" + kv.first + "' for this module kind");
+      return 1;
+    }
+  CFM_CUDA_OK(cudaGetLastError());
+  CFM_CUDA_OK(cudaStreamSynchronize(stream));         // the caller may now free/overwrite its tensors
+  finalized = true;
+  return 0;
+}
+
+// =================================================================================== forward
+namespace {
+
+template <typename TA> struct Dispatch;
+template <> struct Dispatch<float> {
+  static int gemm(Ctx& c, const float* A, int lda, const Linear& L, void* C, int ldc, int M, Epilogue e,
+                  const float* res, float scale, const ConvGeom* g) {
+    ++c.launches;
+    return gemm_f32(A, lda, L.w32, L.b, static_cast<float*>(C), ldc, M, L.N, L.K, e, res, scale, g, c.stream);
+  }
+};
+template <> struct Dispatch<bf16> {
+  static int gemm(Ctx& c, const bf16* A, int lda, const Linear& L, void* C, int ldc, int M, Epilogue e,
+                  const float* res, float scale, const ConvGeom* g) {
+    ++c.launches;
+    return gemm_bf16_tc(A, lda, L.w16, L.b, C, ldc, M, L.N, L.K, e, res, scale, g, c.num_sms, c.stream);
+  }
+};
+
+template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(c.ws.take(static_cast<size_t>(n) * sizeof(TA))); }
+
+#define WS_CHECK(ptr) CFM_REQUIRE((ptr) != nullptr || c.ws.measuring(), "workspace too small; query cfm_workspace_bytes")
+
+// out = res + scale * FFN(LN(x))      (ffn.py:15-23, block.py:19,25)
+template <typename TA>
+int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale, float* out, int64_t M, int d) {
+  const size_t mark = c.ws.mark();
+  TA* a = ws_take<TA>(c, M * d);
+  TA* h = ws_take<TA>(c, M * 4 * d);
+  WS_CHECK(a); WS_CHECK(h);
+  if (!c.ws.measuring()) {
+    ++c.launches;
+    CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.hidden, h, 4 * d, static_cast<int>(M), EPI_BIAS_SWISH, nullptr, 0.f, nullptr));
+    CFM_TRY(Dispatch<TA>::gemm(c, h, 4 * d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, scale, nullptr));
+  }
+  c.ws.reset(mark);
+  return 0;
+}
+
+// projected positional table for one or all layers: P = PE * Wp^T + bp   (attention.py:81)
+template <typename TA>
+int pos_project(Ctx& c, const Linear& wp, const float* div_term, const float* pos_f32, int Tn, int d, TA** out) {
+  const int R = 2 * Tn - 1;
+  TA* pe = ws_take<TA>(c, static_cast<int64_t>(R) * d);
+  TA* pp = ws_take<TA>(c, static_cast<int64_t>(R) * wp.N);
+  WS_CHECK(pe); WS_CHECK(pp);
+  *out = pp;
+  if (c.ws.measuring()) return 0;
+  ++c.launches;
+  if (pos_f32 != nullptr) {
+    if (sizeof(TA) == 4) CFM_CUDA_OK(cudaMemcpyAsync(pe, pos_f32, static_cast<size_t>(R) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
+    else CFM_TRY(cast_f32_to_bf16(pos_f32, reinterpret_cast<bf16*>(pe), static_cast<int64_t>(R) * d, c.stream));
+  } else {
+    CFM_TRY(rel_pos_table<TA>(div_term, pe, Tn, d, c.stream));
+  }
+  return Dispatch<TA>::gemm(c, pe, d, wp, pp, wp.N, R, EPI_BIAS, nullptr, 0.f, nullptr);
+}
+
+// out = res + MHSA(x)      (attention.py:14-18,74-92; block.py:21)
+template <typename TA>
+int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_proj, int ldp, const uint8_t* key_pad,
+             const float* res, float* out, int B, int Tn, int d, int H) {
+  const int64_t M = static_cast<int64_t>(B) * Tn;
+  const size_t mark = c.ws.mark();
+  TA* a = ws_take<TA>(c, M * d);
+  TA* qkv = ws_take<TA>(c, M * 3 * d);
+  TA* ctx = ws_take<TA>(c, M * d);
+  WS_CHECK(a); WS_CHECK(qkv); WS_CHECK(ctx);
+  if (!c.ws.measuring()) {
+    const TA* ain = a;
+    if (pre_ln) {
+      ++c.launches;
+      CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    } else if (sizeof(TA) == 4) {
+      ain = reinterpret_cast<const TA*>(x);
+    } else {
+      ++c.launches;
+      CFM_TRY(cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
+    }
+    CFM_TRY(Dispatch<TA>::gemm(c, ain, d, w.qkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
+    ++c.launches;
+    CFM_TRY(rel_attention<TA>(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
+    CFM_TRY(Dispatch<TA>::gemm(c, ctx, d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
+  }
+  c.ws.reset(mark);
+  return 0;
+}
+
+// out = res + ConvolutionModule(x)      (convolution.py:21-32; block.py:23)
+template <typename TA>
+int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* out, int B, int Tn, int d) {
+  const int64_t M = static_cast<int64_t>(B) * Tn;
+  const size_t mark = c.ws.mark();
+  TA* a = ws_take<TA>(c, M * d);
+  TA* u = ws_take<TA>(c, M * 2 * d);
+  TA* g = ws_take<TA>(c, M * d);
+  WS_CHECK(a); WS_CHECK(u); WS_CHECK(g);
+  if (!c.ws.measuring()) {
+    c.launches += 2;
+    CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, 2 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
+    CFM_TRY(dwconv_glu_bn_swish<TA>(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
+    CFM_TRY(Dispatch<TA>::gemm(c, g, d, w.pw2, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
+  }
+  c.ws.reset(mark);
+  return 0;
+}
+
+// y = ConformerBlock(x)      (block.py:17-29).  xw is an fp32 [M,d] working buffer; y may alias xw.
+template <typename TA>
+int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, const TA* pos_proj, int ldp,
+              const uint8_t* key_pad, int B, int Tn, int d, int H) {
+  const int64_t M = static_cast<int64_t>(B) * Tn;
+  CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d));
+  CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, key_pad, xw, xw, B, Tn, d, H)));
+  CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xw, B, Tn, d));
+  CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xw, xw, 0.5f, xw, M, d));
+  if (!c.ws.measuring()) {
+    ++c.launches;
+    CFM_TRY(layer_norm<float>(xw, w.ln_g, w.ln_b, y, M, d, c.stream));
+  }
+  return 0;
+}
+
+// front-end up to (and excluding) Encoder.linear: h2 [B*T2*F2, C] rows (b,t2,f2), channels-last
+template <typename TA>
+int front_fwd(Ctx& c, const Module& m, const float* mel, int B, int Tin, TA** h2_out) {
+  const int d = m.cfg.d_model, n_mel = m.cfg.n_mel_channels;
+  const int T1 = (Tin - 1) / 2, T2 = (T1 - 1) / 2, F1 = (n_mel - 1) / 2, F2 = (F1 - 1) / 2;
+  CFM_REQUIRE(Tin >= 7 && T2 >= 1 && F2 >= 1, "input too short for two stride-2 3x3 convolutions");
+  const int T1p = T1 + (T1 & 1);
+  TA* out1 = ws_take<TA>(c, static_cast<int64_t>(B) * T1p * F1 * d);
+  TA* h2 = ws_take<TA>(c, static_cast<int64_t>(B) * T2 * F2 * d);
+  WS_CHECK(out1); WS_CHECK(h2);
+  *h2_out = h2;
+  if (c.ws.measuring()) return 0;
+  ++c.launches;
+  CFM_TRY(subsample_conv1<TA>(mel, m.front.c1_w, m.front.c1_b, out1, B, n_mel, Tin, T1, T1p, F1, d, c.stream));
+  ConvGeom g{B, T1p, F1, d, T2, F2};
+  return Dispatch<TA>::gemm(c, out1, 0, m.front.conv2, h2, d, B * T2 * F2, EPI_BIAS_RELU, nullptr, 0.f, &g);
+}
+
+__global__ void permute_front_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows, int F2, int C) {
+  // in [rows][F2][C] -> out [rows][C*F2] with feature c*F2+f (convolution.py:51-52)
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * F2 * C) return;
+  const int64_t r = i / (static_cast<int64_t>(F2) * C);
+  const int rem = static_cast<int>(i - r * F2 * C);
+  const int c = rem / F2, f = rem - c * F2;
+  out[i] = in[(r * F2 + f) * C + c];
+}
+__global__ void permute_front_bf16_kernel(const bf16* __restrict__ in, float* __restrict__ out, int64_t rows, int F2, int C) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * F2 * C) return;
+  const int64_t r = i / (static_cast<int64_t>(F2) * C);
+  const int rem = static_cast<int>(i - r * F2 * C);
+  const int c = rem / F2, f = rem - c * F2;
+  out[i] = __bfloat162float(in[(r * F2 + f) * C + c]);
+}
+
+}  // namespace
+
+template <typename TA>
+int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const uint8_t* key_pad,
+                         const int64_t* len_in, float* y, int64_t* len_out, int B, int frames) {
+  const int d = cfg.d_model, H = cfg.n_heads;
+  switch (op) {
+    case CFM_KIND_FFN:
+      return ffn_fwd<TA>(c, ffn, x, nullptr, 1.f, y, static_cast<int64_t>(B) * frames, d);
+    case CFM_KIND_CONV_MODULE:
+      return conv_fwd<TA>(c, conv, x, nullptr, y, B, frames, d);
+    case CFM_KIND_MHSA:
+    case CFM_KIND_REL_ATTENTION: {
+      TA* pp = nullptr;
+      CFM_TRY(pos_project<TA>(c, attn.pos, div_term, pos, frames, d, &pp));
+      return mhsa_fwd<TA>(c, attn, kind == CFM_KIND_MHSA, x, pp, d, key_pad, nullptr, y, B, frames, d, H);
+    }
+    case CFM_KIND_BLOCK: {
+      TA* pp = nullptr;
+      CFM_TRY(pos_project<TA>(c, blocks[0].attn.pos, div_term, pos, frames, d, &pp));
+      float* xw = ws_take<float>(c, static_cast<int64_t>(B) * frames * d);
+      WS_CHECK(xw);
+      return block_fwd<TA>(c, blocks[0], x, xw, y, pp, d, key_pad, B, frames, d, H);
+    }
+    case CFM_KIND_SUBSAMPLING: {
+      TA* h2 = nullptr;
+      CFM_TRY(front_fwd<TA>(c, *this, x, B, frames, &h2));
+      if (c.ws.measuring()) return 0;
+      const int T2 = ((frames - 1) / 2 - 1) / 2, F2 = freq_bins();
+      const int64_t n = static_cast<int64_t>(B) * T2 * F2 * d;
+      ++c.launches;
+      if (sizeof(TA) == 4)
+        permute_front_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<const float*>(h2), y, static_cast<int64_t>(B) * T2, F2, d);
+      else
+        permute_front_bf16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c.stream>>>(reinterpret_cast<const bf16*>(h2), y, static_cast<int64_t>(B) * T2, F2, d);
+      CFM_CUDA_OK(cudaGetLastError());
+      if (len_in != nullptr && len_out != nullptr) {
+        ++c.launches;
+        CFM_TRY(lengths_and_mask(len_in, len_out, nullptr, B, T2, true, false, c.stream));
+      }
+      return 0;
+    }
+    case CFM_KIND_ENCODER: {
+      const int T2 = ((frames - 1) / 2 - 1) / 2, F2 = freq_bins();
+      const int64_t M = static_cast<int64_t>(B) * T2;
+      TA* h2 = nullptr;
+      CFM_TRY(front_fwd<TA>(c, *this, x, B, frames, &h2));
+      float* xw = ws_take<float>(c, M * d);
+      uint8_t* kp = nullptr;
+      int64_t* lens = nullptr;
+      if (len_in != nullptr) {
+        kp = ws_take<uint8_t>(c, M);
+        lens = ws_take<int64_t>(c, B);
+        WS_CHECK(kp); WS_CHECK(lens);
+      }
+      WS_CHECK(xw);
+      TA* pp = nullptr;
+      CFM_TRY(pos_project<TA>(c, pos_all, div_term, nullptr, T2, d, &pp));
+      if (!c.ws.measuring()) {
+        // Encoder.linear on the channels-last flatten (weight columns permuted at pack time), encoder.py:23
+        CFM_TRY(Dispatch<TA>::gemm(c, h2, F2 * d, lin, xw, d, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
+        if (len_in != nullptr) {
+          ++c.launches;
+          CFM_TRY(lengths_and_mask(len_in, len_out ? len_out : lens, kp, B, T2, true, false, c.stream));
+        }
+      }
+      const int L = cfg.n_blocks;
+      for (int i = 0; i < L; ++i) {
+        float* dst = (i == L - 1) ? y : xw;
+        CFM_TRY(block_fwd<TA>(c, blocks[i], xw, xw, dst, pp + static_cast<int64_t>(i) * d, L * d, kp, B, T2, d, H));
+      }
+      if (L == 0 && !c.ws.measuring())
+        CFM_CUDA_OK(cudaMemcpyAsync(y, xw, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
+      return 0;
+    }
+  }
+  set_error("unknown forward op");
+  return 1;
+}
+
+int Module::forward(int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in,
+                    float* y, int64_t* len_out, int B, int frames, void* workspace, int64_t ws_bytes,
+                    cudaStream_t stream, int64_t* needed) {
+  CFM_REQUIRE(finalized, "module not finalized (call cfm_module_finalize after registering parameters)");
+  CFM_REQUIRE(op == kind || (op == CFM_KIND_MHSA && kind == CFM_KIND_REL_ATTENTION), "forward does not match the module kind");
+  CFM_REQUIRE(B > 0 && frames > 0, "empty batch");
+  Ctx c;
+  c.stream = stream;
+  c.num_sms = num_sms;
+  c.ws.init(needed ? nullptr : workspace, needed ? 0 : static_cast<size_t>(ws_bytes), needed != nullptr);
+  int s = bf16_mode ? forward_impl<bf16>(c, op, x, pos, key_pad, len_in, y, len_out, B, frames)
+                    : forward_impl<float>(c, op, x, pos, key_pad, len_in, y, len_out, B, frames);
+  if (needed) *needed = static_cast<int64_t>(c.ws.peak());
+  last_launches = c.launches;
+  return s;
+}
+
+}  // namespace cfm

@@ -1,0 +1,96 @@
+// Module handle internals (see include/conformer_b200.h for the public ABI).
+#pragma once
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/conformer_b200.h"
+#include "ops.h"
+
+namespace cfm {
+
+class Arena {                        // one cudaMalloc holding every packed weight of a module
+ public:
+  ~Arena() { release(); }
+  int reserve(size_t bytes);
+  void release();
+  void* take(size_t bytes);          // 256-byte aligned; nullptr when exhausted
+ private:
+  void* base_ = nullptr;
+  size_t cap_ = 0, used_ = 0;
+};
+
+class Workspace {                    // bump allocator over the caller's scratch; can also just measure
+ public:
+  void init(void* base, size_t cap, bool measuring) {
+    base_ = static_cast<char*>(base); cap_ = cap; used_ = peak_ = 0; measuring_ = measuring;
+  }
+  void* take(size_t bytes) {
+    const size_t a = (used_ + 255) & ~static_cast<size_t>(255);
+    used_ = a + bytes;
+    if (used_ > peak_) peak_ = used_;
+    if (measuring_ || used_ > cap_) return nullptr;
+    return base_ + a;
+  }
+  size_t mark() const { return used_; }
+  void reset(size_t m) { used_ = m; }
+  size_t peak() const { return peak_; }
+  bool measuring() const { return measuring_; }
+ private:
+  char* base_ = nullptr;
+  size_t cap_ = 0, used_ = 0, peak_ = 0;
+  bool measuring_ = false;
+};
+
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+  Workspace ws;
+};
+
+struct Linear {
+  const float* w32 = nullptr;        // [N,K]
+  bf16* w16 = nullptr;               // [N,K], bf16 mode only
+  const float* b = nullptr;          // [N]
+  int N = 0, K = 0;
+};
+struct FfnW { const float *ln_g = nullptr, *ln_b = nullptr; Linear hidden, out; };
+struct AttnW { const float *ln_g = nullptr, *ln_b = nullptr, *u = nullptr, *v = nullptr; Linear qkv, pos, out; };
+struct ConvW { const float *ln_g = nullptr, *ln_b = nullptr, *dw_w = nullptr, *dw_b = nullptr; int ksize = 0; Linear pw1, pw2; };
+struct BlockW { FfnW ffn1, ffn2; AttnW attn; ConvW conv; const float *ln_g = nullptr, *ln_b = nullptr; };
+struct FrontW { const float *c1_w = nullptr, *c1_b = nullptr; Linear conv2; };
+
+struct ParamRef { const float* data; int64_t numel; bool used; };
+
+struct Module {
+  int kind = 0;
+  cfm_config_t cfg{};
+  std::unordered_map<std::string, ParamRef> params;
+  bool finalized = false, bf16_mode = false;
+  int num_sms = 148;
+  int64_t last_launches = 0;
+  Arena arena;
+  // packed weights (which members are populated depends on `kind`)
+  FfnW ffn;
+  AttnW attn;
+  ConvW conv;
+  FrontW front;
+  Linear lin, pos_all;
+  const float* div_term = nullptr;
+  std::vector<BlockW> blocks;
+
+  int freq_bins() const { return ((cfg.n_mel_channels - 1) / 2 - 1) / 2; }
+  int finalize(int compute_mode, cudaStream_t stream);
+  // needed != nullptr: only measure the workspace the call would use
+  int forward(int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in, float* y,
+              int64_t* len_out, int B, int frames, void* workspace, int64_t ws_bytes, cudaStream_t stream,
+              int64_t* needed);
+  template <typename TA>
+  int forward_impl(Ctx& c, int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in,
+                   float* y, int64_t* len_out, int B, int frames);
+};
+
+}  // namespace cfm
+
+struct cfm_module : public cfm::Module {};

@@ -1,0 +1,85 @@
+// Internal launcher declarations (host side).  Every function enqueues work on `stream`,
+// returns 0 on success and a non-zero status with cfm::set_error() otherwise.  No launcher
+// allocates or synchronises.
+#pragma once
+#include "common.cuh"
+
+namespace cfm {
+
+enum Epilogue {
+  EPI_BIAS = 0,        // C = acc + bias
+  EPI_BIAS_SWISH = 1,  // C = swish(acc + bias)
+  EPI_BIAS_RELU = 2,   // C = relu(acc + bias)
+  EPI_BIAS_RES = 3,    // C(fp32) = res + res_scale * (acc + bias)
+  EPI_BIAS_F32 = 4,    // C(fp32) = acc + bias
+};
+
+// Implicit-im2col description of the A operand for the second subsampling conv
+// (reference: Conv2d(d,d,3,stride 2), model/utils/convolution.py:39,46).
+// The source is conv1's output stored channels-last as [B][T1p][F1][C]; GEMM row m = (b, t2, f2),
+// GEMM k = (kw*3 + kh)*C + c  ->  src[b][2*t2+kw][2*f2+kh][c].
+struct ConvGeom {
+  int B, T1p, F1, C, T2, F2;
+};
+
+// ---- fp32 SIMT path (true fp32 accumulate; the rtol-1e-4 parity path) -------------------------
+int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N,
+             int K, Epilogue epi, const float* res, float res_scale, const ConvGeom* conv,
+             cudaStream_t stream);
+
+// ---- bf16 tcgen05/TMEM/TMA path -----------------------------------------------------------------
+// A [M,K] bf16 row-major (lda elements, multiple of 8), W [N,K] bf16 row-major.  Output bf16 for
+// EPI_BIAS/SWISH/RELU, fp32 for EPI_BIAS_RES/EPI_BIAS_F32.  When conv != nullptr, A is conv1's output and the
+// output rows are ordered (b, t2, f2).
+int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N,
+                 int K, Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
+                 cudaStream_t stream);
+int tc_init();   // resolves cuTensorMapEncodeTiled through the runtime; 0 when usable
+
+// ---- normalisation / elementwise ---------------------------------------------------------------
+template <typename TOut>
+int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,
+               cudaStream_t stream);
+
+// depthwise conv over time fused with GLU (on load), folded BatchNorm and Swish.
+// u [B,T,2d] (pointwise_conv_1 output, value half then gate half), w [ksize][d] (BN-folded,
+// tap-major), bias [d] (BN-folded), y [B,T,d].
+template <typename T>
+int dwconv_glu_bn_swish(const T* u, const float* w, const float* bias, T* y, int B, int Tn, int d, int ksize,
+                        cudaStream_t stream);
+
+// relative-position multi-head self-attention core (model/utils/attention.py:47-72).
+// qkv [B,T,3d] (q | k | v, head h at columns h*dh), pos [2T-1, ldp] (projected table, head h at
+// columns h*dh), u/v = content/position bias [H,dh] fp32, key_pad [B,T] bytes (1 = masked) or null.
+template <typename T>
+int rel_attention(const T* qkv, const T* pos, int ldp, const float* u, const float* v,
+                  const uint8_t* key_pad, T* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
+
+// sinusoid table [2T-1, d] (model/utils/position.py:11-25), row p <-> relative position T-1-p
+template <typename T>
+int rel_pos_table(const float* div_term, T* pe, int Tn, int d, cudaStream_t stream);
+
+// first subsampling conv: x [B,n_mel,Tin] fp32 -> out [B][T1p][F1][C] channels-last, ReLU fused
+template <typename T>
+int subsample_conv1(const float* x, const float* w, const float* bias, T* out, int B, int n_mel, int Tin,
+                    int T1, int T1p, int F1, int C, cudaStream_t stream);
+
+// lengths' = ((L-1)//2-1)//2 ; key_pad[b,t] = t >= lengths'[b]   (convolution.py:55, masking.py:9-13)
+// (mark_valid = true writes the complement, i.e. generate_padding_mask itself)
+int lengths_and_mask(const int64_t* lengths_in, int64_t* lengths_out, uint8_t* key_pad, int B, int Tn,
+                     bool subsample, bool mark_valid, cudaStream_t stream);
+
+// elementwise helpers used by the module-level API and weight packing
+int swish_f32(const float* x, float* y, int64_t n, cudaStream_t stream);
+int glu_lastdim_f32(const float* x, float* y, int64_t rows, int d, cudaStream_t stream);
+int cast_f32_to_bf16(const float* x, bf16* y, int64_t n, cudaStream_t stream);
+int cast_bf16_to_f32(const bf16* x, float* y, int64_t n, cudaStream_t stream);
+// weight packing
+int pack_conv2_weight(const float* w /*[C,C,3,3]*/, float* out /*[C][(kw*3+kh)*C+c]*/, int C, cudaStream_t);
+int pack_linear_weight(const float* w /*[d, C*F2] (c*F2+f)*/, float* out /*[d][f*C+c]*/, int d, int C, int F2,
+                       cudaStream_t);
+int fold_dwconv_bn(const float* w /*[d,1,k]*/, const float* b, const float* bn_w, const float* bn_b,
+                   const float* rm, const float* rv, float eps, float* w_out /*[k][d]*/, float* b_out, int d,
+                   int k, cudaStream_t);
+
+}  // namespace cfm

@@ -1,0 +1,154 @@
+/* conformer_b200 - C ABI of the B200 (sm_100a) Conformer encoder forward path.
+ *
+ * The reference (Alan-404/Conformer) is pure PyTorch and has no FFI: its boundary for this
+ * path is the nn.Module API.  This header is the C-ABI that the drop-in
+ * modules in conformer_b200/modules.py bind with ctypes; each entry point names the reference
+ * interface it stands in for.  INTEGRATION.md shows the binding a maintainer of the reference
+ * would add.
+ *
+ * Conventions
+ *   - every pointer argument is a DEVICE pointer unless its name ends in _host;
+ *   - tensors are dense row-major fp32 unless stated; `lengths` are int64 like torch.long;
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *   - functions return 0 on success; on failure they return non-zero and cfm_last_error()
+ *     (thread-local) describes it.  Nothing throws across the ABI, nothing allocates device
+ *     memory inside a forward call (the caller supplies `workspace`), nothing synchronises;
+ *   - a module handle owns device copies of its (packed) weights; it is tied to the CUDA device
+ *     current at cfm_module_finalize and may be used from one host thread at a time.
+ *   - there is no CPU path: without a CUDA device every compute entry point fails.
+ */
+#ifndef CONFORMER_B200_H_
+#define CONFORMER_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFM_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CFM_API __attribute__((visibility("default")))
+#else
+#define CFM_API
+#endif
+
+typedef struct cfm_module* cfm_module_t;
+
+/* Arithmetic of a finalized module. */
+enum {
+  CFM_COMPUTE_F32 = 0,  /* fp32 storage, fp32 FMA on CUDA cores (parity path, rtol 1e-4)            */
+  CFM_COMPUTE_BF16 = 1  /* bf16 GEMM operands on tcgen05 tensor cores, fp32 accumulate,             */
+                        /* fp32 residual stream / LayerNorm / softmax (= the reference under        */
+                        /* torch.autocast, train.py:232, with bf16 in place of fp16)                */
+};
+
+/* Which reference module a handle stands for (constructor arguments in cfm_config_t). */
+enum {
+  CFM_KIND_ENCODER = 0,      /* Encoder                      model/modules/encoder.py:9-37      */
+  CFM_KIND_BLOCK = 1,        /* ConformerBlock               model/utils/block.py:8-29          */
+  CFM_KIND_FFN = 2,          /* FeedForwardModule            model/utils/ffn.py:5-23            */
+  CFM_KIND_MHSA = 3,         /* MultiHeadSelfAttentionModule model/utils/attention.py:7-18      */
+  CFM_KIND_REL_ATTENTION = 4,/* RelativeMultiHeadAttention   model/utils/attention.py:20-102    */
+  CFM_KIND_CONV_MODULE = 5,  /* ConvolutionModule            model/utils/convolution.py:7-32    */
+  CFM_KIND_SUBSAMPLING = 6   /* ConvolutionSubsampling       model/utils/convolution.py:34-57   */
+};
+
+typedef struct {
+  int32_t n_mel_channels; /* Encoder(n_mel_channels=...)            encoder.py:10 */
+  int32_t n_blocks;       /* Encoder(n_blocks=...)                                */
+  int32_t d_model;        /* d_model / dim / channels of every module             */
+  int32_t n_heads;        /* n_heads                                              */
+  int32_t kernel_size;    /* ConvolutionModule(kernel_size=...)  convolution.py:8 */
+} cfm_config_t;
+
+CFM_API int cfm_abi_version(void);
+CFM_API const char* cfm_last_error(void);
+/* 0 when a CUDA device with compute capability 10.x is current and usable. */
+CFM_API int cfm_device_check(void);
+
+/* ---- module lifecycle --------------------------------------------------------------------- */
+CFM_API int cfm_module_create(int kind, const cfm_config_t* cfg, cfm_module_t* out);
+/* Register one parameter or buffer under the name it has in the reference module's state_dict
+ * (e.g. "layers.3.conv.batch_norm.running_var"); `data` is fp32 on the device and must stay valid
+ * until cfm_module_finalize returns.  Integer buffers (num_batches_tracked) are not registered. */
+CFM_API int cfm_module_set_param(cfm_module_t m, const char* name, const float* data, int64_t numel);
+/* Check that every tensor of the reference state_dict was registered with the right size, then
+ * build the device-side packed weights (BatchNorm folded into the depthwise conv, q/k/v fused,
+ * conv2/linear reordered to channels-last, bf16 copies).  May be called again after new
+ * cfm_module_set_param calls (e.g. after load_state_dict). */
+CFM_API int cfm_module_finalize(cfm_module_t m, int compute, void* stream);
+CFM_API int cfm_module_destroy(cfm_module_t m);
+
+/* ---- stateless operators ------------------------------------------------------------------- */
+/* generate_padding_mask (model/utils/masking.py:4-13): valid[b,t] = t < lengths[b], uint8 [B,max_len] */
+CFM_API int cfm_padding_mask(const int64_t* lengths, int32_t batch, int32_t max_len, uint8_t* valid, void* stream);
+/* RelativePositionalEncoding.forward (model/utils/position.py:11-28): out fp32 [batch, 2T-1, d];
+ * div_term fp32 [d/2] (the module's non-trainable parameter).  batch >= 1 replicates like :26. */
+CFM_API int cfm_rel_pos_encoding(const float* div_term, int32_t batch, int32_t T, int32_t d_model, float* out, void* stream);
+/* Swish.forward / GLU.forward over the last dimension (model/utils/activation.py:4-17) */
+CFM_API int cfm_swish(const float* x, float* y, int64_t numel, void* stream);
+CFM_API int cfm_glu(const float* x, float* y, int64_t rows, int32_t d_out, void* stream);
+/* ConvolutionSubsampling length rule ((L-1)//2-1)//2 (convolution.py:55) */
+CFM_API int cfm_subsampled_lengths(const int64_t* lengths, int64_t* out, int32_t batch, void* stream);
+
+/* ---- module forwards ------------------------------------------------------------------------ */
+/* Bytes of scratch a forward of `m` needs for `batch` sequences of `frames` frames (for the
+ * encoder and the subsampling module `frames` counts INPUT mel frames, otherwise time steps). */
+CFM_API int64_t cfm_workspace_bytes(cfm_module_t m, int32_t batch, int32_t frames);
+
+/* FeedForwardModule.forward: y[rows,d] = out_linear(swish(hidden_linear(LN(x)))) */
+CFM_API int cfm_ffn_forward(cfm_module_t m, const float* x, float* y, int32_t batch, int32_t T, void* workspace,
+                    int64_t workspace_bytes, void* stream);
+/* MultiHeadSelfAttentionModule.forward (KIND_MHSA: LayerNorm first) or
+ * RelativeMultiHeadAttention.forward with q=k=v=x (KIND_REL_ATTENTION).
+ * pos: fp32 [2T-1, d] positional table (one copy; the reference's batch replicas are identical),
+ *      or NULL to build it from the module-independent default div_term.
+ * key_pad: uint8 [B,T], 1 = masked key (the reference's mask[:,0,0,:]), or NULL. */
+CFM_API int cfm_mhsa_forward(cfm_module_t m, const float* x, const float* pos, const uint8_t* key_pad, float* y,
+                     int32_t batch, int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
+/* ConvolutionModule.forward (eval-mode BatchNorm) */
+CFM_API int cfm_conv_module_forward(cfm_module_t m, const float* x, float* y, int32_t batch, int32_t T, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+/* ConformerBlock.forward(x, pos_embedding, mask) */
+CFM_API int cfm_block_forward(cfm_module_t m, const float* x, const float* pos, const uint8_t* key_pad, float* y,
+                      int32_t batch, int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
+/* ConvolutionSubsampling.forward: mel fp32 [B,n_mel,Tin] -> y fp32 [B,T',d*F2] with feature index
+ * c*F2+f (convolution.py:51-52); lengths_in/lengths_out may both be NULL. */
+CFM_API int cfm_subsampling_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y,
+                            int64_t* lengths_out, int32_t batch, int32_t Tin, void* workspace,
+                            int64_t workspace_bytes, void* stream);
+/* Encoder.forward(x, lengths) -> (y [B,T',d] fp32, lengths').  lengths_in NULL = no mask. */
+CFM_API int cfm_encoder_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y,
+                        int64_t* lengths_out, int32_t batch, int32_t Tin, void* workspace,
+                        int64_t workspace_bytes, void* stream);
+/* Same call with HOST buffers (pinned or pageable): copies mel/lengths in, runs the forward and
+ * copies y/lengths' out on `stream`, using workspace for the device staging.  This is the
+ * end-to-end entry point a non-torch caller would use. */
+CFM_API int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host, float* y_host,
+                             int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+CFM_API int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin);
+
+/* Number of kernel launches the last forward on `m` enqueued (for bench.py's gpu_launches). */
+CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
+
+/* ---- low-level kernels exposed for unit tests and benchmarks -------------------------------- */
+/* bf16 tcgen05 GEMM: C = epi(A[M,K] W[N,K]^T + bias); epi: 0 bias, 1 bias+swish, 2 bias+relu,
+ * 3 res + scale*(acc+bias) (C,res fp32; otherwise C bf16).  A,W bf16 (uint16 storage). */
+CFM_API int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
+                  int32_t epi, const float* res, float res_scale, void* stream);
+/* fp32 CUDA-core GEMM with the same epilogues (all fp32). */
+CFM_API int cfm_gemm_f32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                 int32_t epi, const float* res, float res_scale, void* stream);
+/* depthwise stage of the ConvolutionModule on its own: u [B,T,2d] -> y [B,T,d]
+ * (GLU, depthwise conv with BN-folded weights w[k][d] and bias[d], Swish); dtype 0 fp32, 1 bf16. */
+CFM_API int cfm_dwconv_glu_bn_swish(const void* u, const float* w, const float* bias, void* y, int32_t batch, int32_t T,
+                            int32_t d, int32_t ksize, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONFORMER_B200_H_ */

@@ -1,0 +1,185 @@
+"""Module- and encoder-level parity on the GPU, through the drop-in nn.Modules (ctypes -> C ABI ->
+sm_100a kernels), against (a) the golden outputs of the real reference committed under tests/golden
+and (b) the oracle on the same seeded inputs."""
+import pytest
+import torch
+
+import conformer_b200 as cb
+from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE
+from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, synth_decoder_state_dict, synth_encoder_state_dict,
+                                  synth_lengths, synth_logmel)
+from helpers import assert_close_bf16, assert_close_fp32, bf16_report, golden, sub
+from oracle import conformer_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+DEV = "cuda"
+
+
+def _load(mod, sd):
+    mod.load_state_dict(sd, strict=True)
+    return mod.to(DEV).eval()
+
+
+@pytest.fixture(scope="module")
+def subcase():
+    c = SUBMODULE_CFG
+    cfg = c["cfg"]
+    sd = synth_encoder_state_dict(cfg, c["seed"])
+    g = torch.Generator().manual_seed(c["x_seed"])
+    x = torch.randn(c["B"], c["T"], cfg.d_model, generator=g).to(DEV)
+    lengths = torch.tensor(c["lengths"], device=DEV)
+    pos = O.rel_pos_table(c["T"], cfg.d_model, sd["rel_pe.div_term"])[None].expand(c["B"], -1, -1).contiguous().to(DEV)
+    return cfg, sd, x, lengths, pos, golden("submodules")
+
+
+def test_activations_mask_posenc(subcase):
+    cfg, sd, x, lengths, pos, gold = subcase
+    assert_close_fp32(cb.Swish()(x), O.swish(x.cpu()), "swish")
+    assert_close_fp32(cb.GLU(dim=-1)(x), O.glu(x.cpu(), -1), "glu last")
+    assert_close_fp32(cb.GLU(dim=1)(x[:, :40]), O.glu(x[:, :40].cpu(), 1), "glu dim1")
+    valid = cb.generate_padding_mask(lengths)
+    assert valid.dtype == torch.bool and torch.equal(valid.cpu(), gold["padding_mask"])
+    assert torch.equal(cb.generate_padding_mask(lengths, 50).cpu()[:, :41], gold["padding_mask"])
+    pe = _load(cb.RelativePositionalEncoding(cfg.d_model), sub(sd, "rel_pe."))
+    out = pe(x)
+    assert out.shape == (x.shape[0], 2 * x.shape[1] - 1, cfg.d_model)
+    assert_close_fp32(out[0], gold["rel_pe"], "rel_pe")
+    assert torch.equal(out[0], out[-1])
+
+
+def test_ffn_fp32(subcase):
+    cfg, sd, x, _, _, gold = subcase
+    m = _load(cb.FeedForwardModule(cfg.d_model), sub(sd, "layers.0.ffn_1."))
+    assert_close_fp32(m(x), gold["ffn"], "ffn")
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_mhsa_fp32(subcase, masked):
+    cfg, sd, x, lengths, pos, gold = subcase
+    m = _load(cb.MultiHeadSelfAttentionModule(cfg.d_model, cfg.n_heads), sub(sd, "layers.0.attention."))
+    mask = (~cb.generate_padding_mask(lengths))[:, None, None, :] if masked else None
+    assert_close_fp32(m(x, pos, mask), gold["mhsa_mask" if masked else "mhsa_nomask"], "mhsa")
+
+
+def test_rel_attention_fp32_vs_oracle(subcase):
+    cfg, sd, x, lengths, pos, _ = subcase
+    m = _load(cb.RelativeMultiHeadAttention(cfg.d_model, cfg.n_heads), sub(sd, "layers.0.attention.attention."))
+    mask = (~cb.generate_padding_mask(lengths))[:, None, None, :]
+    want = O.rel_attention(sd, "layers.0.attention.attention.", x.cpu(), pos[0].cpu(), mask[:, 0, 0].cpu(), cfg.n_heads)
+    assert_close_fp32(m(x, x, x, pos, mask), want, "rel_attention")
+
+
+def test_conv_module_fp32(subcase):
+    cfg, sd, x, _, _, gold = subcase
+    m = _load(cb.ConvolutionModule(cfg.d_model, cfg.kernel_size), sub(sd, "layers.0.conv."))
+    assert_close_fp32(m(x), gold["conv"], "conv")
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_block_fp32(subcase, masked):
+    cfg, sd, x, lengths, pos, gold = subcase
+    m = _load(cb.ConformerBlock(cfg.d_model, cfg.n_heads, cfg.kernel_size), sub(sd, "layers.0."))
+    mask = (~cb.generate_padding_mask(lengths))[:, None, None, :] if masked else None
+    assert_close_fp32(m(x, pos, mask), gold["block_mask" if masked else "block_nomask"], "block", scale=2.0)
+
+
+def test_subsampling_fp32(subcase):
+    cfg, sd, _, _, _, gold = subcase
+    c = SUBMODULE_CFG
+    m = _load(cb.ConvolutionSubsampling(cfg.d_model), sub(sd, "downsampling_conv."))
+    mel = synth_logmel(c["B"], cfg.n_mel_channels, c["Tin"], seed=77).to(DEV)
+    y, l = m(mel, torch.tensor(c["mel_lengths"], device=DEV))
+    assert_close_fp32(y, gold["subsampling"], "subsampling")
+    assert torch.equal(l.cpu(), gold["subsampling_lengths"])
+
+
+def _encoder_case(case):
+    cfg = case["cfg"]
+    sd = synth_encoder_state_dict(cfg, case["seed"])
+    x = synth_logmel(case["B"], cfg.n_mel_channels, case["Tin"], seed=1000 + case["seed"]).to(DEV)
+    lengths = synth_lengths(case["B"], case["Tin"]).to(DEV) if case["with_lengths"] else None
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
+    return enc, x, lengths, golden("encoder_" + case["name"])
+
+
+@pytest.mark.parametrize("case", ENCODER_CASES, ids=[c["name"] for c in ENCODER_CASES])
+def test_encoder_fp32_vs_reference_golden(case):
+    enc, x, lengths, gold = _encoder_case(case)
+    y, out_len = enc(x, lengths)
+    # two fp32 implementations with different summation orders: 4x the single-op gate over 16 layers
+    assert_close_fp32(y, gold["y"], "encoder fp32", scale=4.0)
+    if lengths is not None:
+        assert torch.equal(out_len.cpu(), gold["out_lengths"])
+    else:
+        assert out_len is None
+
+
+@pytest.mark.parametrize("case", [c for c in ENCODER_CASES if c["cfg"].d_model % 64 == 0],
+                         ids=[c["name"] for c in ENCODER_CASES if c["cfg"].d_model % 64 == 0])
+def test_encoder_bf16_vs_reference_golden(case):
+    enc, x, lengths, gold = _encoder_case(case)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y, out_len = enc(x, lengths)
+    assert y.dtype == torch.float32
+    r = assert_close_bf16(y, gold["y"], "encoder bf16")
+    print("bf16 vs reference fp32:", case["name"], r)
+    y2, _ = enc.set_compute("bf16")(x, lengths)
+    assert torch.equal(y, y2)
+
+
+def test_greedy_ctc_tokens_bit_exact_fp32():
+    c = TOKEN_CASE
+    cfg = c["cfg"]
+    gold = golden("tokens")
+    sd = synth_encoder_state_dict(cfg, c["seed"], prefix="encoder.")
+    sd.update(synth_decoder_state_dict(cfg.d_model, c["vocab"], seed=c["seed"] + 1, peaky=c["peaky"]))
+    model = _load(cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
+    x = synth_logmel(c["B"], cfg.n_mel_channels, c["Tin"], seed=2000 + c["seed"]).to(DEV)
+    lengths = synth_lengths(c["B"], c["Tin"]).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    logits, out_len = model(x, lengths)
+    assert torch.equal(out_len.cpu(), gold["out_lengths"])
+    toks = O.greedy_ctc_batch(logits.cpu(), 0, c["vocab"] - 1)
+    want = [[int(t) for t in row if t >= 0] for row in gold["tokens"]]
+    assert toks == want
+    safe = gold["margin"] > 1e-3
+    assert torch.equal(logits.cpu().argmax(-1)[safe], gold["ids"][safe])
+
+
+def test_cpu_tensors_and_training_mode_fail_loudly():
+    enc = cb.Encoder(80, 1, 64, 4, 7).to(DEV).eval()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 80, 64))
+    enc.train()
+    with pytest.raises(RuntimeError):
+        enc(torch.zeros(1, 80, 64, device=DEV))
+
+
+def test_reload_weights_repacks():
+    cfg = ENCODER_CASES[0]["cfg"]
+    enc, x, lengths, gold = _encoder_case(ENCODER_CASES[0])
+    enc.load_state_dict(synth_encoder_state_dict(cfg, 999))
+    y_other, _ = enc(x, lengths)
+    assert (y_other.cpu() - gold["y"]).abs().max() > 1e-2
+    enc.load_state_dict(synth_encoder_state_dict(cfg, ENCODER_CASES[0]["seed"]))
+    y, _ = enc(x, lengths)
+    assert_close_fp32(y, gold["y"], "reloaded", scale=4.0)
+
+
+@pytest.mark.parametrize("name,cfg,B,Tin", [("C2-M", CONFORMER_M, 8, 1501), ("C3-L", CONFORMER_L, 4, 2001)])
+def test_encoder_bf16_full_length_vs_oracle(name, cfg, B, Tin):
+    """Full utterance lengths of BASELINE configs 2/3 (reduced batch so the fp32 oracle stays quick);
+    oracle = the restated reference run in fp32 on the GPU with TF32 disabled."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sd = synth_encoder_state_dict(cfg, 7)
+    x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=8).to(DEV)
+    lengths = synth_lengths(B, Tin).to(DEV)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
+    y, out_len = enc.set_compute("bf16")(x, lengths)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    want, want_len = O.encoder(sd_dev, x, lengths, cfg.n_heads)
+    assert torch.equal(out_len, want_len)
+    print(name, assert_close_bf16(y, want, name))
