@@ -53,6 +53,8 @@ SIGNATURES = {
     "cfm_encoder_forward_host": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_host_workspace_bytes": (_i64, [_p, _i32, _i32]),
     "cfm_last_launch_count": (_i64, [_p]),
+    "cfm_profile_enable": (C.c_int, [_p, _i32]),
+    "cfm_profile_collect": (C.c_int, [_p, C.POINTER(C.c_double), _i32]),
     "cfm_gemm_bf16": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
     "cfm_gemm_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
     "cfm_dwconv_glu_bn_swish": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -161,6 +161,29 @@ int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, const int64_
 
 int64_t cfm_last_launch_count(cfm_module_t m) { return m ? m->last_launches : -1; }
 
+int cfm_profile_enable(cfm_module_t m, int32_t on) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  m->prof.on = on != 0;
+  m->prof.recs.clear();
+  m->prof.next = 0;
+  return 0;
+}
+
+int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes) {
+  CFM_REQUIRE(m != nullptr && out_host != nullptr && n_classes >= KC_COUNT, "bad profile buffer");
+  for (int i = 0; i < n_classes * 4; ++i) out_host[i] = 0.0;
+  for (const ProfRec& r : m->prof.recs) {
+    CFM_CUDA_OK(cudaEventSynchronize(r.e1));
+    float ms = 0.f;
+    CFM_CUDA_OK(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    double* o = out_host + r.cls * 4;
+    o[0] += 1.0; o[1] += ms; o[2] += r.flops; o[3] += r.bytes;
+  }
+  m->prof.recs.clear();
+  m->prof.next = 0;
+  return 0;
+}
+
 int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K, int32_t epi,
                   const float* res, float res_scale, void* stream) {
   CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 4, "bad GEMM arguments");

@@ -250,6 +250,7 @@ template <> struct Dispatch<float> {
   static int gemm(Ctx& c, const float* A, int lda, const Linear& L, void* C, int ldc, int M, Epilogue e,
                   const float* res, float scale, const ConvGeom* g) {
     ++c.launches;
+    Timed t(c, KC_GEMM_F32, 2.0 * M * L.N * L.K, 4.0 * (static_cast<double>(M) * (L.K + L.N) + static_cast<double>(L.N) * L.K));
     return gemm_f32(A, lda, L.w32, L.b, static_cast<float*>(C), ldc, M, L.N, L.K, e, res, scale, g, c.stream);
   }
 };
@@ -257,11 +258,20 @@ template <> struct Dispatch<bf16> {
   static int gemm(Ctx& c, const bf16* A, int lda, const Linear& L, void* C, int ldc, int M, Epilogue e,
                   const float* res, float scale, const ConvGeom* g) {
     ++c.launches;
+    Timed t(c, KC_GEMM_TC, 2.0 * M * L.N * L.K, 2.0 * (static_cast<double>(M) * (L.K + L.N) + static_cast<double>(L.N) * L.K));
     return gemm_bf16_tc(A, lda, L.w16, L.b, C, ldc, M, L.N, L.K, e, res, scale, g, c.num_sms, c.stream);
   }
 };
 
 template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(c.ws.take(static_cast<size_t>(n) * sizeof(TA))); }
+
+#define KRUN(cls, flops, bytes, call)      \
+  do {                                     \
+    ++c.launches;                          \
+    Timed _t(c, cls, flops, bytes);        \
+    CFM_TRY(call);                         \
+  } while (0)
+#define LN_BYTES(M, d, so) (static_cast<double>(M) * (d) * (4 + (so)))
 
 #define WS_CHECK(ptr) CFM_REQUIRE((ptr) != nullptr || c.ws.measuring(), "workspace too small; query cfm_workspace_bytes")
 
@@ -273,8 +283,7 @@ int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale
   TA* h = ws_take<TA>(c, M * 4 * d);
   WS_CHECK(a); WS_CHECK(h);
   if (!c.ws.measuring()) {
-    ++c.launches;
-    CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.hidden, h, 4 * d, static_cast<int>(M), EPI_BIAS_SWISH, nullptr, 0.f, nullptr));
     CFM_TRY(Dispatch<TA>::gemm(c, h, 4 * d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, scale, nullptr));
   }
@@ -291,12 +300,11 @@ int pos_project(Ctx& c, const Linear& wp, const float* div_term, const float* po
   WS_CHECK(pe); WS_CHECK(pp);
   *out = pp;
   if (c.ws.measuring()) return 0;
-  ++c.launches;
   if (pos_f32 != nullptr) {
     if (sizeof(TA) == 4) CFM_CUDA_OK(cudaMemcpyAsync(pe, pos_f32, static_cast<size_t>(R) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
-    else CFM_TRY(cast_f32_to_bf16(pos_f32, reinterpret_cast<bf16*>(pe), static_cast<int64_t>(R) * d, c.stream));
+    else KRUN(KC_MISC, 0, 6.0 * R * d, cast_f32_to_bf16(pos_f32, reinterpret_cast<bf16*>(pe), static_cast<int64_t>(R) * d, c.stream));
   } else {
-    CFM_TRY(rel_pos_table<TA>(div_term, pe, Tn, d, c.stream));
+    KRUN(KC_MISC, 0, static_cast<double>(R) * d * sizeof(TA), rel_pos_table<TA>(div_term, pe, Tn, d, c.stream));
   }
   return Dispatch<TA>::gemm(c, pe, d, wp, pp, wp.N, R, EPI_BIAS, nullptr, 0.f, nullptr);
 }
@@ -314,17 +322,16 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
   if (!c.ws.measuring()) {
     const TA* ain = a;
     if (pre_ln) {
-      ++c.launches;
-      CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+      KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
     } else if (sizeof(TA) == 4) {
       ain = reinterpret_cast<const TA*>(x);
     } else {
-      ++c.launches;
-      CFM_TRY(cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
+      KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
     }
     CFM_TRY(Dispatch<TA>::gemm(c, ain, d, w.qkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
-    ++c.launches;
-    CFM_TRY(rel_attention<TA>(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
+    // algorithmic work: content + positional + PV = 6*T*d FLOPs per token
+    KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
+         rel_attention<TA>(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, ctx, d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);
@@ -341,10 +348,12 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
   TA* g = ws_take<TA>(c, M * d);
   WS_CHECK(a); WS_CHECK(u); WS_CHECK(g);
   if (!c.ws.measuring()) {
-    c.launches += 2;
-    CFM_TRY(layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, 2 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
-    CFM_TRY(dwconv_glu_bn_swish<TA>(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
+    // algorithmic bytes of the depthwise stage: input [M,d] + output [M,d] + taps; this kernel
+    // also reads the GLU gate half, which is not counted
+    KRUN(KC_DWCONV, 2.0 * w.ksize * M * d, (2.0 * M * d + (w.ksize + 1.0) * d) * sizeof(TA),
+         dwconv_glu_bn_swish<TA>(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, g, d, w.pw2, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);
@@ -361,8 +370,7 @@ int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, cons
   CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xw, B, Tn, d));
   CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xw, xw, 0.5f, xw, M, d));
   if (!c.ws.measuring()) {
-    ++c.launches;
-    CFM_TRY(layer_norm<float>(xw, w.ln_g, w.ln_b, y, M, d, c.stream));
+    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4), layer_norm<float>(xw, w.ln_g, w.ln_b, y, M, d, c.stream));
   }
   return 0;
 }
@@ -379,8 +387,8 @@ int front_fwd(Ctx& c, const Module& m, const float* mel, int B, int Tin, TA** h2
   WS_CHECK(out1); WS_CHECK(h2);
   *h2_out = h2;
   if (c.ws.measuring()) return 0;
-  ++c.launches;
-  CFM_TRY(subsample_conv1<TA>(mel, m.front.c1_w, m.front.c1_b, out1, B, n_mel, Tin, T1, T1p, F1, d, c.stream));
+  KRUN(KC_CONV1, 18.0 * d * F1 * T1 * B, 4.0 * B * n_mel * Tin + static_cast<double>(B) * T1 * F1 * d * sizeof(TA),
+       subsample_conv1<TA>(mel, m.front.c1_w, m.front.c1_b, out1, B, n_mel, Tin, T1, T1p, F1, d, c.stream));
   ConvGeom g{B, T1p, F1, d, T2, F2};
   return Dispatch<TA>::gemm(c, out1, 0, m.front.conv2, h2, d, B * T2 * F2, EPI_BIAS_RELU, nullptr, 0.f, &g);
 }
@@ -492,6 +500,7 @@ int Module::forward(int op, const float* x, const float* pos, const uint8_t* key
   Ctx c;
   c.stream = stream;
   c.num_sms = num_sms;
+  c.prof = &prof;
   c.ws.init(needed ? nullptr : workspace, needed ? 0 : static_cast<size_t>(ws_bytes), needed != nullptr);
   int s = bf16_mode ? forward_impl<bf16>(c, op, x, pos, key_pad, len_in, y, len_out, B, frames)
                     : forward_impl<float>(c, op, x, pos, key_pad, len_in, y, len_out, B, frames);

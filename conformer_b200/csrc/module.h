@@ -42,11 +42,49 @@ class Workspace {                    // bump allocator over the caller's scratch
   bool measuring_ = false;
 };
 
+// kernel classes for the optional per-launch CUDA-event profile (bench.py's roofline numbers)
+enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_F32, KC_LAYERNORM, KC_ATTENTION, KC_DWCONV, KC_CONV1, KC_MISC, KC_COUNT };
+
+struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  size_t next = 0;
+  cudaEvent_t get() {
+    if (next == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    return pool[next++];
+  }
+  ~Profiler() { for (auto e : pool) cudaEventDestroy(e); }
+};
+
 struct Ctx {
   cudaStream_t stream = nullptr;
   int num_sms = 148;
   int64_t launches = 0;
   Workspace ws;
+  Profiler* prof = nullptr;
+};
+
+// brackets one kernel launch with events on the launching stream when profiling is enabled
+struct Timed {
+  Ctx& c;
+  ProfRec rec;
+  bool live;
+  Timed(Ctx& ctx, int cls, double flops, double bytes) : c(ctx), live(ctx.prof != nullptr && ctx.prof->on) {
+    if (!live) return;
+    rec = ProfRec{cls, flops, bytes, c.prof->get(), c.prof->get()};
+    cudaEventRecord(rec.e0, c.stream);
+  }
+  ~Timed() {
+    if (!live) return;
+    cudaEventRecord(rec.e1, c.stream);
+    c.prof->recs.push_back(rec);
+  }
 };
 
 struct Linear {
@@ -71,6 +109,7 @@ struct Module {
   int num_sms = 148;
   int64_t last_launches = 0;
   Arena arena;
+  Profiler prof;
   // packed weights (which members are populated depends on `kind`)
   FfnW ffn;
   AttnW attn;

@@ -195,7 +195,31 @@ class _Native(nn.Module):
 
     @property
     def last_launch_count(self) -> int:
-        return sum(int(lib().cfm_last_launch_count(h)) for h, _, _ in self._handles.values())
+        """Kernel launches enqueued by the most recent forward (any compute mode)."""
+        return max([int(lib().cfm_last_launch_count(h)) for h, _, _ in self._handles.values()] or [0])
+
+    KERNEL_CLASSES = ("gemm_tcgen05", "gemm_fp32", "layer_norm", "attention", "dwconv", "conv1", "misc")
+
+    def profile(self, on: bool) -> None:
+        """Bracket every kernel launch of subsequent forwards with CUDA events (see cfm_profile_enable)."""
+        self._native()
+        for h, _, _ in self._handles.values():
+            check(lib().cfm_profile_enable(h, 1 if on else 0))
+
+    def collect_profile(self) -> Dict[str, Dict[str, float]]:
+        """Per kernel class: launches, milliseconds, algorithmic flops and bytes since the last collect."""
+        n = len(self.KERNEL_CLASSES)
+        out: Dict[str, Dict[str, float]] = {}
+        for h, _, _ in self._handles.values():
+            buf = (C.c_double * (n * 4))()
+            check(lib().cfm_profile_collect(h, buf, n))
+            for i, name in enumerate(self.KERNEL_CLASSES):
+                e = out.setdefault(name, dict(launches=0.0, ms=0.0, flops=0.0, bytes=0.0))
+                e["launches"] += buf[i * 4]
+                e["ms"] += buf[i * 4 + 1]
+                e["flops"] += buf[i * 4 + 2]
+                e["bytes"] += buf[i * 4 + 3]
+        return out
 
 
 def _key_pad(mask: Optional[torch.Tensor], B: int, T: int) -> Optional[torch.Tensor]:

@@ -135,6 +135,13 @@ CFM_API int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, 
 /* Number of kernel launches the last forward on `m` enqueued (for bench.py's gpu_launches). */
 CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 
+/* Optional per-launch profile: when enabled every kernel launch of a forward on `m` is bracketed by
+ * CUDA events on the launching stream.  cfm_profile_collect waits for them and fills, per kernel class
+ * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc), four
+ * doubles: launches, total milliseconds, algorithmic FLOPs, algorithmic bytes. */
+CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
+CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);
+
 /* ---- low-level kernels exposed for unit tests and benchmarks -------------------------------- */
 /* bf16 tcgen05 GEMM: C = epi(A[M,K] W[N,K]^T + bias); epi: 0 bias, 1 bias+swish, 2 bias+relu,
  * 3 res + scale*(acc+bias) (C,res fp32; otherwise C bf16).  A,W bf16 (uint16 storage). */
