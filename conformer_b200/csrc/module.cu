@@ -263,6 +263,16 @@ template <> struct Dispatch<bf16> {
   }
 };
 
+inline int attention_any(const float* qkv, const float* pos, int ldp, const float* u, const float* v, const uint8_t* kp,
+                         float* ctx, int B, int Tn, int H, int dh, cudaStream_t st) {
+  return rel_attention<float>(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+}
+inline int attention_any(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* kp,
+                         bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t st) {
+  if (dh == 64) return rel_attention_bf16_mma(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+  return rel_attention<bf16>(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+}
+
 template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(c.ws.take(static_cast<size_t>(n) * sizeof(TA))); }
 
 #define KRUN(cls, flops, bytes, call)      \
@@ -331,7 +341,7 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
     CFM_TRY(Dispatch<TA>::gemm(c, ain, d, w.qkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
     // algorithmic work: content + positional + PV = 6*T*d FLOPs per token
     KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
-         rel_attention<TA>(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
+         attention_any(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, ctx, d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);

@@ -183,3 +183,29 @@ def test_encoder_bf16_full_length_vs_oracle(name, cfg, B, Tin):
     want, want_len = O.encoder(sd_dev, x, lengths, cfg.n_heads)
     assert torch.equal(out_len, want_len)
     print(name, assert_close_bf16(y, want, name))
+
+
+@pytest.mark.parametrize("T", [1, 17, 63, 64, 65, 130, 374])
+@pytest.mark.parametrize("masked", [False, True])
+def test_rel_attention_bf16_tensor_core_vs_oracle(T, masked):
+    """Head size 64 routes to the tensor-core flash kernel (in-tile relative shift); tile edges at 64."""
+    d, H, B = 128, 2, 3
+    g = torch.Generator().manual_seed(100 + T)
+    sd = {k[len("layers.0.attention.attention."):]: v for k, v in
+          synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 40).items()
+          if k.startswith("layers.0.attention.attention.")}
+    # larger biases/weights so that the positional term matters
+    sd = {k: (v * 3.0 if "proj.weight" in k and "out" not in k else v) for k, v in sd.items()}
+    x = torch.randn(B, T, d, generator=g)
+    pos = O.rel_pos_table(T, d)
+    lengths = torch.tensor([T, max(1, T // 2), 1])
+    key_is_pad = ~O.padding_mask(lengths, T) if masked else None
+    want = O.rel_attention(sd, "", x, pos, key_is_pad, H)
+    m = _load(cb.RelativeMultiHeadAttention(d, H), sd).set_compute("bf16")
+    mask = key_is_pad[:, None, None, :].to(DEV) if masked else None
+    xd = x.to(DEV)
+    got = m(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask)
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 2e-2, rel
+    m32 = m.set_compute("fp32")
+    assert_close_fp32(m32(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask), want, "fp32 attention", scale=2.0)
