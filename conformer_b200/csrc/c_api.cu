@@ -190,6 +190,12 @@ int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int3
   int dev = 0, sms = 0;
   CFM_CUDA_OK(cudaGetDevice(&dev));
   CFM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  if (epi == EPI_BIAS_RES) {
+    CFM_REQUIRE(res != nullptr, "residual epilogue without residual");
+    if (res != static_cast<const float*>(C))       // the kernel accumulates into C in place
+      CFM_CUDA_OK(cudaMemcpyAsync(C, res, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToDevice, S(stream)));
+    res = static_cast<const float*>(C);
+  }
   return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C, N, M, N, K,
                       static_cast<Epilogue>(epi), res, res_scale, nullptr, sms, S(stream));
 }

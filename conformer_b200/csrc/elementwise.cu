@@ -27,6 +27,47 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
   for (int c = lane; c < d; c += 32) yr[c] = from_f32<TOut>((xr[c] - mean) * rstd * gamma[c] + beta[c]);
 }
 
+// Vectorised variant for d = 128 * NV: each lane keeps its 4*NV values in registers (one pass over HBM),
+// loads them as float4 (coalesced 512 B per warp request) and stores 8-byte (bf16) or 16-byte (fp32) vectors.
+template <typename TOut, int NV>
+__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* __restrict__ x,
+                                                             const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, TOut* __restrict__ y,
+                                                             int64_t rows) {
+  constexpr int D = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+  float4 v[NV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i] = xr[i * 32 + lane];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+    const float o0 = v[i].x * rstd * g4.x + b4.x, o1 = v[i].y * rstd * g4.y + b4.y;
+    const float o2 = v[i].z * rstd * g4.z + b4.z, o3 = v[i].w * rstd * g4.w + b4.w;
+    if (sizeof(TOut) == 4) {
+      reinterpret_cast<float4*>(y + row * D)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
+    } else {
+      reinterpret_cast<uint2*>(y + row * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+    }
+  }
+}
+
 template <typename T>
 __global__ void rel_pos_table_kernel(const float* __restrict__ div_term, T* __restrict__ pe, int Tn, int d) {
   const int half = d >> 1;
@@ -113,7 +154,16 @@ template <typename TOut>
 int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,
                cudaStream_t stream) {
   CFM_REQUIRE(rows > 0 && d > 0, "empty layer_norm");
-  layer_norm_kernel<TOut><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows, d);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
+                         reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
+  if (aligned && d == 256)
+    layer_norm_vec_kernel<TOut, 2><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+  else if (aligned && d == 512)
+    layer_norm_vec_kernel<TOut, 4><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+  else if (aligned && d == 128)
+    layer_norm_vec_kernel<TOut, 1><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+  else
+    layer_norm_kernel<TOut><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows, d);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

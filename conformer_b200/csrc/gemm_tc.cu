@@ -4,15 +4,18 @@
 //     ring guarded by full/empty mbarriers;
 //   * tcgen05.mma (kind::f16, M=128, N=BLOCK_N, K=16) issued by one thread, accumulators in TMEM,
 //     double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   * 8 epilogue warps read the accumulator with tcgen05.ld (one thread = one output row) and apply
-//     bias / Swish / ReLU / (residual + scale) before storing;
+//   * 8 epilogue warps read the accumulator with tcgen05.ld (one thread = one output row), apply
+//     bias / Swish / ReLU / (residual + scale), and write the tile into a 128-byte-swizzled staging
+//     buffer (conflict-free 16-byte stores) from which ONE thread issues TMA stores - global traffic
+//     is fully coalesced and M/N tails are clipped by the tensor map.  The residual tile is fetched by
+//     TMA into the same staging buffer while the MMAs of the tile are still running;
 //   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule, N-tiles innermost so the
 //     CTAs running together share the same rows of A in L2.
 //
 // CONV mode turns the second front-end convolution (Conv2d(d,d,3,stride 2), convolution.py:39,46)
 // into an implicit GEMM: the A tile for tap (kh,kw) is a strided box of conv1's channels-last output
 // fetched by a 5-D tensor map (the stride-2 time axis is split into (pair, parity)), so no im2col
-// buffer exists.
+// buffer exists; its output tile goes out through a 4-D map over [B][T2][F2][C].
 #include <mutex>
 
 #include "ops.h"
@@ -22,41 +25,53 @@ namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
+constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
+constexpr int CBLK_BYTES = BLOCK_M * 128;                      // one staging block: 128 rows x 128 bytes
+constexpr int SMEM_LIMIT = 227 * 1024;
 
-template <int BLOCK_N> struct Cfg {
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+constexpr bool epi_out_f32(int epi) { return epi == EPI_BIAS_RES || epi == EPI_BIAS_F32; }
+
+template <int BLOCK_N, bool OUT_F32> struct Cfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;                 // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int CBLK_COLS = OUT_F32 ? 32 : 64;          // columns per staging block
+  static constexpr int NUM_CBLK = BLOCK_N / CBLK_COLS;
+  static constexpr int CBUF_BYTES = NUM_CBLK * CBLK_BYTES;
+  static constexpr int AUX_BYTES = 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - CBUF_BYTES - AUX_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;                // two accumulator stages
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CBUF_BYTES + AUX_BYTES;
+  static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_kb;
   const float* bias;
-  const float* res;
   float res_scale;
-  void* C;
-  int ldc;
   // conv mode
   int T2, F2, TCH, kb_per_tap;
 };
 
 template <int BLOCK_N, int EPI, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  using C_ = Cfg<BLOCK_N>;
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, GemmParams p) {
+  constexpr bool OUT_F32 = epi_out_f32(EPI);
+  using C_ = Cfg<BLOCK_N, OUT_F32>;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C_::STAGE_BYTES);
+  uint8_t* cbuf = smem + STAGES * C_::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cbuf + C_::CBUF_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* res_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
@@ -64,6 +79,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -74,6 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
     }
+    mbar_init(res_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, C_::TMEM_COLS);
@@ -148,85 +165,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = warp - 4;
     const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
     const int col_half = ew >> 2;
-    const int r_in_tile = q * 32 + lane;
+    const int row = q * 32 + lane;                             // row inside the tile
+    const bool leader = (threadIdx.x == 128);
+    const uint32_t row_off = row * 128;
+    const int sw = row & 7;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const int n0 = n_tile * BLOCK_N;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      int64_t out_row;
-      bool row_ok;
-      if (CONV) {
-        const int ct = m_tile % p.TCH, cf = (m_tile / p.TCH) % p.F2, cb = m_tile / (p.TCH * p.F2);
-        const int t2 = ct * BLOCK_M + r_in_tile;
-        row_ok = t2 < p.T2;
-        out_row = (static_cast<int64_t>(cb) * p.T2 + t2) * p.F2 + cf;
-      } else {
-        out_row = static_cast<int64_t>(m_tile) * BLOCK_M + r_in_tile;
-        row_ok = out_row < p.M;
+      // staging buffer must have been drained by the previous tile's TMA store
+      if (leader) {
+        bulk_wait_read0();
+        if (EPI == EPI_BIAS_RES) {
+          int nblk = 0;
+          for (int blk = 0; blk < C_::NUM_CBLK; ++blk) nblk += (n0 + blk * C_::CBLK_COLS < p.N) ? 1 : 0;
+          mbar_expect_tx(res_bar, nblk * CBLK_BYTES);
+          for (int blk = 0; blk < C_::NUM_CBLK; ++blk)
+            if (n0 + blk * C_::CBLK_COLS < p.N)
+              tma_load_2d(cbuf + blk * CBLK_BYTES, &tmC, res_bar, n0 + blk * C_::CBLK_COLS, m_tile * BLOCK_M);
+        }
       }
+      named_bar_sync(1, NUM_EPI_THREADS);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
+      if (EPI == EPI_BIAS_RES) mbar_wait(res_bar, acc_it & 1);
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
         const int col_in_tile = col_half * (BLOCK_N / 2) + ch * 32;
-        const int col0 = n_tile * BLOCK_N + col_in_tile;
+        const int col0 = n0 + col_in_tile;
         uint32_t r[32];
         tmem_ld_32x32(t_row + col_in_tile, r);
         tmem_ld_wait();
-        if (row_ok && col0 < p.N) {
+        if (col0 < p.N) {
+          float v[32];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {                         // groups of 8 columns
-            const int col = col0 + g * 8;
-            if (col + 8 <= p.N) {
-              float v[8];
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+          if (p.bias != nullptr) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 4));
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            for (int g = 0; g < 8; ++g) {
+              if (col0 + g * 4 + 4 <= p.N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
+                v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
               }
-              if (EPI == EPI_BIAS_SWISH) {
+            }
+          }
+          if (EPI == EPI_BIAS_SWISH) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = swish_fast(v[i]);
-              }
-              if (EPI == EPI_BIAS_RELU) {
+            for (int i = 0; i < 32; ++i) v[i] = swish_fast(v[i]);
+          }
+          if (EPI == EPI_BIAS_RELU) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (OUT_F32) {
+            // 32 fp32 columns = one full 128-byte row of staging block (col_in_tile / 32)
+            uint8_t* blk = cbuf + (col_in_tile >> 5) * CBLK_BYTES + row_off;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4* dst = reinterpret_cast<float4*>(blk + ((j ^ sw) << 4));
+              float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              if (EPI == EPI_BIAS_RES) {
+                const float4 rr = *dst;
+                o.x = fmaf(p.res_scale, o.x, rr.x); o.y = fmaf(p.res_scale, o.y, rr.y);
+                o.z = fmaf(p.res_scale, o.z, rr.z); o.w = fmaf(p.res_scale, o.w, rr.w);
               }
-              if (EPI == EPI_BIAS_F32) {
-                float* cr = reinterpret_cast<float*>(p.C) + out_row * p.ldc + col;
-                *reinterpret_cast<float4*>(cr) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(cr + 4) = make_float4(v[4], v[5], v[6], v[7]);
-              } else if (EPI == EPI_BIAS_RES) {
-                const float* rr = p.res + out_row * p.ldc + col;
-                const float4 r0 = *reinterpret_cast<const float4*>(rr);
-                const float4 r1 = *reinterpret_cast<const float4*>(rr + 4);
-                float4 o0, o1;
-                o0.x = fmaf(p.res_scale, v[0], r0.x); o0.y = fmaf(p.res_scale, v[1], r0.y);
-                o0.z = fmaf(p.res_scale, v[2], r0.z); o0.w = fmaf(p.res_scale, v[3], r0.w);
-                o1.x = fmaf(p.res_scale, v[4], r1.x); o1.y = fmaf(p.res_scale, v[5], r1.y);
-                o1.z = fmaf(p.res_scale, v[6], r1.z); o1.w = fmaf(p.res_scale, v[7], r1.w);
-                float* cr = reinterpret_cast<float*>(p.C) + out_row * p.ldc + col;
-                *reinterpret_cast<float4*>(cr) = o0;
-                *reinterpret_cast<float4*>(cr + 4) = o1;
-              } else {
-                uint4 o;
-                o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-                o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-                bf16* cr = reinterpret_cast<bf16*>(p.C) + out_row * p.ldc + col;
-                *reinterpret_cast<uint4*>(cr) = o;
-              }
+              *dst = o;
+            }
+          } else {
+            // 32 bf16 columns = half a 128-byte row of staging block (col_in_tile / 64)
+            uint8_t* blk = cbuf + (col_in_tile >> 6) * CBLK_BYTES + row_off;
+            const int j0 = (col_in_tile & 63) >> 3;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+              o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = o;
             }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);              // accumulator stage may be overwritten
+      fence_proxy_async();                                     // staging writes -> visible to the TMA engine
+      named_bar_sync(1, NUM_EPI_THREADS);
+      if (leader) {
+        for (int blk = 0; blk < C_::NUM_CBLK; ++blk) {
+          const int col = n0 + blk * C_::CBLK_COLS;
+          if (col >= p.N) continue;
+          if (CONV) {
+            const int ct = m_tile % p.TCH, cf = (m_tile / p.TCH) % p.F2, cb = m_tile / (p.TCH * p.F2);
+            tma_store_4d(&tmC, cbuf + blk * CBLK_BYTES, col, cf, ct * BLOCK_M, cb);
+          } else {
+            tma_store_2d(&tmC, cbuf + blk * CBLK_BYTES, col, m_tile * BLOCK_M);
+          }
+        }
+        bulk_commit();
+      }
     }
+    if (leader) bulk_wait0();                                   // all output tiles have left shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -244,20 +284,24 @@ EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 int g_init_status = -1;
 
-int encode_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems, uint32_t box_inner,
-              uint32_t box_outer) {
-  cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld_elems * 2};
-  cuuint32_t box[2] = {box_inner, box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+           const cuuint64_t* strides, const cuuint32_t* box, const char* what) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(2d) failed with CUresult " + std::to_string(static_cast<int>(r)));
+    set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed with CUresult " + std::to_string(static_cast<int>(r)));
     return 3;
   }
   return 0;
+}
+
+int encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
+                   uint32_t box_inner, uint32_t box_outer, const char* what) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, what);
 }
 
 int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
@@ -266,44 +310,42 @@ int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
   cuuint64_t dims[5] = {C, F1, 2, static_cast<cuuint64_t>(g.T1p / 2), static_cast<cuuint64_t>(g.B)};
   cuuint64_t strides[4] = {C * 2, F1 * C * 2, 2 * F1 * C * 2, static_cast<cuuint64_t>(g.T1p) * F1 * C * 2};
   cuuint32_t box[5] = {BLOCK_K, 1, 1, BLOCK_M, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(5d) failed with CUresult " + std::to_string(static_cast<int>(r)));
-    return 3;
-  }
-  return 0;
+  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, "conv A");
 }
 
 template <int BLOCK_N, int EPI, bool CONV>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms, cudaStream_t stream) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int num_sms,
+           cudaStream_t stream) {
+  using C_ = Cfg<BLOCK_N, epi_out_f32(EPI)>;
   auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV>;
   static bool attr_done = false;
   if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BLOCK_N>::SMEM_BYTES));
+    CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
     attr_done = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, Cfg<BLOCK_N>::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 template <int BLOCK_N, bool CONV>
-int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, Epilogue epi, int num_sms,
-               cudaStream_t stream) {
+int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, Epilogue epi,
+               int num_sms, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BIAS: return launch<BLOCK_N, EPI_BIAS, CONV>(tmA, tmB, p, num_sms, stream);
-    case EPI_BIAS_SWISH: return launch<BLOCK_N, EPI_BIAS_SWISH, CONV>(tmA, tmB, p, num_sms, stream);
-    case EPI_BIAS_RELU: return launch<BLOCK_N, EPI_BIAS_RELU, CONV>(tmA, tmB, p, num_sms, stream);
-    case EPI_BIAS_RES: return launch<BLOCK_N, EPI_BIAS_RES, CONV>(tmA, tmB, p, num_sms, stream);
-    case EPI_BIAS_F32: return launch<BLOCK_N, EPI_BIAS_F32, CONV>(tmA, tmB, p, num_sms, stream);
+    case EPI_BIAS: return launch<BLOCK_N, EPI_BIAS, CONV>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS_SWISH: return launch<BLOCK_N, EPI_BIAS_SWISH, CONV>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS_RELU: return launch<BLOCK_N, EPI_BIAS_RELU, CONV>(tmA, tmB, tmC, p, num_sms, stream);
+    default: break;
   }
-  set_error("unknown epilogue");
+  set_error("unsupported epilogue for this tile shape");
   return 1;
+}
+int launch_epi_f32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                   Epilogue epi, int num_sms, cudaStream_t stream) {
+  if (epi == EPI_BIAS_RES) return launch<128, EPI_BIAS_RES, false>(tmA, tmB, tmC, p, num_sms, stream);
+  return launch<128, EPI_BIAS_F32, false>(tmA, tmB, tmC, p, num_sms, stream);
 }
 
 }  // namespace
@@ -332,44 +374,59 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
   CFM_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   CFM_REQUIRE(K % 8 == 0 && N % 8 == 0 && ldc % 8 == 0, "tensor-core GEMM needs K, N, ldc multiples of 8");
   CFM_REQUIRE((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 &&
-                  (reinterpret_cast<uintptr_t>(C) & 15) == 0,
+                  (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (reinterpret_cast<uintptr_t>(bias) & 15) == 0,
               "operands must be 16-byte aligned");
-  CFM_REQUIRE(epi != EPI_BIAS_RES || res != nullptr, "residual epilogue without residual");
+  const bool out_f32 = epi_out_f32(epi);
+  // the residual is read through the output tensor map: the update is in place (x += scale * (A W^T + b))
+  CFM_REQUIRE(epi != EPI_BIAS_RES || res == static_cast<const float*>(C), "residual epilogue updates C in place (res must alias C)");
+  CFM_REQUIRE(conv == nullptr || !out_f32, "conv mode has a bf16 output");
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.bias = bias; p.res = res; p.res_scale = res_scale; p.C = C; p.ldc = ldc;
+  p.bias = bias; p.res_scale = res_scale;
   p.num_kb = static_cast<int>(ceil_div(K, BLOCK_K));
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmC;
   if (conv != nullptr) {
     CFM_REQUIRE(conv->C % BLOCK_K == 0, "implicit-GEMM conv needs channels to be a multiple of 64");
-    CFM_REQUIRE(conv->T1p % 2 == 0 && K == 9 * conv->C, "bad conv geometry");
+    CFM_REQUIRE(conv->T1p % 2 == 0 && K == 9 * conv->C && N == conv->C && ldc == conv->C, "bad conv geometry");
     CFM_REQUIRE(M == conv->B * conv->T2 * conv->F2, "conv GEMM row count mismatch");
     p.T2 = conv->T2; p.F2 = conv->F2;
     p.TCH = static_cast<int>(ceil_div(conv->T2, BLOCK_M));
     p.kb_per_tap = conv->C / BLOCK_K;
     p.num_m_tiles = conv->B * conv->F2 * p.TCH;
     CFM_TRY(encode_conv_5d(&tmA, A, *conv));
+    // output [B][T2][F2][C] as (c, f2, t2, b), one (128 t2) x (64 c) block per store
+    const uint64_t Cc = conv->C, F2 = conv->F2, T2 = conv->T2;
+    cuuint64_t dims[4] = {Cc, F2, T2, static_cast<cuuint64_t>(conv->B)};
+    cuuint64_t strides[3] = {Cc * 2, F2 * Cc * 2, T2 * F2 * Cc * 2};
+    cuuint32_t box[4] = {64, 1, BLOCK_M, 1};
+    CFM_TRY(encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, C, dims, strides, box, "conv C"));
   } else {
     CFM_REQUIRE(lda % 8 == 0, "lda must be a multiple of 8");
     p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
-    CFM_TRY(encode_2d(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda), BLOCK_K,
-                      BLOCK_M));
+    CFM_TRY(encode_2d_bf16(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
+                           BLOCK_K, BLOCK_M, "A"));
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * (out_f32 ? 4 : 2)};
+    cuuint32_t box[2] = {out_f32 ? 32u : 64u, BLOCK_M};
+    CFM_TRY(encode(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dims,
+                   strides, box, "C"));
   }
   // tile width: 256 halves the A re-reads, 128 quantises better over the SMs; pick the cheaper schedule
   auto cost = [&](int bn) {
     const int64_t tiles = static_cast<int64_t>(p.num_m_tiles) * ceil_div(N, bn);
     return ceil_div(tiles, num_sms) * bn;
   };
-  const bool use256 = (N > 128) && (cost(256) <= cost(128));
+  const bool use256 = !out_f32 && (N > 128) && (cost(256) <= cost(128));
   const int bn = use256 ? 256 : 128;
   p.num_n_tiles = static_cast<int>(ceil_div(N, bn));
-  CFM_TRY(encode_2d(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
-                    static_cast<uint32_t>(bn)));
+  CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
+                         static_cast<uint32_t>(bn), "W"));
+  if (out_f32) return launch_epi_f32(tmA, tmB, tmC, p, epi, num_sms, stream);
   if (conv != nullptr)
-    return use256 ? launch_epi<256, true>(tmA, tmB, p, epi, num_sms, stream)
-                  : launch_epi<128, true>(tmA, tmB, p, epi, num_sms, stream);
-  return use256 ? launch_epi<256, false>(tmA, tmB, p, epi, num_sms, stream)
-                : launch_epi<128, false>(tmA, tmB, p, epi, num_sms, stream);
+    return use256 ? launch_epi<256, true>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                  : launch_epi<128, true>(tmA, tmB, tmC, p, epi, num_sms, stream);
+  return use256 ? launch_epi<256, false>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                : launch_epi<128, false>(tmA, tmB, tmC, p, epi, num_sms, stream);
 }
 
 }  // namespace cfm

@@ -258,6 +258,12 @@ template <> struct Dispatch<bf16> {
   static int gemm(Ctx& c, const bf16* A, int lda, const Linear& L, void* C, int ldc, int M, Epilogue e,
                   const float* res, float scale, const ConvGeom* g) {
     ++c.launches;
+    if (e == EPI_BIAS_RES && res != static_cast<const float*>(C)) {
+      // the tensor-core kernel updates C in place; seed it with the residual when the caller wants a copy
+      CFM_CUDA_OK(cudaMemcpy2DAsync(C, static_cast<size_t>(ldc) * 4, res, static_cast<size_t>(ldc) * 4,
+                                    static_cast<size_t>(L.N) * 4, M, cudaMemcpyDeviceToDevice, c.stream));
+      res = static_cast<const float*>(C);
+    }
     Timed t(c, KC_GEMM_TC, 2.0 * M * L.N * L.K, 2.0 * (static_cast<double>(M) * (L.K + L.N) + static_cast<double>(L.N) * L.K));
     return gemm_bf16_tc(A, lda, L.w16, L.b, C, ldc, M, L.N, L.K, e, res, scale, g, c.num_sms, c.stream);
   }
