@@ -9,6 +9,7 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 }  // namespace cfm
 
+namespace cfm { extern unsigned long long* g_gemm_trace; }
 using namespace cfm;
 
 namespace {
@@ -186,7 +187,7 @@ int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes) {
 
 int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K, int32_t epi,
                   const float* res, float res_scale, void* stream) {
-  CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 4, "bad GEMM arguments");
+  CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 5, "bad GEMM arguments");
   int dev = 0, sms = 0;
   CFM_CUDA_OK(cudaGetDevice(&dev));
   CFM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -196,9 +197,16 @@ int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int3
       CFM_CUDA_OK(cudaMemcpyAsync(C, res, static_cast<size_t>(M) * N * 4, cudaMemcpyDeviceToDevice, S(stream)));
     res = static_cast<const float*>(C);
   }
-  return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C, N, M, N, K,
-                      static_cast<Epilogue>(epi), res, res_scale, nullptr, sms, S(stream));
+  return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C,
+                      epi == EPI_BIAS_GLU ? N / 2 : N, M, N, K, static_cast<Epilogue>(epi), res, res_scale, nullptr, sms,
+                      S(stream));
 }
+/* debug: device buffer receiving 8 globaltimer stamps per tile of CTA 0 of the next tcgen05 GEMMs (NULL = off) */
+__attribute__((visibility("default"))) int cfm_debug_set_gemm_trace(void* dev_buf) {
+  cfm::g_gemm_trace = static_cast<unsigned long long*>(dev_buf);
+  return 0;
+}
+
 int cfm_gemm_f32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, int32_t epi,
                  const float* res, float res_scale, void* stream) {
   CFM_REQUIRE(A && W && C && epi >= 0 && epi <= 4, "bad GEMM arguments");

@@ -113,6 +113,76 @@ __global__ void __launch_bounds__(256) dwconv_kernel(const T* __restrict__ u, co
   }
 }
 
+
+// ---- depthwise conv, bf16 fast path -------------------------------------------------------------
+// Input already gated (GLU fused into the pointwise_conv_1 GEMM epilogue).  One CTA = 64 time steps x 64
+// channels of one utterance: the (64+k-1) x 64 halo tile is fetched with 16-byte loads (8 channels per
+// thread), widened to fp32 in shared memory, and every thread then produces 8 consecutive time steps of a
+// CHANNEL PAIR from a register window, so the 31-tap MAC runs as packed fma.rn.f32x2 (two channels per
+// instruction) with one conflict-free 64-bit shared load per window element.
+constexpr int DV_TT = 64, DV_CH = 64, DV_RT = 8;
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  ra = (static_cast<uint64_t>(__float_as_uint(a.y)) << 32) | __float_as_uint(a.x);
+  rb = (static_cast<uint64_t>(__float_as_uint(b.y)) << 32) | __float_as_uint(b.x);
+  rc = (static_cast<uint64_t>(__float_as_uint(c.y)) << 32) | __float_as_uint(c.x);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return make_float2(__uint_as_float(static_cast<uint32_t>(rd)), __uint_as_float(static_cast<uint32_t>(rd >> 32)));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) dwconv_bf16_kernel(const bf16* __restrict__ g, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, bf16* __restrict__ y, int Tn,
+                                                          int d) {
+  constexpr int HALF = (KS - 1) / 2, ROWS = DV_TT + KS - 1;
+  __shared__ __align__(16) float gs[ROWS * DV_CH];
+  __shared__ __align__(16) float ws[KS * DV_CH];
+  const int b = blockIdx.z, c0 = blockIdx.y * DV_CH, t0 = blockIdx.x * DV_TT;
+  const int tid = threadIdx.x;
+  for (int idx = tid; idx < ROWS * (DV_CH / 8); idx += 256) {
+    const int r = idx >> 3, v = idx & 7;
+    const int t = t0 - HALF + r;
+    uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+    if (t >= 0 && t < Tn) raw = *reinterpret_cast<const uint4*>(g + (static_cast<int64_t>(b) * Tn + t) * d + c0 + v * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    float4 lo, hi;
+    lo.x = __low2float(h[0]); lo.y = __high2float(h[0]); lo.z = __low2float(h[1]); lo.w = __high2float(h[1]);
+    hi.x = __low2float(h[2]); hi.y = __high2float(h[2]); hi.z = __low2float(h[3]); hi.w = __high2float(h[3]);
+    float4* dst = reinterpret_cast<float4*>(&gs[r * DV_CH + v * 8]);
+    dst[0] = lo;
+    dst[1] = hi;
+  }
+  for (int idx = tid; idx < KS * DV_CH; idx += 256) {
+    const int j = idx / DV_CH, c = idx - j * DV_CH;
+    ws[idx] = w[static_cast<int64_t>(j) * d + c0 + c];
+  }
+  __syncthreads();
+  const int cp = tid & 31, tg = tid >> 5;                      // channel pair, time group (8 outputs)
+  const int tl = tg * DV_RT;
+  if (t0 + tl >= Tn) return;
+  const float2 bc = *reinterpret_cast<const float2*>(bias + c0 + 2 * cp);
+  float2 acc[DV_RT];
+#pragma unroll
+  for (int i = 0; i < DV_RT; ++i) acc[i] = bc;
+  float2 win[DV_RT + KS - 1];
+#pragma unroll
+  for (int i = 0; i < DV_RT + KS - 1; ++i) win[i] = *reinterpret_cast<const float2*>(&gs[(tl + i) * DV_CH + 2 * cp]);
+#pragma unroll
+  for (int j = 0; j < KS; ++j) {
+    const float2 wj = *reinterpret_cast<const float2*>(&ws[j * DV_CH + 2 * cp]);
+#pragma unroll
+    for (int i = 0; i < DV_RT; ++i) acc[i] = ffma2(wj, win[i + j], acc[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < DV_RT; ++i) {
+    const int t = t0 + tl + i;
+    if (t < Tn)
+      *reinterpret_cast<uint32_t*>(y + (static_cast<int64_t>(b) * Tn + t) * d + c0 + 2 * cp) =
+          pack_bf16x2(swish_tanh(acc[i].x), swish_tanh(acc[i].y));
+  }
+}
+
 }  // namespace
 
 template <typename T>
@@ -148,4 +218,15 @@ int dwconv_glu_bn_swish(const T* u, const float* w, const float* bias, T* y, int
 template int dwconv_glu_bn_swish<float>(const float*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
 template int dwconv_glu_bn_swish<bf16>(const bf16*, const float*, const float*, bf16*, int, int, int, int, cudaStream_t);
 
+}  // namespace cfm
+
+namespace cfm {
+int dwconv_bn_swish_bf16(const bf16* g, const float* w, const float* bias, bf16* y, int B, int Tn, int d, int ksize,
+                         cudaStream_t stream) {
+  CFM_REQUIRE(d % DV_CH == 0 && ksize == 31, "fast depthwise path needs channels % 64 == 0 and kernel size 31");
+  dim3 grid(static_cast<unsigned>(ceil_div(Tn, DV_TT)), static_cast<unsigned>(d / DV_CH), static_cast<unsigned>(B));
+  dwconv_bf16_kernel<31><<<grid, 256, 0, stream>>>(g, w, bias, y, Tn, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 }  // namespace cfm

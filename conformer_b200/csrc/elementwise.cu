@@ -146,6 +146,16 @@ __global__ void fold_dwconv_bn_kernel(const float* __restrict__ w, const float* 
   b_out[c] = (b[c] - rm[c]) * s + bn_b[c];
 }
 
+__global__ void pack_glu_rows_kernel(const float* __restrict__ w, float* __restrict__ out, int d, int K) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= 2LL * d * K) return;
+  const int r = static_cast<int>(i / K), k = static_cast<int>(i - static_cast<int64_t>(r) * K);
+  const int grp = r >> 6, in_grp = r & 63;                   // packed row r = 64*grp + (gate ? 32 : 0) + j
+  const int c = grp * 32 + (in_grp & 31);
+  const int src = (in_grp >= 32 ? d : 0) + c;
+  out[i] = w[static_cast<int64_t>(src) * K + k];
+}
+
 inline unsigned blocks_for(int64_t n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
 
 }  // namespace
@@ -215,6 +225,12 @@ int pack_conv2_weight(const float* w, float* out, int C, cudaStream_t stream) {
 }
 int pack_linear_weight(const float* w, float* out, int d, int C, int F2, cudaStream_t stream) {
   pack_linear_kernel<<<blocks_for(static_cast<int64_t>(d) * C * F2, 256), 256, 0, stream>>>(w, out, d, C, F2);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int pack_glu_rows(const float* w, float* out, int d, int K, cudaStream_t stream) {
+  CFM_REQUIRE(d % 32 == 0, "GLU row packing needs channels to be a multiple of 32");
+  pack_glu_rows_kernel<<<blocks_for(2LL * d * K, 256), 256, 0, stream>>>(w, out, d, K);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

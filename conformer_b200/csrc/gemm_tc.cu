@@ -7,8 +7,9 @@
 //   * 8 epilogue warps read the accumulator with tcgen05.ld (one thread = one output row), apply
 //     bias / Swish / ReLU / (residual + scale), and write the tile into a 128-byte-swizzled staging
 //     buffer (conflict-free 16-byte stores) from which ONE thread issues TMA stores - global traffic
-//     is fully coalesced and M/N tails are clipped by the tensor map.  The residual tile is fetched by
-//     TMA into the same staging buffer while the MMAs of the tile are still running;
+//     is fully coalesced and M/N tails are clipped by the tensor map.  The residual epilogue never reads
+//     the residual: the tile scale*(acc+bias) leaves through a TMA *reduction* store (cp.reduce.async.bulk
+//     .add.f32), i.e. the in-place update x += ... is performed by the L2;
 //   * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule, N-tiles innermost so the
 //     CTAs running together share the same rows of A in L2.
 //
@@ -24,7 +25,7 @@ namespace cfm {
 namespace {
 
 constexpr int BLOCK_M = 128, BLOCK_K = 64, UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 16;
 constexpr int NUM_EPI_THREADS = NUM_EPI_WARPS * 32;
 constexpr int NUM_THREADS = 128 + NUM_EPI_THREADS;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -33,17 +34,22 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 constexpr bool epi_out_f32(int epi) { return epi == EPI_BIAS_RES || epi == EPI_BIAS_F32; }
 
-template <int BLOCK_N, bool OUT_F32> struct Cfg {
+template <int BLOCK_N, int EPI> struct Cfg {
+  static constexpr bool OUT_F32 = epi_out_f32(EPI);
+  static constexpr bool GLU = (EPI == EPI_BIAS_GLU);
+  static constexpr int OUT_N = GLU ? BLOCK_N / 2 : BLOCK_N;    // output columns per tile
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int CBLK_COLS = OUT_F32 ? 32 : 64;          // columns per staging block
-  static constexpr int NUM_CBLK = BLOCK_N / CBLK_COLS;
+  static constexpr int NUM_CBLK = OUT_N / CBLK_COLS;
   static constexpr int CBUF_BYTES = NUM_CBLK * CBLK_BYTES;
-  static constexpr int AUX_BYTES = 1024 /*alignment slack*/ + 256 /*barriers*/;
-  static constexpr int STAGES_FIT = (SMEM_LIMIT - CBUF_BYTES - AUX_BYTES) / STAGE_BYTES;
+  // bf16 128-wide tiles can afford two staging buffers, so a TMA store drains while the next tile is written
+  static constexpr int CBUF_COUNT = (!OUT_F32 && OUT_N == 128) ? 2 : 1;
+  static constexpr int AUX_BYTES = 1024 /*alignment slack*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias*/;
+  static constexpr int STAGES_FIT = (SMEM_LIMIT - CBUF_COUNT * CBUF_BYTES - AUX_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                // two accumulator stages
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CBUF_BYTES + AUX_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CBUF_COUNT * CBUF_BYTES + AUX_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
 };
 
@@ -54,19 +60,34 @@ struct GemmParams {
   float res_scale;
   // conv mode
   int T2, F2, TCH, kb_per_tap;
+  // optional timeline of CTA 0 (debug): 8 globaltimer stamps per tile
+  unsigned long long* trace;
 };
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot)                                                                         \
+  do {                                                                                      \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + (slot)] = gtime(); \
+  } while (0)
 
 template <int BLOCK_N, int EPI, bool CONV>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmParams p) {
   constexpr bool OUT_F32 = epi_out_f32(EPI);
-  using C_ = Cfg<BLOCK_N, OUT_F32>;
+  constexpr bool GLU = (EPI == EPI_BIAS_GLU);
+  static_assert(!GLU || BLOCK_N == 256, "the GLU epilogue pairs two 32-column chunks per warp");
+  using C_ = Cfg<BLOCK_N, EPI>;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* cbuf = smem + STAGES * C_::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cbuf + C_::CBUF_BYTES);
+  float* bias_s = reinterpret_cast<float*>(cbuf + C_::CBUF_COUNT * C_::CBUF_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -114,6 +135,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (kb == 0) TRACE(0);
+        if (kb == p.num_kb - 1) TRACE(1);
         if (lane == 0) {
           uint8_t* sa = smem + s * C_::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -139,12 +162,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aph ^ 1);                     // epilogue has drained this accumulator
       tc_fence_after();
+      TRACE(2);
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
       for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
+        if (kb == 0) TRACE(3);
+        if (kb == p.num_kb - 1) TRACE(4);
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
           const uint32_t sb = sa + A_STAGE_BYTES;
@@ -161,110 +187,131 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue (16 warps)
+    // warp -> TMEM lane quadrant (warp % 4, a hardware restriction) x column group (BLOCK_N / 4 columns)
     const int ew = warp - 4;
-    const int q = warp & 3;                                    // TMEM lane quadrant this warp may read
-    const int col_half = ew >> 2;
+    const int q = warp & 3;
+    const int cgrp = ew >> 2;
+    constexpr int COLS_PER_WARP = BLOCK_N / 4;
+    constexpr int NCH = COLS_PER_WARP / 32;                    // 32-column chunks per warp (1 or 2)
     const int row = q * 32 + lane;                             // row inside the tile
-    const bool leader = (threadIdx.x == 128);
+    const int tid_e = threadIdx.x - 128;
+    const bool leader = (tid_e == 0);
     const uint32_t row_off = row * 128;
     const int sw = row & 7;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
       const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
-      const int n0 = n_tile * BLOCK_N;
+      const int n0 = n_tile * BLOCK_N;                        // first GEMM column of the tile
+      const int o0 = n_tile * C_::OUT_N;                      // first OUTPUT column of the tile
+      const int out_n = GLU ? (p.N >> 1) : p.N;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
-      // staging buffer must have been drained by the previous tile's TMA store
+      uint8_t* cb = cbuf + (C_::CBUF_COUNT == 2 ? (acc_it & 1) * C_::CBUF_BYTES : 0);
+      // the staging buffer must have been drained by the TMA store that last used it
       if (leader) {
-        bulk_wait_read0();
-        if (EPI == EPI_BIAS_RES) {
-          int nblk = 0;
-          for (int blk = 0; blk < C_::NUM_CBLK; ++blk) nblk += (n0 + blk * C_::CBLK_COLS < p.N) ? 1 : 0;
-          mbar_expect_tx(res_bar, nblk * CBLK_BYTES);
-          for (int blk = 0; blk < C_::NUM_CBLK; ++blk)
-            if (n0 + blk * C_::CBLK_COLS < p.N)
-              tma_load_2d(cbuf + blk * CBLK_BYTES, &tmC, res_bar, n0 + blk * C_::CBLK_COLS, m_tile * BLOCK_M);
-        }
+        if (C_::CBUF_COUNT == 2) bulk_wait_read1(); else bulk_wait_read0();
       }
+      if (tid_e < BLOCK_N) bias_s[tid_e] = (p.bias != nullptr && n0 + tid_e < p.N) ? __ldg(p.bias + n0 + tid_e) : 0.f;
       named_bar_sync(1, NUM_EPI_THREADS);
+      if (warp == 4) TRACE(5);
       mbar_wait(&tfull_bar[as], aph);
       tc_fence_after();
-      if (EPI == EPI_BIAS_RES) mbar_wait(res_bar, acc_it & 1);
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-#pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
-        const int col_in_tile = col_half * (BLOCK_N / 2) + ch * 32;
-        const int col0 = n0 + col_in_tile;
-        uint32_t r[32];
-        tmem_ld_32x32(t_row + col_in_tile, r);
-        tmem_ld_wait();
-        if (col0 < p.N) {
-          float v[32];
+      if (warp == 4) TRACE(6);
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + cgrp * COLS_PER_WARP;
+      uint32_t r[NCH][32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              if (col0 + g * 4 + 4 <= p.N) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + g * 4));
-                v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-              }
-            }
-          }
-          if (EPI == EPI_BIAS_SWISH) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = swish_fast(v[i]);
-          }
-          if (EPI == EPI_BIAS_RELU) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (OUT_F32) {
-            // 32 fp32 columns = one full 128-byte row of staging block (col_in_tile / 32)
-            uint8_t* blk = cbuf + (col_in_tile >> 5) * CBLK_BYTES + row_off;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4* dst = reinterpret_cast<float4*>(blk + ((j ^ sw) << 4));
-              float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-              if (EPI == EPI_BIAS_RES) {
-                const float4 rr = *dst;
-                o.x = fmaf(p.res_scale, o.x, rr.x); o.y = fmaf(p.res_scale, o.y, rr.y);
-                o.z = fmaf(p.res_scale, o.z, rr.z); o.w = fmaf(p.res_scale, o.w, rr.w);
-              }
-              *dst = o;
-            }
-          } else {
-            // 32 bf16 columns = half a 128-byte row of staging block (col_in_tile / 64)
-            uint8_t* blk = cbuf + (col_in_tile >> 6) * CBLK_BYTES + row_off;
-            const int j0 = (col_in_tile & 63) >> 3;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-              o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-              *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = o;
-            }
-          }
-        }
-      }
+      for (int ch = 0; ch < NCH; ++ch) tmem_ld_32x32(t_row + ch * 32, r[ch]);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);              // accumulator stage may be overwritten
+      if (GLU) {
+        // this warp's 64 GEMM columns are 32 value columns followed by their 32 gate columns
+        const int gc = cgrp * COLS_PER_WARP;                   // GEMM column (in tile) of the value half
+        const int oc = cgrp * 32;                              // output column in the tile
+        if (o0 + oc < out_n) {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float a = __uint_as_float(r[0][i]) + bias_s[gc + i];
+            const float gte = __uint_as_float(r[NCH - 1][i]) + bias_s[gc + 32 + i];
+            v[i] = a * sigmoid_tanh(gte);                      // activation.py:16-17
+          }
+          uint8_t* blk = cb + (oc >> 6) * CBLK_BYTES + row_off;
+          const int j0 = (oc & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+            o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = o;
+          }
+        }
+      }
+#pragma unroll
+      for (int ch = 0; ch < (GLU ? 0 : NCH); ++ch) {
+        const int col_in_tile = cgrp * COLS_PER_WARP + ch * 32;
+        if (n0 + col_in_tile >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[col_in_tile + g * 4]);   // smem broadcast
+          v[g * 4 + 0] = __uint_as_float(r[ch][g * 4 + 0]) + b4.x;
+          v[g * 4 + 1] = __uint_as_float(r[ch][g * 4 + 1]) + b4.y;
+          v[g * 4 + 2] = __uint_as_float(r[ch][g * 4 + 2]) + b4.z;
+          v[g * 4 + 3] = __uint_as_float(r[ch][g * 4 + 3]) + b4.w;
+        }
+        if (EPI == EPI_BIAS_SWISH) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = swish_tanh(v[i]);
+        }
+        if (EPI == EPI_BIAS_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (OUT_F32) {
+          // 32 fp32 columns = one full 128-byte row of staging block (col_in_tile / 32)
+          uint8_t* blk = cb + (col_in_tile >> 5) * CBLK_BYTES + row_off;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* dst = reinterpret_cast<float4*>(blk + ((j ^ sw) << 4));
+            float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+            if (EPI == EPI_BIAS_RES) {                         // the residual itself is added by the TMA reduction
+              o.x *= p.res_scale; o.y *= p.res_scale; o.z *= p.res_scale; o.w *= p.res_scale;
+            }
+            *dst = o;
+          }
+        } else {
+          // 32 bf16 columns = half a 128-byte row of staging block (col_in_tile / 64)
+          uint8_t* blk = cb + (col_in_tile >> 6) * CBLK_BYTES + row_off;
+          const int j0 = (col_in_tile & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+            o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+            *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = o;
+          }
+        }
+      }
       fence_proxy_async();                                     // staging writes -> visible to the TMA engine
       named_bar_sync(1, NUM_EPI_THREADS);
       if (leader) {
         for (int blk = 0; blk < C_::NUM_CBLK; ++blk) {
-          const int col = n0 + blk * C_::CBLK_COLS;
-          if (col >= p.N) continue;
+          const int col = o0 + blk * C_::CBLK_COLS;
+          if (col >= out_n) continue;
           if (CONV) {
-            const int ct = m_tile % p.TCH, cf = (m_tile / p.TCH) % p.F2, cb = m_tile / (p.TCH * p.F2);
-            tma_store_4d(&tmC, cbuf + blk * CBLK_BYTES, col, cf, ct * BLOCK_M, cb);
+            const int ct = m_tile % p.TCH, cf = (m_tile / p.TCH) % p.F2, cbi = m_tile / (p.TCH * p.F2);
+            tma_store_4d(&tmC, cb + blk * CBLK_BYTES, col, cf, ct * BLOCK_M, cbi);
+          } else if (EPI == EPI_BIAS_RES) {
+            tma_reduce_add_2d(&tmC, cb + blk * CBLK_BYTES, col, m_tile * BLOCK_M);   // C += scale * (acc + bias)
           } else {
-            tma_store_2d(&tmC, cbuf + blk * CBLK_BYTES, col, m_tile * BLOCK_M);
+            tma_store_2d(&tmC, cb + blk * CBLK_BYTES, col, m_tile * BLOCK_M);
           }
         }
         bulk_commit();
       }
+      if (warp == 4) TRACE(7);
     }
     if (leader) bulk_wait0();                                   // all output tiles have left shared memory
   }
@@ -316,7 +363,7 @@ int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
 template <int BLOCK_N, int EPI, bool CONV>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int num_sms,
            cudaStream_t stream) {
-  using C_ = Cfg<BLOCK_N, epi_out_f32(EPI)>;
+  using C_ = Cfg<BLOCK_N, EPI>;
   auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -337,6 +384,9 @@ int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
     case EPI_BIAS: return launch<BLOCK_N, EPI_BIAS, CONV>(tmA, tmB, tmC, p, num_sms, stream);
     case EPI_BIAS_SWISH: return launch<BLOCK_N, EPI_BIAS_SWISH, CONV>(tmA, tmB, tmC, p, num_sms, stream);
     case EPI_BIAS_RELU: return launch<BLOCK_N, EPI_BIAS_RELU, CONV>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS_GLU:
+      if (BLOCK_N == 256 && !CONV) return launch<256, EPI_BIAS_GLU, false>(tmA, tmB, tmC, p, num_sms, stream);
+      break;
     default: break;
   }
   set_error("unsupported epilogue for this tile shape");
@@ -367,6 +417,8 @@ int tc_init() {
   return g_init_status;
 }
 
+unsigned long long* g_gemm_trace = nullptr;      // debug hook (cfm_debug_set_gemm_trace)
+
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N, int K,
                  Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
                  cudaStream_t stream) {
@@ -382,7 +434,7 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
   CFM_REQUIRE(conv == nullptr || !out_f32, "conv mode has a bf16 output");
   GemmParams p{};
   p.M = M; p.N = N; p.K = K;
-  p.bias = bias; p.res_scale = res_scale;
+  p.bias = bias; p.res_scale = res_scale; p.trace = g_gemm_trace;
   p.num_kb = static_cast<int>(ceil_div(K, BLOCK_K));
   CUtensorMap tmA, tmB, tmC;
   if (conv != nullptr) {
@@ -405,7 +457,8 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
     p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
     CFM_TRY(encode_2d_bf16(&tmA, A, static_cast<uint64_t>(K), static_cast<uint64_t>(M), static_cast<uint64_t>(lda),
                            BLOCK_K, BLOCK_M, "A"));
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+    CFM_REQUIRE(epi != EPI_BIAS_GLU || N % 64 == 0, "GLU epilogue needs N to be a multiple of 64");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(epi == EPI_BIAS_GLU ? N / 2 : N), static_cast<cuuint64_t>(M)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * (out_f32 ? 4 : 2)};
     cuuint32_t box[2] = {out_f32 ? 32u : 64u, BLOCK_M};
     CFM_TRY(encode(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dims,
@@ -416,7 +469,7 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
     const int64_t tiles = static_cast<int64_t>(p.num_m_tiles) * ceil_div(N, bn);
     return ceil_div(tiles, num_sms) * bn;
   };
-  const bool use256 = !out_f32 && (N > 128) && (cost(256) <= cost(128));
+  const bool use256 = epi == EPI_BIAS_GLU || (!out_f32 && (N > 128) && (cost(256) <= cost(128)));
   const int bn = use256 ? 256 : 128;
   p.num_n_tiles = static_cast<int>(ceil_div(N, bn));
   CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,

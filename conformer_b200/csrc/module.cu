@@ -120,7 +120,18 @@ struct Packer {
   void conv(ConvW& w, const std::string& pre, int d, int k) {
     w.ln_g = vec(pre + "layer_norm.weight", d);
     w.ln_b = vec(pre + "layer_norm.bias", d);
-    linear(w.pw1, pre + "pointwise_conv_1", 2 * d, d);
+    w.glu_fused = bf16_mode && d % 64 == 0 && k == 31;
+    if (w.glu_fused) {
+      // value/gate rows interleaved per 32 channels so that the GEMM epilogue can apply GLU (activation.py:16-17)
+      const float* w1 = param(pre + "pointwise_conv_1.weight", 2LL * d * d);
+      const float* b1 = param(pre + "pointwise_conv_1.bias", 2LL * d);
+      float* w1p = alloc_f32(2LL * d * d);
+      float* b1p = alloc_f32(2LL * d);
+      if (!status && (pack_glu_rows(w1, w1p, d, d, stream) || pack_glu_rows(b1, b1p, d, 1, stream))) status = 2;
+      finish_linear(w.pw1, w1p, b1p, 2 * d, d);
+    } else {
+      linear(w.pw1, pre + "pointwise_conv_1", 2 * d, d);
+    }
     linear(w.pw2, pre + "pointwise_conv_2", d, d);
     const float* dw = param(pre + "deepwise_conv.weight", static_cast<int64_t>(d) * k);
     const float* db = param(pre + "deepwise_conv.bias", d);
@@ -279,6 +290,14 @@ inline int attention_any(const bf16* qkv, const bf16* pos, int ldp, const float*
   return rel_attention<bf16>(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
 }
 
+inline int dwconv_fast(const float*, const float*, const float*, float*, int, int, int, int, cudaStream_t) {
+  set_error("fused-GLU depthwise path is bf16 only");
+  return 1;
+}
+inline int dwconv_fast(const bf16* g, const float* w, const float* b, bf16* y, int B, int Tn, int d, int k, cudaStream_t st) {
+  return dwconv_bn_swish_bf16(g, w, b, y, B, Tn, d, k, st);
+}
+
 template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(c.ws.take(static_cast<size_t>(n) * sizeof(TA))); }
 
 #define KRUN(cls, flops, bytes, call)      \
@@ -365,11 +384,17 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
   WS_CHECK(a); WS_CHECK(u); WS_CHECK(g);
   if (!c.ws.measuring()) {
     KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
-    CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, 2 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
-    // algorithmic bytes of the depthwise stage: input [M,d] + output [M,d] + taps; this kernel
-    // also reads the GLU gate half, which is not counted
-    KRUN(KC_DWCONV, 2.0 * w.ksize * M * d, (2.0 * M * d + (w.ksize + 1.0) * d) * sizeof(TA),
-         dwconv_glu_bn_swish<TA>(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
+    // algorithmic bytes of the depthwise stage: input [M,d] + output [M,d] + taps
+    const double dw_bytes = (2.0 * M * d + (w.ksize + 1.0) * d) * sizeof(TA);
+    if (w.glu_fused) {
+      CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, d, static_cast<int>(M), EPI_BIAS_GLU, nullptr, 0.f, nullptr));
+      KRUN(KC_DWCONV, 2.0 * w.ksize * M * d, dw_bytes, dwconv_fast(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
+    } else {
+      CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, 2 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
+      // (this variant also reads the GLU gate half, which is not counted)
+      KRUN(KC_DWCONV, 2.0 * w.ksize * M * d, dw_bytes,
+           dwconv_glu_bn_swish<TA>(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
+    }
     CFM_TRY(Dispatch<TA>::gemm(c, g, d, w.pw2, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);

@@ -95,7 +95,12 @@ struct Linear {
 };
 struct FfnW { const float *ln_g = nullptr, *ln_b = nullptr; Linear hidden, out; };
 struct AttnW { const float *ln_g = nullptr, *ln_b = nullptr, *u = nullptr, *v = nullptr; Linear qkv, pos, out; };
-struct ConvW { const float *ln_g = nullptr, *ln_b = nullptr, *dw_w = nullptr, *dw_b = nullptr; int ksize = 0; Linear pw1, pw2; };
+struct ConvW {
+  const float *ln_g = nullptr, *ln_b = nullptr, *dw_w = nullptr, *dw_b = nullptr;
+  int ksize = 0;
+  bool glu_fused = false;            // pw1 rows packed for the GEMM's GLU epilogue (bf16 fast path)
+  Linear pw1, pw2;
+};
 struct BlockW { FfnW ffn1, ffn2; AttnW attn; ConvW conv; const float *ln_g = nullptr, *ln_b = nullptr; };
 struct FrontW { const float *c1_w = nullptr, *c1_b = nullptr; Linear conv2; };
 

@@ -12,6 +12,8 @@ enum Epilogue {
   EPI_BIAS_RELU = 2,   // C = relu(acc + bias)
   EPI_BIAS_RES = 3,    // C(fp32) = res + res_scale * (acc + bias)
   EPI_BIAS_F32 = 4,    // C(fp32) = acc + bias
+  EPI_BIAS_GLU = 5,    // C[:, c] = (acc+bias)[a(c)] * sigmoid((acc+bias)[g(c)]), N/2 outputs; weight rows packed
+                       // per 64-row group as 32 value rows then their 32 gate rows (tensor-core path only)
 };
 
 // Implicit-im2col description of the A operand for the second subsampling conv
@@ -47,6 +49,12 @@ int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, i
 template <typename T>
 int dwconv_glu_bn_swish(const T* u, const float* w, const float* bias, T* y, int B, int Tn, int d, int ksize,
                         cudaStream_t stream);
+// bf16 variant whose input already went through GLU (fused into the pointwise_conv_1 GEMM epilogue):
+// g [B,T,d] -> y [B,T,d]; 16-byte loads, packed fp32x2 FMAs, time halo in shared memory.
+int dwconv_bn_swish_bf16(const bf16* g, const float* w, const float* bias, bf16* y, int B, int Tn, int d, int ksize,
+                         cudaStream_t stream);
+// reorder the 2d rows of pointwise_conv_1 (weight [2d,K] or bias with K=1) for EPI_BIAS_GLU
+int pack_glu_rows(const float* w, float* out, int d, int K, cudaStream_t stream);
 
 // relative-position multi-head self-attention core (model/utils/attention.py:47-72).
 // qkv [B,T,3d] (q | k | v, head h at columns h*dh), pos [2T-1, ldp] (projected table, head h at

@@ -144,7 +144,8 @@ CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_clas
 
 /* ---- low-level kernels exposed for unit tests and benchmarks -------------------------------- */
 /* bf16 tcgen05 GEMM: C = epi(A[M,K] W[N,K]^T + bias); epi: 0 bias, 1 bias+swish, 2 bias+relu,
- * 3 res + scale*(acc+bias) (C,res fp32; otherwise C bf16).  A,W bf16 (uint16 storage). */
+ * 3 res + scale*(acc+bias), 4 acc+bias (C,res fp32; otherwise C bf16), 5 GLU: C is [M,N/2] and W's rows are
+ * packed per 64-row group as 32 value rows followed by their 32 gate rows.  A,W bf16 (uint16 storage). */
 CFM_API int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
                   int32_t epi, const float* res, float res_scale, void* stream);
 /* fp32 CUDA-core GEMM with the same epilogues (all fp32). */

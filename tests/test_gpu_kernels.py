@@ -79,3 +79,22 @@ def test_dwconv_stage(B, T, d, k, dtype):
     want = conv * torch.sigmoid(conv)
     tol = dict(rtol=1e-5, atol=1e-5) if dtype == torch.float32 else dict(rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(y.double(), want, **tol)
+
+
+@pytest.mark.parametrize("M,d,K", [(300, 64, 128), (1000, 256, 256), (777, 512, 512)])
+def test_gemm_bf16_glu_epilogue(M, d, K):
+    """EPI 5: out[:, c] = (A W^T + b)[c] * sigmoid((A W^T + b)[c + d]) with the value/gate rows of W packed
+    per 64-row group (32 value rows, then their 32 gate rows)."""
+    g = torch.Generator(device="cuda").manual_seed(M + d)
+    A = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    W = (torch.randn(2 * d, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(2 * d, device="cuda", generator=g)
+    r = torch.arange(2 * d, device="cuda")
+    src = torch.where((r & 63) >= 32, d, 0) + (r >> 6) * 32 + (r & 31)
+    Wp, bp = W[src].contiguous(), bias[src].contiguous()
+    out = torch.full((M, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    check(lib().cfm_gemm_bf16(A.data_ptr(), Wp.data_ptr(), bp.data_ptr(), out.data_ptr(), M, 2 * d, K, 5, None, 0.0,
+                              _stream()))
+    acc = A.double() @ W.double().T + bias.double()
+    want = acc[:, :d] * torch.sigmoid(acc[:, d:])
+    torch.testing.assert_close(out.double(), want, rtol=1e-2, atol=1e-2)

@@ -209,3 +209,18 @@ def test_rel_attention_bf16_tensor_core_vs_oracle(T, masked):
     assert rel < 2e-2, rel
     m32 = m.set_compute("fp32")
     assert_close_fp32(m32(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask), want, "fp32 attention", scale=2.0)
+
+
+@pytest.mark.parametrize("d,T", [(256, 150), (512, 70), (64, 40)])
+def test_conv_module_bf16_vs_oracle(d, T):
+    """bf16 ConvolutionModule: GLU fused into the pointwise GEMM epilogue + packed-fp32x2 depthwise kernel
+    (d % 64 == 0, k = 31), against the fp32 oracle."""
+    B = 3
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 50 + d), "layers.0.conv.")
+    g = torch.Generator().manual_seed(d + T)
+    x = torch.randn(B, T, d, generator=g)
+    want = O.conv_module(sd, "", x)
+    m = _load(cb.ConvolutionModule(d, 31), sd).set_compute("bf16")
+    got = m(x.to(DEV))
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1.5e-2, rel
