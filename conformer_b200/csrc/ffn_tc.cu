@@ -1,0 +1,350 @@
+// Fused FeedForwardModule half-step for d_model = 256 on tcgen05 tensor cores:
+//
+//     x[M,256] += scale * ( swish( LN(x) W1^T + b1 ) W2^T + b2 )      (ffn.py:15-23 + block.py:19,25)
+//
+// One CTA owns 128 rows.  Nothing but x, the weights and the updated x touches global memory:
+//   prologue   16 warps LayerNorm their rows (fp32, two-pass in registers) and write the bf16 A operand
+//              straight into the 128B-swizzled K-major layout the MMA descriptors expect;
+//   main loop  the 1024 hidden units are processed in 8 chunks of 128:
+//                GEMM1(c): acc1[c&1] (TMEM, 128 cols)  = LN(x) . W1[c]^T          (K = 256)
+//                epilogue: hidden = bf16(swish(acc1 + b1)) -> shared memory, again in MMA layout
+//                GEMM2(c): acc2 (TMEM, 256 cols)      += hidden . W2[:, c]^T      (K = 128)
+//              software-pipelined (GEMM1(c+1) is issued before GEMM2(c)) so the tensor pipe keeps working
+//              while the 16 epilogue warps run the Swish; W1/W2 tiles stream through a TMA/mbarrier ring;
+//   epilogue   scale*(acc2 + b2) is staged (aliasing the now-dead operand buffers) and leaves through a TMA
+//              reduction store, i.e. the residual add is executed by the L2 (x is never re-read).
+// TMEM: 2 x 128 (acc1 double buffer) + 256 (acc2) = 512 columns.
+#include "ops.h"
+
+namespace cfm {
+namespace {
+
+constexpr int D = 256, HID = 4 * D, BM = 128, HC = 128, NCHUNK = HID / HC;
+constexpr int KB = 64;                                     // K elements per 128-byte swizzled row
+constexpr int XS_BYTES = (D / KB) * BM * 128;              // 64 KB: LN(x) as 4 k-blocks
+constexpr int HS_BYTES = (HC / KB) * BM * 128;             // 32 KB per hidden buffer
+constexpr int STAGE_BYTES = 32 * 1024, STAGES = 3;
+constexpr int NUM_EPI_WARPS = 16, NUM_EPI_THREADS = NUM_EPI_WARPS * 32, NUM_THREADS = 128 + NUM_EPI_THREADS;
+constexpr int SMEM_BYTES = 1024 + XS_BYTES + 2 * HS_BYTES + STAGES * STAGE_BYTES + 256;
+static_assert(SMEM_BYTES <= 227 * 1024, "fused FFN shared memory budget");
+constexpr int OUT_BLK_BYTES = BM * 128;                    // staging block: 128 rows x 32 fp32
+static_assert((D / 32) * OUT_BLK_BYTES <= XS_BYTES + 2 * HS_BYTES, "output staging must fit the operand buffers");
+
+struct FfnParams {
+  const float* x;
+  const float* ln_g;
+  const float* ln_b;
+  const float* b1;
+  const float* b2;
+  float scale;
+  int M;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                 const __grid_constant__ CUtensorMap tmX, FfnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* xs = smem;
+  uint8_t* hs = xs + XS_BYTES;                               // two hidden buffers
+  uint8_t* ring = hs + 2 * HS_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* xs_full = empty_bar + STAGES;
+  uint64_t* acc1_full = xs_full + 1;      // [2]
+  uint64_t* acc1_empty = acc1_full + 2;   // [2]
+  uint64_t* hs_full = acc1_empty + 2;     // [2]
+  uint64_t* hs_empty = hs_full + 2;       // [2]
+  uint64_t* acc2_full = hs_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(xs_full, NUM_EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc1_full[s], 1);
+      mbar_init(&acc1_empty[s], NUM_EPI_WARPS);
+      mbar_init(&hs_full[s], NUM_EPI_WARPS);
+      mbar_init(&hs_empty[s], 1);
+    }
+    mbar_init(acc2_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tm_acc2 = tmem_base + 2 * HC;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ weight producer
+    // consumption order: G1(0) G1(1) G2(0) G1(2) G2(1) ... G1(7) G2(6) G2(7); each GEMM uses two ring stages
+    uint32_t it = 0;
+    auto load_g1 = [&](int c) {
+      for (int s2 = 0; s2 < 2; ++s2, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        if (lane == 0) {
+          uint8_t* dst = ring + s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(dst, &tmW1, &full_bar[s], (2 * s2) * KB, c * HC);               // W1[c*128.., k-block 2*s2]
+          tma_load_2d(dst + 16384, &tmW1, &full_bar[s], (2 * s2 + 1) * KB, c * HC);   // k-block 2*s2+1
+        }
+        __syncwarp();
+      }
+    };
+    auto load_g2 = [&](int c) {
+      for (int s2 = 0; s2 < 2; ++s2, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+        if (lane == 0) {
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(ring + s * STAGE_BYTES, &tmW2, &full_bar[s], c * HC + s2 * KB, 0);  // W2[:, c*128 + s2*64 ..]
+        }
+        __syncwarp();
+      }
+    };
+    load_g1(0);
+    for (int c = 0; c < NCHUNK; ++c) {
+      if (c + 1 < NCHUNK) load_g1(c + 1);
+      load_g2(c);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);     // 128 x 128
+    constexpr uint32_t idesc2 = umma_idesc_bf16(BM, D);      // 128 x 256
+    uint32_t it = 0;
+    auto gemm1 = [&](int c) {
+      const int b = c & 1;
+      mbar_wait(&acc1_empty[b], ((c >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int s2 = 0; s2 < 2; ++s2, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sb = smem_u32(ring + s * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint32_t sa = smem_u32(xs + (2 * s2 + kk) * (BM * 128));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              tc_mma_f16(tmem_base + b * HC, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + kk * 16384 + k * 32),
+                         idesc1, (s2 | kk | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);
+          if (s2 == 1) tc_commit(&acc1_full[b]);
+        }
+        __syncwarp();
+      }
+    };
+    auto gemm2 = [&](int c) {
+      const int b = c & 1;
+      mbar_wait(&hs_full[b], (c >> 1) & 1);
+      tc_fence_after();
+      for (int s2 = 0; s2 < 2; ++s2, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(hs + b * HS_BYTES + s2 * (BM * 128));
+          const uint32_t sb = smem_u32(ring + s * STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16(tm_acc2, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc2,
+                       (c | s2 | k) != 0 ? 1u : 0u);
+          tc_commit(&empty_bar[s]);
+          if (s2 == 1) {
+            tc_commit(&hs_empty[b]);
+            if (c == NCHUNK - 1) tc_commit(acc2_full);
+          }
+        }
+        __syncwarp();
+      }
+    };
+    mbar_wait(xs_full, 0);
+    tc_fence_after();
+    gemm1(0);
+    for (int c = 0; c < NCHUNK; ++c) {
+      if (c + 1 < NCHUNK) gemm1(c + 1);
+      gemm2(c);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ LN prologue + epilogues (16 warps)
+    const int ew = warp - 4;
+    const int q = warp & 3, cgrp = ew >> 2;
+    const int tid_e = threadIdx.x - 128;
+    // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7; lane owns columns 8*lane .. 8*lane+7
+    {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane + 1);
+      const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane);
+      const float4 be1 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane + 1);
+      float4 a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = m0 + ew * 8 + i;
+        if (row < p.M) {
+          const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(row) * D);
+          a[i] = xr[2 * lane];
+          b[i] = xr[2 * lane + 1];
+        } else {
+          a[i] = b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = ew * 8 + i;
+        float s = (a[i].x + a[i].y) + (a[i].z + a[i].w) + (b[i].x + b[i].y) + (b[i].z + b[i].w);
+        const float mean = warp_sum(s) * (1.0f / D);
+        a[i].x -= mean; a[i].y -= mean; a[i].z -= mean; a[i].w -= mean;
+        b[i].x -= mean; b[i].y -= mean; b[i].z -= mean; b[i].w -= mean;
+        float v = (a[i].x * a[i].x + a[i].y * a[i].y) + (a[i].z * a[i].z + a[i].w * a[i].w) +
+                  (b[i].x * b[i].x + b[i].y * b[i].y) + (b[i].z * b[i].z + b[i].w * b[i].w);
+        const float rstd = rsqrtf(warp_sum(v) * (1.0f / D) + 1e-5f);
+        uint4 o;
+        o.x = pack_bf16x2(a[i].x * rstd * g0.x + be0.x, a[i].y * rstd * g0.y + be0.y);
+        o.y = pack_bf16x2(a[i].z * rstd * g0.z + be0.z, a[i].w * rstd * g0.w + be0.w);
+        o.z = pack_bf16x2(b[i].x * rstd * g1.x + be1.x, b[i].y * rstd * g1.y + be1.y);
+        o.w = pack_bf16x2(b[i].z * rstd * g1.z + be1.z, b[i].w * rstd * g1.w + be1.w);
+        // column 8*lane -> k-block lane/8, 16-byte chunk lane%8 of row r (128B swizzle)
+        *reinterpret_cast<uint4*>(xs + (lane >> 3) * (BM * 128) + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = o;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(xs_full);
+    }
+    // ---- per-chunk epilogue: hidden = bf16(swish(acc1 + b1)) into the MMA A layout
+    const int row = q * 32 + lane;
+    const int sw = row & 7;
+    for (int c = 0; c < NCHUNK; ++c) {
+      const int b = c & 1;
+      mbar_wait(&acc1_full[b], (c >> 1) & 1);
+      tc_fence_after();
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc1_empty[b]);
+      float v[32];
+      const float* bias = p.b1 + c * HC + cgrp * 32;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + g);
+        v[g * 4 + 0] = swish_tanh(__uint_as_float(r[g * 4 + 0]) + b4.x);
+        v[g * 4 + 1] = swish_tanh(__uint_as_float(r[g * 4 + 1]) + b4.y);
+        v[g * 4 + 2] = swish_tanh(__uint_as_float(r[g * 4 + 2]) + b4.z);
+        v[g * 4 + 3] = swish_tanh(__uint_as_float(r[g * 4 + 3]) + b4.w);
+      }
+      mbar_wait(&hs_empty[b], ((c >> 1) & 1) ^ 1);             // GEMM2(c-2) has finished reading this buffer
+      // hidden column cgrp*32 .. +31 of the chunk -> k-block cgrp/2, chunks (cgrp&1)*4 .. +3
+      uint8_t* dst = hs + b * HS_BYTES + (cgrp >> 1) * (BM * 128) + row * 128;
+      const int j0 = (cgrp & 1) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+        o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+        *reinterpret_cast<uint4*>(dst + (((j0 + j) ^ sw) << 4)) = o;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&hs_full[b]);
+    }
+    // ---- final epilogue: x += scale * (acc2 + b2) through a TMA reduction store
+    mbar_wait(acc2_full, 0);
+    tc_fence_after();
+    uint8_t* stage_out = smem;                                 // aliases xs/hs: every MMA has completed
+#pragma unroll 1
+    for (int ch = 0; ch < 2; ++ch) {
+      const int col = cgrp * 64 + ch * 32;
+      uint32_t r[32];
+      tmem_ld_32x32(tm_acc2 + (static_cast<uint32_t>(q * 32) << 16) + col, r);
+      tmem_ld_wait();
+      uint8_t* blk = stage_out + (col >> 5) * OUT_BLK_BYTES + row * 128;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);
+        float4 o;
+        o.x = p.scale * (__uint_as_float(r[j * 4 + 0]) + b4.x);
+        o.y = p.scale * (__uint_as_float(r[j * 4 + 1]) + b4.y);
+        o.z = p.scale * (__uint_as_float(r[j * 4 + 2]) + b4.z);
+        o.w = p.scale * (__uint_as_float(r[j * 4 + 3]) + b4.w);
+        *reinterpret_cast<float4*>(blk + ((j ^ sw) << 4)) = o;
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    named_bar_sync(1, NUM_EPI_THREADS);
+    if (tid_e == 0) {
+      for (int blk = 0; blk < D / 32; ++blk) tma_reduce_add_2d(&tmX, stage_out + blk * OUT_BLK_BYTES, blk * 32, m0);
+      bulk_commit();
+      bulk_wait0();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+bool ffn_fused_supported(int d) { return d == D; }
+
+int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
+                   const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream) {
+  (void)num_sms;
+  CFM_TRY(tc_init());
+  CFM_REQUIRE(d == D, "fused FFN kernel is specialised for d_model = 256");
+  CFM_REQUIRE(M > 0, "empty FFN");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
+                reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(b1) |
+                reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "fused FFN operands must be 16-byte aligned");
+  CUtensorMap tmW1, tmW2, tmX;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(HID)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+    cuuint32_t box[2] = {KB, HC};
+    CFM_TRY(encode_tmap(&tmW1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W1, dims, strides, box, "ffn W1"));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(HID), static_cast<cuuint64_t>(D)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(HID) * 2};
+    cuuint32_t box[2] = {KB, D};
+    CFM_TRY(encode_tmap(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W2, dims, strides, box, "ffn W2"));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 4};
+    cuuint32_t box[2] = {32, BM};
+    CFM_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, dims, strides, box, "ffn x"));
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_done = true;
+  }
+  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M};
+  const int grid = static_cast<int>(ceil_div(M, BM));
+  ffn_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, p);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cfm

@@ -328,27 +328,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
+}  // namespace
+int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                const cuuint64_t* strides, const cuuint32_t* box, const char* what);
+namespace {
 std::once_flag g_once;
 int g_init_status = -1;
 
-int encode(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
-           const cuuint64_t* strides, const cuuint32_t* box, const char* what) {
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = g_encode(tm, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed with CUresult " + std::to_string(static_cast<int>(r)));
-    return 3;
-  }
-  return 0;
-}
-
+using ::cfm::encode_tmap;
 int encode_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld_elems,
                    uint32_t box_inner, uint32_t box_outer, const char* what) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld_elems * 2};
   cuuint32_t box[2] = {box_inner, box_outer};
-  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, what);
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, what);
 }
 
 int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
@@ -357,7 +350,7 @@ int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
   cuuint64_t dims[5] = {C, F1, 2, static_cast<cuuint64_t>(g.T1p / 2), static_cast<cuuint64_t>(g.B)};
   cuuint64_t strides[4] = {C * 2, F1 * C * 2, 2 * F1 * C * 2, static_cast<cuuint64_t>(g.T1p) * F1 * C * 2};
   cuuint32_t box[5] = {BLOCK_K, 1, 1, BLOCK_M, 1};
-  return encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, "conv A");
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, "conv A");
 }
 
 template <int BLOCK_N, int EPI, bool CONV>
@@ -399,6 +392,19 @@ int launch_epi_f32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 }
 
 }  // namespace
+
+int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+           const cuuint64_t* strides, const cuuint32_t* box, const char* what) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(tm, dt, rank, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error(std::string("cuTensorMapEncodeTiled(") + what + ") failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return 3;
+  }
+  return 0;
+}
+
 
 int tc_init() {
   std::call_once(g_once, [] {
@@ -451,7 +457,7 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
     cuuint64_t dims[4] = {Cc, F2, T2, static_cast<cuuint64_t>(conv->B)};
     cuuint64_t strides[3] = {Cc * 2, F2 * Cc * 2, T2 * F2 * Cc * 2};
     cuuint32_t box[4] = {64, 1, BLOCK_M, 1};
-    CFM_TRY(encode(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, C, dims, strides, box, "conv C"));
+    CFM_TRY(encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, C, dims, strides, box, "conv C"));
   } else {
     CFM_REQUIRE(lda % 8 == 0, "lda must be a multiple of 8");
     p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
@@ -461,7 +467,7 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(epi == EPI_BIAS_GLU ? N / 2 : N), static_cast<cuuint64_t>(M)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * (out_f32 ? 4 : 2)};
     cuuint32_t box[2] = {out_f32 ? 32u : 64u, BLOCK_M};
-    CFM_TRY(encode(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dims,
+    CFM_TRY(encode_tmap(&tmC, out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, C, dims,
                    strides, box, "C"));
   }
   // tile width: 256 halves the A re-reads, 128 quantises better over the SMs; pick the cheaper schedule

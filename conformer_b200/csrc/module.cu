@@ -311,8 +311,21 @@ template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(
 #define WS_CHECK(ptr) CFM_REQUIRE((ptr) != nullptr || c.ws.measuring(), "workspace too small; query cfm_workspace_bytes")
 
 // out = res + scale * FFN(LN(x))      (ffn.py:15-23, block.py:19,25)
+inline bool ffn_fast_ok(const float*, int) { return false; }
+inline bool ffn_fast_ok(const bf16*, int d) { return ffn_fused_supported(d); }
+
 template <typename TA>
 int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale, float* out, int64_t M, int d) {
+  if (ffn_fast_ok(static_cast<const TA*>(nullptr), d)) {
+    // fused LN -> GEMM -> Swish -> GEMM -> residual kernel; `out` must hold the residual before it runs
+    if (c.ws.measuring()) return 0;
+    if (res == nullptr) CFM_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * d * 4, c.stream));
+    else if (res != out) CFM_CUDA_OK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
+    ++c.launches;
+    Timed t(c, KC_FFN_FUSED, 16.0 * M * d * d, 8.0 * M * d + 16.0 * d * d);
+    return ffn_fused_bf16(x, out, w.ln_g, w.ln_b, w.hidden.w16, w.hidden.b, w.out.w16, w.out.b, scale, static_cast<int>(M), d,
+                          c.num_sms, c.stream);
+  }
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
   TA* h = ws_take<TA>(c, M * 4 * d);

@@ -37,6 +37,17 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
                  int K, Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
                  cudaStream_t stream);
 int tc_init();   // resolves cuTensorMapEncodeTiled through the runtime; 0 when usable
+// 128-byte-swizzled tiled tensor map (call tc_init() first)
+int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,
+                const cuuint64_t* strides, const cuuint32_t* box, const char* what);
+
+// Fused FeedForwardModule half-step on the tensor cores (d_model = 256):
+//   x[M,256] += scale * (swish(LN(x_in) W1^T + b1) W2^T + b2)        (ffn.py:15-23, block.py:19,25)
+// LayerNorm in the prologue, the [M,1024] hidden activation never leaves the SM.  x_in may alias x (the
+// block's in-place residual update); x must already hold the residual (or zeros).
+int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
+                   const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream);
+bool ffn_fused_supported(int d);
 
 // ---- normalisation / elementwise ---------------------------------------------------------------
 template <typename TOut>

@@ -224,3 +224,19 @@ def test_conv_module_bf16_vs_oracle(d, T):
     got = m(x.to(DEV))
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     assert rel < 1.5e-2, rel
+
+
+@pytest.mark.parametrize("rows", [(1, 1), (2, 100), (3, 374), (5, 128)])
+def test_ffn_module_bf16_fused_vs_oracle(rows):
+    """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel."""
+    B, T = rows
+    d = 256
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 60), "layers.0.ffn_1.")
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    x = torch.randn(B, T, d, generator=g) * 1.5 + 0.3
+    want = O.feed_forward(sd, "", x)
+    m = _load(cb.FeedForwardModule(d), sd).set_compute("bf16")
+    got = m(x.to(DEV))
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1e-2, rel
+    assert torch.isfinite(got).all()
