@@ -272,7 +272,7 @@ def main():
         k["share"] = k["ms_per_step"] / prof_total if prof_total else None
     dom_name = max(kernels, key=lambda n: kernels[n]["ms_per_step"])
     dom = kernels[dom_name]
-    if "tflops" in dom and dom_name in ("gemm_tcgen05", "attention", "gemm_fp32", "ffn_fused"):
+    if "tflops" in dom and dom_name in ("gemm_tcgen05", "attention", "gemm_fp32", "ffn_fused", "ln_gemm"):
         roof = {"kernel": dom_name, "bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tensor"],
                 "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tensor"], "traffic": None,
                 "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)"}
@@ -281,7 +281,7 @@ def main():
                 "frac": (dom.get("gbs") or 0.0) / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} hbm_gbs"}
     if "dwconv" in kernels and "gbs" in kernels["dwconv"]:
         kernels["dwconv"]["hbm_frac"] = kernels["dwconv"]["gbs"] / peaks["hbm"]
-    for n in ("gemm_tcgen05", "attention", "ffn_fused"):
+    for n in ("gemm_tcgen05", "attention", "ffn_fused", "ln_gemm"):
         if n in kernels and "tflops" in kernels[n]:
             kernels[n]["tensor_frac"] = kernels[n]["tflops"] / peaks["tensor"]
 

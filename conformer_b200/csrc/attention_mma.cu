@@ -48,6 +48,11 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 // byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][128 B] tile, XOR-swizzled
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 __global__ void __launch_bounds__(NWARP * 32, 2)
@@ -109,10 +114,11 @@ rel_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ 
           const __nv_bfloat162 t = *reinterpret_cast<const __nv_bfloat162*>(base + rb * row_stride + col);
           b0 = __low2float(t); b1 = __high2float(t);
         }
-        qu[ks][half * 2 + 0] = pack_bf16x2(a0 + u0, a1 + u1);
-        qu[ks][half * 2 + 1] = pack_bf16x2(b0 + u0, b1 + u1);
-        qv[ks][half * 2 + 0] = pack_bf16x2(a0 + v0, a1 + v1);
-        qv[ks][half * 2 + 1] = pack_bf16x2(b0 + v0, b1 + v1);
+        // the softmax scale (1/sqrt(dh), in log2 units) is folded into the query operands
+        qu[ks][half * 2 + 0] = pack_bf16x2((a0 + u0) * scale_log2e, (a1 + u1) * scale_log2e);
+        qu[ks][half * 2 + 1] = pack_bf16x2((b0 + u0) * scale_log2e, (b1 + u1) * scale_log2e);
+        qv[ks][half * 2 + 0] = pack_bf16x2((a0 + v0) * scale_log2e, (a1 + v1) * scale_log2e);
+        qv[ks][half * 2 + 1] = pack_bf16x2((b0 + v0) * scale_log2e, (b1 + v1) * scale_log2e);
       }
     }
   }
@@ -165,7 +171,18 @@ rel_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ 
       *reinterpret_cast<float2*>(&skew[(g + 8) * SKEW_LD + n * 8 + 2 * c]) = make_float2(ps[2], ps[3]);
     }
     __syncwarp();
-    // ---- add the shifted positional term, scale, mask, online softmax
+    // ---- usable-key bitmask of this tile (warp-uniform; all ones on the common fully-valid tile)
+    uint32_t vm[2] = {0xffffffffu, 0xffffffffu};
+    bool need_mask = false;
+    if (j0 + AK > Tn || key_pad != nullptr) {
+      const int ja = j0 + lane, jb = ja + 32;
+      const bool va = ja < Tn && (key_pad == nullptr || key_pad[static_cast<int64_t>(b) * Tn + ja] == 0);
+      const bool vb = jb < Tn && (key_pad == nullptr || key_pad[static_cast<int64_t>(b) * Tn + jb] == 0);
+      vm[0] = __ballot_sync(0xffffffffu, va);
+      vm[1] = __ballot_sync(0xffffffffu, vb);
+      need_mask = (vm[0] & vm[1]) != 0xffffffffu;
+    }
+    // ---- add the shifted positional term, mask, online softmax (scores are already in log2 units)
     float tmax[2] = {-CUDART_INF_F, -CUDART_INF_F};
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
@@ -173,11 +190,10 @@ rel_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ 
       for (int e = 0; e < 4; ++e) {
         const int rl = g + (e >> 1) * 8;                      // local row 0..15
         const int jl = n * 8 + 2 * c + (e & 1);               // key within the tile
-        const int j = j0 + jl;
-        const bool dead = (j >= Tn) || (key_pad != nullptr && key_pad[static_cast<int64_t>(b) * Tn + j] != 0);
-        const float v = (s[n][e] + skew[rl * SKEW_LD + jl - rl + 15]) * scale_log2e;
-        s[n][e] = dead ? -CUDART_INF_F : v;
-        tmax[e >> 1] = fmaxf(tmax[e >> 1], s[n][e]);
+        float v = s[n][e] + skew[rl * SKEW_LD + jl - rl + 15];
+        if (need_mask && ((vm[n >> 2] >> (jl & 31)) & 1u) == 0) v = -CUDART_INF_F;
+        s[n][e] = v;
+        tmax[e >> 1] = fmaxf(tmax[e >> 1], v);
       }
     }
     __syncwarp();                                             // skew patch is rewritten next tile
@@ -188,15 +204,15 @@ rel_attention_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ 
       tmax[r] = fmaxf(tmax[r], __shfl_xor_sync(0xffffffffu, tmax[r], 2));
       const float m_new = fmaxf(m_run[r], tmax[r]);
       m_use[r] = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      alpha[r] = exp2f(m_run[r] - m_use[r]);
+      alpha[r] = ex2_approx(m_run[r] - m_use[r]);
       m_run[r] = m_new;
     }
     float psum[2] = {0.f, 0.f};
     uint32_t pa[4][4];                                        // P as A fragments for the 4 key k-steps
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float p0 = exp2f(s[n][0] - m_use[0]), p1 = exp2f(s[n][1] - m_use[0]);
-      const float p2 = exp2f(s[n][2] - m_use[1]), p3 = exp2f(s[n][3] - m_use[1]);
+      const float p0 = ex2_approx(s[n][0] - m_use[0]), p1 = ex2_approx(s[n][1] - m_use[0]);
+      const float p2 = ex2_approx(s[n][2] - m_use[1]), p3 = ex2_approx(s[n][3] - m_use[1]);
       psum[0] += p0 + p1;
       psum[1] += p2 + p3;
       pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0, p1);

@@ -49,6 +49,64 @@ __global__ void __launch_bounds__(256) subsample_conv1_kernel(const float* __res
   }
 }
 
+// bf16 variant: one thread = 8 channels of one (t, f) output (16-byte stores; every broadcast shared-memory
+// read of an input pixel feeds 8 FMAs), the frequency axis is split over the remaining thread groups.
+__global__ void __launch_bounds__(256) subsample_conv1_bf16_kernel(const float* __restrict__ x,
+                                                                   const float* __restrict__ w,
+                                                                   const float* __restrict__ bias,
+                                                                   bf16* __restrict__ out, int n_mel, int Tin, int T1,
+                                                                   int T1p, int F1, int C) {
+  extern __shared__ float xs[];                       // [n_mel][2*C1_TT+1]
+  constexpr int XW = 2 * C1_TT + 1;
+  const int b = blockIdx.y, t0 = blockIdx.x * C1_TT;
+  for (int i = threadIdx.x; i < n_mel * XW; i += blockDim.x) {
+    const int m = i / XW, j = i - m * XW;
+    const int t = 2 * t0 + j;
+    xs[i] = (t < Tin) ? x[(static_cast<int64_t>(b) * n_mel + m) * Tin + t] : 0.f;
+  }
+  __syncthreads();
+  const int groups = C >> 3;                          // 8-channel groups
+  const int ngrp = blockDim.x / groups;               // thread groups along the frequency axis (>= 1)
+  const int cg = threadIdx.x % groups, fg = threadIdx.x / groups;
+  if (fg >= ngrp) return;
+  float wr[8][9], br[8];
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    br[ch] = bias[8 * cg + ch];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) wr[ch][i] = w[(8 * cg + ch) * 9 + i];
+  }
+  for (int tt = 0; tt < C1_TT; ++tt) {
+    const int t1 = t0 + tt;
+    if (t1 >= T1p) break;
+    bf16* orow = out + ((static_cast<int64_t>(b) * T1p + t1) * F1) * C + 8 * cg;
+    for (int f = fg; f < F1; f += ngrp) {
+      float a[8];
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) a[ch] = br[ch];
+      if (t1 < T1) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const float xv = xs[(2 * f + kh) * XW + 2 * tt + kw];
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) a[ch] = fmaf(wr[ch][kh * 3 + kw], xv, a[ch]);
+          }
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) a[ch] = fmaxf(a[ch], 0.f);
+      } else {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) a[ch] = 0.f;     // padding row (T1p = T1 rounded up to even)
+      }
+      uint4 o;
+      o.x = pack_bf16x2(a[0], a[1]); o.y = pack_bf16x2(a[2], a[3]);
+      o.z = pack_bf16x2(a[4], a[5]); o.w = pack_bf16x2(a[6], a[7]);
+      *reinterpret_cast<uint4*>(orow + static_cast<int64_t>(f) * C) = o;
+    }
+  }
+}
+
 // ---- depthwise conv -----------------------------------------------------------------------------
 constexpr int DW_CH = 64;      // channels per block (one per thread column)
 constexpr int DW_TT = 64;      // output time steps per block
@@ -191,7 +249,12 @@ int subsample_conv1(const float* x, const float* w, const float* bias, T* out, i
   CFM_REQUIRE(B > 0 && T1 > 0 && F1 > 0, "input too short for the subsampling convs");
   dim3 grid(static_cast<unsigned>(ceil_div(T1p, C1_TT)), static_cast<unsigned>(B));
   const size_t smem = static_cast<size_t>(n_mel) * (2 * C1_TT + 1) * sizeof(float);
-  subsample_conv1_kernel<T><<<grid, 256, smem, stream>>>(x, w, bias, out, n_mel, Tin, T1, T1p, F1, C);
+  if (sizeof(T) == 2 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0) {
+    subsample_conv1_bf16_kernel<<<grid, 256, smem, stream>>>(x, w, bias, reinterpret_cast<bf16*>(out), n_mel, Tin, T1,
+                                                             T1p, F1, C);
+  } else {
+    subsample_conv1_kernel<T><<<grid, 256, smem, stream>>>(x, w, bias, out, n_mel, Tin, T1, T1p, F1, C);
+  }
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -229,8 +229,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     // ---- per-chunk epilogue: hidden = bf16(swish(acc1 + b1)) into the MMA A layout
     const int row = q * 32 + lane;
     const int sw = row & 7;
+    const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
     for (int c = 0; c < NCHUNK; ++c) {
       const int b = c & 1;
+      float4 bc[8];                                            // issued before the wait: L2 latency overlaps it
+#pragma unroll
+      for (int g = 0; g < 8; ++g) bc[g] = __ldg(b1v + c * (HC / 4) + g);
       mbar_wait(&acc1_full[b], (c >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
@@ -240,10 +244,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc1_empty[b]);
       float v[32];
-      const float* bias = p.b1 + c * HC + cgrp * 32;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias) + g);
+        const float4 b4 = bc[g];
         v[g * 4 + 0] = swish_tanh(__uint_as_float(r[g * 4 + 0]) + b4.x);
         v[g * 4 + 1] = swish_tanh(__uint_as_float(r[g * 4 + 1]) + b4.y);
         v[g * 4 + 2] = swish_tanh(__uint_as_float(r[g * 4 + 2]) + b4.z);
@@ -292,7 +295,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     if (tid_e == 0) {
       for (int blk = 0; blk < D / 32; ++blk) tma_reduce_add_2d(&tmX, stage_out + blk * OUT_BLK_BYTES, blk * 32, m0);
       bulk_commit();
-      bulk_wait0();
+      bulk_wait_read0();                                       // smem may be released; the L2 finishes the adds
     }
   }
   tc_fence_before();

@@ -49,6 +49,12 @@ int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* 
                    const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream);
 bool ffn_fused_supported(int d);
 
+// LayerNorm-fused projection (d_model = 256, N % 256 == 0): out = epi(LN(x) W^T + b), bf16 out.
+// glu = true applies the GLU epilogue on W packed by pack_glu_rows (out has N/2 columns).
+int ln_gemm_bf16(const float* x, const float* ln_g, const float* ln_b, const bf16* W, const float* bias, bf16* out,
+                 int ldc, int M, int N, int d, bool glu, cudaStream_t stream);
+bool ln_gemm_supported(int d, int N);
+
 // ---- normalisation / elementwise ---------------------------------------------------------------
 template <typename TOut>
 int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,

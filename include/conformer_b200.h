@@ -137,7 +137,7 @@ CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 
 /* Optional per-launch profile: when enabled every kernel launch of a forward on `m` is bracketed by
  * CUDA events on the launching stream.  cfm_profile_collect waits for them and fills, per kernel class
- * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN), four
+ * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN, 8 LayerNorm-fused GEMM), four
  * doubles: launches, total milliseconds, algorithmic FLOPs, algorithmic bytes. */
 CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
 CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);

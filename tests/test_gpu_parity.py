@@ -240,3 +240,20 @@ def test_ffn_module_bf16_fused_vs_oracle(rows):
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     assert rel < 1e-2, rel
     assert torch.isfinite(got).all()
+
+
+@pytest.mark.parametrize("B,T", [(1, 5), (2, 130), (4, 374)])
+def test_mhsa_module_bf16_ln_fused_vs_oracle(B, T):
+    """d_model = 256 in bf16 mode: LayerNorm is fused into the q|k|v projection kernel (ln_gemm)."""
+    d, H = 256, 4
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 70), "layers.0.attention.")
+    g = torch.Generator().manual_seed(B * 100 + T)
+    x = torch.randn(B, T, d, generator=g) * 2.0 - 0.5
+    pos = O.rel_pos_table(T, d)
+    lengths = torch.tensor([T] + [max(1, T // 2)] * (B - 1))
+    pad = ~O.padding_mask(lengths, T)
+    want = O.mhsa_module(sd, "", x, pos, pad, H)
+    m = _load(cb.MultiHeadSelfAttentionModule(d, H), sd).set_compute("bf16")
+    got = m(x.to(DEV), pos[None].expand(B, -1, -1).to(DEV), pad[:, None, None, :].to(DEV))
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 2e-2, rel
