@@ -36,14 +36,16 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, synth_encoder_state_dict, synth_lengths,  # noqa: E402
-                                  synth_logmel, subsampled_frames)
+from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, EncoderConfig, synth_encoder_state_dict,  # noqa: E402
+                                  synth_lengths, synth_logmel, subsampled_frames)
 
 WORKLOADS = {
     # name: (cfg, batch per GPU, mel frames, variable lengths, description)
     "C2": (CONFORMER_M, 64, 1501, False, "Conformer-M encoder fwd, 64x15s, bf16 (BASELINE configs[1])"),
     "C3": (CONFORMER_L, 32, 2001, True, "Conformer-L encoder fwd, 32x20s var-len, bf16 (BASELINE configs[2])"),
     "C5": (CONFORMER_M, 16, 6001, False, "Conformer-M encoder fwd, 16x60s long-form, bf16 (BASELINE configs[4])"),
+    # tiny shape used only by the CPU multi-process tests of the harness itself
+    "T0": (EncoderConfig(80, 2, 64, 4, 31), 2, 101, True, "harness self-test (not a benchmark workload)"),
 }
 FRAME_SEC = 0.01   # hop 160 @ 16 kHz (train.py:105,109)
 
@@ -96,6 +98,24 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(sm)}
+
+
+def rank_seed(rank: int) -> int:
+    """Each rank benchmarks its own utterances (the batch shards by utterance)."""
+    return 1234 + rank
+
+
+def max_over_ranks(ms: float, dist, device) -> float:
+    """Step time of the job = the slowest rank's device-timed interval."""
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def whole_job_rtfx(world: int, secs_per_rank_step: float, ms_per_step: float) -> float:
+    """Weak scaling: every rank processes secs_per_rank_step of audio per step."""
+    return world * secs_per_rank_step / (ms_per_step * 1e-3)
 
 
 def audio_seconds(lengths, batch, t_in):
@@ -198,7 +218,7 @@ def main():
     enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
     enc.load_state_dict(sd)
     enc = enc.to(dev).eval().set_compute(args.compute)
-    x_host = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=1234 + rank).pin_memory()
+    x_host = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=rank_seed(rank)).pin_memory()
     lengths_host = synth_lengths(batch, t_in).pin_memory() if var_len else None
     x = x_host.to(dev)
     lengths = lengths_host.to(dev) if var_len else None
@@ -220,10 +240,7 @@ def main():
             fn()
         e1.record()
         barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if dist is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item() / steps
+        return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
 
     with torch.inference_mode():
         step_dev = lambda: enc(x, lengths)                                              # noqa: E731
@@ -288,7 +305,7 @@ def main():
     from oracle.conformer_oracle import encoder_flops
     flops = encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
     line = {
-        "metric": "encoder audio-seconds per second (RTFx)", "value": world * secs_per_step / (ms_dev * 1e-3),
+        "metric": "encoder audio-seconds per second (RTFx)", "value": whole_job_rtfx(world, secs_per_step, ms_dev),
         "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.compute == "bf16" else "f32", "data": "synthetic",
@@ -296,7 +313,7 @@ def main():
                    "audio_seconds_per_gpu_step": secs_per_step, "parallelism": f"dp{world} (independent replicas)",
                    "l2": "no flush needed: one step streams ~1.3 GB of activations (conv1 output alone 958 MB) "
                          "through the 126 MB L2"},
-        "e2e": {"value": world * secs_per_step / (ms_e2e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e2e,
+        "e2e": {"value": whole_job_rtfx(world, secs_per_step, ms_e2e), "unit": "audio-s/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": x_host.numel() * 4 + (lengths_host.numel() * 8 if var_len else 0),
                 "d2h_bytes_per_step": y_host.numel() * 4 + (lo_host.numel() * 8 if var_len else 0),
                 "api": "cfm_encoder_forward_host (Encoder.forward_host): pinned host mel -> device -> forward -> host"},

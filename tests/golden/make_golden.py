@@ -163,3 +163,17 @@ if __name__ == "__main__":
     for c in ENCODER_CASES:
         run_encoder_case(**c)
     run_tokens()
+
+
+def dump_state_dict_keys():
+    """Key/shape table of the real reference modules, for the CPU-only contract test."""
+    import json
+    enc = Encoder(80, 2, 32, 2, 7)
+    conf = Conformer(370, 80, 2, 32, 2, 7, 64, 1)
+    with open(os.path.join(HERE, "state_dict_keys.json"), "w") as fh:
+        json.dump({"encoder": {k: list(v.shape) for k, v in enc.state_dict().items()},
+                   "conformer": {k: list(v.shape) for k, v in conf.state_dict().items()}}, fh, indent=0)
+
+
+if __name__ == "__main__":
+    dump_state_dict_keys()

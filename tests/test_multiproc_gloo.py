@@ -1,0 +1,60 @@
+"""world_size-2 CPU (gloo) tests of the multi-rank harness logic: max-over-ranks timing, per-rank shards,
+whole-job aggregation, and the reference arm under torchrun (rank 0 alone runs and prints)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import bench
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mine = 10.0 + 5.0 * rank                         # rank 1 is the slow one
+        job_ms = bench.max_over_ranks(mine, dist, "cpu")
+        from conformer_b200.synth import synth_logmel
+        x = synth_logmel(2, 80, 50, seed=bench.rank_seed(rank))
+        sums = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(sums, x.double().sum().reshape(1))
+        out.put((rank, job_ms, [float(s) for s in sums], bench.whole_job_rtfx(world, 9.6, job_ms)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_max_over_ranks_and_distinct_shards():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, job_ms, sums, value in res:
+        assert job_ms == 15.0                            # the slowest rank defines the step
+        assert sums[0] != sums[1]                        # ranks benchmark different utterances
+        assert abs(value - 2 * 9.6 / 0.015) < 1e-6       # whole-job aggregate, not per-GPU
+
+
+def test_reference_arm_under_torchrun_rank0_only():
+    port = 31500 + os.getpid() % 2000
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+           "--steps", "1", "--warmup", "1", "--config", "T0"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
