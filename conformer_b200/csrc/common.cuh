@@ -130,6 +130,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
                                             int c2, int c3, int c4) {
   asm volatile(
@@ -251,6 +257,23 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
   d |= static_cast<uint64_t>(1) << 46;                            // descriptor version (Blackwell)
   d |= static_cast<uint64_t>(2) << 61;                            // SWIZZLE_128B
   return d;
+}
+// Same swizzle, MN-major operand: rows of the tile are K indices, each row holds 64 contiguous MN elements
+// (128 bytes, one swizzle atom along MN); 8-row K groups are 1024 B apart (SBO); LBO (stride between 64-element
+// MN atoms) is unused for N <= 64.  Advance the start address by 16 rows (2048 B) per K=16 MMA.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// Instruction descriptor: bf16 x bf16 -> fp32, A K-major, B MN-major (e.g. V stored [key][dh] in P.V)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
 }
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {

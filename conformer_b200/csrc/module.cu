@@ -287,7 +287,12 @@ inline int attention_any(const float* qkv, const float* pos, int ldp, const floa
 }
 inline int attention_any(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* kp,
                          bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t st) {
-  if (dh == 64) return rel_attention_bf16_mma(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+  if (dh == 64) {
+    // CFM_ATTN=mma selects the mma.sync kernel (kept for A/B comparison); default is the tcgen05 kernel
+    static const bool use_mma = [] { const char* e = getenv("CFM_ATTN"); return e != nullptr && e[0] == 'm'; }();
+    if (use_mma) return rel_attention_bf16_mma(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+    return rel_attention_bf16_tc(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
+  }
   return rel_attention<bf16>(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
 }
 

@@ -84,6 +84,10 @@ int rel_attention(const T* qkv, const T* pos, int ldp, const float* u, const flo
 int rel_attention_bf16_mma(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
                            const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
 
+// bf16 tcgen05/TMEM flash variant (S, shifted positional scores and P.V on 5th-gen tensor cores), head size 64
+int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
+                          const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
+
 // sinusoid table [2T-1, d] (model/utils/position.py:11-25), row p <-> relative position T-1-p
 template <typename T>
 int rel_pos_table(const float* div_term, T* pe, int Tn, int d, cudaStream_t stream);
