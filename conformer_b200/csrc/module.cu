@@ -415,9 +415,23 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
 }
 
 // out = res + ConvolutionModule(x)      (convolution.py:21-32; block.py:23)
+inline bool conv_fast_ok(const float*, const ConvW&, int) { return false; }
+inline bool conv_fast_ok(const bf16*, const ConvW& w, int d) {
+  static const bool off = [] { const char* e = getenv("CFM_CONV_FUSED"); return e != nullptr && e[0] == '0'; }();
+  return !off && w.glu_fused && conv_module_fused_supported(d, w.ksize);
+}
+
 template <typename TA>
 int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* out, int B, int Tn, int d) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
+  if (conv_fast_ok(static_cast<const TA*>(nullptr), w, d) && out != x) {
+    // single fused kernel: LN -> pw1 -> GLU -> depthwise+BN+Swish -> pw2 -> +residual
+    if (c.ws.measuring()) return 0;
+    ++c.launches;
+    Timed t(c, KC_CONV_FUSED, 6.0 * M * d * d + 2.0 * w.ksize * M * d, (res ? 12.0 : 8.0) * M * d + 6.0 * d * d);
+    return conv_module_fused_bf16(x, res, out, w.ln_g, w.ln_b, w.pw1.w16, w.pw1.b, w.dw_w, w.dw_b, w.pw2.w16, w.pw2.b, B, Tn,
+                                  d, w.ksize, c.stream);
+  }
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
   TA* u = ws_take<TA>(c, M * 2 * d);
@@ -456,11 +470,19 @@ int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, cons
   const int64_t M = static_cast<int64_t>(B) * Tn;
   CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d));
   CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, key_pad, xw, xw, B, Tn, d, H)));
-  CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xw, B, Tn, d));
-  CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xw, xw, 0.5f, xw, M, d));
-  if (!c.ws.measuring()) {
-    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4), layer_norm<float>(xw, w.ln_g, w.ln_b, y, M, d, c.stream));
+  // the fused conv-module kernel reads a time halo, so it writes a second residual buffer instead of updating in place
+  const size_t mark = c.ws.mark();
+  float* xc = xw;
+  if (conv_fast_ok(static_cast<const TA*>(nullptr), w.conv, d)) {
+    xc = ws_take<float>(c, M * d);
+    WS_CHECK(xc);
   }
+  CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xc, B, Tn, d));
+  CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xc, xc, 0.5f, xc, M, d));
+  if (!c.ws.measuring()) {
+    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4), layer_norm<float>(xc, w.ln_g, w.ln_b, y, M, d, c.stream));
+  }
+  c.ws.reset(mark);
   return 0;
 }
 

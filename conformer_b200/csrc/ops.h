@@ -55,6 +55,15 @@ int ln_gemm_bf16(const float* x, const float* ln_g, const float* ln_b, const bf1
                  int ldc, int M, int N, int d, bool glu, cudaStream_t stream);
 bool ln_gemm_supported(int d, int N);
 
+// Fused ConvolutionModule on the tensor cores (d_model = 256, kernel size 31):
+//   out = res + pw2(swish(bn(dw(glu(pw1(LN(x)))))))        (convolution.py:21-32, block.py:23)
+// W1p/b1p packed by pack_glu_rows, dw_w/dw_b BN-folded (fold_dwconv_bn).  res may be null or alias x; out must
+// not alias x (tiles read a 15-frame halo of their neighbours).
+int conv_module_fused_bf16(const float* x, const float* res, float* out, const float* ln_g, const float* ln_b,
+                           const bf16* W1p, const float* b1p, const float* dw_w, const float* dw_b, const bf16* W2,
+                           const float* b2, int B, int Tn, int d, int ksize, cudaStream_t stream);
+bool conv_module_fused_supported(int d, int ksize);
+
 // ---- normalisation / elementwise ---------------------------------------------------------------
 template <typename TOut>
 int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,

@@ -198,7 +198,7 @@ class _Native(nn.Module):
         """Kernel launches enqueued by the most recent forward (any compute mode)."""
         return max([int(lib().cfm_last_launch_count(h)) for h, _, _ in self._handles.values()] or [0])
 
-    KERNEL_CLASSES = ("gemm_tcgen05", "gemm_fp32", "layer_norm", "attention", "dwconv", "conv1", "misc", "ffn_fused", "ln_gemm")
+    KERNEL_CLASSES = ("gemm_tcgen05", "gemm_fp32", "layer_norm", "attention", "dwconv", "conv1", "misc", "ffn_fused", "ln_gemm", "conv_fused")
 
     def profile(self, on: bool) -> None:
         """Bracket every kernel launch of subsequent forwards with CUDA events (see cfm_profile_enable)."""

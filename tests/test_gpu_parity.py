@@ -226,6 +226,41 @@ def test_conv_module_bf16_vs_oracle(d, T):
     assert rel < 1.5e-2, rel
 
 
+@pytest.mark.parametrize("T", [1, 15, 16, 95, 96, 97, 111, 112, 192, 193, 374, 499])
+def test_conv_module_bf16_fused_tile_edges(T):
+    """d_model = 256, k = 31 in bf16 mode routes ConvolutionModule to the single fused kernel (LN -> pw1 -> GLU ->
+    depthwise+BN+Swish -> pw2): 96-frame tiles with a 15-frame halo, so lengths around 96k and 96k+-15 are the
+    edges; the stand-alone module has no residual, the block test below covers the residual epilogue."""
+    B, d = 3, 256
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 51), "layers.0.conv.")
+    g = torch.Generator().manual_seed(7000 + T)
+    x = torch.randn(B, T, d, generator=g) * 1.5 + 0.25
+    want = O.conv_module(sd, "", x)
+    m = _load(cb.ConvolutionModule(d, 31), sd).set_compute("bf16")
+    got = m(x.to(DEV))
+    assert torch.isfinite(got).all()
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1.5e-2, rel
+    assert (got.cpu() - want).abs().max() < 0.1
+
+
+@pytest.mark.parametrize("T", [40, 200])
+def test_block_bf16_fused_conv_residual(T):
+    """ConformerBlock in bf16 at d_model = 256: fused FFN, tcgen05 attention and the fused conv module writing
+    res + conv into the second residual buffer."""
+    B, d, H = 2, 256, 4
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 52), "layers.0.")
+    g = torch.Generator().manual_seed(7100 + T)
+    x = torch.randn(B, T, d, generator=g)
+    pos = O.rel_pos_table(T, d)
+    lengths = torch.tensor([T, max(1, T // 3)])
+    pad = ~O.padding_mask(lengths, T)
+    want = O.conformer_block(sd, "", x, pos, pad, H)
+    m = _load(cb.ConformerBlock(d, H, 31), sd).set_compute("bf16")
+    got = m(x.to(DEV), pos[None].expand(B, -1, -1).to(DEV), pad[:, None, None, :].to(DEV))
+    print(assert_close_bf16(got, want, "block bf16"))
+
+
 @pytest.mark.parametrize("rows", [(1, 1), (2, 100), (3, 374), (5, 128)])
 def test_ffn_module_bf16_fused_vs_oracle(rows):
     """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel."""

@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Timeline (ns) of CTA (0,0,0) of the tcgen05 attention kernel (debug).
+per tile j: MMA: [0] got TMEM buffer [1] K/V/window landed [2] P_j ready -> issue PV | softmax (warp 4):
+[3] top [4] O_{j-1} ready [5] S,PS_j ready [6] max exchanged [7] P_j published"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import conformer_b200 as cb  # noqa: E402
+from conformer_b200._lib import lib  # noqa: E402
+from conformer_b200.synth import EncoderConfig, synth_encoder_state_dict  # noqa: E402
+
+B, T, d, H = 64, 374, 256, 4
+sd = {k[len("layers.0.attention.attention."):]: v for k, v in synth_encoder_state_dict(EncoderConfig(80, 1, d, H, 31), 1).items()
+      if k.startswith("layers.0.attention.attention.")}
+m = cb.RelativeMultiHeadAttention(d, H)
+m.load_state_dict(sd)
+m = m.cuda().eval().set_compute("bf16")
+x = torch.randn(B, T, d, device="cuda")
+pos = torch.randn(1, 2 * T - 1, d, device="cuda")
+for _ in range(3):
+    m(x, x, x, pos, None)
+trace = torch.zeros(128, dtype=torch.int64, device="cuda")
+fn = lib().cfm_debug_set_gemm_trace
+fn.argtypes = [C.c_void_p]
+torch.cuda.synchronize()
+fn(trace.data_ptr())
+m(x, x, x, pos, None)
+torch.cuda.synchronize()
+fn(None)
+t = trace.cpu().view(16, 8)
+t0 = int(t[t > 0].min())
+for j in range(8):
+    if int(t[j].max()) == 0:
+        break
+    print(f"tile {j}: " + " ".join(f"{(int(v) - t0) if v > 0 else -1:6d}" for v in t[j]))
