@@ -52,6 +52,7 @@ SIGNATURES = {
     "cfm_encoder_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_forward_host": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_host_workspace_bytes": (_i64, [_p, _i32, _i32]),
+    "cfm_set_attention_kernel": (C.c_int, [_i32]),
     "cfm_last_launch_count": (_i64, [_p]),
     "cfm_profile_enable": (C.c_int, [_p, _i32]),
     "cfm_profile_collect": (C.c_int, [_p, C.POINTER(C.c_double), _i32]),

@@ -3,19 +3,21 @@
 //   score[i,j] = ((q_i+u).k_j + (q_i+v).p[T-1+j-i]) / sqrt(dh)         (attention.py:47-56, shift :94-102)
 //
 // One CTA = 128 query rows of one (batch, head); keys walked in tiles of 64.  Warp roles:
-//   warp 0      TMA producer: K tile [64x64], V tile [64x64] (3-D maps over q|k|v, rows past T zero-filled) and the
-//               192-row window of the projected positional table this (query tile, key tile) pair can touch
-//               (2-D map, negative / past-the-end rows zero-filled) into a 2-stage ring;
-//   warp 1      MMA issuer: S = (q+u) K^T (128x64) and PS = (q+v) Pwin^T (128x192) into TMEM, later O_j = P V
-//               (128x64, V is the MN-major B operand).  TMEM holds two {S|O, PS} buffers (2 x 256 columns) so the
-//               MMAs of tile j+1 run while the softmax warps work on tile j;
-//   warps 4-7   softmax, one thread = one query row (no cross-thread reductions).  The Transformer-XL shift is a
-//               per-row column offset 127-i into PS: its warp-uniform part is folded into the tcgen05.ld column
-//               address, the per-lane part (31-lane) goes through a private shared-memory row (written as float2,
-//               read back at a lane-dependent offset, bank-conflict free) - no [T,2T-1] tensor is ever formed.
-//               Online softmax in fp32 with exp2 (scale folded into Q); P is written as bf16 straight into the
-//               MMA's 128B-swizzled A layout; O_j is read back from TMEM and merged into a register accumulator
-//               (acc = acc*alpha + O_j), so TMEM never needs rescaling.
+//   warp 0, 3   TMA producers: K tile [64x64] + the 192-row window of the projected positional table this
+//               (query tile, key tile) pair can touch (2-D map, negative / past-the-end rows zero-filled), and the
+//               V tile [64x64] (3-D maps over q|k|v, rows past T zero-filled), as two 2-stage rings;
+//   warp 1      MMA issuer: S = (q+u) K^T (128x64) and PS = (q+v) Pwin^T (128x192) into TMEM, then O += P V
+//               (128x64, V is the MN-major B operand) - O ACCUMULATES IN TMEM over all key tiles.  S/PS of tile
+//               j+1 are issued as soon as every softmax thread has pulled tile j into registers;
+//   warps 4-11  softmax, 256 threads: thread = (query row, half of the tile's keys); warps w+4 and w+8 share
+//               TMEM lane quadrant w and take keys 0-31 / 32-63.  The Transformer-XL shift is a per-row column
+//               offset 127-i into PS: its warp-uniform part is folded into the tcgen05.ld column address, the
+//               per-lane part (31-lane) goes through a private shared-memory row (float4 stores, reads at a
+//               lane-dependent offset, both bank-conflict free) - no [T,2T-1] tensor is ever formed.
+//               Online softmax in fp32 with exp2 (scale folded into Q) and LAZY rescaling: the reference maximum
+//               of a row only moves when the tile maximum exceeds it by more than 2^8, and only then is the row
+//               of O in TMEM rescaled (tcgen05.ld / st), so the common tile costs no accumulator traffic at all.
+//               P is written as bf16 straight into the MMA's 128B-swizzled A layout.
 // Masked keys (and keys past T) get weight exactly 0.
 #include <math_constants.h>
 
@@ -29,15 +31,17 @@ constexpr int WIN = BQ + BKV;                         // 192 window rows per (qu
 constexpr int Q_BYTES = BQ * 128;                     // 16 KB: [128 x 64] bf16, 128B swizzle
 constexpr int KV_BYTES = BKV * 128;                   // 8 KB
 constexpr int WIN_BYTES = WIN * 128;                  // 24 KB
-constexpr int STAGE_BYTES = 2 * KV_BYTES + WIN_BYTES; // K | V | window = 40 KB
-constexpr int STAGES = 2;
+constexpr int KP_BYTES = KV_BYTES + WIN_BYTES;        // K | window = 32 KB per stage
 constexpr int P_BYTES = BQ * 128;                     // 16 KB: [128 x 64 keys] bf16
-constexpr int SKEW_LD = 98;                           // floats per private row: 96 used; 98 % 32 == 2 -> conflict free
-constexpr int SKEW_BYTES = 4 * 32 * SKEW_LD * 4;      // 4 softmax warps
-constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + STAGES * STAGE_BYTES + 2 * P_BYTES + SKEW_BYTES + 256;
+constexpr int NUM_SM_WARPS = 8, NUM_SM_THREADS = NUM_SM_WARPS * 32;
+constexpr int SKEW_LD = 68;                           // floats per private row: 64 used; pitch 68 -> conflict free
+constexpr int SKEW_BYTES = NUM_SM_THREADS * SKEW_LD * 4;
+constexpr int XCHG_BYTES = 3 * 2 * BQ * 4;            // tile-max exchange (double buffered) + row-sum exchange
+constexpr int SMEM_BYTES = 1024 + 2 * Q_BYTES + 2 * KP_BYTES + 2 * KV_BYTES + P_BYTES + SKEW_BYTES + XCHG_BYTES + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "attention shared memory budget");
-constexpr int NUM_THREADS = 256;                      // warps 0,1: TMA / MMA; 2: TMEM alloc; 3: idle; 4-7: softmax
-constexpr int TM_BUF = 256;                           // TMEM columns per buffer: S|O at +0 (64), PS at +64 (192)
+constexpr int NUM_THREADS = 128 + NUM_SM_THREADS;     // warps 0,3: TMA; 1: MMA; 2: TMEM alloc; 4-11: softmax
+constexpr int TM_S = 0, TM_PS = 64, TM_O = 256;       // TMEM columns: S (64) | PS (192) | O (64)
+constexpr float RESCALE_THRESHOLD = 8.0f;             // log2 units: P stays below 2^8
 
 struct AttnParams {
   const bf16* qkv;
@@ -47,7 +51,18 @@ struct AttnParams {
   bf16* ctx;
   int Tn, H;
   float scale_log2e;
+  unsigned long long* trace;     // debug: globaltimer stamps of CTA (0,0,0)
 };
+__device__ __forceinline__ unsigned long long atime_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATRACE(slot)                                                                                              \
+  do {                                                                                                            \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 128) \
+      p.trace[(slot)] = atime_ns();                                                                               \
+  } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {
   float y;
@@ -61,16 +76,21 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* qu_s = smem;
   uint8_t* qv_s = qu_s + Q_BYTES;
-  uint8_t* ring = qv_s + Q_BYTES;
-  uint8_t* p_s = ring + STAGES * STAGE_BYTES;          // two P buffers
-  float* skew = reinterpret_cast<float*>(p_s + 2 * P_BYTES);
-  uint64_t* kv_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(skew) + SKEW_BYTES);
-  uint64_t* kv_empty = kv_full + 2;
-  uint64_t* sp_full = kv_empty + 2;
-  uint64_t* spo_empty = sp_full + 2;
-  uint64_t* p_full = spo_empty + 2;
-  uint64_t* o_full = p_full + 2;
-  uint64_t* q_full = o_full + 2;
+  uint8_t* kp_ring = qv_s + Q_BYTES;                   // 2 x (K | window)
+  uint8_t* v_ring = kp_ring + 2 * KP_BYTES;            // 2 x V
+  uint8_t* p_s = v_ring + 2 * KV_BYTES;
+  float* skew = reinterpret_cast<float*>(p_s + P_BYTES);
+  float* xmax = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(skew) + SKEW_BYTES);   // [2 buffers][2 halves][128]
+  float* xsum = xmax + 2 * 2 * BQ;                                                          // [2 halves][128]
+  uint64_t* kp_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + XCHG_BYTES);
+  uint64_t* kp_empty = kp_full + 2;
+  uint64_t* v_full = kp_empty + 2;
+  uint64_t* v_empty = v_full + 2;
+  uint64_t* sp_full = v_empty + 2;
+  uint64_t* s_read = sp_full + 1;
+  uint64_t* p_full = s_read + 1;
+  uint64_t* o_done = p_full + 1;
+  uint64_t* q_full = o_done + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(q_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,35 +104,47 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&sp_full[s], 1);
-      mbar_init(&spo_empty[s], 4);
-      mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1);
+      mbar_init(&kp_full[s], 1);
+      mbar_init(&kp_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
-    mbar_init(q_full, 4);
+    mbar_init(sp_full, 1);
+    mbar_init(s_read, NUM_SM_WARPS);
+    mbar_init(p_full, NUM_SM_WARPS);
+    mbar_init(o_done, 1);
+    mbar_init(q_full, NUM_SM_WARPS);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer: K + positional window
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
-      mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+      mbar_wait(&kp_empty[s], ((j >> 1) & 1) ^ 1);
       if (lane == 0) {
-        uint8_t* st = ring + s * STAGE_BYTES;
+        uint8_t* st = kp_ring + s * KP_BYTES;
         const int j0 = j * BKV;
-        mbar_expect_tx(&kv_full[s], STAGE_BYTES);
-        tma_load_3d(st, &tmQKV, &kv_full[s], d + h * DH, j0, b);                    // K rows j0..j0+63
-        tma_load_3d(st + KV_BYTES, &tmQKV, &kv_full[s], 2 * d + h * DH, j0, b);     // V rows
+        mbar_expect_tx(&kp_full[s], KP_BYTES);
+        tma_load_3d(st, &tmQKV, &kp_full[s], d + h * DH, j0, b);                    // K rows j0..j0+63
         // window entry w <-> table row (T-1 + j0 - i0 - 127) + w
-        tma_load_2d(st + 2 * KV_BYTES, &tmPos, &kv_full[s], h * DH, Tn - 1 + j0 - i0 - (BQ - 1));
+        tma_load_2d(st + KV_BYTES, &tmPos, &kp_full[s], h * DH, Tn - 1 + j0 - i0 - (BQ - 1));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ TMA producer: V
+    for (int j = 0; j < ntiles; ++j) {
+      const int s = j & 1;
+      mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+      if (lane == 0) {
+        mbar_expect_tx(&v_full[s], KV_BYTES);
+        tma_load_3d(v_ring + s * KV_BYTES, &tmQKV, &v_full[s], 2 * d + h * DH, j * BKV, b);
       }
       __syncwarp();
     }
@@ -122,21 +154,18 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     constexpr uint32_t idesc_ps = umma_idesc_bf16(BQ, WIN);         // 128 x 192
     constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(BQ, DH);      // 128 x 64, B (=V) MN-major
     auto issue_sp = [&](int j) {
-      const int buf = j & 1, s = j & 1;
-      mbar_wait(&spo_empty[buf], ((j >> 1) & 1) ^ 1);
-      mbar_wait(&kv_full[s], (j >> 1) & 1);
+      const int s = j & 1;
+      mbar_wait(&kp_full[s], (j >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sk = smem_u32(ring + s * STAGE_BYTES), sw = sk + 2 * KV_BYTES;
-        const uint32_t squ = smem_u32(qu_s), sqv = smem_u32(qv_s);
-        const uint32_t ts = tmem_base + buf * TM_BUF, tps = ts + BKV;
+      if (elect_one()) {
+        const uint32_t sk = umma_desc_lo(smem_u32(kp_ring + s * KP_BYTES)), sw = sk + (KV_BYTES >> 4);
+        const uint32_t squ = umma_desc_lo(smem_u32(qu_s)), sqv = umma_desc_lo(smem_u32(qv_s));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(ts, umma_desc_k_sw128(squ + k * 32), umma_desc_k_sw128(sk + k * 32), idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tmem_base + TM_S, squ + k * 2, sk + k * 2, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(tps, umma_desc_k_sw128(sqv + k * 32), umma_desc_k_sw128(sw + k * 32), idesc_ps, k != 0 ? 1u : 0u);
-        tc_commit(&sp_full[buf]);
+        for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tmem_base + TM_PS, sqv + k * 2, sw + k * 2, idesc_ps, k != 0 ? 1u : 0u);
+        tc_commit(sp_full);
+        tc_commit(&kp_empty[s]);                                    // K + window may be refilled
       }
       __syncwarp();
     };
@@ -144,33 +173,38 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     tc_fence_after();
     issue_sp(0);
     for (int j = 0; j < ntiles; ++j) {
-      if (j + 1 < ntiles) issue_sp(j + 1);
-      const int buf = j & 1, s = j & 1;
-      mbar_wait(&p_full[buf], (j >> 1) & 1);           // P_j written (and S_j fully read: its columns become O_j)
+      const int s = j & 1;
+      if (j + 1 < ntiles) {
+        mbar_wait(s_read, j & 1);                                   // every softmax thread holds tile j in registers
+        tc_fence_after();
+        issue_sp(j + 1);
+      }
+      mbar_wait(p_full, j & 1);                                     // P_j written (and O rescaled where needed)
+      mbar_wait(&v_full[s], (j >> 1) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sp = smem_u32(p_s + buf * P_BYTES);
-        const uint32_t sv = smem_u32(ring + s * STAGE_BYTES + KV_BYTES);
+      if (elect_one()) {
+        const uint32_t sp = umma_desc_lo(smem_u32(p_s));
+        const uint32_t sv = umma_desc_lo(smem_u32(v_ring + s * KV_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)                      // K = 64 keys in steps of 16 (V: 16 rows = 2048 B)
-          tc_mma_f16(tmem_base + buf * TM_BUF, umma_desc_k_sw128(sp + k * 32), umma_desc_mn_sw128(sv + k * 2048), idesc_pv,
-                     k != 0 ? 1u : 0u);
-        tc_commit(&o_full[buf]);
-        tc_commit(&kv_empty[s]);
+        for (int k = 0; k < 4; ++k)                                 // K = 64 keys in steps of 16 (V: 16 rows = 2048 B)
+          tc_mma_f16_lo(tmem_base + TM_O, sp + k * 2, sv + k * (2048 >> 4), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        tc_commit(o_done);
+        tc_commit(&v_empty[s]);
       }
       __syncwarp();
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ softmax warps: thread = query row
-    const int w = warp & 3;                              // TMEM lane quadrant
+    // ------------------------------------------------------------------ softmax: thread = (query row, key half)
+    const int w = warp & 3, grp = (warp - 4) >> 2;       // TMEM lane quadrant (hardware rule: warp % 4), key half
     const int row = w * 32 + lane;
     const int qi = i0 + row;
     const int sw = row & 7;
-    // ---- Q operands: (q+u)*c and (q+v)*c as bf16 in the MMA's A layout, c = log2(e)/sqrt(dh)
+    // ---- Q operands: (q+u)*c and (q+v)*c as bf16 in the MMA's A layout, c = log2(e)/sqrt(dh); half a row per thread
     {
       const bf16* qrow = p.qkv + (static_cast<int64_t>(b) * Tn + (qi < Tn ? qi : 0)) * (3 * d) + h * DH;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const int ch = grp * 4 + c4;
         uint4 raw = make_uint4(0u, 0u, 0u, 0u);
         if (qi < Tn) raw = *reinterpret_cast<const uint4*>(qrow + ch * 8);
         const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
@@ -195,121 +229,122 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full);
     }
-    float* myrow = skew + (w * 32 + lane) * SKEW_LD;
+    float* myrow = skew + (grp * BQ + row) * SKEW_LD;
     const int shift = 31 - lane;                         // per-lane part of the relative shift
-    const uint32_t lane_addr = static_cast<uint32_t>(w * 32) << 16;
-    float acc[DH];
-#pragma unroll
-    for (int c = 0; c < DH; ++c) acc[c] = 0.f;
-    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
+    const uint32_t t_s = tlane + TM_S + 32 * grp;                      // content scores of this thread's 32 keys
+    const uint32_t t_ps = tlane + TM_PS + 32 * grp + 32 * (3 - w);     // 64-column window holding their positional scores
+    const uint32_t t_o = tlane + TM_O + 32 * grp;                      // the half of the O row this thread rescales
+    uint8_t* prow = p_s + row * 128;
+    float m_ref = -CUDART_INF_F, l_part = 0.f;
 
-    for (int j = 0; j <= ntiles; ++j) {
-      // ---- merge O_{j-1} (its P.V finished) and hand its TMEM buffer back
-      if (j > 0) {
-        const int pb = (j - 1) & 1;
-        mbar_wait(&o_full[pb], ((j - 1) >> 1) & 1);
-        tc_fence_after();
-        uint32_t o0[32], o1[32];
-        tmem_ld_32x32(tmem_base + lane_addr + pb * TM_BUF, o0);
-        tmem_ld_32x32(tmem_base + lane_addr + pb * TM_BUF + 32, o1);
+    for (int j = 0; j < ntiles; ++j) {
+      // ---- usable-key bitmask of this thread's 32 keys (warp-uniform)
+      uint32_t vm = 0xffffffffu;
+      {
+        const int jk = j * BKV + 32 * grp;
+        if (jk + 32 > Tn || p.key_pad != nullptr) {
+          const int ja = jk + lane;
+          const bool va = ja < Tn && (p.key_pad == nullptr || p.key_pad[static_cast<int64_t>(b) * Tn + ja] == 0);
+          vm = __ballot_sync(0xffffffffu, va);
+        }
+      }
+      if (warp == 4) ATRACE(8 * j + 0);
+      mbar_wait(sp_full, j & 1);
+      tc_fence_after();
+      if (warp == 4) ATRACE(8 * j + 1);
+      float sc[32];
+      float tmax = -CUDART_INF_F;
+      {
+        uint32_t r0[32], r1[32], s0[32];
+        tmem_ld_32x32(t_ps, r0);
+        tmem_ld_32x32(t_ps + 32, r1);
+        tmem_ld_32x32(t_s, s0);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&spo_empty[pb]);
+        if (lane == 0) mbar_arrive(s_read);              // the S/PS columns may be overwritten by tile j+1
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          acc[c] = fmaf(acc[c], alpha_prev, __uint_as_float(o0[c]));
-          acc[32 + c] = fmaf(acc[32 + c], alpha_prev, __uint_as_float(o1[c]));
+        for (int e = 0; e < 8; ++e) {
+          *reinterpret_cast<float4*>(myrow + 4 * e) = make_float4(__uint_as_float(r0[4 * e]), __uint_as_float(r0[4 * e + 1]),
+                                                                  __uint_as_float(r0[4 * e + 2]), __uint_as_float(r0[4 * e + 3]));
+          *reinterpret_cast<float4*>(myrow + 32 + 4 * e) = make_float4(__uint_as_float(r1[4 * e]), __uint_as_float(r1[4 * e + 1]),
+                                                                       __uint_as_float(r1[4 * e + 2]), __uint_as_float(r1[4 * e + 3]));
         }
-      }
-      if (j == ntiles) break;
-      const int buf = j & 1;
-      const int j0 = j * BKV;
-      // ---- usable-key bitmask of this tile (warp-uniform)
-      uint32_t vm0 = 0xffffffffu, vm1 = 0xffffffffu;
-      bool need_mask = false;
-      if (j0 + BKV > Tn || p.key_pad != nullptr) {
-        const int ja = j0 + lane, jb = ja + 32;
-        const bool va = ja < Tn && (p.key_pad == nullptr || p.key_pad[static_cast<int64_t>(b) * Tn + ja] == 0);
-        const bool vb = jb < Tn && (p.key_pad == nullptr || p.key_pad[static_cast<int64_t>(b) * Tn + jb] == 0);
-        vm0 = __ballot_sync(0xffffffffu, va);
-        vm1 = __ballot_sync(0xffffffffu, vb);
-        need_mask = (vm0 & vm1) != 0xffffffffu;
-      }
-      mbar_wait(&sp_full[buf], (j >> 1) & 1);
-      tc_fence_after();
-      // ---- positional scores: PS columns [32*(3-w), +96) -> private smem row (float2 stores)
-      const uint32_t tps = tmem_base + lane_addr + buf * TM_BUF + BKV + 32 * (3 - w);
-#pragma unroll
-      for (int ch = 0; ch < 3; ++ch) {
-        uint32_t r[32];
-        tmem_ld_32x32(tps + ch * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e)
-          *reinterpret_cast<float2*>(myrow + ch * 32 + 2 * e) =
-              make_float2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1]));
-      }
-      // ---- content scores + shifted positional scores, mask, tile max
-      float sc[BKV];
-      {
-        uint32_t s0[32], s1[32];
-        tmem_ld_32x32(tmem_base + lane_addr + buf * TM_BUF, s0);
-        tmem_ld_32x32(tmem_base + lane_addr + buf * TM_BUF + 32, s1);
-        tmem_ld_wait();
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          sc[jj] = __uint_as_float(s0[jj]) + myrow[shift + jj];
-          sc[32 + jj] = __uint_as_float(s1[jj]) + myrow[shift + 32 + jj];
+          float v = __uint_as_float(s0[jj]) + myrow[shift + jj];
+          if (((vm >> jj) & 1u) == 0) v = -CUDART_INF_F;
+          sc[jj] = v;
+          tmax = fmaxf(tmax, v);
         }
       }
-      float tmax = -CUDART_INF_F;
-      if (need_mask) {
+      if (warp == 4) ATRACE(8 * j + 2);
+      // ---- tile maximum of the whole row: exchange with the thread that holds the other 32 keys
+      float* xm = xmax + (j & 1) * 2 * BQ;
+      xm[grp * BQ + row] = tmax;
+      named_bar_sync(1 + w, 64);
+      const float t_row = fmaxf(tmax, xm[(grp ^ 1) * BQ + row]);
+      // ---- lazy rescaling: move the reference maximum only when the tile exceeds it by more than the threshold
+      const float m_new = (t_row > m_ref + RESCALE_THRESHOLD) ? t_row : m_ref;
+      if (j > 0) {
+        mbar_wait(o_done, (j - 1) & 1);                  // P.V of tile j-1 retired: P buffer free, O stable
+        if (__any_sync(0xffffffffu, m_new != m_ref)) {
+          tc_fence_after();
+          const float f = ex2f(m_ref - m_new);           // 1 for rows whose reference did not move
+          uint32_t o[32];
+          tmem_ld_32x32(t_o, o);
+          tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          if (((vm0 >> jj) & 1u) == 0) sc[jj] = -CUDART_INF_F;
-          if (((vm1 >> jj) & 1u) == 0) sc[32 + jj] = -CUDART_INF_F;
+          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+          tmem_st_32x32(t_o, o);
+          tmem_st_wait();
+          l_part *= f;
         }
       }
-#pragma unroll
-      for (int jj = 0; jj < BKV; ++jj) tmax = fmaxf(tmax, sc[jj]);
-      const float m_new = fmaxf(m_run, tmax);
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = ex2f(m_run - m_use);
-      m_run = m_new;
-      // ---- P = exp2(s - m) as bf16 into the A layout of the P.V MMA
+      m_ref = m_new;
+      const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
+      if (warp == 4) ATRACE(8 * j + 3);
+      // ---- P = exp2(s - m) as bf16 into the A layout of the P.V MMA (this thread: 4 chunks of 8 keys)
       float psum = 0.f;
-      uint8_t* prow = p_s + buf * P_BYTES + row * 128;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int c4 = 0; c4 < 4; ++c4) {
         uint32_t o[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2f(sc[ch * 8 + 2 * e] - m_use), p1 = ex2f(sc[ch * 8 + 2 * e + 1] - m_use);
+          const float p0 = ex2f(sc[c4 * 8 + 2 * e] - m_use), p1 = ex2f(sc[c4 * 8 + 2 * e + 1] - m_use);
           psum += p0 + p1;
           o[e] = pack_bf16x2(p0, p1);
         }
-        *reinterpret_cast<uint4*>(prow + ((ch ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(prow + (((grp * 4 + c4) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      l_run = l_run * alpha + psum;
-      alpha_prev = alpha;
+      l_part += psum;
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[buf]);
+      if (lane == 0) mbar_arrive(p_full);
+      if (warp == 4) ATRACE(8 * j + 4);
     }
-    // ---- normalise and store this row of the context
+    // ---- epilogue: O / l, this thread's 32 of the 64 output columns
+    xsum[grp * BQ + row] = l_part;
+    mbar_wait(o_done, (ntiles - 1) & 1);
+    tc_fence_after();
+    uint32_t o[32];
+    tmem_ld_32x32(t_o, o);
+    tmem_ld_wait();
+    named_bar_sync(1 + w, 64);
+    const float l_tot = l_part + xsum[(grp ^ 1) * BQ + row];
+    const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
     if (qi < Tn) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* orow = p.ctx + (static_cast<int64_t>(b) * Tn + qi) * d + h * DH;
+      bf16* orow = p.ctx + (static_cast<int64_t>(b) * Tn + qi) * d + h * DH + 32 * grp;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        uint4 o;
-        o.x = pack_bf16x2(acc[ch * 8 + 0] * inv, acc[ch * 8 + 1] * inv);
-        o.y = pack_bf16x2(acc[ch * 8 + 2] * inv, acc[ch * 8 + 3] * inv);
-        o.z = pack_bf16x2(acc[ch * 8 + 4] * inv, acc[ch * 8 + 5] * inv);
-        o.w = pack_bf16x2(acc[ch * 8 + 6] * inv, acc[ch * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(orow + ch * 8) = o;
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 v4;
+        v4.x = pack_bf16x2(__uint_as_float(o[ch * 8 + 0]) * inv, __uint_as_float(o[ch * 8 + 1]) * inv);
+        v4.y = pack_bf16x2(__uint_as_float(o[ch * 8 + 2]) * inv, __uint_as_float(o[ch * 8 + 3]) * inv);
+        v4.z = pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv);
+        v4.w = pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(orow + ch * 8) = v4;
       }
     }
   }
@@ -322,6 +357,8 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 }
 
 }  // namespace
+
+extern unsigned long long* g_gemm_trace;
 
 int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
                           const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream) {
@@ -349,7 +386,7 @@ int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float
     CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  AttnParams p{qkv, u, v, key_pad, ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh))};
+  AttnParams p{qkv, u, v, key_pad, ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   rel_attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
   CFM_CUDA_OK(cudaGetLastError());

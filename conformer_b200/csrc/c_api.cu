@@ -9,7 +9,7 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 }  // namespace cfm
 
-namespace cfm { extern unsigned long long* g_gemm_trace; }
+namespace cfm { extern unsigned long long* g_gemm_trace; extern int g_attention_kernel; }
 using namespace cfm;
 
 namespace {
@@ -200,6 +200,11 @@ int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int3
   return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C,
                       epi == EPI_BIAS_GLU ? N / 2 : N, M, N, K, static_cast<Epilogue>(epi), res, res_scale, nullptr, sms,
                       S(stream));
+}
+int cfm_set_attention_kernel(int32_t mode) {
+  CFM_REQUIRE(mode >= -1 && mode <= 1, "attention kernel mode must be -1, 0 or 1");
+  cfm::g_attention_kernel = mode;
+  return 0;
 }
 /* debug: device buffer receiving 8 globaltimer stamps per tile of CTA 0 of the next tcgen05 GEMMs (NULL = off) */
 __attribute__((visibility("default"))) int cfm_debug_set_gemm_trace(void* dev_buf) {

@@ -112,7 +112,7 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer: 8 W1p stages, 4 W2 stages
@@ -139,12 +139,11 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
       }
       mbar_wait(&full_bar[s], (it / STAGES) & 1);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(xs + kb * (BM * 128)), sb = smem_u32(ring + s * STAGE_BYTES);
+      if (elect_one()) {
+        const uint32_t sa = umma_desc_lo(smem_u32(xs + kb * (BM * 128))), sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
         const uint32_t dcol = tmem_base + (g == 1 ? 256u : 0u);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma_f16(dcol, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_f16_lo(dcol, sa + k * 2, sb + k * 2, idesc, (kb | k) != 0 ? 1u : 0u);
         tc_commit(&empty_bar[s]);
         if (kb == 3) tc_commit(g == 0 ? &acc1_full[0] : (g == 1 ? &acc1_full[1] : acc2_full));
       }

@@ -85,7 +85,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
   const uint32_t tm_acc2 = tmem_base + 2 * HC;
 
   if (warp == 0) {
@@ -134,15 +134,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sb = smem_u32(ring + s * STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
-            const uint32_t sa = smem_u32(xs + (2 * s2 + kk) * (BM * 128));
+            const uint32_t sa = umma_desc_lo(smem_u32(xs + (2 * s2 + kk) * (BM * 128)));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              tc_mma_f16(tmem_base + b * HC, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + kk * 16384 + k * 32),
-                         idesc1, (s2 | kk | k) != 0 ? 1u : 0u);
+              tc_mma_f16_lo(tmem_base + b * HC, sa + k * 2, sb + kk * (16384 >> 4) + k * 2, idesc1, (s2 | kk | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);
           if (s2 == 1) tc_commit(&acc1_full[b]);
@@ -158,13 +157,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(hs + b * HS_BYTES + s2 * (BM * 128));
-          const uint32_t sb = smem_u32(ring + s * STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t sa = umma_desc_lo(smem_u32(hs + b * HS_BYTES + s2 * (BM * 128)));
+          const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tm_acc2, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc2,
-                       (c | s2 | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tm_acc2, sa + k * 2, sb + k * 2, idesc2, (c | s2 | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);
           if (s2 == 1) {
             tc_commit(&hs_empty[b]);

@@ -114,11 +114,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(res_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C_::TMEM_COLS);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);               // whole TMEM: the CTA owns the SM, base is 0
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -171,15 +171,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (kb == 0) TRACE(3);
         if (kb == p.num_kb - 1) TRACE(4);
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + s * C_::STAGE_BYTES);
-          const uint32_t sb = sa + A_STAGE_BYTES;
+        if (elect_one()) {
+          const uint32_t sa = umma_desc_lo(smem_u32(smem + s * C_::STAGE_BYTES));
+          const uint32_t sb = sa + (A_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_k_sw128(sa + k * UMMA_K * 2);
-            const uint64_t db = umma_desc_k_sw128(sb + k * UMMA_K * 2);
-            tc_mma_f16(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);                            // smem slot free once these MMAs retire
           if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);   // accumulator complete
         }
@@ -319,7 +316,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C_::TMEM_COLS);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

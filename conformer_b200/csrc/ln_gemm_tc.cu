@@ -73,7 +73,7 @@ ln_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer
@@ -103,13 +103,11 @@ ln_gemm_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ 
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(xs + kb * KBLK_BYTES);
-          const uint32_t sb = smem_u32(ring + s * STAGE_BYTES);
+        if (elect_one()) {
+          const uint32_t sa = umma_desc_lo(smem_u32(xs + kb * KBLK_BYTES));
+          const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma_f16(tmem_base + b * NC, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tmem_base + b * NC, sa + k * 2, sb + k * 2, idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(&empty_bar[s]);
           if (kb == D / KB - 1) tc_commit(&acc_full[b]);
         }

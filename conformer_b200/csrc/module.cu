@@ -9,6 +9,8 @@
 
 namespace cfm {
 
+int g_attention_kernel = 0;          // cfm_set_attention_kernel
+
 // =================================================================================== arena
 int Arena::reserve(size_t bytes) {
   release();
@@ -112,6 +114,11 @@ struct Packer {
     finish_linear(w.qkv, wq, bq, 3 * d, d);
     linear(w.pos, pre + "pos_proj", d, d);
     linear(w.out, pre + "out_proj", d, d);
+    w.wpT = nullptr;
+    if (bf16_mode && !status && rel_attention_fact_supported(d, d / H)) {
+      w.wpT = alloc_bf16(static_cast<int64_t>(d) * d);
+      if (!status && pack_pos_fact(w.pos.w32, w.wpT, d, d / H, stream)) status = 2;
+    }
   }
   void mhsa(AttnW& w, const std::string& pre, int d, int H) {
     w.ln_g = vec(pre + "layer_norm.weight", d);
@@ -169,7 +176,7 @@ size_t arena_bytes_for(const Module& m) {
   for (const auto& kv : m.params) total += static_cast<size_t>(kv.second.numel);
   // fp32 copy + bf16 copy + per-tensor 256-byte alignment slack + the fused pos_proj copy
   const size_t d = m.cfg.d_model;
-  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 6 + (1 << 16);
+  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 8 + (1 << 16);
 }
 
 }  // namespace
@@ -379,10 +386,51 @@ int pos_project(Ctx& c, const Linear& wp, const float* div_term, const float* po
   return Dispatch<TA>::gemm(c, pe, d, wp, pp, wp.N, R, EPI_BIAS, nullptr, 0.f, nullptr);
 }
 
-// out = res + MHSA(x)      (attention.py:14-18,74-92; block.py:21)
+// sinusoid tables of the factorised positional term (bf16 path, d_model 256): cos|sin of t*w_k as bf16 and fp16
+struct FactPos { const bf16* e16 = nullptr; const void* r16 = nullptr; };
+// Which kernel computes the positional term when the table is the module's own sinusoids (bf16, d_model 256):
+// cfm_set_attention_kernel(1) forces the factorised kernel, (-1) the relative-shift kernel; by default the factorised
+// kernel takes long sequences (its per-CTA prologue - projecting and rotating the queries - amortises over the key
+// tiles; measured on B200: T=1499 194 us vs 233 us, T=374 89 us vs 82 us).  CFM_ATTN=fact|skew|mma overrides (A/B runs).
+inline int fact_mode() {
+  static const int env_mode = [] {
+    const char* e = getenv("CFM_ATTN");
+    if (e == nullptr) return 0;
+    return e[0] == 'f' ? 1 : (e[0] == 's' || e[0] == 'm') ? -1 : 0;
+  }();
+  return env_mode != 0 ? env_mode : g_attention_kernel;
+}
+constexpr int FACT_MIN_FRAMES = 768;
+inline bool fact_ok(const float*, const AttnW&, int, int, int) { return false; }
+inline bool fact_ok(const bf16*, const AttnW& w, int d, int H, int Tn) {
+  if (fact_mode() < 0 || w.wpT == nullptr || !rel_attention_fact_supported(d, d / H)) return false;
+  return fact_mode() > 0 || Tn >= FACT_MIN_FRAMES;
+}
 template <typename TA>
-int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_proj, int ldp, const uint8_t* key_pad,
-             const float* res, float* out, int B, int Tn, int d, int H) {
+int fact_tables(Ctx& c, const float* div_term, int Tn, int d, FactPos* fp) {
+  bf16* e16 = ws_take<bf16>(c, static_cast<int64_t>(Tn) * d);
+  bf16* r16 = ws_take<bf16>(c, static_cast<int64_t>(Tn) * d);       // fp16 payload, same size
+  WS_CHECK(e16); WS_CHECK(r16);
+  fp->e16 = e16; fp->r16 = r16;
+  if (c.ws.measuring()) return 0;
+  KRUN(KC_MISC, 0, 4.0 * Tn * d, pos_fact_tables(div_term, e16, r16, Tn, d, c.stream));
+  return 0;
+}
+inline int attention_fact_any(const float*, const AttnW&, const FactPos&, const uint8_t*, float*, int, int, int, int, cudaStream_t) {
+  set_error("factorised attention is bf16 only");
+  return 1;
+}
+inline int attention_fact_any(const bf16* qkv, const AttnW& w, const FactPos& fp, const uint8_t* kp, bf16* ctx, int B, int Tn,
+                              int H, int dh, cudaStream_t st) {
+  return rel_attention_bf16_fact(qkv, w.wpT, fp.e16, fp.r16, w.u, w.v, kp, ctx, B, Tn, H, dh, st);
+}
+
+// out = res + MHSA(x)      (attention.py:14-18,74-92; block.py:21)
+// Positional scores come either from a projected table (pos_proj, any `pos` the caller supplied) or, when fp is
+// given, from the factorised sinusoid form (the encoder's own rel_pe table).
+template <typename TA>
+int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_proj, int ldp, const FactPos* fp,
+             const uint8_t* key_pad, const float* res, float* out, int B, int Tn, int d, int H) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
@@ -406,8 +454,13 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
       CFM_TRY(Dispatch<TA>::gemm(c, ain, d, w.qkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
     }
     // algorithmic work: content + positional + PV = 6*T*d FLOPs per token
-    KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
-         attention_any(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
+    if (fp != nullptr) {
+      KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
+           attention_fact_any(qkv, w, *fp, key_pad, ctx, B, Tn, H, d / H, c.stream));
+    } else {
+      KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
+           attention_any(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
+    }
     CFM_TRY(Dispatch<TA>::gemm(c, ctx, d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);
@@ -465,11 +518,11 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
 
 // y = ConformerBlock(x)      (block.py:17-29).  xw is an fp32 [M,d] working buffer; y may alias xw.
 template <typename TA>
-int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, const TA* pos_proj, int ldp,
+int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, const TA* pos_proj, int ldp, const FactPos* fp,
               const uint8_t* key_pad, int B, int Tn, int d, int H) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
   CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d));
-  CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, key_pad, xw, xw, B, Tn, d, H)));
+  CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, fp, key_pad, xw, xw, B, Tn, d, H)));
   // the fused conv-module kernel reads a time halo, so it writes a second residual buffer instead of updating in place
   const size_t mark = c.ws.mark();
   float* xc = xw;
@@ -535,16 +588,27 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
       return conv_fwd<TA>(c, conv, x, nullptr, y, B, frames, d);
     case CFM_KIND_MHSA:
     case CFM_KIND_REL_ATTENTION: {
+      // no table supplied: the module's own sinusoids, factorised (the workspace query covers both routes)
+      const bool can_fact = fact_ok(static_cast<const TA*>(nullptr), attn, d, H, frames);
+      const bool fact = pos == nullptr && can_fact;
+      FactPos fp;
       TA* pp = nullptr;
-      CFM_TRY(pos_project<TA>(c, attn.pos, div_term, pos, frames, d, &pp));
-      return mhsa_fwd<TA>(c, attn, kind == CFM_KIND_MHSA, x, pp, d, key_pad, nullptr, y, B, frames, d, H);
+      if (can_fact && (fact || c.ws.measuring())) CFM_TRY(fact_tables<TA>(c, div_term, frames, d, &fp));
+      if (!fact || c.ws.measuring()) CFM_TRY(pos_project<TA>(c, attn.pos, div_term, pos, frames, d, &pp));
+      return mhsa_fwd<TA>(c, attn, kind == CFM_KIND_MHSA, x, fact ? static_cast<const TA*>(nullptr) : pp, d, fact ? &fp : nullptr,
+                          key_pad, nullptr, y, B, frames, d, H);
     }
     case CFM_KIND_BLOCK: {
-      TA* pp = nullptr;
-      CFM_TRY(pos_project<TA>(c, blocks[0].attn.pos, div_term, pos, frames, d, &pp));
       float* xw = ws_take<float>(c, static_cast<int64_t>(B) * frames * d);
       WS_CHECK(xw);
-      return block_fwd<TA>(c, blocks[0], x, xw, y, pp, d, key_pad, B, frames, d, H);
+      const bool can_fact = fact_ok(static_cast<const TA*>(nullptr), blocks[0].attn, d, H, frames);
+      const bool fact = pos == nullptr && can_fact;
+      FactPos fp;
+      TA* pp = nullptr;
+      if (can_fact && (fact || c.ws.measuring())) CFM_TRY(fact_tables<TA>(c, div_term, frames, d, &fp));
+      if (!fact || c.ws.measuring()) CFM_TRY(pos_project<TA>(c, blocks[0].attn.pos, div_term, pos, frames, d, &pp));
+      return block_fwd<TA>(c, blocks[0], x, xw, y, fact ? static_cast<const TA*>(nullptr) : pp, d, fact ? &fp : nullptr, key_pad, B,
+                           frames, d, H);
     }
     case CFM_KIND_SUBSAMPLING: {
       TA* h2 = nullptr;
@@ -579,7 +643,10 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
       }
       WS_CHECK(xw);
       TA* pp = nullptr;
-      CFM_TRY(pos_project<TA>(c, pos_all, div_term, nullptr, T2, d, &pp));
+      FactPos fp;
+      const bool fact = cfg.n_blocks > 0 && fact_ok(static_cast<const TA*>(nullptr), blocks[0].attn, d, H, T2);
+      if (fact) CFM_TRY(fact_tables<TA>(c, div_term, T2, d, &fp));
+      else CFM_TRY(pos_project<TA>(c, pos_all, div_term, nullptr, T2, d, &pp));
       if (!c.ws.measuring()) {
         // Encoder.linear on the channels-last flatten (weight columns permuted at pack time), encoder.py:23
         CFM_TRY(Dispatch<TA>::gemm(c, h2, F2 * d, lin, xw, d, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
@@ -591,7 +658,8 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
       const int L = cfg.n_blocks;
       for (int i = 0; i < L; ++i) {
         float* dst = (i == L - 1) ? y : xw;
-        CFM_TRY(block_fwd<TA>(c, blocks[i], xw, xw, dst, pp + static_cast<int64_t>(i) * d, L * d, kp, B, T2, d, H));
+        CFM_TRY(block_fwd<TA>(c, blocks[i], xw, xw, dst, fact ? nullptr : pp + static_cast<int64_t>(i) * d, L * d, fact ? &fp : nullptr,
+                              kp, B, T2, d, H));
       }
       if (L == 0 && !c.ws.measuring())
         CFM_CUDA_OK(cudaMemcpyAsync(y, xw, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));

@@ -94,7 +94,11 @@ struct Linear {
   int N = 0, K = 0;
 };
 struct FfnW { const float *ln_g = nullptr, *ln_b = nullptr; Linear hidden, out; };
-struct AttnW { const float *ln_g = nullptr, *ln_b = nullptr, *u = nullptr, *v = nullptr; Linear qkv, pos, out; };
+struct AttnW {
+  const float *ln_g = nullptr, *ln_b = nullptr, *u = nullptr, *v = nullptr;
+  Linear qkv, pos, out;
+  bf16* wpT = nullptr;               // pos_proj packed per head for the factorised positional term (bf16, d = 256)
+};
 struct ConvW {
   const float *ln_g = nullptr, *ln_b = nullptr, *dw_w = nullptr, *dw_b = nullptr;
   int ksize = 0;

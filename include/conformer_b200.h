@@ -132,12 +132,19 @@ CFM_API int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, cons
                              int64_t workspace_bytes, void* stream);
 CFM_API int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin);
 
+/* Which kernel evaluates the relative positional term of the bf16 attention when the caller did not supply a table
+ * (the encoder's own RelativePositionalEncoding, position.py:11-28) and d_model = 256, head size 64:
+ *   0 = automatic (by sequence length), 1 = factorised (rotated query x absolute sinusoid key table, no relative
+ *   shift), -1 = relative-shift kernel on the projected table (attention.py:94-102 evaluated in-tile).
+ * Both are implementations of the same reference arithmetic; process-wide, takes effect on the next forward. */
+CFM_API int cfm_set_attention_kernel(int32_t mode);
+
 /* Number of kernel launches the last forward on `m` enqueued (for bench.py's gpu_launches). */
 CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 
 /* Optional per-launch profile: when enabled every kernel launch of a forward on `m` is bracketed by
  * CUDA events on the launching stream.  cfm_profile_collect waits for them and fills, per kernel class
- * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN, 8 LayerNorm-fused GEMM), four
+ * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN, 8 LayerNorm-fused GEMM, 9 fused conv module), four
  * doubles: launches, total milliseconds, algorithmic FLOPs, algorithmic bytes. */
 CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
 CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);

@@ -211,6 +211,42 @@ def test_rel_attention_bf16_tensor_core_vs_oracle(T, masked):
     assert_close_fp32(m32(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask), want, "fp32 attention", scale=2.0)
 
 
+@pytest.mark.parametrize("T", [1, 17, 63, 64, 65, 127, 128, 129, 200, 374, 700])
+@pytest.mark.parametrize("masked", [False, True])
+def test_rel_attention_bf16_factorised_vs_oracle(T, masked):
+    """d_model 256 / head size 64 called WITHOUT a positional table uses the module's own sinusoids through the
+    factorised kernel (rotated query x absolute key table, no relative shift); the oracle gets the reference's
+    [2T-1, d] table.  Tile edges at 64 keys / 128 queries."""
+    d, H, B = 256, 4, 3
+    g = torch.Generator().manual_seed(300 + T)
+    sd = {k[len("layers.0.attention.attention."):]: v for k, v in
+          synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 41).items()
+          if k.startswith("layers.0.attention.attention.")}
+    # larger projections so that both the content and the positional term matter (scores of a few units)
+    sd = {k: (v * 3.0 if "proj.weight" in k and "out" not in k else v) for k, v in sd.items()}
+    x = torch.randn(B, T, d, generator=g)
+    pos = O.rel_pos_table(T, d)
+    lengths = torch.tensor([T, max(1, T // 2), 1])
+    key_is_pad = ~O.padding_mask(lengths, T) if masked else None
+    want = O.rel_attention(sd, "", x, pos, key_is_pad, H)
+    m = _load(cb.RelativeMultiHeadAttention(d, H), sd).set_compute("bf16")
+    mask = key_is_pad[:, None, None, :].to(DEV) if masked else None
+    xd = x.to(DEV)
+    from conformer_b200._lib import check, lib
+    check(lib().cfm_set_attention_kernel(1))
+    try:
+        got = m(xd, xd, xd, None, mask)
+    finally:
+        check(lib().cfm_set_attention_kernel(0))
+    assert torch.isfinite(got).all()
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    # the relative-shift kernel on the same inputs (explicit table) is the yardstick
+    got_skew = m(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask)
+    rel_skew = ((got_skew.cpu() - want).norm() / want.norm()).item()
+    print(f"T={T} factorised rel {rel:.2e}  shift-kernel rel {rel_skew:.2e}")
+    assert rel < 2e-2, (rel, rel_skew)
+
+
 @pytest.mark.parametrize("d,T", [(256, 150), (512, 70), (64, 40)])
 def test_conv_module_bf16_vs_oracle(d, T):
     """bf16 ConvolutionModule: GLU fused into the pointwise GEMM epilogue + packed-fp32x2 depthwise kernel

@@ -22,18 +22,20 @@ m = m.cuda().eval().set_compute("bf16")
 x = torch.randn(B, T, d, device="cuda")
 pos = torch.randn(1, 2 * T - 1, d, device="cuda")
 for _ in range(3):
-    m(x, x, x, pos, None)
+    m(x, x, x, None, None)
 trace = torch.zeros(128, dtype=torch.int64, device="cuda")
 fn = lib().cfm_debug_set_gemm_trace
 fn.argtypes = [C.c_void_p]
 torch.cuda.synchronize()
 fn(trace.data_ptr())
-m(x, x, x, pos, None)
+m(x, x, x, None, None)
 torch.cuda.synchronize()
 fn(None)
-t = trace.cpu().view(16, 8)
-t0 = int(t[t > 0].min())
+t = trace.cpu()[64:]
+t0 = int(t[0])
+print("prologue: start 0, Q written %d, ab ready %d, Q' written %d, end %d" % tuple(int(t[i]) - t0 for i in (1, 2, 3, 4)))
 for j in range(8):
-    if int(t[j].max()) == 0:
+    r = t[8 + 4 * j: 12 + 4 * j]
+    if int(r.max()) == 0:
         break
-    print(f"tile {j}: " + " ".join(f"{(int(v) - t0) if v > 0 else -1:6d}" for v in t[j]))
+    print(f"tile {j}: [8 only tile 0: loop start] {int(r[0]) - t0:6d}  top {int(r[1]) - t0:6d}  max/rescale done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
