@@ -19,7 +19,7 @@
 namespace cfm {
 namespace {
 
-constexpr int D = 256, HID = 4 * D, BM = 128, HC = 128, NCHUNK = HID / HC;
+constexpr int D = 256, HID = 4 * D, BM = 128, HC = 128, NCHUNK = HID / HC;   // NCHUNK = 8
 constexpr int KB = 64;                                     // K elements per 128-byte swizzled row
 constexpr int XS_BYTES = (D / KB) * BM * 128;              // 64 KB: LN(x) as 4 k-blocks
 constexpr int HS_BYTES = (HC / KB) * BM * 128;             // 32 KB per hidden buffer
@@ -38,6 +38,36 @@ struct FfnParams {
   const float* b2;
   float scale;
   int M;
+  int num_tiles;
+};
+
+// Work items of one CTA.  With T row tiles on G CTAs, every CTA first takes T / G whole tiles; each of the T % G
+// left-over tiles is then shared by G / (T % G) CTAs, each taking a contiguous range of its 8 HIDDEN chunks, so the
+// last wave is as full as the first (187 tiles on 148 SMs: 39 tiles shared by 3-4 CTAs each).  Partial items add
+// their share of the output with the same TMA reduction store (the L2 sums them); b2 is added by the item that
+// owns chunk 0.
+struct Item { int tile, cb, ce; };
+struct ItemIter {
+  int c, G, R, L, r;
+  bool tail_done;
+  __device__ ItemIter(int cta, int grid, int tiles) : c(cta), G(grid), R(tiles / grid), L(tiles % grid), r(0), tail_done(false) {}
+  __device__ bool next(Item& it) {
+    if (r < R) {
+      it = Item{r * G + c, 0, NCHUNK};
+      ++r;
+      return true;
+    }
+    if (tail_done || L == 0) return false;
+    tail_done = true;
+    // left-over tile lt is shared by the CTAs [lt*G/L, (lt+1)*G/L): one partial item per CTA, no straddling
+    const int lt = static_cast<int>(static_cast<long long>(c) * L / G);
+    const int first = (lt * G + L - 1) / L, last = ((lt + 1) * G + L - 1) / L;     // CTAs of this tile: [first, last)
+    const int k = last - first, j = c - first;
+    const int cb = j * NCHUNK / k, ce = (j + 1) * NCHUNK / k;
+    if (cb >= ce) return false;
+    it = Item{R * G + lt, cb, ce};
+    return true;
+  }
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -59,7 +89,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1);
@@ -90,7 +119,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer
-    // consumption order: G1(0) G1(1) G2(0) G1(2) G2(1) ... G1(7) G2(6) G2(7); each GEMM uses two ring stages
+    // consumption order per item: G1(cb) G1(cb+1) G2(cb) G1(cb+2) G2(cb+1) ... G2(ce-1); each GEMM uses two ring stages
     uint32_t it = 0;
     auto load_g1 = [&](int c) {
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
@@ -116,19 +145,23 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         __syncwarp();
       }
     };
-    load_g1(0);
-    for (int c = 0; c < NCHUNK; ++c) {
-      if (c + 1 < NCHUNK) load_g1(c + 1);
-      load_g2(c);
+    ItemIter items(blockIdx.x, gridDim.x, p.num_tiles);
+    Item w;
+    while (items.next(w)) {
+      load_g1(w.cb);
+      for (int c = w.cb; c < w.ce; ++c) {
+        if (c + 1 < w.ce) load_g1(c + 1);
+        load_g2(c);
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);     // 128 x 128
     constexpr uint32_t idesc2 = umma_idesc_bf16(BM, D);      // 128 x 256
-    uint32_t it = 0;
-    auto gemm1 = [&](int c) {
-      const int b = c & 1;
-      mbar_wait(&acc1_empty[b], ((c >> 1) & 1) ^ 1);
+    uint32_t it = 0, gc1 = 0, gc2 = 0;                        // ring slot counter, chunks issued to GEMM1 / GEMM2 so far
+    auto gemm1 = [&]() {
+      const int b = gc1 & 1;
+      mbar_wait(&acc1_empty[b], ((gc1 >> 1) & 1) ^ 1);
       tc_fence_after();
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
         const int s = it % STAGES;
@@ -148,10 +181,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         }
         __syncwarp();
       }
+      ++gc1;
     };
-    auto gemm2 = [&](int c) {
-      const int b = c & 1;
-      mbar_wait(&hs_full[b], (c >> 1) & 1);
+    auto gemm2 = [&](bool first, bool last) {
+      const int b = gc2 & 1;
+      mbar_wait(&hs_full[b], (gc2 >> 1) & 1);
       tc_fence_after();
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
         const int s = it % STAGES;
@@ -161,28 +195,41 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           const uint32_t sa = umma_desc_lo(smem_u32(hs + b * HS_BYTES + s2 * (BM * 128)));
           const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tm_acc2, sa + k * 2, sb + k * 2, idesc2, (c | s2 | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tm_acc2, sa + k * 2, sb + k * 2, idesc2, (!first || (s2 | k) != 0) ? 1u : 0u);
           tc_commit(&empty_bar[s]);
           if (s2 == 1) {
             tc_commit(&hs_empty[b]);
-            if (c == NCHUNK - 1) tc_commit(acc2_full);
+            if (last) tc_commit(acc2_full);
           }
         }
         __syncwarp();
       }
+      ++gc2;
     };
-    mbar_wait(xs_full, 0);
-    tc_fence_after();
-    gemm1(0);
-    for (int c = 0; c < NCHUNK; ++c) {
-      if (c + 1 < NCHUNK) gemm1(c + 1);
-      gemm2(c);
+    ItemIter items(blockIdx.x, gridDim.x, p.num_tiles);
+    Item w;
+    for (uint32_t n = 0; items.next(w); ++n) {
+      mbar_wait(xs_full, n & 1);                               // LN(x) of this item staged (and acc2 of the last one drained)
+      tc_fence_after();
+      gemm1();
+      for (int c = w.cb; c < w.ce; ++c) {
+        if (c + 1 < w.ce) gemm1();
+        gemm2(c == w.cb, c == w.ce - 1);
+      }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ LN prologue + epilogues (16 warps)
     const int ew = warp - 4;
     const int q = warp & 3, cgrp = ew >> 2;
     const int tid_e = threadIdx.x - 128;
+    ItemIter items(blockIdx.x, gridDim.x, p.num_tiles);
+    Item w;
+    uint32_t gc = 0;                                            // chunks processed so far (acc1 / hs double buffers)
+    const int row = q * 32 + lane;
+    const int sw = row & 7;
+    const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
+    for (uint32_t n = 0; items.next(w); ++n) {
+    const int m0 = w.tile * BM;
     // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7; lane owns columns 8*lane .. 8*lane+7
     {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane);
@@ -224,15 +271,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       if (lane == 0) mbar_arrive(xs_full);
     }
     // ---- per-chunk epilogue: hidden = bf16(swish(acc1 + b1)) into the MMA A layout
-    const int row = q * 32 + lane;
-    const int sw = row & 7;
-    const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
-    for (int c = 0; c < NCHUNK; ++c) {
-      const int b = c & 1;
+    for (int c = w.cb; c < w.ce; ++c, ++gc) {
+      const int b = gc & 1;
       float4 bc[8];                                            // issued before the wait: L2 latency overlaps it
 #pragma unroll
       for (int g = 0; g < 8; ++g) bc[g] = __ldg(b1v + c * (HC / 4) + g);
-      mbar_wait(&acc1_full[b], (c >> 1) & 1);
+      mbar_wait(&acc1_full[b], (gc >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32, r);
@@ -249,7 +293,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         v[g * 4 + 2] = swish_tanh(__uint_as_float(r[g * 4 + 2]) + b4.z);
         v[g * 4 + 3] = swish_tanh(__uint_as_float(r[g * 4 + 3]) + b4.w);
       }
-      mbar_wait(&hs_empty[b], ((c >> 1) & 1) ^ 1);             // GEMM2(c-2) has finished reading this buffer
+      mbar_wait(&hs_empty[b], ((gc >> 1) & 1) ^ 1);            // the GEMM2 two chunks back has finished reading this buffer
       // hidden column cgrp*32 .. +31 of the chunk -> k-block cgrp/2, chunks (cgrp&1)*4 .. +3
       uint8_t* dst = hs + b * HS_BYTES + (cgrp >> 1) * (BM * 128) + row * 128;
       const int j0 = (cgrp & 1) * 4;
@@ -265,7 +309,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       if (lane == 0) mbar_arrive(&hs_full[b]);
     }
     // ---- final epilogue: x += scale * (acc2 + b2) through a TMA reduction store
-    mbar_wait(acc2_full, 0);
+    mbar_wait(acc2_full, n & 1);
     tc_fence_after();
     uint8_t* stage_out = smem;                                 // aliases xs/hs: every MMA has completed
 #pragma unroll 1
@@ -277,7 +321,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       uint8_t* blk = stage_out + (col >> 5) * OUT_BLK_BYTES + row * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (w.cb == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);       // bias once per row tile
         float4 o;
         o.x = p.scale * (__uint_as_float(r[j * 4 + 0]) + b4.x);
         o.y = p.scale * (__uint_as_float(r[j * 4 + 1]) + b4.y);
@@ -294,6 +339,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       bulk_commit();
       bulk_wait_read0();                                       // smem may be released; the L2 finishes the adds
     }
+    named_bar_sync(1, NUM_EPI_THREADS);                        // staging (= the operand buffers) is free for the next item
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -309,7 +356,6 @@ bool ffn_fused_supported(int d) { return d == D; }
 
 int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
                    const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream) {
-  (void)num_sms;
   CFM_TRY(tc_init());
   CFM_REQUIRE(d == D, "fused FFN kernel is specialised for d_model = 256");
   CFM_REQUIRE(M > 0, "empty FFN");
@@ -340,8 +386,9 @@ int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* 
     CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M};
-  const int grid = static_cast<int>(ceil_div(M, BM));
+  const int tiles = static_cast<int>(ceil_div(M, BM));
+  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M, tiles};
+  const int grid = tiles < num_sms ? tiles : num_sms;
   ffn_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -297,9 +297,11 @@ def test_block_bf16_fused_conv_residual(T):
     print(assert_close_bf16(got, want, "block bf16"))
 
 
-@pytest.mark.parametrize("rows", [(1, 1), (2, 100), (3, 374), (5, 128)])
+@pytest.mark.parametrize("rows", [(1, 1), (2, 100), (3, 374), (5, 128), (64, 374), (40, 500), (149, 128), (300, 127)])
 def test_ffn_module_bf16_fused_vs_oracle(rows):
-    """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel."""
+    """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel.  More than 148
+    row tiles (one per SM) exercises the balanced schedule: left-over tiles are split along the hidden dimension
+    across CTAs and summed by the reduction store."""
     B, T = rows
     d = 256
     sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 60), "layers.0.ffn_1.")
