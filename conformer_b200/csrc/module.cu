@@ -163,6 +163,11 @@ struct Packer {
   void front(FrontW& w, const std::string& pre, int d) {
     w.c1_w = vec(pre + "conv_1.weight", static_cast<int64_t>(d) * 9);
     w.c1_b = vec(pre + "conv_1.bias", d);
+    w.c1_w16 = nullptr;
+    if (bf16_mode && !status && conv1_tc_supported(d)) {
+      w.c1_w16 = alloc_bf16(static_cast<int64_t>(d) * 64);
+      if (!status && pack_conv1_weight(w.c1_w, w.c1_w16, d, stream)) status = 2;
+    }
     const float* w2 = param(pre + "conv_2.weight", static_cast<int64_t>(d) * d * 9);
     float* w2p = alloc_f32(static_cast<int64_t>(d) * d * 9);
     float* b2 = const_cast<float*>(vec(pre + "conv_2.bias", d));
@@ -551,8 +556,15 @@ int front_fwd(Ctx& c, const Module& m, const float* mel, int B, int Tin, TA** h2
   WS_CHECK(out1); WS_CHECK(h2);
   *h2_out = h2;
   if (c.ws.measuring()) return 0;
-  KRUN(KC_CONV1, 18.0 * d * F1 * T1 * B, 4.0 * B * n_mel * Tin + static_cast<double>(B) * T1 * F1 * d * sizeof(TA),
-       subsample_conv1<TA>(mel, m.front.c1_w, m.front.c1_b, out1, B, n_mel, Tin, T1, T1p, F1, d, c.stream));
+  static const bool conv1_simt = [] { const char* e = getenv("CFM_CONV1"); return e != nullptr && e[0] == 's'; }();
+  if (sizeof(TA) == 2 && m.front.c1_w16 != nullptr && !conv1_simt) {
+    KRUN(KC_CONV1, 18.0 * d * F1 * T1 * B, 4.0 * B * n_mel * Tin + static_cast<double>(B) * T1 * F1 * d * sizeof(TA),
+         subsample_conv1_tc(mel, m.front.c1_w16, m.front.c1_b, reinterpret_cast<bf16*>(out1), B, n_mel, Tin, T1, T1p, F1, d,
+                            c.num_sms, c.stream));
+  } else {
+    KRUN(KC_CONV1, 18.0 * d * F1 * T1 * B, 4.0 * B * n_mel * Tin + static_cast<double>(B) * T1 * F1 * d * sizeof(TA),
+         subsample_conv1<TA>(mel, m.front.c1_w, m.front.c1_b, out1, B, n_mel, Tin, T1, T1p, F1, d, c.stream));
+  }
   ConvGeom g{B, T1p, F1, d, T2, F2};
   return Dispatch<TA>::gemm(c, out1, 0, m.front.conv2, h2, d, B * T2 * F2, EPI_BIAS_RELU, nullptr, 0.f, &g);
 }

@@ -106,7 +106,11 @@ struct ConvW {
   Linear pw1, pw2;
 };
 struct BlockW { FfnW ffn1, ffn2; AttnW attn; ConvW conv; const float *ln_g = nullptr, *ln_b = nullptr; };
-struct FrontW { const float *c1_w = nullptr, *c1_b = nullptr; Linear conv2; };
+struct FrontW {
+  const float *c1_w = nullptr, *c1_b = nullptr;
+  bf16* c1_w16 = nullptr;            // conv_1 weight packed [C][64] for the tensor-core kernel (bf16 mode, C = 256)
+  Linear conv2;
+};
 
 struct ParamRef { const float* data; int64_t numel; bool used; };
 

@@ -116,6 +116,12 @@ template <typename T>
 int subsample_conv1(const float* x, const float* w, const float* bias, T* out, int B, int n_mel, int Tin,
                     int T1, int T1p, int F1, int C, cudaStream_t stream);
 
+// tensor-core variant for C = 256 (bf16 out; the 3x3 patch is one K=16 MMA step): w_packed = pack_conv1_weight(w)
+int subsample_conv1_tc(const float* mel, const bf16* w_packed, const float* bias, bf16* out, int B, int n_mel, int Tin, int T1,
+                       int T1p, int F1, int C, int num_sms, cudaStream_t stream);
+int pack_conv1_weight(const float* w /*[C,1,3,3]*/, bf16* out /*[C][64]*/, int C, cudaStream_t stream);
+bool conv1_tc_supported(int C);
+
 // lengths' = ((L-1)//2-1)//2 ; key_pad[b,t] = t >= lengths'[b]   (convolution.py:55, masking.py:9-13)
 // (mark_valid = true writes the complement, i.e. generate_padding_mask itself)
 int lengths_and_mask(const int64_t* lengths_in, int64_t* lengths_out, uint8_t* key_pad, int B, int Tn,

@@ -211,6 +211,23 @@ def test_rel_attention_bf16_tensor_core_vs_oracle(T, masked):
     assert_close_fp32(m32(xd, xd, xd, pos[None].expand(B, -1, -1).to(DEV), mask), want, "fp32 attention", scale=2.0)
 
 
+@pytest.mark.parametrize("B,Tin", [(1, 7), (2, 64), (3, 101), (2, 303), (5, 1501)])
+def test_subsampling_bf16_tensor_core_front_end(B, Tin):
+    """channels = 256 in bf16 mode: conv_1 runs as a K=16 tensor-core GEMM over 3x3 patches (inputs rounded to bf16,
+    as the reference's autocast conv2d does), conv_2 as the implicit GEMM; odd and even T1, tile tails, tiny inputs."""
+    d = 256
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 90), "downsampling_conv.")
+    x = synth_logmel(B, 80, Tin, seed=91 + Tin)
+    lengths = torch.tensor([Tin] + [max(7, Tin // 2)] * (B - 1))
+    want, want_len = O.conv_subsampling(sd, "", x, lengths)
+    m = _load(cb.ConvolutionSubsampling(d), sd).set_compute("bf16")
+    got, got_len = m(x.to(DEV), lengths.to(DEV))
+    assert torch.equal(got_len.cpu(), want_len)
+    assert torch.isfinite(got).all()
+    rel = ((got.cpu() - want).norm() / want.norm()).item()
+    assert rel < 1e-2, rel
+
+
 @pytest.mark.parametrize("T", [1, 17, 63, 64, 65, 127, 128, 129, 200, 374, 700])
 @pytest.mark.parametrize("masked", [False, True])
 def test_rel_attention_bf16_factorised_vs_oracle(T, masked):
