@@ -60,8 +60,8 @@ __device__ __forceinline__ unsigned long long atime_ns() {
 }
 #define ATRACE(slot)                                                                                              \
   do {                                                                                                            \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 128) \
-      p.trace[(slot)] = atime_ns();                                                                               \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 64) \
+      p.trace[64 + (slot)] = atime_ns();                                                                               \
   } while (0)
 
 __device__ __forceinline__ float ex2f(float x) {

@@ -21,21 +21,32 @@ m.load_state_dict(sd)
 m = m.cuda().eval().set_compute("bf16")
 x = torch.randn(B, T, d, device="cuda")
 pos = torch.randn(1, 2 * T - 1, d, device="cuda")
+POS = None if os.environ.get('ATTN_POS', 'none') == 'none' else pos
+lib().cfm_set_attention_kernel(1)
 for _ in range(3):
-    m(x, x, x, None, None)
+    m(x, x, x, POS, None)
 trace = torch.zeros(128, dtype=torch.int64, device="cuda")
 fn = lib().cfm_debug_set_gemm_trace
 fn.argtypes = [C.c_void_p]
 torch.cuda.synchronize()
 fn(trace.data_ptr())
-m(x, x, x, None, None)
+m(x, x, x, POS, None)
 torch.cuda.synchronize()
 fn(None)
 t = trace.cpu()[64:]
-t0 = int(t[0])
-print("prologue: start 0, Q written %d, ab ready %d, Q' written %d, end %d" % tuple(int(t[i]) - t0 for i in (1, 2, 3, 4)))
-for j in range(8):
-    r = t[8 + 4 * j: 12 + 4 * j]
-    if int(r.max()) == 0:
-        break
-    print(f"tile {j}: [8 only tile 0: loop start] {int(r[0]) - t0:6d}  top {int(r[1]) - t0:6d}  max/rescale done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
+if os.environ.get("ATTN_POS", "none") == "none":
+    t0 = int(t[0])
+    print("factorised kernel. prologue: start 0, Q written %d, ab ready %d, Q' written %d, end %d" % tuple(int(t[i]) - t0 for i in (1, 2, 3, 4)))
+    for j in range(8):
+        r = t[8 + 4 * j: 12 + 4 * j]
+        if int(r.max()) == 0:
+            break
+        print(f"tile {j}: top {int(r[1]) - t0:6d}  max/rescale done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
+else:
+    t0 = int(t[0])
+    for j in range(8):
+        r = t[8 * j: 8 * j + 5]
+        if int(r.max()) == 0:
+            break
+        print(f"shift kernel tile {j}: top {int(r[0]) - t0:6d}  S/PS ready {int(r[1]) - t0:6d}  skewed+max {int(r[2]) - t0:6d}  "
+              f"rescale done {int(r[3]) - t0:6d}  P written {int(r[4]) - t0:6d}")
