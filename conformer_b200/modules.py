@@ -187,10 +187,11 @@ class _Native(nn.Module):
         need = lib().cfm_workspace_bytes(h, batch, frames)
         if need < 0:
             check(1)
-        ws = self._ws.get(device)
+        key = (device, _stream())          # forwards on different streams may overlap on the device
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(int(need), device=device, dtype=torch.uint8)
-            self._ws[device] = ws
+            self._ws[key] = ws
         return ws
 
     @property
@@ -491,7 +492,9 @@ class Encoder(_Native):
                      lengths_out_host: Optional[torch.Tensor] = None, device=None) -> None:
         """End-to-end call with HOST (ideally pinned) buffers through cfm_encoder_forward_host: the
         H2D copy of the mel batch, the forward and the D2H copy of the result are enqueued on the
-        current stream.  ``y_host`` must be fp32 [B, T', d]."""
+        current stream.  ``y_host`` must be fp32 [B, T', d].  Everything is stream-ordered and asynchronous, so a
+        serving loop can alternate two streams (and two output buffers) to overlap one batch's copies with the
+        next batch's compute; each stream gets its own device staging workspace."""
         assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
         B, _, Tin = x_host.shape
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
@@ -499,10 +502,12 @@ class Encoder(_Native):
         need = lib().cfm_encoder_host_workspace_bytes(h, B, Tin)
         if need < 0:
             check(1)
-        ws = self._ws.get(("host", device))
+        # one staging workspace per (device, stream): calls on different streams may overlap on the device
+        key = ("host", device, _stream())
+        ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(int(need), device=device, dtype=torch.uint8)
-            self._ws[("host", device)] = ws
+            self._ws[key] = ws
         check(lib().cfm_encoder_forward_host(h, x_host.data_ptr(), _ptr(lengths_host), y_host.data_ptr(),
                                              _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream()))
 
