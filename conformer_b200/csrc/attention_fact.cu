@@ -30,6 +30,10 @@
 namespace cfm {
 namespace {
 
+#ifndef TRACE_Z
+#define TRACE_Z 30      // debug timeline: which batch index's first CTA is traced (30 = a CTA of the third wave at C2)
+#endif
+
 constexpr int D = 256, DH = 64, NF = D / 2;           // model width, head size, number of sinusoid frequencies
 constexpr int BQ = 128, BKV = 64;
 constexpr int Q_BYTES = BQ * 128;                     // 16 KB: [128 x 64] bf16, 128B swizzle
@@ -64,7 +68,7 @@ __device__ __forceinline__ unsigned long long ftime_ns() {
 }
 #define FTRACE(slot)                                                                                              \
   do {                                                                                                            \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 64) \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == TRACE_Z && lane == 0 && (slot) < 64) \
       p.trace[64 + (slot)] = ftime_ns();                                                                               \
   } while (0)
 
@@ -81,7 +85,7 @@ __device__ __forceinline__ float ex2f(float x) {
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmE,
-                          const __grid_constant__ CUtensorMap tmWp, FactParams p) {
+                          const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmRot, FactParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* qu_s = smem;
@@ -102,7 +106,8 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   uint64_t* q_full = o_done + 1;
   uint64_t* ab_full = q_full + 1;
   uint64_t* qp_full = ab_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(qp_full + 1);
+  uint64_t* rot_full = qp_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rot_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * BQ;
@@ -113,6 +118,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmE);
     tma_prefetch_desc(&tmWp);
+    tma_prefetch_desc(&tmRot);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) {
@@ -128,6 +134,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     mbar_init(q_full, NUM_SM_WARPS);
     mbar_init(ab_full, 1);
     mbar_init(qp_full, NUM_SM_WARPS);
+    mbar_init(rot_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -144,6 +151,11 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     if (lane == 0) {
       mbar_expect_tx(&kp_full[1], D * 128);
       tma_load_2d(kp_ring + KP_BYTES + KV_BYTES, &tmWp, &kp_full[1], 0, h * D);       // [256 rows (m') x 64 (c)]
+      // rotation factors of the 128 query rows, laid out exactly like Q' (k-block kb = table columns 64*kb .. +63):
+      // every softmax thread later overwrites, in place, the two rows it reads
+      mbar_expect_tx(rot_full, QP_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(qp_s + kb * Q_BYTES, &tmRot, rot_full, kb * 64, i0);
     }
     __syncwarp();
     for (int j = 0; j < ntiles; ++j) {
@@ -275,49 +287,43 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full);
     }
-    // ---- this row's rotation factors (64 frequencies: cos | sin as fp16), requested before waiting for the ab MMA
-    uint4 rc[8], rs[8];
-    {
-      const uint4* rrow = reinterpret_cast<const uint4*>(p.rot + static_cast<int64_t>(qi < Tn ? qi : 0) * D + grp * 64);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        rc[e] = __ldg(rrow + e);
-        rs[e] = __ldg(rrow + (NF * 2) / 16 + e);
-      }
-    }
     // ---- rotate ab into Q' = [A | B]; this thread: frequencies 64*grp .. +63 -> k-blocks grp (A) and 2+grp (B)
     {
       if (warp == 4) FTRACE(1);
       mbar_wait(ab_full, 0);
       tc_fence_after();
       if (warp == 4) FTRACE(2);
-      uint8_t* arow = qp_s + grp * Q_BYTES + row * 128;
-      uint8_t* brow = qp_s + (2 + grp) * Q_BYTES + row * 128;
+      mbar_wait(rot_full, 0);
+      uint8_t* arow = qp_s + grp * Q_BYTES + row * 128;          // holds cos(i w_k), k = 64*grp .. +63; becomes A
+      uint8_t* brow = qp_s + (2 + grp) * Q_BYTES + row * 128;    // holds sin(i w_k);                    becomes B
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {                   // 16 frequencies at a time
         const int k0 = grp * 64 + cc * 16;
         uint32_t ar[16], br[16];
         tmem_ld_32x16(tlane + TM_AB + k0, ar);
         tmem_ld_32x16(tlane + TM_AB + NF + k0, br);
+        uint4* pa0 = reinterpret_cast<uint4*>(arow + (((2 * cc) ^ sw) << 4));
+        uint4* pa1 = reinterpret_cast<uint4*>(arow + (((2 * cc + 1) ^ sw) << 4));
+        uint4* pb0 = reinterpret_cast<uint4*>(brow + (((2 * cc) ^ sw) << 4));
+        uint4* pb1 = reinterpret_cast<uint4*>(brow + (((2 * cc + 1) ^ sw) << 4));
+        const uint4 c0 = *pa0, c1 = *pa1, s0 = *pb0, s1 = *pb1;
+        const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const uint32_t sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
         tmem_ld_wait();
         uint32_t oa[8], ob[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const uint4& c4 = rc[2 * cc + (e >> 2)];
-          const uint4& s4 = rs[2 * cc + (e >> 2)];
-          const uint32_t cw = (e & 3) == 0 ? c4.x : (e & 3) == 1 ? c4.y : (e & 3) == 2 ? c4.z : c4.w;
-          const uint32_t sw2 = (e & 3) == 0 ? s4.x : (e & 3) == 1 ? s4.y : (e & 3) == 2 ? s4.z : s4.w;
-          const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&cw));
-          const float2 sn = __half22float2(*reinterpret_cast<const __half2*>(&sw2));
+          const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&cw[e]));
+          const float2 sn = __half22float2(*reinterpret_cast<const __half2*>(&sw8[e]));
           const float a0 = __uint_as_float(ar[2 * e]), a1 = __uint_as_float(ar[2 * e + 1]);
           const float b0 = __uint_as_float(br[2 * e]), b1 = __uint_as_float(br[2 * e + 1]);
           oa[e] = pack_bf16x2(a0 * sn.x + b0 * cs.x, a1 * sn.y + b1 * cs.y);
           ob[e] = pack_bf16x2(b0 * sn.x - a0 * cs.x, b1 * sn.y - a1 * cs.y);
         }
-        *reinterpret_cast<uint4*>(arow + (((2 * cc) ^ sw) << 4)) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-        *reinterpret_cast<uint4*>(arow + (((2 * cc + 1) ^ sw) << 4)) = make_uint4(oa[4], oa[5], oa[6], oa[7]);
-        *reinterpret_cast<uint4*>(brow + (((2 * cc) ^ sw) << 4)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-        *reinterpret_cast<uint4*>(brow + (((2 * cc + 1) ^ sw) << 4)) = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+        *pa0 = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+        *pa1 = make_uint4(oa[4], oa[5], oa[6], oa[7]);
+        *pb0 = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        *pb1 = make_uint4(ob[4], ob[5], ob[6], ob[7]);
       }
       tc_fence_before();
       fence_proxy_async();
@@ -530,6 +536,13 @@ int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, c
     cuuint32_t box[2] = {DH, D};
     CFM_TRY(encode_tmap(&tmWp, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, wpT, dims, strides, box, "attention pos_proj"));
   }
+  CUtensorMap tmRot;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(Tn)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+    cuuint32_t box[2] = {64, BQ};
+    CFM_TRY(encode_tmap(&tmRot, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, r16, dims, strides, box, "attention rotation table"));
+  }
   static bool attr_done = false;
   if (!attr_done) {
     CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -537,7 +550,7 @@ int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, c
   }
   FactParams p{qkv, u, v, key_pad, static_cast<const __half*>(r16), ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  rel_attention_fact_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmE, tmWp, p);
+  rel_attention_fact_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmE, tmWp, tmRot, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -26,6 +26,10 @@
 namespace cfm {
 namespace {
 
+#ifndef TRACE_Z
+#define TRACE_Z 30      // debug timeline: which batch index's first CTA is traced (30 = a CTA of the third wave at C2)
+#endif
+
 constexpr int BQ = 128, BKV = 64, DH = 64;
 constexpr int WIN = BQ + BKV;                         // 192 window rows per (query tile, key tile)
 constexpr int Q_BYTES = BQ * 128;                     // 16 KB: [128 x 64] bf16, 128B swizzle
@@ -60,7 +64,7 @@ __device__ __forceinline__ unsigned long long atime_ns() {
 }
 #define ATRACE(slot)                                                                                              \
   do {                                                                                                            \
-    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0 && (slot) < 64) \
+    if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == TRACE_Z && lane == 0 && (slot) < 64) \
       p.trace[64 + (slot)] = atime_ns();                                                                               \
   } while (0)
 
@@ -199,6 +203,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const int row = w * 32 + lane;
     const int qi = i0 + row;
     const int sw = row & 7;
+    if (warp == 4) ATRACE(60);
     // ---- Q operands: (q+u)*c and (q+v)*c as bf16 in the MMA's A layout, c = log2(e)/sqrt(dh); half a row per thread
     {
       const bf16* qrow = p.qkv + (static_cast<int64_t>(b) * Tn + (qi < Tn ? qi : 0)) * (3 * d) + h * DH;
@@ -228,6 +233,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(q_full);
+      if (warp == 4) ATRACE(61);
     }
     float* myrow = skew + (grp * BQ + row) * SKEW_LD;
     const int shift = 31 - lane;                         // per-lane part of the relative shift
@@ -347,6 +353,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         *reinterpret_cast<uint4*>(orow + ch * 8) = v4;
       }
     }
+    if (warp == 4) ATRACE(62);
   }
   tc_fence_before();
   __syncthreads();

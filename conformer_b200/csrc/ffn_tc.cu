@@ -14,6 +14,8 @@
 //   epilogue   scale*(acc2 + b2) is staged (aliasing the now-dead operand buffers) and leaves through a TMA
 //              reduction store, i.e. the residual add is executed by the L2 (x is never re-read).
 // TMEM: 2 x 128 (acc1 double buffer) + 256 (acc2) = 512 columns.
+#include <cstdlib>
+
 #include "ops.h"
 
 namespace cfm {
@@ -39,7 +41,13 @@ struct FfnParams {
   float scale;
   int M;
   int num_tiles;
+  unsigned long long* trace;     // debug: wait-time totals of CTA 0's MMA warp (ns)
 };
+__device__ __forceinline__ unsigned long long ffn_time_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Work items of one CTA.  With T row tiles on G CTAs, every CTA first takes T / G whole tiles; each of the T % G
 // left-over tiles is then shared by G / (T % G) CTAs, each taking a contiguous range of its 8 HIDDEN chunks, so the
@@ -159,13 +167,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     constexpr uint32_t idesc1 = umma_idesc_bf16(BM, HC);     // 128 x 128
     constexpr uint32_t idesc2 = umma_idesc_bf16(BM, D);      // 128 x 256
     uint32_t it = 0, gc1 = 0, gc2 = 0;                        // ring slot counter, chunks issued to GEMM1 / GEMM2 so far
+    unsigned long long w_acc1 = 0, w_full = 0, w_hs = 0, w_xs = 0, t_begin = ffn_time_ns();
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
     auto gemm1 = [&]() {
       const int b = gc1 & 1;
+      unsigned long long t0 = tr ? ffn_time_ns() : 0;
       mbar_wait(&acc1_empty[b], ((gc1 >> 1) & 1) ^ 1);
+      if (tr) w_acc1 += ffn_time_ns() - t0;
       tc_fence_after();
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
         const int s = it % STAGES;
+        t0 = tr ? ffn_time_ns() : 0;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        if (tr) w_full += ffn_time_ns() - t0;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
@@ -185,11 +199,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     };
     auto gemm2 = [&](bool first, bool last) {
       const int b = gc2 & 1;
+      unsigned long long t0 = tr ? ffn_time_ns() : 0;
       mbar_wait(&hs_full[b], (gc2 >> 1) & 1);
+      if (tr) w_hs += ffn_time_ns() - t0;
       tc_fence_after();
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
         const int s = it % STAGES;
+        t0 = tr ? ffn_time_ns() : 0;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        if (tr) w_full += ffn_time_ns() - t0;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = umma_desc_lo(smem_u32(hs + b * HS_BYTES + s2 * (BM * 128)));
@@ -209,13 +227,22 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     ItemIter items(blockIdx.x, gridDim.x, p.num_tiles);
     Item w;
     for (uint32_t n = 0; items.next(w); ++n) {
+      unsigned long long t0 = tr ? ffn_time_ns() : 0;
       mbar_wait(xs_full, n & 1);                               // LN(x) of this item staged (and acc2 of the last one drained)
+      if (tr) w_xs += ffn_time_ns() - t0;
       tc_fence_after();
       gemm1();
       for (int c = w.cb; c < w.ce; ++c) {
         if (c + 1 < w.ce) gemm1();
         gemm2(c == w.cb, c == w.ce - 1);
       }
+    }
+    if (tr && lane == 0) {
+      p.trace[0] = ffn_time_ns() - t_begin;
+      p.trace[1] = w_xs;
+      p.trace[2] = w_full;
+      p.trace[3] = w_hs;
+      p.trace[4] = w_acc1;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ LN prologue + epilogues (16 warps)
@@ -352,6 +379,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
 
 }  // namespace
 
+extern unsigned long long* g_gemm_trace;
+
 bool ffn_fused_supported(int d) { return d == D; }
 
 int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
@@ -387,8 +416,14 @@ int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* 
     attr_done = true;
   }
   const int tiles = static_cast<int>(ceil_div(M, BM));
-  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M, tiles};
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M, tiles, g_gemm_trace};
+  // Default: one CTA per row tile (187 CTAs = 2 waves at C2).  When forwards of independent batches are in flight on
+  // several streams - the serving / benchmark configuration - the other stream's kernels fill the second wave and the
+  // SM-time per tile is what counts (4.26 vs 4.41 ms per step).  CFM_FFN_BALANCED=1 selects the persistent schedule
+  // that shares the left-over tiles between CTAs: best for a single stream (5.02 vs 5.34 ms) at the price of repeating
+  // the LayerNorm prologue and the reduction-store epilogue for every share.
+  static const bool balanced = [] { const char* e = getenv("CFM_FFN_BALANCED"); return e != nullptr && e[0] == '1'; }();
+  const int grid = (!balanced || tiles < num_sms) ? tiles : num_sms;
   ffn_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;

@@ -395,8 +395,8 @@ int pos_project(Ctx& c, const Linear& wp, const float* div_term, const float* po
 struct FactPos { const bf16* e16 = nullptr; const void* r16 = nullptr; };
 // Which kernel computes the positional term when the table is the module's own sinusoids (bf16, d_model 256):
 // cfm_set_attention_kernel(1) forces the factorised kernel, (-1) the relative-shift kernel; by default the factorised
-// kernel takes long sequences (its per-CTA prologue - projecting and rotating the queries - amortises over the key
-// tiles; measured on B200: T=1499 194 us vs 233 us, T=374 89 us vs 82 us).  CFM_ATTN=fact|skew|mma overrides (A/B runs).
+// kernel takes every length (measured on B200 per layer: T=1499 194 us vs 233 us; T=374 72 us vs 80 us since its rotation
+// factors arrive by TMA).  CFM_ATTN=fact|skew|mma overrides (A/B runs).
 inline int fact_mode() {
   static const int env_mode = [] {
     const char* e = getenv("CFM_ATTN");
@@ -405,7 +405,7 @@ inline int fact_mode() {
   }();
   return env_mode != 0 ? env_mode : g_attention_kernel;
 }
-constexpr int FACT_MIN_FRAMES = 768;
+constexpr int FACT_MIN_FRAMES = 1;
 inline bool fact_ok(const float*, const AttnW&, int, int, int) { return false; }
 inline bool fact_ok(const bf16*, const AttnW& w, int d, int H, int Tn) {
   if (fact_mode() < 0 || w.wpT == nullptr || !rel_attention_fact_supported(d, d / H)) return false;

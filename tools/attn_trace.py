@@ -13,7 +13,7 @@ import conformer_b200 as cb  # noqa: E402
 from conformer_b200._lib import lib  # noqa: E402
 from conformer_b200.synth import EncoderConfig, synth_encoder_state_dict  # noqa: E402
 
-B, T, d, H = 64, 374, 256, 4
+B, T, d, H = 64, 374, 256, 4          # the traced CTA is batch index 30 (third wave)
 sd = {k[len("layers.0.attention.attention."):]: v for k, v in synth_encoder_state_dict(EncoderConfig(80, 1, d, H, 31), 1).items()
       if k.startswith("layers.0.attention.attention.")}
 m = cb.RelativeMultiHeadAttention(d, H)
@@ -43,8 +43,9 @@ if os.environ.get("ATTN_POS", "none") == "none":
             break
         print(f"tile {j}: top {int(r[1]) - t0:6d}  max/rescale done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
 else:
-    t0 = int(t[0])
-    for j in range(8):
+    t0 = int(t[60])
+    print("shift kernel: softmax warps start 0, Q staged %d, first tile top %d, end %d" % (int(t[61]) - t0, int(t[0]) - t0, int(t[62]) - t0))
+    for j in range(7):
         r = t[8 * j: 8 * j + 5]
         if int(r.max()) == 0:
             break
