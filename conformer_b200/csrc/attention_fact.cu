@@ -14,13 +14,22 @@
 // 5.7-5.)  bf16 rounding now falls on Q' and E instead of on the projected table; measured score error is the same
 // as the reference's own autocast path.
 //
-// One CTA = 128 query rows of one (batch, head); keys in tiles of 64.
-//   warp 0, 3   TMA producers: pos_proj slice of the head (once), then per key tile K [64x64] + E [64x256], and V;
-//   warp 1      MMA issuer: prologue ab = (q+v) Wp_h (128x256 into TMEM); per tile S = (q+u) K^T + Q' E^T (K = 64 + 256,
+// The query block of the fused q|k|v projection is packed for this kernel as  Qs = c (q + u),  c = log2(e)/sqrt(dh)
+// (content bias and softmax scale folded into the projection's weight and bias, pack_q_fact), so the query tile is used
+// exactly as TMA delivers it; the positional bias enters as the per-head constant  c (v - u) Wp_h  added to ab.
+//
+// One CTA = 128 query rows of one (batch, head); keys in tiles of 64.  Every A operand of the score / context MMAs
+// lives in TENSOR MEMORY (Qs, Q', P): with A in shared memory an M=128, N=64 step needs 192 B/clk of operand reads, above
+// the 128 B/clk port (measured 85 clk per step); with A in TMEM only B (K, E, V) is read and a step takes its 32 clk.
+//   warp 0, 3   TMA producers: Qs tile, pos_proj slice of the head, rotation factors (once), then per key tile
+//               K [64x64] + E [64x256] through a 3-stage ring, and V;
+//   warp 1      MMA issuer: prologue ab = Qs Wp_h (128x256 into TMEM); per tile S = Qs K^T + Q' E^T (K = 64 + 256,
 //               double-buffered in TMEM) and O += P V, O accumulating in TMEM over all key tiles;
-//   warps 4-11  256 softmax threads, thread = (query row, half of the tile's keys): rotate ab into Q' (prologue), then
-//               online softmax in fp32 with exp2 (scale folded into Q) and lazy rescaling of O (only when the row
-//               maximum grows by more than 2^8); P goes to shared memory as the bf16 A operand of P V.
+//   warps 4-11  256 softmax threads, thread = (query row, half of the tile's keys): copy Qs into TMEM and rotate ab
+//               into Q' (prologue), then online softmax in fp32 with exp2 and lazy rescaling of O (only when the row
+//               maximum grows by more than 2^8); each key half keeps its own maximum, sum and O accumulator (merged in
+//               the epilogue), so the two threads of a row never synchronise inside the key loop.  P overwrites, as bf16,
+//               columns of its own S buffer in TMEM and is the TMEM-resident A operand of P V.
 // Masked keys (and keys past T) get weight exactly 0.
 #include <cuda_fp16.h>
 #include <math_constants.h>
@@ -37,29 +46,32 @@ namespace {
 constexpr int D = 256, DH = 64, NF = D / 2;           // model width, head size, number of sinusoid frequencies
 constexpr int BQ = 128, BKV = 64;
 constexpr int Q_BYTES = BQ * 128;                     // 16 KB: [128 x 64] bf16, 128B swizzle
-constexpr int QP_BYTES = (D / 64) * Q_BYTES;          // 64 KB: Q' as 4 k-blocks
+constexpr int ROT_BYTES = (D / 64) * Q_BYTES;         // 64 KB: rotation factors of the 128 query rows, 4 k-blocks
 constexpr int KV_BYTES = BKV * 128;                   // 8 KB
 constexpr int E_BYTES = (D / 64) * KV_BYTES;          // 32 KB: E tile as 4 k-blocks of [64 keys x 64]
 constexpr int KP_BYTES = KV_BYTES + E_BYTES;          // K | E = 40 KB per stage
+constexpr int NS = 3;                                 // K | E ring stages
 constexpr int NUM_SM_WARPS = 8, NUM_SM_THREADS = NUM_SM_WARPS * 32;
 constexpr int XCHG_BYTES = 3 * 2 * BQ * 4;            // tile-max exchange (double buffered) + row-sum exchange
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + QP_BYTES + Q_BYTES + 2 * KP_BYTES + 2 * KV_BYTES + XCHG_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + ROT_BYTES + NS * KP_BYTES + 2 * KV_BYTES + XCHG_BYTES + 256;
 static_assert(SMEM_BYTES <= 227 * 1024, "attention shared memory budget");
 static_assert(D * 128 <= E_BYTES, "the pos_proj slice must fit the E region of a ring stage");
 constexpr int NUM_THREADS = 128 + NUM_SM_THREADS;     // warps 0,3: TMA; 1: MMA; 2: TMEM alloc; 4-11: softmax
-constexpr int TM_S = 0, TM_O = 128, TM_AB = 256;      // TMEM columns: S0 | S1 (64 each), O (64), ab (256)
+// TMEM columns.  Prologue: ab (256 fp32 columns).  Main loop, over the dead ab: S0 | S1 (64 each; each key half of P_j
+// overwrites, as bf16 pairs, the first 16 columns of its own half of S_j) and one O accumulator per key half (64 each).
+// Throughout: Q' (256 bf16 = 128 columns) and Qs (64 bf16 = 32).
+constexpr int TM_AB = 0, TM_S = 0, TM_O = 128, TM_QP = 256, TM_Q = 384;
 constexpr float RESCALE_THRESHOLD = 8.0f;             // log2 units: P stays below 2^8
 
 struct FactParams {
-  const bf16* qkv;
-  const float* ub;
-  const float* vb;
+  const float* pos_const;   // [H][256]: c (v_h - u_h) Wp_h in the packed column order of wpT
   const uint8_t* key_pad;
-  const __half* rot;    // [T][256] fp16: cos(i w_k) | sin(i w_k) (query rotation; abs error 2^-12, far below bf16 Q')
   bf16* ctx;
   int Tn, H;
-  float scale_log2e;
-  unsigned long long* trace;     // debug: globaltimer stamps of CTA (0,0,0)
+  uint32_t tmem_zero;       // always 0: the TMEM base as a kernel parameter keeps every TMEM operand address a uniform
+                            // register + immediate (a literal base makes ptxas build each one in a vector register
+                            // and move it over with R2UR: ~56 clk per issued MMA instead of < 32)
+  unsigned long long* trace;     // debug: globaltimer stamps of one CTA
 };
 __device__ __forceinline__ unsigned long long ftime_ns() {
   unsigned long long t;
@@ -88,20 +100,18 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
                           const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmRot, FactParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint8_t* qu_s = smem;
-  uint8_t* qp_s = qu_s + Q_BYTES;                      // Q' (4 k-blocks)
-  uint8_t* p_s = qp_s + QP_BYTES;                      // (q+v) during the prologue, P afterwards
-  uint8_t* kp_ring = p_s + Q_BYTES;                    // 2 x (K | E)
-  uint8_t* v_ring = kp_ring + 2 * KP_BYTES;            // 2 x V
+  uint8_t* q_s = smem;                                 // Qs tile as TMA delivers it
+  uint8_t* rot_s = q_s + Q_BYTES;                      // rotation factors, laid out like a [128 x 256] K-major operand
+  uint8_t* kp_ring = rot_s + ROT_BYTES;                // NS x (K | E)
+  uint8_t* v_ring = kp_ring + NS * KP_BYTES;           // 2 x V
   float* xmax = reinterpret_cast<float*>(v_ring + 2 * KV_BYTES);    // [2 buffers][2 halves][128]
   float* xsum = xmax + 2 * 2 * BQ;                                   // [2 halves][128]
   uint64_t* kp_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + XCHG_BYTES);
-  uint64_t* kp_empty = kp_full + 2;
-  uint64_t* v_full = kp_empty + 2;
+  uint64_t* kp_empty = kp_full + NS;
+  uint64_t* v_full = kp_empty + NS;
   uint64_t* v_empty = v_full + 2;
   uint64_t* s_full = v_empty + 2;       // [2]
-  uint64_t* s_read = s_full + 2;        // [2]
-  uint64_t* p_full = s_read + 2;
+  uint64_t* p_full = s_full + 2;
   uint64_t* o_done = p_full + 1;
   uint64_t* q_full = o_done + 1;
   uint64_t* ab_full = q_full + 1;
@@ -121,17 +131,18 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     tma_prefetch_desc(&tmRot);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&kp_full[s], 1);
       mbar_init(&kp_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_read[s], NUM_SM_WARPS);
     }
     mbar_init(p_full, NUM_SM_WARPS);
     mbar_init(o_done, 1);
-    mbar_init(q_full, NUM_SM_WARPS);
+    mbar_init(q_full, 1);
     mbar_init(ab_full, 1);
     mbar_init(qp_full, NUM_SM_WARPS);
     mbar_init(rot_full, 1);
@@ -141,25 +152,27 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
+  const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot) + p.tmem_zero;
 
-  // ring stage 1 is filled once more than stage 0: its first fill is the pos_proj slice of the prologue
-  auto fill_index = [](int j) { return (j & 1) ? (j >> 1) + 1 : (j >> 1); };
+  // the last ring stage is filled once more than the others: its first fill is the pos_proj slice of the prologue
+  auto fill_index = [](int j) { return j / NS + (j % NS == NS - 1 ? 1 : 0); };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: pos_proj slice, then K + E tiles
     if (lane == 0) {
-      mbar_expect_tx(&kp_full[1], D * 128);
-      tma_load_2d(kp_ring + KP_BYTES + KV_BYTES, &tmWp, &kp_full[1], 0, h * D);       // [256 rows (m') x 64 (c)]
-      // rotation factors of the 128 query rows, laid out exactly like Q' (k-block kb = table columns 64*kb .. +63):
-      // every softmax thread later overwrites, in place, the two rows it reads
-      mbar_expect_tx(rot_full, QP_BYTES);
+      mbar_expect_tx(q_full, Q_BYTES);                                                 // rows past T arrive as zeros
+      tma_load_3d(q_s, &tmQKV, q_full, h * DH, i0, b);
+      tma_load_3d(q_s + KV_BYTES, &tmQKV, q_full, h * DH, i0 + BKV, b);
+      mbar_expect_tx(&kp_full[NS - 1], D * 128);
+      tma_load_2d(kp_ring + (NS - 1) * KP_BYTES + KV_BYTES, &tmWp, &kp_full[NS - 1], 0, h * D);   // [256 rows (m') x 64 (c)]
+      // rotation factors of the 128 query rows (k-block kb = table columns 64*kb .. +63)
+      mbar_expect_tx(rot_full, ROT_BYTES);
 #pragma unroll
-      for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(qp_s + kb * Q_BYTES, &tmRot, rot_full, kb * 64, i0);
+      for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(rot_s + kb * Q_BYTES, &tmRot, rot_full, kb * 64, i0);
     }
     __syncwarp();
     for (int j = 0; j < ntiles; ++j) {
-      const int s = j & 1, n = fill_index(j);
+      const int s = j % NS, n = fill_index(j);
       mbar_wait(&kp_empty[s], (n & 1) ^ 1);
       if (lane == 0) {
         uint8_t* st = kp_ring + s * KP_BYTES;
@@ -187,34 +200,33 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     constexpr uint32_t idesc_ab = umma_idesc_bf16(BQ, D);           // 128 x 256
     constexpr uint32_t idesc_s = umma_idesc_bf16(BQ, BKV);          // 128 x 64
     constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(BQ, DH);      // 128 x 64, B (=V) MN-major
-    // ---- prologue: ab = (q+v) Wp_h   [128 x 256], K = 64
+    // ---- prologue: ab = Qs Wp_h   [128 x 256], K = 64 (both operands in shared memory: N = 256 amortises the A reads)
     mbar_wait(q_full, 0);
-    mbar_wait(&kp_full[1], 0);
+    mbar_wait(&kp_full[NS - 1], 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t sa = umma_desc_lo(smem_u32(p_s)), sb = umma_desc_lo(smem_u32(kp_ring + KP_BYTES + KV_BYTES));
+      const uint32_t sa = umma_desc_lo(smem_u32(q_s)), sb = umma_desc_lo(smem_u32(kp_ring + (NS - 1) * KP_BYTES + KV_BYTES));
 #pragma unroll
       for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tmem_base + TM_AB, sa + k * 2, sb + k * 2, idesc_ab, k != 0 ? 1u : 0u);
       tc_commit(ab_full);
-      tc_commit(&kp_empty[1]);
+      tc_commit(&kp_empty[NS - 1]);
     }
     __syncwarp();
     auto issue_s = [&](int j) {
-      const int s = j & 1, n = fill_index(j);
+      const int s = j % NS, n = fill_index(j);
       mbar_wait(&kp_full[s], n & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t sk = umma_desc_lo(smem_u32(kp_ring + s * KP_BYTES)), se = sk + (KV_BYTES >> 4);
-        const uint32_t squ = umma_desc_lo(smem_u32(qu_s)), sqp = umma_desc_lo(smem_u32(qp_s));
-        const uint32_t ts = tmem_base + TM_S + s * BKV;
+        const uint32_t ts = tmem_base + TM_S + (j & 1) * BKV;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tc_mma_f16_lo(ts, squ + k * 2, sk + k * 2, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) tc_mma_f16_ts(ts, tmem_base + TM_Q + k * 8, sk + k * 2, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
         for (int kb = 0; kb < D / 64; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_f16_lo(ts, sqp + kb * (Q_BYTES >> 4) + k * 2, se + kb * (KV_BYTES >> 4) + k * 2, idesc_s, 1u);
-        tc_commit(&s_full[s]);
+            tc_mma_f16_ts(ts, tmem_base + TM_QP + (kb * 4 + k) * 8, se + kb * (KV_BYTES >> 4) + k * 2, idesc_s, 1u);
+        tc_commit(&s_full[j & 1]);
         tc_commit(&kp_empty[s]);                                    // K + E may be refilled
       }
       __syncwarp();
@@ -224,22 +236,25 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     issue_s(0);
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
-      if (j + 1 < ntiles) {
-        if (j >= 1) {
-          mbar_wait(&s_read[(j + 1) & 1], ((j - 1) >> 1) & 1);      // tile j-1 left this S buffer
-          tc_fence_after();
-        }
-        issue_s(j + 1);
-      }
-      mbar_wait(p_full, j & 1);                                     // P_j written (and O rescaled where needed)
+      // S_{j+1} goes to the buffer that held S_{j-1} / P_{j-1}: P_{j-1}.V was issued in the previous iteration and
+      // the tensor pipe executes in issue order, so no handshake is needed
+      FTRACE(36 + 4 * j);
+      if (j + 1 < ntiles) issue_s(j + 1);
+      FTRACE(37 + 4 * j);
+      mbar_wait(p_full, j & 1);                                     // P_j in TMEM (and O rescaled where needed)
+      FTRACE(38 + 4 * j);
       mbar_wait(&v_full[s], (j >> 1) & 1);
+      FTRACE(39 + 4 * j);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sp = umma_desc_lo(smem_u32(p_s));
+        const uint32_t tp = tmem_base + TM_S + s * BKV;
         const uint32_t sv = umma_desc_lo(smem_u32(v_ring + s * KV_BYTES));
 #pragma unroll
-        for (int k = 0; k < 4; ++k)                                 // K = 64 keys in steps of 16 (V: 16 rows = 2048 B)
-          tc_mma_f16_lo(tmem_base + TM_O, sp + k * 2, sv + k * (2048 >> 4), idesc_pv, (j | k) != 0 ? 1u : 0u);
+        for (int g = 0; g < 2; ++g)                                 // key half g: keys 32g .. 32g+31 -> its own O
+#pragma unroll
+          for (int k = 0; k < 2; ++k)                               // K = 32 keys in steps of 16 (V: 16 rows = 2048 B)
+            tc_mma_f16_ts(tmem_base + TM_O + 64 * g, tp + 32 * g + k * 8, sv + (2 * g + k) * (2048 >> 4), idesc_pv,
+                          (j | k) != 0 ? 1u : 0u);
         tc_commit(o_done);
         tc_commit(&v_empty[s]);
       }
@@ -252,87 +267,74 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     const int qi = i0 + row;
     const int sw = row & 7;
     const uint32_t tlane = tmem_base + (static_cast<uint32_t>(w * 32) << 16);
-    if (warp == 4) FTRACE(0);
-    // ---- Q operands: (q+u)*c and (q+v)*c as bf16 in the MMA's A layout, c = log2(e)/sqrt(dh); half a row per thread
-    {
-      const bf16* qrow = p.qkv + (static_cast<int64_t>(b) * Tn + (qi < Tn ? qi : 0)) * (3 * d) + h * DH;
-      uint4 raw[4];
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        raw[c4] = make_uint4(0u, 0u, 0u, 0u);
-        if (qi < Tn) raw[c4] = *reinterpret_cast<const uint4*>(qrow + (grp * 4 + c4) * 8);
-      }
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        const int ch = grp * 4 + c4;
-        const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&raw[c4]);
-        const float4 ua = __ldg(reinterpret_cast<const float4*>(p.ub + h * DH + ch * 8));
-        const float4 ub2 = __ldg(reinterpret_cast<const float4*>(p.ub + h * DH + ch * 8 + 4));
-        const float4 va = __ldg(reinterpret_cast<const float4*>(p.vb + h * DH + ch * 8));
-        const float4 vb2 = __ldg(reinterpret_cast<const float4*>(p.vb + h * DH + ch * 8 + 4));
-        const float uu[8] = {ua.x, ua.y, ua.z, ua.w, ub2.x, ub2.y, ub2.z, ub2.w};
-        const float vv[8] = {va.x, va.y, va.z, va.w, vb2.x, vb2.y, vb2.z, vb2.w};
-        uint32_t ou[4], ov[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float q0 = __low2float(q2[e]), q1 = __high2float(q2[e]);
-          ou[e] = pack_bf16x2((q0 + uu[2 * e]) * p.scale_log2e, (q1 + uu[2 * e + 1]) * p.scale_log2e);
-          ov[e] = pack_bf16x2((q0 + vv[2 * e]) * p.scale_log2e, (q1 + vv[2 * e + 1]) * p.scale_log2e);
-        }
-        const uint32_t off = row * 128 + ((ch ^ sw) << 4);
-        *reinterpret_cast<uint4*>(qu_s + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *reinterpret_cast<uint4*>(p_s + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(q_full);
+    if (warp == 4) {
+      FTRACE(0);
+      if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == TRACE_Z && lane == 0) p.trace[64 + 6] = clock64();
     }
-    // ---- rotate ab into Q' = [A | B]; this thread: frequencies 64*grp .. +63 -> k-blocks grp (A) and 2+grp (B)
+    // ---- Qs: shared memory (as delivered by TMA; the prologue MMA reads it there) -> TMEM, half a row per thread
+    {
+      mbar_wait(q_full, 0);
+      uint32_t qr[16];
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint4 v4 = *reinterpret_cast<const uint4*>(q_s + row * 128 + (((grp * 4 + c4) ^ sw) << 4));
+        qr[4 * c4 + 0] = v4.x; qr[4 * c4 + 1] = v4.y; qr[4 * c4 + 2] = v4.z; qr[4 * c4 + 3] = v4.w;
+      }
+      tmem_st_32x16(tlane + TM_Q + 16 * grp, qr);
+    }
+    // ---- rotate ab into Q' = [A | B] (TMEM); this thread: frequencies 64*grp .. +63 of its row
     {
       if (warp == 4) FTRACE(1);
+      mbar_wait(rot_full, 0);
       mbar_wait(ab_full, 0);
       tc_fence_after();
       if (warp == 4) FTRACE(2);
-      mbar_wait(rot_full, 0);
-      uint8_t* arow = qp_s + grp * Q_BYTES + row * 128;          // holds cos(i w_k), k = 64*grp .. +63; becomes A
-      uint8_t* brow = qp_s + (2 + grp) * Q_BYTES + row * 128;    // holds sin(i w_k);                    becomes B
+      const uint8_t* crow = rot_s + grp * Q_BYTES + row * 128;          // cos(i w_k), k = 64*grp .. +63
+      const uint8_t* srow = rot_s + (2 + grp) * Q_BYTES + row * 128;    // sin(i w_k)
+      const float* pc = p.pos_const + h * D;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {                   // 16 frequencies at a time
         const int k0 = grp * 64 + cc * 16;
         uint32_t ar[16], br[16];
         tmem_ld_32x16(tlane + TM_AB + k0, ar);
         tmem_ld_32x16(tlane + TM_AB + NF + k0, br);
-        uint4* pa0 = reinterpret_cast<uint4*>(arow + (((2 * cc) ^ sw) << 4));
-        uint4* pa1 = reinterpret_cast<uint4*>(arow + (((2 * cc + 1) ^ sw) << 4));
-        uint4* pb0 = reinterpret_cast<uint4*>(brow + (((2 * cc) ^ sw) << 4));
-        uint4* pb1 = reinterpret_cast<uint4*>(brow + (((2 * cc + 1) ^ sw) << 4));
-        const uint4 c0 = *pa0, c1 = *pa1, s0 = *pb0, s1 = *pb1;
+        const uint4 c0 = *reinterpret_cast<const uint4*>(crow + (((2 * cc) ^ sw) << 4));
+        const uint4 c1 = *reinterpret_cast<const uint4*>(crow + (((2 * cc + 1) ^ sw) << 4));
+        const uint4 s0 = *reinterpret_cast<const uint4*>(srow + (((2 * cc) ^ sw) << 4));
+        const uint4 s1 = *reinterpret_cast<const uint4*>(srow + (((2 * cc + 1) ^ sw) << 4));
         const uint32_t cw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
         const uint32_t sw8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        float ka[16], kb2[16];                           // positional-bias constants (warp-uniform addresses)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float4 va = __ldg(reinterpret_cast<const float4*>(pc + k0) + e);
+          const float4 vb = __ldg(reinterpret_cast<const float4*>(pc + NF + k0) + e);
+          ka[4 * e] = va.x; ka[4 * e + 1] = va.y; ka[4 * e + 2] = va.z; ka[4 * e + 3] = va.w;
+          kb2[4 * e] = vb.x; kb2[4 * e + 1] = vb.y; kb2[4 * e + 2] = vb.z; kb2[4 * e + 3] = vb.w;
+        }
         tmem_ld_wait();
         uint32_t oa[8], ob[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&cw[e]));
           const float2 sn = __half22float2(*reinterpret_cast<const __half2*>(&sw8[e]));
-          const float a0 = __uint_as_float(ar[2 * e]), a1 = __uint_as_float(ar[2 * e + 1]);
-          const float b0 = __uint_as_float(br[2 * e]), b1 = __uint_as_float(br[2 * e + 1]);
+          const float a0 = __uint_as_float(ar[2 * e]) + ka[2 * e], a1 = __uint_as_float(ar[2 * e + 1]) + ka[2 * e + 1];
+          const float b0 = __uint_as_float(br[2 * e]) + kb2[2 * e], b1 = __uint_as_float(br[2 * e + 1]) + kb2[2 * e + 1];
           oa[e] = pack_bf16x2(a0 * sn.x + b0 * cs.x, a1 * sn.y + b1 * cs.y);
           ob[e] = pack_bf16x2(b0 * sn.x - a0 * cs.x, b1 * sn.y - a1 * cs.y);
         }
-        *pa0 = make_uint4(oa[0], oa[1], oa[2], oa[3]);
-        *pa1 = make_uint4(oa[4], oa[5], oa[6], oa[7]);
-        *pb0 = make_uint4(ob[0], ob[1], ob[2], ob[3]);
-        *pb1 = make_uint4(ob[4], ob[5], ob[6], ob[7]);
+        tmem_st_32x8(tlane + TM_QP + (k0 >> 1), oa);
+        tmem_st_32x8(tlane + TM_QP + ((NF + k0) >> 1), ob);
       }
+      tmem_st_wait();
       tc_fence_before();
-      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(qp_full);
       if (warp == 4) FTRACE(3);
     }
-    const uint32_t t_o = tlane + TM_O + 32 * grp;        // the half of the O row this thread rescales
-    uint8_t* prow = p_s + row * 128;
+    // Each key half of a row runs its own online softmax (reference maximum, row sum, O accumulator): the two threads
+    // of a row never talk inside the key loop; the halves are merged once, in the epilogue.
+    const uint32_t t_o = tlane + TM_O + 64 * grp;        // this thread's O accumulator (64 columns)
     float m_ref = -CUDART_INF_F, l_part = 0.f;
 
     // usable-key bitmask of this thread's 32 keys of tile j (warp-uniform)
@@ -343,115 +345,173 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const bool va = ja < Tn && (p.key_pad == nullptr || p.key_pad[static_cast<int64_t>(b) * Tn + ja] == 0);
       return __ballot_sync(0xffffffffu, va);
     };
-    // pull this thread's 32 scores of tile j out of TMEM and hand the S buffer back
-    auto load_scores = [&](int j, uint32_t (&s0)[32]) {
-      const int buf = j & 1;
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
+    // rescale this key half's O accumulator and row sum when its reference maximum moves (P.V of tile jdone retired)
+    auto move_reference = [&](float m_to, int jdone) {
+      mbar_wait(o_done, jdone & 1);
       tc_fence_after();
-      tmem_ld_32x32(tlane + TM_S + buf * BKV + 32 * grp, s0);
-      tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_read[buf]);          // this S buffer may be overwritten by tile j+2
+      const float f = (m_to == m_ref) ? 1.f : ex2f(m_ref - m_to);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + 32 * hh, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
+        tmem_st_32x32(t_o + 32 * hh, o);
+      }
+      tmem_st_wait();
+      l_part *= f;
+      m_ref = m_to;
     };
-    auto mask_and_max = [&](uint32_t (&s0)[32], uint32_t vm) -> float {
+    // Exact tile: all 32 scores first, their maximum, the lazy-rescale rule, then P.  Used for the first tile and
+    // whenever a streamed tile meets a score far above the reference.
+    auto exact_tile = [&](int j, uint32_t vm, uint32_t (&pk)[16], float& psum) {
+      uint32_t sc[32];
+      tmem_ld_32x32(tlane + TM_S + (j & 1) * BKV + 32 * grp, sc);
+      tmem_ld_wait();
       if (vm != 0xffffffffu) {
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj)
-          if (((vm >> jj) & 1u) == 0) s0[jj] = __float_as_uint(-CUDART_INF_F);
+          if (((vm >> jj) & 1u) == 0) sc[jj] = __float_as_uint(-CUDART_INF_F);
       }
-      float m0 = max3f(__uint_as_float(s0[0]), __uint_as_float(s0[1]), __uint_as_float(s0[2]));
-      float m1 = max3f(__uint_as_float(s0[3]), __uint_as_float(s0[4]), __uint_as_float(s0[5]));
+      float m0 = max3f(__uint_as_float(sc[0]), __uint_as_float(sc[1]), __uint_as_float(sc[2]));
+      float m1 = max3f(__uint_as_float(sc[3]), __uint_as_float(sc[4]), __uint_as_float(sc[5]));
 #pragma unroll
       for (int jj = 6; jj < 30; jj += 4) {
-        m0 = max3f(m0, __uint_as_float(s0[jj]), __uint_as_float(s0[jj + 1]));
-        m1 = max3f(m1, __uint_as_float(s0[jj + 2]), __uint_as_float(s0[jj + 3]));
+        m0 = max3f(m0, __uint_as_float(sc[jj]), __uint_as_float(sc[jj + 1]));
+        m1 = max3f(m1, __uint_as_float(sc[jj + 2]), __uint_as_float(sc[jj + 3]));
       }
-      return max3f(m0, m1, fmaxf(__uint_as_float(s0[30]), __uint_as_float(s0[31])));
+      const float tmax = max3f(m0, m1, fmaxf(__uint_as_float(sc[30]), __uint_as_float(sc[31])));
+      const float m_to = (tmax > m_ref + RESCALE_THRESHOLD) ? tmax : m_ref;
+      if (j > 0) {
+        if (__any_sync(0xffffffffu, m_to != m_ref)) move_reference(m_to, j - 1);
+      }
+      m_ref = m_to;
+      const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float p0 = ex2f(__uint_as_float(sc[2 * e]) - m_use);
+        const float p1 = ex2f(__uint_as_float(sc[2 * e + 1]) - m_use);
+        ps0 += p0;
+        ps1 += p1;
+        pk[e] = pack_bf16x2(p0, p1);
+      }
+      psum = ps0 + ps1;
     };
 
-    uint32_t sc[32];
+    // Key loop.  TMEM reads (64 B/clk) and the exponentials (MUFU) each take about 512 clocks per tile, so from the second
+    // tile on the scores are STREAMED in chunks of 8 columns against the reference maximum the half already has: the
+    // next chunk's tcgen05.ld is in flight while the current one goes through ex2.  The tile maximum falls out of the
+    // same pass and moves the reference (lazily, by the 2^8 rule) before the NEXT tile.  A score more than 2^60 above
+    // the reference (P would overflow; also the case of a half that has seen no usable key yet) redoes the tile exactly.
+    constexpr float STREAM_GUARD = 60.0f;
+    float m_pend = m_ref;
     if (warp == 4) FTRACE(8);
-    load_scores(0, sc);
-    float tmax = mask_and_max(sc, key_mask(0));
     for (int j = 0; j < ntiles; ++j) {
       const int buf = j & 1;
-      if (warp == 4) FTRACE(9 + 4 * j);
-      // ---- tile maximum of the whole row: exchange with the thread that holds the other 32 keys
-      float* xm = xmax + buf * 2 * BQ;
-      xm[grp * BQ + row] = tmax;
-      named_bar_sync(1 + w, 64);
-      const float t_row = fmaxf(tmax, xm[(grp ^ 1) * BQ + row]);
-      // ---- lazy rescaling: move the reference maximum only when the tile exceeds it by more than the threshold
-      const float m_new = (t_row > m_ref + RESCALE_THRESHOLD) ? t_row : m_ref;
+      const uint32_t vm = key_mask(j);
+      const uint32_t t_s = tlane + TM_S + buf * BKV + 32 * grp;
+      uint32_t pk[16];
+      float psum;
+      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      tc_fence_after();
+      // (S_j complete implies P.V of tile j-2 complete - the tensor pipe runs in issue order - so the parity wait on
+      // o_done for tile j-1 inside move_reference cannot alias an older phase, however far this warp has run ahead)
       if (j > 0) {
-        mbar_wait(o_done, (j - 1) & 1);                  // P.V of tile j-1 retired: P buffer free, O stable
-        if (__any_sync(0xffffffffu, m_new != m_ref)) {
-          tc_fence_after();
-          const float f = ex2f(m_ref - m_new);           // 1 for rows whose reference did not move
-          uint32_t o[32];
-          tmem_ld_32x32(t_o, o);
-          tmem_ld_wait();
+        if (__any_sync(0xffffffffu, m_pend != m_ref)) move_reference(m_pend, j - 1);
+      }
+      if (warp == 4) FTRACE(9 + 4 * j);
+      if (j == 0) {
+        exact_tile(0, vm, pk, psum);
+        m_pend = m_ref;
+      } else {
+        const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
+        float ps0 = 0.f, ps1 = 0.f, t0 = -CUDART_INF_F, t1 = -CUDART_INF_F;
+        uint32_t ca[8], cb[8];
+        auto chunk = [&](const uint32_t (&cur)[8], int c) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * f);
-          tmem_st_32x32(t_o, o);
-          tmem_st_wait();
-          l_part *= f;
+          for (int e = 0; e < 4; ++e) {
+            float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
+            if (vm != 0xffffffffu) {
+              if (((vm >> (8 * c + 2 * e)) & 1u) == 0) s0 = -CUDART_INF_F;
+              if (((vm >> (8 * c + 2 * e + 1)) & 1u) == 0) s1 = -CUDART_INF_F;
+            }
+            t0 = fmaxf(t0, s0);
+            t1 = fmaxf(t1, s1);
+            const float p0 = ex2f(s0 - m_use), p1 = ex2f(s1 - m_use);
+            ps0 += p0;
+            ps1 += p1;
+            pk[4 * c + e] = pack_bf16x2(p0, p1);
+          }
+        };
+        tmem_ld_32x8(t_s, ca);
+        tmem_ld_wait_for(ca);
+        tmem_ld_32x8(t_s + 8, cb);
+        chunk(ca, 0);
+        tmem_ld_wait_for(cb);
+        tmem_ld_32x8(t_s + 16, ca);
+        chunk(cb, 1);
+        tmem_ld_wait_for(ca);
+        tmem_ld_32x8(t_s + 24, cb);
+        chunk(ca, 2);
+        tmem_ld_wait_for(cb);
+        chunk(cb, 3);
+        const float tmax = fmaxf(t0, t1);
+        psum = ps0 + ps1;
+        if (__any_sync(0xffffffffu, tmax > m_ref + STREAM_GUARD)) {
+          exact_tile(j, vm, pk, psum);
+          m_pend = m_ref;
+        } else {
+          m_pend = (tmax > m_ref + RESCALE_THRESHOLD) ? tmax : m_ref;
         }
       }
-      m_ref = m_new;
-      const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
       if (warp == 4) FTRACE(10 + 4 * j);
-      // ---- P = exp2(s - m) as bf16 into the A layout of the P.V MMA (this thread: 4 chunks of 8 keys)
-      float psum0 = 0.f, psum1 = 0.f;
-#pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
-        uint32_t o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = ex2f(__uint_as_float(sc[c4 * 8 + 2 * e]) - m_use);
-          const float p1 = ex2f(__uint_as_float(sc[c4 * 8 + 2 * e + 1]) - m_use);
-          psum0 += p0;
-          psum1 += p1;
-          o[e] = pack_bf16x2(p0, p1);
-        }
-        *reinterpret_cast<uint4*>(prow + (((grp * 4 + c4) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-      l_part += psum0 + psum1;
+      // ---- P_j of this key half (bf16 pairs) overwrites columns of S_j that only this thread reads
+      tmem_st_32x16(t_s, pk);
+      tmem_st_wait();
+      l_part += psum;
       tc_fence_before();
-      fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (warp == 4) FTRACE(11 + 4 * j);
-      if (j + 1 < ntiles) {
-        const uint32_t vm_next = key_mask(j + 1);
-        load_scores(j + 1, sc);
-        tmax = mask_and_max(sc, vm_next);
-      }
     }
-    // ---- epilogue: O / l, this thread's 32 of the 64 output columns
+    // ---- epilogue: merge the two key halves, O = (f0 O0 + f1 O1) / (f0 l0 + f1 l1), f_g = 2^(m_g - max(m0, m1));
+    //      this thread writes 32 of the row's 64 output columns
+    xmax[grp * BQ + row] = m_ref;
     xsum[grp * BQ + row] = l_part;
     mbar_wait(o_done, (ntiles - 1) & 1);
     tc_fence_after();
-    uint32_t o[32];
-    tmem_ld_32x32(t_o, o);
+    uint32_t o0[32], o1[32];
+    tmem_ld_32x32(tlane + TM_O + 32 * grp, o0);
+    tmem_ld_32x32(tlane + TM_O + 64 + 32 * grp, o1);
     tmem_ld_wait();
     named_bar_sync(1 + w, 64);
-    const float l_tot = l_part + xsum[(grp ^ 1) * BQ + row];
+    const float m_oth = xmax[(grp ^ 1) * BQ + row], l_oth = xsum[(grp ^ 1) * BQ + row];
+    const float m_all = fmaxf(m_ref, m_oth);
+    const float f_me = (m_ref == -CUDART_INF_F) ? 0.f : ex2f(m_ref - m_all);
+    const float f_oth = (m_oth == -CUDART_INF_F) ? 0.f : ex2f(m_oth - m_all);
+    const float l_tot = f_me * l_part + f_oth * l_oth;
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    const float w0 = (grp == 0 ? f_me : f_oth) * inv, w1 = (grp == 0 ? f_oth : f_me) * inv;
     if (qi < Tn) {
       bf16* orow = p.ctx + (static_cast<int64_t>(b) * Tn + qi) * d + h * DH + 32 * grp;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint4 v4;
-        v4.x = pack_bf16x2(__uint_as_float(o[ch * 8 + 0]) * inv, __uint_as_float(o[ch * 8 + 1]) * inv);
-        v4.y = pack_bf16x2(__uint_as_float(o[ch * 8 + 2]) * inv, __uint_as_float(o[ch * 8 + 3]) * inv);
-        v4.z = pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv);
-        v4.w = pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv);
-        *reinterpret_cast<uint4*>(orow + ch * 8) = v4;
+        uint32_t r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = ch * 8 + 2 * e;
+          r[e] = pack_bf16x2(__uint_as_float(o0[c]) * w0 + __uint_as_float(o1[c]) * w1,
+                             __uint_as_float(o0[c + 1]) * w0 + __uint_as_float(o1[c + 1]) * w1);
+        }
+        *reinterpret_cast<uint4*>(orow + ch * 8) = make_uint4(r[0], r[1], r[2], r[3]);
       }
     }
-    if (warp == 4) FTRACE(4);
+    if (warp == 4) {
+      FTRACE(4);
+      if (p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == TRACE_Z && lane == 0) p.trace[64 + 7] = clock64();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -487,9 +547,45 @@ __global__ void pack_pos_fact_kernel(const float* __restrict__ wp, bf16* __restr
   out[idx] = __float2bfloat16_rn(wp[static_cast<int64_t>(h * dh + c) * d + m]);
 }
 
+// query rows of the fused q|k|v projection for this kernel: W <- c W, b <- c (b + u)      (in place, rows [0, d))
+__global__ void pack_q_fact_kernel(float* __restrict__ w, float* __restrict__ bias, const float* __restrict__ u, int d, float c) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx < static_cast<int64_t>(d) * d) w[idx] *= c;
+  if (idx < d) bias[idx] = c * (bias[idx] + u[idx]);
+}
+
+// out[h][m'] = c * sum_cc (v - u)[h*dh + cc] * Wp[h*dh + cc][m(m')]      (m(m') as in pack_pos_fact_kernel)
+__global__ void pos_const_fact_kernel(const float* __restrict__ wp, const float* __restrict__ u, const float* __restrict__ v,
+                                      float* __restrict__ out, int d, int dh, float c) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int H = d / dh;
+  if (idx >= H * d) return;
+  const int h = idx / d, mp = idx - h * d;
+  const int m = mp < d / 2 ? 2 * mp : 2 * (mp - d / 2) + 1;
+  float acc = 0.f;
+  for (int cc = 0; cc < dh; ++cc) acc += (v[h * dh + cc] - u[h * dh + cc]) * wp[static_cast<int64_t>(h * dh + cc) * d + m];
+  out[idx] = c * acc;
+}
+
 }  // namespace
 
 extern unsigned long long* g_gemm_trace;
+
+int pack_q_fact(float* wq, float* bq, const float* u, int d, int dh, cudaStream_t stream) {
+  const int64_t n = static_cast<int64_t>(d) * d;
+  pack_q_fact_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(wq, bq, u, d,
+                                                                               1.4426950408889634f / sqrtf(static_cast<float>(dh)));
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int pos_const_fact(const float* wp, const float* u, const float* v, float* out, int d, int dh, cudaStream_t stream) {
+  const int n = (d / dh) * d;
+  pos_const_fact_kernel<<<(n + 255) / 256, 256, 0, stream>>>(wp, u, v, out, d, dh,
+                                                             1.4426950408889634f / sqrtf(static_cast<float>(dh)));
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 bool rel_attention_fact_supported(int d, int dh) { return d == D && dh == DH; }
 
@@ -508,9 +604,8 @@ int pack_pos_fact(const float* wp, bf16* out, int d, int dh, cudaStream_t stream
   return 0;
 }
 
-int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, const void* r16, const float* u,
-                            const float* v, const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh,
-                            cudaStream_t stream) {
+int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, const void* r16, const float* pos_const,
+                            const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(dh == DH && H * dh == D, "factorised attention is specialised for d_model 256, head size 64");
   CFM_REQUIRE(B > 0 && Tn > 0 && B <= 65535, "bad attention shape");
@@ -548,7 +643,7 @@ int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, c
     CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  FactParams p{qkv, u, v, key_pad, static_cast<const __half*>(r16), ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace};
+  FactParams p{pos_const, key_pad, ctx, Tn, H, 0u, g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   rel_attention_fact_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmE, tmWp, tmRot, p);
   CFM_CUDA_OK(cudaGetLastError());

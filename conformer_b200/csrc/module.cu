@@ -118,6 +118,17 @@ struct Packer {
     if (bf16_mode && !status && rel_attention_fact_supported(d, d / H)) {
       w.wpT = alloc_bf16(static_cast<int64_t>(d) * d);
       if (!status && pack_pos_fact(w.pos.w32, w.wpT, d, d / H, stream)) status = 2;
+      // second copy of the fused projection with content bias and softmax scale folded into the query rows
+      float* wq2 = alloc_f32(3LL * d * d);
+      float* bq2 = alloc_f32(3LL * d);
+      float* pcst = alloc_f32(static_cast<int64_t>(H) * d);
+      if (!status) {
+        cudaMemcpyAsync(wq2, wq, static_cast<size_t>(3) * d * d * 4, cudaMemcpyDeviceToDevice, stream);
+        cudaMemcpyAsync(bq2, bq, static_cast<size_t>(3) * d * 4, cudaMemcpyDeviceToDevice, stream);
+        if (pack_q_fact(wq2, bq2, w.u, d, d / H, stream) || pos_const_fact(w.pos.w32, w.u, w.v, pcst, d, d / H, stream)) status = 2;
+      }
+      finish_linear(w.qkv_fact, wq2, bq2, 3 * d, d);
+      w.pos_const = pcst;
     }
   }
   void mhsa(AttnW& w, const std::string& pre, int d, int H) {
@@ -181,7 +192,7 @@ size_t arena_bytes_for(const Module& m) {
   for (const auto& kv : m.params) total += static_cast<size_t>(kv.second.numel);
   // fp32 copy + bf16 copy + per-tensor 256-byte alignment slack + the fused pos_proj copy
   const size_t d = m.cfg.d_model;
-  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 8 + (1 << 16);
+  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 32 + (1 << 16);
 }
 
 }  // namespace
@@ -427,7 +438,7 @@ inline int attention_fact_any(const float*, const AttnW&, const FactPos&, const 
 }
 inline int attention_fact_any(const bf16* qkv, const AttnW& w, const FactPos& fp, const uint8_t* kp, bf16* ctx, int B, int Tn,
                               int H, int dh, cudaStream_t st) {
-  return rel_attention_bf16_fact(qkv, w.wpT, fp.e16, fp.r16, w.u, w.v, kp, ctx, B, Tn, H, dh, st);
+  return rel_attention_bf16_fact(qkv, w.wpT, fp.e16, fp.r16, w.pos_const, kp, ctx, B, Tn, H, dh, st);
 }
 
 // out = res + MHSA(x)      (attention.py:14-18,74-92; block.py:21)
@@ -444,10 +455,11 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
   WS_CHECK(a); WS_CHECK(qkv); WS_CHECK(ctx);
   if (!c.ws.measuring()) {
     const TA* ain = a;
+    const Linear& wqkv = fp != nullptr ? w.qkv_fact : w.qkv;      // the factorised kernel wants c (q + u) as its queries
     if (pre_ln && ln_gemm_ok(static_cast<const TA*>(nullptr), d, 3 * d)) {
       // LayerNorm fused into the q|k|v projection (A operand normalised on chip)
       KRUN(KC_LN_GEMM, 2.0 * M * 3 * d * d, 4.0 * M * d + 2.0 * M * 3 * d + 6.0 * d * d,
-           ln_gemm_any(x, w.ln_g, w.ln_b, w.qkv, qkv, 3 * d, static_cast<int>(M), d, false, c.stream));
+           ln_gemm_any(x, w.ln_g, w.ln_b, wqkv, qkv, 3 * d, static_cast<int>(M), d, false, c.stream));
     } else {
       if (pre_ln) {
         KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
@@ -456,7 +468,7 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
       } else {
         KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
       }
-      CFM_TRY(Dispatch<TA>::gemm(c, ain, d, w.qkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
+      CFM_TRY(Dispatch<TA>::gemm(c, ain, d, wqkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
     }
     // algorithmic work: content + positional + PV = 6*T*d FLOPs per token
     if (fp != nullptr) {

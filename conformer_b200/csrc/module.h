@@ -98,6 +98,8 @@ struct AttnW {
   const float *ln_g = nullptr, *ln_b = nullptr, *u = nullptr, *v = nullptr;
   Linear qkv, pos, out;
   bf16* wpT = nullptr;               // pos_proj packed per head for the factorised positional term (bf16, d = 256)
+  Linear qkv_fact;                   // q|k|v with the query rows as c (Wq x + bq + u) for the factorised kernel
+  const float* pos_const = nullptr;  // [H][d]: c (v - u) Wp_h (factorised kernel)
 };
 struct ConvW {
   const float *ln_g = nullptr, *ln_b = nullptr, *dw_w = nullptr, *dw_b = nullptr;

@@ -100,9 +100,13 @@ int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float
 // bf16 tcgen05 variant for d_model 256 / head size 64 with the sinusoidal positional term factorised into a rotated
 // query times an absolute key table (no relative shift, no projected [2T-1,d] table; attention_fact.cu).
 // wpT = pack_pos_fact(pos_proj.weight); e16 (bf16) / r16 (fp16) = pos_fact_tables(div_term): [T][d] = cos(t w_k) | sin(t w_k).
-int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, const void* r16, const float* u,
-                            const float* v, const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh,
-                            cudaStream_t stream);
+// The query block of qkv must come from a projection packed by pack_q_fact (c (q + u), c = log2(e)/sqrt(dh));
+// pos_const = pos_const_fact(...) = c (v - u) Wp per head.
+int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, const void* r16, const float* pos_const,
+                            const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
+int pack_q_fact(float* wq /*[d,d] in place*/, float* bq /*[d] in place*/, const float* u, int d, int dh, cudaStream_t stream);
+int pos_const_fact(const float* wp /*[d,d]*/, const float* u, const float* v, float* out /*[H][d]*/, int d, int dh,
+                   cudaStream_t stream);
 bool rel_attention_fact_supported(int d, int dh);
 int pos_fact_tables(const float* div_term, bf16* e16, void* r16, int Tn, int d, cudaStream_t stream);
 int pack_pos_fact(const float* wp /*[d,d]*/, bf16* out /*[H][d][dh]*/, int d, int dh, cudaStream_t stream);

@@ -37,11 +37,18 @@ t = trace.cpu()[64:]
 if os.environ.get("ATTN_POS", "none") == "none":
     t0 = int(t[0])
     print("factorised kernel. prologue: start 0, Q written %d, ab ready %d, Q' written %d, end %d" % tuple(int(t[i]) - t0 for i in (1, 2, 3, 4)))
+    print("SM clock during the traced CTA: %.0f MHz" % ((int(t[7]) - int(t[6])) * 1e3 / max(1, int(t[4]) - int(t[0]))))
     for j in range(8):
         r = t[8 + 4 * j: 12 + 4 * j]
         if int(r.max()) == 0:
             break
-        print(f"tile {j}: top {int(r[1]) - t0:6d}  max/rescale done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
+        print(f"tile {j}: S ready {int(r[1]) - t0:6d}  exp done {int(r[2]) - t0:6d}  P written {int(r[3]) - t0:6d}")
+    for j in range(7):
+        r = t[36 + 4 * j: 40 + 4 * j]
+        if int(r.max()) == 0:
+            break
+        print(f"MMA warp, tile {j}: loop top {int(r[0]) - t0:6d}  S_{j + 1} issued (K|E landed) {int(r[1]) - t0:6d}  "
+              f"P_{j} ready {int(r[2]) - t0:6d}  V ready {int(r[3]) - t0:6d}")
 else:
     t0 = int(t[60])
     print("shift kernel: softmax warps start 0, Q staged %d, first tile top %d, end %d" % (int(t[61]) - t0, int(t[0]) - t0, int(t[62]) - t0))
