@@ -472,6 +472,9 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       tmem_st_wait();
       l_part += psum;
       tc_fence_before();
+      // The warps run decoupled and S_{j+1} is issued before P_j is awaited, so this warp may be a whole tile ahead of the
+      // slowest one: its arrival for tile j must not be counted in the still-open phase of tile j-1.
+      if (j > 0) mbar_wait(p_full, (j - 1) & 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (warp == 4) FTRACE(11 + 4 * j);
@@ -480,6 +483,9 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     //      this thread writes 32 of the row's 64 output columns
     xmax[grp * BQ + row] = m_ref;
     xsum[grp * BQ + row] = l_part;
+    // (two waits: P.V of tile ntiles-3 is known complete - S of the last tile was issued after it - so the parity wait for
+    // tile ntiles-2 cannot alias, and after it neither can the one for the last tile)
+    if (ntiles >= 2) mbar_wait(o_done, (ntiles - 2) & 1);
     mbar_wait(o_done, (ntiles - 1) & 1);
     tc_fence_after();
     uint32_t o0[32], o1[32];

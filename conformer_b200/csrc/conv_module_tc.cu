@@ -51,6 +51,9 @@ struct ConvParams {
   const float* dw_b;     // [256]     BN-folded
   const float* b2;
   float* out;
+  const float* ln2_g;    // nullable: also write a_out = LN(out; ln2_g, ln2_b) as bf16, the normalised input of the
+  const float* ln2_b;    //           half-step FFN that follows the conv module in the block (ffn.py:16)
+  bf16* a_out;
   int Tn;
   unsigned long long* trace;     // debug: globaltimer stamps of CTA (0,0)
 };
@@ -314,6 +317,11 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
     {
       const float4 b2a = __ldg(reinterpret_cast<const float4*>(p.b2) + 2 * lane);
       const float4 b2b = __ldg(reinterpret_cast<const float4*>(p.b2) + 2 * lane + 1);
+      float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, ba = ga, bb = ga;
+      if (p.a_out != nullptr) {
+        ga = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + 2 * lane); gb = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + 2 * lane + 1);
+        ba = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + 2 * lane); bb = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + 2 * lane + 1);
+      }
 #pragma unroll 4
       for (int o = cw; o < TO; o += NUM_CW) {
         const int t = t_out0 + o;
@@ -332,6 +340,19 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
         float4* orow = reinterpret_cast<float4*>(p.out + goff) + 2 * lane;
         orow[0] = v0;
         orow[1] = v1;
+        if (p.a_out != nullptr) {                                  // the whole frame is in this warp: LayerNorm it
+          const float mean = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w)) * (1.0f / D);
+          v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
+          v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
+          const float rstd = rsqrtf(warp_sum((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w) +
+                                             (v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w)) * (1.0f / D) + 1e-5f);
+          uint4 o4;
+          o4.x = pack_bf16x2(v0.x * rstd * ga.x + ba.x, v0.y * rstd * ga.y + ba.y);
+          o4.y = pack_bf16x2(v0.z * rstd * ga.z + ba.z, v0.w * rstd * ga.w + ba.w);
+          o4.z = pack_bf16x2(v1.x * rstd * gb.x + bb.x, v1.y * rstd * gb.y + bb.y);
+          o4.w = pack_bf16x2(v1.z * rstd * gb.z + bb.z, v1.w * rstd * gb.w + bb.w);
+          reinterpret_cast<uint4*>(p.a_out + goff)[lane] = o4;
+        }
       }
     }
     CTRACE(9);
@@ -352,7 +373,8 @@ bool conv_module_fused_supported(int d, int ksize) { return d == D && ksize == K
 
 int conv_module_fused_bf16(const float* x, const float* res, float* out, const float* ln_g, const float* ln_b,
                            const bf16* W1p, const float* b1p, const float* dw_w, const float* dw_b, const bf16* W2,
-                           const float* b2, int B, int Tn, int d, int ksize, cudaStream_t stream) {
+                           const float* b2, const float* ln2_g, const float* ln2_b, bf16* a_out, int B, int Tn, int d,
+                           int ksize, cudaStream_t stream) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(d == D && ksize == KS, "fused conv module kernel is specialised for d_model = 256, kernel size 31");
   CFM_REQUIRE(B > 0 && Tn > 0 && B <= 65535, "bad conv module shape");
@@ -380,7 +402,10 @@ int conv_module_fused_bf16(const float* x, const float* res, float* out, const f
     CFM_CUDA_OK(cudaFuncSetAttribute(conv_module_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
-  ConvParams p{x, res, ln_g, ln_b, b1p, dw_w, dw_b, b2, out, Tn, g_gemm_trace};
+  CFM_REQUIRE(a_out == nullptr || (ln2_g != nullptr && ln2_b != nullptr), "a_out needs the following LayerNorm's parameters");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(a_out) | reinterpret_cast<uintptr_t>(ln2_g) | reinterpret_cast<uintptr_t>(ln2_b)) & 15) == 0,
+              "fused conv module operands must be 16-byte aligned");
+  ConvParams p{x, res, ln_g, ln_b, b1p, dw_w, dw_b, b2, out, ln2_g, ln2_b, a_out, Tn, g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TO)), static_cast<unsigned>(B));
   conv_module_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, p);
   CFM_CUDA_OK(cudaGetLastError());

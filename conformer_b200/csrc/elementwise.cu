@@ -68,6 +68,48 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* __rest
   }
 }
 
+// Two LayerNorms in one pass over a row of d = 256:  y = LN(x; g1, b1) (fp32: the block output, block.py:27) and
+// a = LN(y; g2, b2) (bf16: the normalised input of the NEXT block's first half-step FFN, ffn.py:16).  The fused FFN
+// kernel then starts from one TMA load of `a` instead of every CTA pulling 128 KB of fp32 rows and normalising them.
+__global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* __restrict__ x, const float* __restrict__ g1,
+                                                              const float* __restrict__ b1, float* __restrict__ y,
+                                                              const float* __restrict__ g2, const float* __restrict__ b2,
+                                                              bf16* __restrict__ a, int64_t rows) {
+  constexpr int D = 256;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * D) + 2 * lane;    // lane owns columns 8*lane .. 8*lane+7
+  float v[8];
+  {
+    const float4 p0 = xr[0], p1 = xr[1];
+    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+  }
+  auto normalise = [&](const float* gamma, const float* beta) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane + 1);
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + 2 * lane), bb = __ldg(reinterpret_cast<const float4*>(beta) + 2 * lane + 1);
+    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = v[i] * rstd * gg[i] + be[i];
+  };
+  normalise(g1, b1);
+  float4* yr = reinterpret_cast<float4*>(y + row * D) + 2 * lane;
+  yr[0] = make_float4(v[0], v[1], v[2], v[3]);
+  yr[1] = make_float4(v[4], v[5], v[6], v[7]);
+  normalise(g2, b2);
+  reinterpret_cast<uint4*>(a + row * D)[lane] =
+      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
 template <typename T>
 __global__ void rel_pos_table_kernel(const float* __restrict__ div_term, T* __restrict__ pe, int Tn, int d) {
   const int half = d >> 1;
@@ -174,6 +216,17 @@ int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, i
     layer_norm_vec_kernel<TOut, 1><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
   else
     layer_norm_kernel<TOut><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int layer_norm_dual(const float* x, const float* g1, const float* b1, float* y, const float* g2, const float* b2, bf16* a,
+                    int64_t rows, int d, cudaStream_t stream) {
+  CFM_REQUIRE(d == 256, "layer_norm_dual is specialised for d_model = 256");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(a) |
+                reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(g2) |
+                reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "layer_norm_dual operands must be 16-byte aligned");
+  if (rows <= 0) return 0;
+  layer_norm_dual_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

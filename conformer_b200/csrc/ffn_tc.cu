@@ -78,9 +78,12 @@ struct ItemIter {
   }
 };
 
+// PRE: the A operand LN(x) arrives already normalised (bf16 [M,256], tensor map tmA) and is TMA-loaded into the
+// MMA layout; otherwise the 16 epilogue warps read x and normalise it.
+template <bool PRE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmX, FfnParams p) {
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA, FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* xs = smem;
@@ -102,13 +105,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
+    if (PRE) tma_prefetch_desc(&tmA);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(xs_full, NUM_EPI_WARPS);
+    mbar_init(xs_full, PRE ? 1 : NUM_EPI_WARPS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc1_full[s], 1);
       mbar_init(&acc1_empty[s], NUM_EPI_WARPS);
@@ -257,8 +261,15 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
     for (uint32_t n = 0; items.next(w); ++n) {
     const int m0 = w.tile * BM;
+    if (PRE) {
+      // ---- A operand: four [128 rows x 64] k-blocks straight into the swizzled MMA layout (rows past M arrive as zeros)
+      if (tid_e == 0) {
+        mbar_expect_tx(xs_full, XS_BYTES);
+#pragma unroll
+        for (int kb = 0; kb < D / KB; ++kb) tma_load_2d(xs + kb * (BM * 128), &tmA, xs_full, kb * KB, m0);
+      }
+    } else {
     // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7; lane owns columns 8*lane .. 8*lane+7
-    {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane);
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane + 1);
       const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane);
@@ -383,15 +394,25 @@ extern unsigned long long* g_gemm_trace;
 
 bool ffn_fused_supported(int d) { return d == D; }
 
-int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
-                   const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream) {
+int ffn_fused_bf16(const float* x_in, const bf16* a_pre, float* x, const float* ln_g, const float* ln_b, const bf16* W1,
+                   const float* b1, const bf16* W2, const float* b2, float scale, int M, int d, int num_sms,
+                   cudaStream_t stream) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(d == D, "fused FFN kernel is specialised for d_model = 256");
   CFM_REQUIRE(M > 0, "empty FFN");
   CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
                 reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(b1) |
                 reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "fused FFN operands must be 16-byte aligned");
-  CUtensorMap tmW1, tmW2, tmX;
+  CFM_REQUIRE((reinterpret_cast<uintptr_t>(a_pre) & 15) == 0, "fused FFN operands must be 16-byte aligned");
+  CUtensorMap tmW1, tmW2, tmX, tmA;
+  if (a_pre != nullptr) {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
+    cuuint32_t box[2] = {KB, BM};
+    CFM_TRY(encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_pre, dims, strides, box, "ffn normalised input"));
+  } else {
+    tmA = CUtensorMap{};
+  }
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(HID)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
@@ -412,19 +433,20 @@ int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* 
   }
   static bool attr_done = false;
   if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_done = true;
   }
   const int tiles = static_cast<int>(ceil_div(M, BM));
   FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M, tiles, g_gemm_trace};
-  // Default: one CTA per row tile (187 CTAs = 2 waves at C2).  When forwards of independent batches are in flight on
-  // several streams - the serving / benchmark configuration - the other stream's kernels fill the second wave and the
-  // SM-time per tile is what counts (4.26 vs 4.41 ms per step).  CFM_FFN_BALANCED=1 selects the persistent schedule
-  // that shares the left-over tiles between CTAs: best for a single stream (5.02 vs 5.34 ms) at the price of repeating
-  // the LayerNorm prologue and the reduction-store epilogue for every share.
-  static const bool balanced = [] { const char* e = getenv("CFM_FFN_BALANCED"); return e != nullptr && e[0] == '1'; }();
+  // Default: persistent CTAs, left-over row tiles shared along the hidden dimension (187 tiles on 148 SMs: the last wave
+  // is as full as the first).  With the pre-normalised A operand a share's prologue is one 64 KB TMA load, and the
+  // schedule wins on a single stream (4.66 vs 4.93 ms per C2 step) and ties with two streams in flight (4.01 vs 3.98).
+  // CFM_FFN_BALANCED=0 selects one CTA per row tile.
+  static const bool balanced = [] { const char* e = getenv("CFM_FFN_BALANCED"); return e == nullptr || e[0] != '0'; }();
   const int grid = (!balanced || tiles < num_sms) ? tiles : num_sms;
-  ffn_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, p);
+  if (a_pre != nullptr) ffn_fused_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, tmA, p);
+  else ffn_fused_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, tmA, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

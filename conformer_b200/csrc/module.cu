@@ -359,8 +359,10 @@ inline int ln_gemm_any(const float* x, const float* g, const float* b, const Lin
 inline bool ffn_fast_ok(const float*, int) { return false; }
 inline bool ffn_fast_ok(const bf16*, int d) { return ffn_fused_supported(d); }
 
+// a_pre (bf16 mode, nullable): LN(x) already computed by the kernel that produced x.
 template <typename TA>
-int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale, float* out, int64_t M, int d) {
+int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale, float* out, int64_t M, int d,
+            const bf16* a_pre = nullptr) {
   if (ffn_fast_ok(static_cast<const TA*>(nullptr), d)) {
     // fused LN -> GEMM -> Swish -> GEMM -> residual kernel; `out` must hold the residual before it runs
     if (c.ws.measuring()) return 0;
@@ -368,8 +370,8 @@ int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale
     else if (res != out) CFM_CUDA_OK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
     ++c.launches;
     Timed t(c, KC_FFN_FUSED, 16.0 * M * d * d, 8.0 * M * d + 16.0 * d * d);
-    return ffn_fused_bf16(x, out, w.ln_g, w.ln_b, w.hidden.w16, w.hidden.b, w.out.w16, w.out.b, scale, static_cast<int>(M), d,
-                          c.num_sms, c.stream);
+    return ffn_fused_bf16(x, a_pre, out, w.ln_g, w.ln_b, w.hidden.w16, w.hidden.b, w.out.w16, w.out.b, scale,
+                          static_cast<int>(M), d, c.num_sms, c.stream);
   }
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
@@ -491,16 +493,19 @@ inline bool conv_fast_ok(const bf16*, const ConvW& w, int d) {
   return !off && w.glu_fused && conv_module_fused_supported(d, w.ksize);
 }
 
+// next_ln / a_out (fused kernel only, nullable): also emit LN(out; next_ln) as bf16 for the FFN that follows.
 template <typename TA>
-int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* out, int B, int Tn, int d) {
+int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* out, int B, int Tn, int d,
+             const FfnW* next_ln = nullptr, bf16* a_out = nullptr) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
   if (conv_fast_ok(static_cast<const TA*>(nullptr), w, d) && out != x) {
     // single fused kernel: LN -> pw1 -> GLU -> depthwise+BN+Swish -> pw2 -> +residual
     if (c.ws.measuring()) return 0;
     ++c.launches;
     Timed t(c, KC_CONV_FUSED, 6.0 * M * d * d + 2.0 * w.ksize * M * d, (res ? 12.0 : 8.0) * M * d + 6.0 * d * d);
-    return conv_module_fused_bf16(x, res, out, w.ln_g, w.ln_b, w.pw1.w16, w.pw1.b, w.dw_w, w.dw_b, w.pw2.w16, w.pw2.b, B, Tn,
-                                  d, w.ksize, c.stream);
+    return conv_module_fused_bf16(x, res, out, w.ln_g, w.ln_b, w.pw1.w16, w.pw1.b, w.dw_w, w.dw_b, w.pw2.w16, w.pw2.b,
+                                  a_out ? next_ln->ln_g : nullptr, a_out ? next_ln->ln_b : nullptr, a_out, B, Tn, d, w.ksize,
+                                  c.stream);
   }
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
@@ -534,23 +539,37 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
 }
 
 // y = ConformerBlock(x)      (block.py:17-29).  xw is an fp32 [M,d] working buffer; y may alias xw.
+// bf16 fast path: the producers of an FFN's input also emit its LayerNorm-ed bf16 copy, so the fused FFN kernel starts
+// from one TMA load: a1_pre = LN(x; ffn_1) from the previous block's final LayerNorm (nullable); when next_ffn1 is
+// given, this block's final LayerNorm writes LN(y; next_ffn1) into a1_next for the block that follows.
 template <typename TA>
 int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, const TA* pos_proj, int ldp, const FactPos* fp,
-              const uint8_t* key_pad, int B, int Tn, int d, int H) {
+              const uint8_t* key_pad, int B, int Tn, int d, int H, const bf16* a1_pre = nullptr,
+              const FfnW* next_ffn1 = nullptr, bf16* a1_next = nullptr) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
-  CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d));
+  CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d, a1_pre));
   CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, fp, key_pad, xw, xw, B, Tn, d, H)));
   // the fused conv-module kernel reads a time halo, so it writes a second residual buffer instead of updating in place
   const size_t mark = c.ws.mark();
   float* xc = xw;
+  bf16* a2 = nullptr;                                   // LN(conv output; ffn_2) from the fused conv module's epilogue
   if (conv_fast_ok(static_cast<const TA*>(nullptr), w.conv, d)) {
     xc = ws_take<float>(c, M * d);
     WS_CHECK(xc);
+    if (ffn_fast_ok(static_cast<const TA*>(nullptr), d)) {
+      a2 = ws_take<bf16>(c, M * d);
+      WS_CHECK(a2);
+    }
   }
-  CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xc, B, Tn, d));
-  CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xc, xc, 0.5f, xc, M, d));
+  CFM_TRY(conv_fwd<TA>(c, w.conv, xw, xw, xc, B, Tn, d, &w.ffn2, a2));
+  CFM_TRY(ffn_fwd<TA>(c, w.ffn2, xc, xc, 0.5f, xc, M, d, a2));
   if (!c.ws.measuring()) {
-    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4), layer_norm<float>(xc, w.ln_g, w.ln_b, y, M, d, c.stream));
+    if (a1_next != nullptr && next_ffn1 != nullptr) {
+      KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4) + 2.0 * M * d,
+           layer_norm_dual(xc, w.ln_g, w.ln_b, y, next_ffn1->ln_g, next_ffn1->ln_b, a1_next, M, d, c.stream));
+    } else {
+      KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 4), layer_norm<float>(xc, w.ln_g, w.ln_b, y, M, d, c.stream));
+    }
   }
   c.ws.reset(mark);
   return 0;
@@ -680,10 +699,18 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
         }
       }
       const int L = cfg.n_blocks;
+      // LN(block output; next block's ffn_1) travels between blocks as bf16 (fused-FFN fast path only)
+      bf16* a1 = nullptr;
+      if (L > 1 && ffn_fast_ok(static_cast<const TA*>(nullptr), d)) {
+        a1 = ws_take<bf16>(c, M * d);
+        WS_CHECK(a1);
+      }
       for (int i = 0; i < L; ++i) {
         float* dst = (i == L - 1) ? y : xw;
+        const bool to_next = a1 != nullptr && i + 1 < L;
         CFM_TRY(block_fwd<TA>(c, blocks[i], xw, xw, dst, fact ? nullptr : pp + static_cast<int64_t>(i) * d, L * d, fact ? &fp : nullptr,
-                              kp, B, T2, d, H));
+                              kp, B, T2, d, H, (a1 != nullptr && i > 0) ? a1 : nullptr, to_next ? &blocks[i + 1].ffn1 : nullptr,
+                              to_next ? a1 : nullptr));
       }
       if (L == 0 && !c.ws.measuring())
         CFM_CUDA_OK(cudaMemcpyAsync(y, xw, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));

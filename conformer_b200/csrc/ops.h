@@ -45,8 +45,11 @@ int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* b
 //   x[M,256] += scale * (swish(LN(x_in) W1^T + b1) W2^T + b2)        (ffn.py:15-23, block.py:19,25)
 // LayerNorm in the prologue, the [M,1024] hidden activation never leaves the SM.  x_in may alias x (the
 // block's in-place residual update); x must already hold the residual (or zeros).
-int ffn_fused_bf16(const float* x_in, float* x, const float* ln_g, const float* ln_b, const bf16* W1, const float* b1,
-                   const bf16* W2, const float* b2, float scale, int M, int d, int num_sms, cudaStream_t stream);
+// a_pre (nullable): LN(x_in) already normalised as bf16 [M,d] by the producer of x_in (layer_norm_dual or the fused conv
+// module); the kernel then TMA-loads it instead of reading and normalising x_in.
+int ffn_fused_bf16(const float* x_in, const bf16* a_pre, float* x, const float* ln_g, const float* ln_b, const bf16* W1,
+                   const float* b1, const bf16* W2, const float* b2, float scale, int M, int d, int num_sms,
+                   cudaStream_t stream);
 bool ffn_fused_supported(int d);
 
 // LayerNorm-fused projection (d_model = 256, N % 256 == 0): out = epi(LN(x) W^T + b), bf16 out.
@@ -61,13 +64,18 @@ bool ln_gemm_supported(int d, int N);
 // not alias x (tiles read a 15-frame halo of their neighbours).
 int conv_module_fused_bf16(const float* x, const float* res, float* out, const float* ln_g, const float* ln_b,
                            const bf16* W1p, const float* b1p, const float* dw_w, const float* dw_b, const bf16* W2,
-                           const float* b2, int B, int Tn, int d, int ksize, cudaStream_t stream);
+                           const float* b2, const float* ln2_g, const float* ln2_b, bf16* a_out /*nullable: LN(out; ln2) as bf16*/,
+                           int B, int Tn, int d, int ksize, cudaStream_t stream);
 bool conv_module_fused_supported(int d, int ksize);
 
 // ---- normalisation / elementwise ---------------------------------------------------------------
 template <typename TOut>
 int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,
                cudaStream_t stream);
+// y = LN(x; g1, b1) (fp32) and a = LN(y; g2, b2) (bf16) in one pass (d = 256): block-final LayerNorm plus the next
+// block's ffn_1 LayerNorm
+int layer_norm_dual(const float* x, const float* g1, const float* b1, float* y, const float* g2, const float* b2, bf16* a,
+                    int64_t rows, int d, cudaStream_t stream);
 
 // depthwise conv over time fused with GLU (on load), folded BatchNorm and Swish.
 // u [B,T,2d] (pointwise_conv_1 output, value half then gate half), w [ksize][d] (BN-folded,
