@@ -344,6 +344,18 @@ def main():
     else:
         roof = {"kernel": dom_name, "bound": "hbm", "achieved": dom.get("gbs"), "peak": peaks["hbm"], "unit": "GB/s",
                 "frac": (dom.get("gbs") or 0.0) / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} hbm_gbs"}
+    # roofline.traffic: DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+    try:
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        names = {"ffn_fused": ["ffn_fused_kernel"], "attention": ["rel_attention_fact_kernel", "rel_attention_tc_kernel"],
+                 "conv_fused": ["conv_module_fused_kernel"], "gemm_tcgen05": ["gemm_tc_kernel"], "conv1": ["conv1_tc_kernel"]}
+        for k, e in tr["kernels"].items():
+            if any(k.startswith(n) for n in names.get(dom_name, [])):
+                roof["traffic"] = e["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/ncu_traffic.json (" + os.path.basename(tr["source"]) + "): " + k
+                break
+    except (OSError, ValueError, KeyError):
+        pass
     if "dwconv" in kernels and "gbs" in kernels["dwconv"]:
         kernels["dwconv"]["hbm_frac"] = kernels["dwconv"]["gbs"] / peaks["hbm"]
     for n in ("gemm_tcgen05", "attention", "ffn_fused", "ln_gemm"):

@@ -17,6 +17,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",
          "-diag-suppress", "177,550"]
+if os.environ.get("CFM_DEBUG_MBAR") == "1":          # debug: mbarrier waits time out and report (common.cuh)
+    FLAGS.append("-DCFM_MBAR_TIMEOUT")
 
 
 def _sources():

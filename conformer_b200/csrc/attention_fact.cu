@@ -117,7 +117,8 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   uint64_t* ab_full = q_full + 1;
   uint64_t* qp_full = ab_full + 1;
   uint64_t* rot_full = qp_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rot_full + 1);
+  uint64_t* o_final = rot_full + 1;     // completes once, after the last P.V (a parity wait on o_done could alias)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * BQ;
@@ -146,6 +147,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     mbar_init(ab_full, 1);
     mbar_init(qp_full, NUM_SM_WARPS);
     mbar_init(rot_full, 1);
+    mbar_init(o_final, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -257,6 +259,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
                           (j | k) != 0 ? 1u : 0u);
         tc_commit(o_done);
         tc_commit(&v_empty[s]);
+        if (j == ntiles - 1) tc_commit(o_final);
       }
       __syncwarp();
     }
@@ -472,9 +475,12 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       tmem_st_wait();
       l_part += psum;
       tc_fence_before();
-      // The warps run decoupled and S_{j+1} is issued before P_j is awaited, so this warp may be a whole tile ahead of the
-      // slowest one: its arrival for tile j must not be counted in the still-open phase of tile j-1.
-      if (j > 0) mbar_wait(p_full, (j - 1) & 1);
+      // Consumer -> producer handshake.  S_{j+1} is issued BEFORE the MMA warp waits for P_j, so without it the softmax
+      // warps could complete the p_full phases of tiles j and j+1 while the MMA warp is still between its issue loop and
+      // its poll - its parity wait would then alias and never return (seen once per ~10^5 CTAs).  P.V of tile j-1
+      // complete implies the MMA warp has consumed phase j-1; it was issued a whole tile ago, so this wait is free, and
+      // every warp follows the o_done phases one by one (no aliasing in move_reference either).
+      if (j > 0) mbar_wait(o_done, (j - 1) & 1);
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
       if (warp == 4) FTRACE(11 + 4 * j);
@@ -483,10 +489,9 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     //      this thread writes 32 of the row's 64 output columns
     xmax[grp * BQ + row] = m_ref;
     xsum[grp * BQ + row] = l_part;
-    // (two waits: P.V of tile ntiles-3 is known complete - S of the last tile was issued after it - so the parity wait for
-    // tile ntiles-2 cannot alias, and after it neither can the one for the last tile)
-    if (ntiles >= 2) mbar_wait(o_done, (ntiles - 2) & 1);
-    mbar_wait(o_done, (ntiles - 1) & 1);
+    // (o_done cannot be used here: this warp has not followed its phases, and a parity wait issued after BOTH of the last
+    // two P.V commits would wait for a phase that never completes)
+    mbar_wait(o_final, 0);
     tc_fence_after();
     uint32_t o0[32], o1[32];
     tmem_ld_32x32(tlane + TM_O + 32 * grp, o0);

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #include <string>
 
@@ -118,10 +119,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef CFM_MBAR_TIMEOUT
+// Debug build (CFM_DEBUG_MBAR=1 python -m conformer_b200.build): a wait that lasts more than ~1 s reports who was waiting
+// for what and gives up, so that a deadlock becomes a diagnosable wrong result instead of a hung device.
+static __device__ __noinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > (1ll << 31)) {
+      if ((threadIdx.x & 31) == 0)
+        printf("mbar timeout: block (%d,%d,%d) warp %d barrier smem 0x%x parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x >> 5, smem_u32(bar), parity);
+      return;
+    }
+  }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+#endif
 
 // TMA tiled loads, completion on an mbarrier (bytes).  Coordinates innermost first.
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {

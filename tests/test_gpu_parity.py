@@ -347,3 +347,29 @@ def test_mhsa_module_bf16_ln_fused_vs_oracle(B, T):
     got = m(x.to(DEV), pos[None].expand(B, -1, -1).to(DEV), pad[:, None, None, :].to(DEV))
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     assert rel < 2e-2, rel
+
+
+@pytest.mark.timeout(240)
+def test_repeated_two_stream_forwards_do_not_hang_or_drift():
+    """Regression for a barrier-protocol deadlock seen once per ~1e5 attention CTAs (softmax warps lapping the MMA warp):
+    many Conformer-M forwards on two streams must all complete and give the same result (up to the order of the L2
+    reduction adds of the residual stream)."""
+    cfg = cb.EncoderConfig(80, 4, 256, 4, 31)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size),
+                synth_encoder_state_dict(cfg, 5)).set_compute("bf16")
+    from conformer_b200.synth import synth_logmel
+    x = synth_logmel(32, 80, 1501, seed=9).to(DEV)
+    lengths = torch.full((32,), 1501, dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    ref = None
+    with torch.no_grad():
+        for i in range(600):
+            with torch.cuda.stream(streams[i & 1]):
+                y, _ = enc(x, lengths)
+            if i % 100 == 99:
+                torch.cuda.synchronize()
+                assert torch.isfinite(y).all()
+                s = y.float().abs().sum().item()
+                ref = s if ref is None else ref
+                assert abs(s - ref) <= 1e-3 * abs(ref), (i, s, ref)
+    torch.cuda.synchronize()

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Summarise ncu output (run here, no GPU needed):
-    python tools/ncu_summary.py gpurun_out/<tag>_launches.csv gpurun_out/<tag>_full.ncu-rep > profiles/<name>.md
-launch list -> per-kernel launch counts / total time / share; full capture -> key counters per kernel."""
+    python tools/ncu_summary.py gpurun_out/<tag>_launches.csv gpurun_out/<tag>_full.ncu-rep [profiles/ncu_traffic.json] > profiles/<name>.md
+launch list -> per-kernel launch counts / total time / share; full capture -> key counters per kernel; the optional third
+argument receives {kernel: DRAM bytes read + written per launch}, which bench.py reports as roofline.traffic."""
 import collections
 import csv
 import io
@@ -63,8 +64,17 @@ def full(path):
     idx = {h: i for i, h in enumerate(hdr)}
     print("\n## `ncu --set full` capture (one window of consecutive launches inside a step)\n")
     seen = set()
+    traffic = {}
+    to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     for r in rows[2:]:
         k = short(r[idx["Kernel Name"]])
+        try:
+            t = sum(float(r[idx[m]].replace(",", "")) * to_bytes[units[idx[m]]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            e = traffic.setdefault(k, {"dram_bytes_per_launch": 0.0, "launches": 0})
+            e["dram_bytes_per_launch"] += t
+            e["launches"] += 1
+        except (KeyError, ValueError):
+            pass
         if k in seen:
             continue
         seen.add(k)
@@ -73,9 +83,16 @@ def full(path):
             if m in idx:
                 print(f"* {label}: {r[idx[m]]} {units[idx[m]]}")
         print()
+    for e in traffic.values():
+        e["dram_bytes_per_launch"] /= max(1, e["launches"])
+    return traffic
 
 
 if __name__ == "__main__":
     launches(sys.argv[1])
     if len(sys.argv) > 2:
-        full(sys.argv[2])
+        tr = full(sys.argv[2])
+        if len(sys.argv) > 3:
+            import json
+            json.dump({"source": sys.argv[2], "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the captured launches of each kernel (ncu --set full, cold caches)",
+                       "kernels": tr}, open(sys.argv[3], "w"), indent=1)
