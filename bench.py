@@ -347,12 +347,13 @@ def main():
     # roofline.traffic: DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
     try:
         tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
-        names = {"ffn_fused": ["ffn_fused_kernel"], "attention": ["rel_attention_fact_kernel", "rel_attention_tc_kernel"],
+        names = {"ffn_fused": ["ffn_fused_kernel<1>", "ffn_fused_kernel"], "attention": ["rel_attention_fact_kernel", "rel_attention_tc_kernel"],
                  "conv_fused": ["conv_module_fused_kernel"], "gemm_tcgen05": ["gemm_tc_kernel"], "conv1": ["conv1_tc_kernel"]}
-        for k, e in tr["kernels"].items():
-            if any(k.startswith(n) for n in names.get(dom_name, [])):
-                roof["traffic"] = e["dram_bytes_per_launch"]
-                roof["traffic_source"] = "profiles/ncu_traffic.json (" + os.path.basename(tr["source"]) + "): " + k
+        for n in names.get(dom_name, []):
+            hit = [k for k in tr["kernels"] if k.startswith(n)]
+            if hit:
+                roof["traffic"] = tr["kernels"][hit[0]]["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/ncu_traffic.json (" + os.path.basename(tr["source"]) + "): " + hit[0]
                 break
     except (OSError, ValueError, KeyError):
         pass
