@@ -7,10 +7,13 @@
 //              straight into the 128B-swizzled K-major layout the MMA descriptors expect;
 //   main loop  the 1024 hidden units are processed in 8 chunks of 128:
 //                GEMM1(c): acc1[c&1] (TMEM, 128 cols)  = LN(x) . W1[c]^T          (K = 256)
-//                epilogue: hidden = bf16(swish(acc1 + b1)) -> shared memory, again in MMA layout
-//                GEMM2(c): acc2 (TMEM, 256 cols)      += hidden . W2[:, c]^T      (K = 128)
+//                epilogue: hidden = bf16(swish(acc1 + b1)) written IN PLACE over acc1[c&1] in tensor memory
+//                GEMM2(c): acc2 (TMEM, 256 cols)      += hidden . W2[:, c]^T      (K = 128, A operand from TMEM)
 //              software-pipelined (GEMM1(c+1) is issued before GEMM2(c)) so the tensor pipe keeps working
-//              while the 16 epilogue warps run the Swish; W1/W2 tiles stream through a TMA/mbarrier ring;
+//              while the 16 epilogue warps run the Swish; W1/W2 tiles stream through a TMA/mbarrier ring.
+//              The loop is bound by the shared-memory port (128 B/clk): per chunk the MMAs read 128 KB (GEMM1, both
+//              operands) + 64 KB (GEMM2, W2 only) and TMA writes 128 KB of weights = 2560 clk against 2048 clk of
+//              tensor time; with the hidden tile in shared memory it was 3072 clk (measured 1.56 us per chunk);
 //   epilogue   scale*(acc2 + b2) is staged (aliasing the now-dead operand buffers) and leaves through a TMA
 //              reduction store, i.e. the residual add is executed by the L2 (x is never re-read).
 // TMEM: 2 x 128 (acc1 double buffer) + 256 (acc2) = 512 columns.
@@ -87,16 +90,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* xs = smem;
-  uint8_t* hs = xs + XS_BYTES;                               // two hidden buffers
+  uint8_t* hs = xs + XS_BYTES;                               // (with xs: staging of the output tile only; the hidden tile lives in TMEM)
   uint8_t* ring = hs + 2 * HS_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* xs_full = empty_bar + STAGES;
   uint64_t* acc1_full = xs_full + 1;      // [2]
-  uint64_t* acc1_empty = acc1_full + 2;   // [2]
-  uint64_t* hs_full = acc1_empty + 2;     // [2]
-  uint64_t* hs_empty = hs_full + 2;       // [2]
-  uint64_t* acc2_full = hs_empty + 2;
+  uint64_t* hs_full = acc1_full + 2;      // [2]
+  uint64_t* acc2_full = hs_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -115,9 +116,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     mbar_init(xs_full, PRE ? 1 : NUM_EPI_WARPS);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc1_full[s], 1);
-      mbar_init(&acc1_empty[s], NUM_EPI_WARPS);
       mbar_init(&hs_full[s], NUM_EPI_WARPS);
-      mbar_init(&hs_empty[s], 1);
     }
     mbar_init(acc2_full, 1);
     fence_mbar_init();
@@ -174,11 +173,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     unsigned long long w_acc1 = 0, w_full = 0, w_hs = 0, w_xs = 0, t_begin = ffn_time_ns();
     const bool tr = p.trace != nullptr && blockIdx.x == 0;
     auto gemm1 = [&]() {
+      // acc1[b] last held the hidden tile of the chunk two back: its GEMM2 was issued before this GEMM1 and the tensor
+      // pipe executes in issue order, and that GEMM2 was itself issued after the Swish warps had finished with the
+      // buffer (hs_full) - no further handshake is needed
       const int b = gc1 & 1;
-      unsigned long long t0 = tr ? ffn_time_ns() : 0;
-      mbar_wait(&acc1_empty[b], ((gc1 >> 1) & 1) ^ 1);
-      if (tr) w_acc1 += ffn_time_ns() - t0;
-      tc_fence_after();
+      unsigned long long t0 = 0;
       for (int s2 = 0; s2 < 2; ++s2, ++it) {
         const int s = it % STAGES;
         t0 = tr ? ffn_time_ns() : 0;
@@ -214,15 +213,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         if (tr) w_full += ffn_time_ns() - t0;
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t sa = umma_desc_lo(smem_u32(hs + b * HS_BYTES + s2 * (BM * 128)));
+          // hidden units 16*kg .. +15 of the chunk (kg = 4*s2 + k): bf16 pairs in columns 32*(kg/2) + 8*(kg%2) .. +7 of acc1[b]
+          const uint32_t ta = tmem_base + b * HC + s2 * 64;
           const uint32_t sb = umma_desc_lo(smem_u32(ring + s * STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tm_acc2, sa + k * 2, sb + k * 2, idesc2, (!first || (s2 | k) != 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            tc_mma_f16_ts(tm_acc2, ta + 32 * (k >> 1) + 8 * (k & 1), sb + k * 2, idesc2, (!first || (s2 | k) != 0) ? 1u : 0u);
           tc_commit(&empty_bar[s]);
-          if (s2 == 1) {
-            tc_commit(&hs_empty[b]);
-            if (last) tc_commit(acc2_full);
-          }
+          if (s2 == 1 && last) tc_commit(acc2_full);
         }
         __syncwarp();
       }
@@ -317,11 +315,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       mbar_wait(&acc1_full[b], (gc >> 1) & 1);
       tc_fence_after();
       uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32, r);
+      const uint32_t t_acc1 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32;
+      tmem_ld_32x32(t_acc1, r);
       tmem_ld_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc1_empty[b]);
       float v[32];
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -331,18 +327,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         v[g * 4 + 2] = swish_tanh(__uint_as_float(r[g * 4 + 2]) + b4.z);
         v[g * 4 + 3] = swish_tanh(__uint_as_float(r[g * 4 + 3]) + b4.w);
       }
-      mbar_wait(&hs_empty[b], ((gc >> 1) & 1) ^ 1);            // the GEMM2 two chunks back has finished reading this buffer
-      // hidden column cgrp*32 .. +31 of the chunk -> k-block cgrp/2, chunks (cgrp&1)*4 .. +3
-      uint8_t* dst = hs + b * HS_BYTES + (cgrp >> 1) * (BM * 128) + row * 128;
-      const int j0 = (cgrp & 1) * 4;
+      // hidden units cgrp*32 .. +31 of the chunk, as bf16 pairs, over the first 16 of the 32 accumulator columns this
+      // thread has just read (only this thread touches them): the TMEM-resident A operand of GEMM2
+      uint32_t pk[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 o;
-        o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-        o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-        *reinterpret_cast<uint4*>(dst + (((j0 + j) ^ sw) << 4)) = o;
-      }
-      fence_proxy_async();
+      for (int e = 0; e < 16; ++e) pk[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+      tmem_st_32x16(t_acc1, pk);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hs_full[b]);
     }
