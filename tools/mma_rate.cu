@@ -195,6 +195,16 @@ __global__ void __launch_bounds__(384, 1) mma_noise_kernel(long long* out, int b
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 32; k += 4) acc ^= r[k];
+      } else if (NOISE == 4) {                 // arithmetic only: ex2 + fma chains, as the softmax warps run
+        float a = __uint_as_float(0x3f800000u + acc), b = 0.5f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          float e;
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a - b));
+          b = fmaf(e, 0.25f, b);
+          a = fmaf(a, 0.999f, e);
+        }
+        acc += __float_as_uint(a + b);
       } else if (NOISE == 3) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) r[i] = acc + i;
@@ -296,6 +306,55 @@ void run_rw(int nwarps, long long* d_out) {
          e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+// P.V form: B operand MN-major ([16 keys x 64] rows per K step, 2048 B apart), N = 64, A in TMEM
+__global__ void __launch_bounds__(128, 1) mma_bmn_kernel(long long* out, int iters, uint32_t tmem_zero) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* b_s = smem;                 // V tile [64 keys x 64] bf16 (8 KB)
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 8192);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 8192 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) tmem_alloc(slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_whole_sm(slot) + tmem_zero;
+  if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16_bmn(128, 64);
+    const uint32_t sb = umma_desc_lo(smem_u32(b_s));
+    long long t0 = 0, t1 = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+      t0 = clock64();
+      if (elect_one()) {
+        for (int i = 0; i < iters; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tc_mma_f16_ts(tmem + 128, tmem + 256 + k * 8, sb + k * (2048 >> 4), idesc, 1u);
+        }
+        tc_commit(bar);
+      }
+      __syncwarp();
+      mbar_wait(bar, rep & 1);
+      t1 = clock64();
+    }
+    if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+void run_bmn(long long* d_out) {
+  const int iters = 256, smem = 1024 + 8192 + 64;
+  mma_bmn_kernel<<<1, 128, smem>>>(d_out, iters, 0u);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long clk = 0;
+  cudaMemcpy(&clk, d_out, 8, cudaMemcpyDeviceToHost);
+  printf("N=64  A tmem, B MN-major (P.V form)          : %7.1f clk per MMA (floor 32)%s\n", static_cast<double>(clk) / (iters * 4),
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 template <int N, bool A_TMEM, int NACC>
 void run(const char* name, int grid, long long* d_out) {
   const int iters = 256, smem = 1024 + 16384 + 32768 + 64;
@@ -319,9 +378,11 @@ int main() {
   run_noise<true, 1>("A tmem, 8 warps tcgen05.ld x32", d_out);
   run_noise<true, 3>("A tmem, 8 warps tcgen05.st x32", d_out);
   run_noise<true, 2>("A tmem, 8 warps ld.shared (8 x 16 B)", d_out);
+  run_noise<true, 4>("A tmem, 8 warps ex2 + fma chains", d_out);
   run_noise<false, 0>("A smem, no noise", d_out);
   run_noise<false, 1>("A smem, 8 warps tcgen05.ld x32", d_out);
   run_noise<false, 2>("A smem, 8 warps ld.shared (8 x 16 B)", d_out);
+  run_bmn(d_out);
   run_batch<64>(1, d_out);
   run_batch<64>(148, d_out);
   run_batch<128>(1, d_out);
