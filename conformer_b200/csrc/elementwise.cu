@@ -75,39 +75,57 @@ __global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* __res
                                                               const float* __restrict__ b1, float* __restrict__ y,
                                                               const float* __restrict__ g2, const float* __restrict__ b2,
                                                               bf16* __restrict__ a, int64_t rows) {
-  constexpr int D = 256;
+  constexpr int D = 256, RPW = 2;                                  // rows per warp: both rows' loads are in flight together
   const int lane = threadIdx.x & 31;
-  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * D) + 2 * lane;    // lane owns columns 8*lane .. 8*lane+7
-  float v[8];
-  {
-    const float4 p0 = xr[0], p1 = xr[1];
-    v[0] = p0.x; v[1] = p0.y; v[2] = p0.z; v[3] = p0.w; v[4] = p1.x; v[5] = p1.y; v[6] = p1.z; v[7] = p1.w;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
+  float v[RPW][8];                                                 // lane owns columns 8*lane .. 8*lane+7
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    if (row0 + r < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (row0 + r) * D) + 2 * lane;
+      const float4 p0 = xr[0], p1 = xr[1];
+      v[r][0] = p0.x; v[r][1] = p0.y; v[r][2] = p0.z; v[r][3] = p0.w; v[r][4] = p1.x; v[r][5] = p1.y; v[r][6] = p1.z; v[r][7] = p1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[r][i] = 0.f;
+    }
   }
-  auto normalise = [&](const float* gamma, const float* beta) {
+  float gg[2][8], be[2][8];
+  {
+    const float* gs[2] = {g1, g2};
+    const float* bs[2] = {b1, b2};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 ga = __ldg(reinterpret_cast<const float4*>(gs[k]) + 2 * lane), gb = __ldg(reinterpret_cast<const float4*>(gs[k]) + 2 * lane + 1);
+      const float4 ba = __ldg(reinterpret_cast<const float4*>(bs[k]) + 2 * lane), bb = __ldg(reinterpret_cast<const float4*>(bs[k]) + 2 * lane + 1);
+      gg[k][0] = ga.x; gg[k][1] = ga.y; gg[k][2] = ga.z; gg[k][3] = ga.w; gg[k][4] = gb.x; gg[k][5] = gb.y; gg[k][6] = gb.z; gg[k][7] = gb.w;
+      be[k][0] = ba.x; be[k][1] = ba.y; be[k][2] = ba.z; be[k][3] = ba.w; be[k][4] = bb.x; be[k][5] = bb.y; be[k][6] = bb.z; be[k][7] = bb.w;
+    }
+  }
+  auto normalise = [&](float (&w)[8], int k) {
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s += v[i];
+    for (int i = 0; i < 8; ++i) s += w[i];
     const float mean = warp_sum(s) * (1.0f / D);
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { v[i] -= mean; q += v[i] * v[i]; }
+    for (int i = 0; i < 8; ++i) { w[i] -= mean; q += w[i] * w[i]; }
     const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
-    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane), gb = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * lane + 1);
-    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta) + 2 * lane), bb = __ldg(reinterpret_cast<const float4*>(beta) + 2 * lane + 1);
-    const float gg[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
-    const float be[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = v[i] * rstd * gg[i] + be[i];
+    for (int i = 0; i < 8; ++i) w[i] = w[i] * rstd * gg[k][i] + be[k][i];
   };
-  normalise(g1, b1);
-  float4* yr = reinterpret_cast<float4*>(y + row * D) + 2 * lane;
-  yr[0] = make_float4(v[0], v[1], v[2], v[3]);
-  yr[1] = make_float4(v[4], v[5], v[6], v[7]);
-  normalise(g2, b2);
-  reinterpret_cast<uint4*>(a + row * D)[lane] =
-      make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    if (row0 + r >= rows) break;                                   // warp-uniform
+    normalise(v[r], 0);
+    float4* yr = reinterpret_cast<float4*>(y + (row0 + r) * D) + 2 * lane;
+    yr[0] = make_float4(v[r][0], v[r][1], v[r][2], v[r][3]);
+    yr[1] = make_float4(v[r][4], v[r][5], v[r][6], v[r][7]);
+    normalise(v[r], 1);
+    reinterpret_cast<uint4*>(a + (row0 + r) * D)[lane] = make_uint4(pack_bf16x2(v[r][0], v[r][1]), pack_bf16x2(v[r][2], v[r][3]),
+                                                                    pack_bf16x2(v[r][4], v[r][5]), pack_bf16x2(v[r][6], v[r][7]));
+  }
 }
 
 template <typename T>
@@ -226,7 +244,7 @@ int layer_norm_dual(const float* x, const float* g1, const float* b1, float* y, 
                 reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(g2) |
                 reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "layer_norm_dual operands must be 16-byte aligned");
   if (rows <= 0) return 0;
-  layer_norm_dual_kernel<<<blocks_for(rows, 8), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
+  layer_norm_dual_kernel<<<blocks_for(rows, 16), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
