@@ -6,10 +6,10 @@ any forward does.
 """
 from .modules import (GLU, Conformer, ConformerBlock, ConvolutionModule, ConvolutionSubsampling, Decoder, Encoder,
                       FeedForwardModule, MultiHeadSelfAttentionModule, RelativeMultiHeadAttention,
-                      RelativePositionalEncoding, Swish, generate_padding_mask)
+                      RelativePositionalEncoding, Swish, generate_padding_mask, greedy_ctc_decode)
 from .synth import CONFORMER_L, CONFORMER_M, CONFORMER_S, EncoderConfig
 
 __all__ = ["GLU", "Conformer", "ConformerBlock", "ConvolutionModule", "ConvolutionSubsampling", "Decoder", "Encoder",
            "FeedForwardModule", "MultiHeadSelfAttentionModule", "RelativeMultiHeadAttention",
-           "RelativePositionalEncoding", "Swish", "generate_padding_mask", "EncoderConfig", "CONFORMER_S",
+           "RelativePositionalEncoding", "Swish", "generate_padding_mask", "greedy_ctc_decode", "EncoderConfig", "CONFORMER_S",
            "CONFORMER_M", "CONFORMER_L"]

@@ -70,6 +70,12 @@ int cfm_padding_mask(const int64_t* lengths, int32_t batch, int32_t max_len, uin
   return lengths_and_mask(lengths, nullptr, valid, batch, max_len, false, true, S(stream));
 }
 
+int cfm_ctc_greedy_decode(const float* logits, int32_t batch, int32_t T, int32_t vocab, int32_t pad_id, int32_t unk_id,
+                          int32_t* tokens, int32_t* counts, void* stream) {
+  CFM_REQUIRE(logits != nullptr && tokens != nullptr && counts != nullptr, "bad CTC decode arguments");
+  return ctc_greedy_decode(logits, batch, T, vocab, pad_id, unk_id, tokens, counts, S(stream));
+}
+
 int cfm_rel_pos_encoding(const float* div_term, int32_t batch, int32_t T, int32_t d_model, float* out, void* stream) {
   CFM_REQUIRE(div_term != nullptr && out != nullptr && batch > 0, "bad positional-encoding arguments");
   CFM_TRY(rel_pos_table<float>(div_term, out, T, d_model, S(stream)));

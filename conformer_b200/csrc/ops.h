@@ -68,6 +68,11 @@ int conv_module_fused_bf16(const float* x, const float* res, float* out, const f
                            int B, int Tn, int d, int ksize, cudaStream_t stream);
 bool conv_module_fused_supported(int d, int ksize);
 
+// ---- greedy CTC decode (processing/processor.py:301-328, id level; ctc.cu) ----------------------
+// tokens int32 [B,T]: collapsed ids, -1 after counts[b] entries
+int ctc_greedy_decode(const float* logits /*[B,T,V]*/, int B, int T, int V, int pad_id, int unk_id, int32_t* tokens,
+                      int32_t* counts, cudaStream_t stream);
+
 // ---- normalisation / elementwise ---------------------------------------------------------------
 template <typename TOut>
 int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, int64_t rows, int d,

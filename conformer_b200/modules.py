@@ -92,6 +92,25 @@ def generate_padding_mask(lengths: torch.Tensor, max_length: Optional[int] = Non
     return out.view(torch.bool)
 
 
+def greedy_ctc_decode(logits: torch.Tensor, pad_id: int = 0, unk_id: Optional[int] = None):
+    """processing/processor.py:301-328 at token-id level, on the device: argmax over the vocabulary, skip pad (the CTC
+    blank) and unk without resetting the previous id, collapse repeats; every row over the full padded length.
+    logits [B, T, V] (CUDA).  Returns (tokens int32 [B, T] padded with -1, counts int32 [B]); `unk_id` defaults to the
+    last vocabulary entry (processor.py:114)."""
+    if not logits.is_cuda:
+        raise RuntimeError("conformer_b200: logits must be a CUDA tensor (there is no CPU path)")
+    if logits.dim() != 3:
+        raise ValueError("logits must be [batch, frames, vocab]")
+    B, T, V = logits.shape
+    lg = logits.detach().to(torch.float32).contiguous()
+    tokens = torch.empty((B, T), device=logits.device, dtype=torch.int32)
+    counts = torch.zeros((B,), device=logits.device, dtype=torch.int32)
+    if B and T:
+        check(lib().cfm_ctc_greedy_decode(lg.data_ptr(), B, T, V, int(pad_id), int(V - 1 if unk_id is None else unk_id),
+                                          tokens.data_ptr(), counts.data_ptr(), _stream()))
+    return tokens, counts
+
+
 # =============================================================================== native handle plumbing
 class _Native(nn.Module):
     """Owns the cfm_module_t handles (one per compute mode) of a mirror module."""

@@ -88,6 +88,14 @@ CFM_API int cfm_padding_mask(const int64_t* lengths, int32_t batch, int32_t max_
 /* RelativePositionalEncoding.forward (model/utils/position.py:11-28): out fp32 [batch, 2T-1, d];
  * div_term fp32 [d/2] (the module's non-trainable parameter).  batch >= 1 replicates like :26. */
 CFM_API int cfm_rel_pos_encoding(const float* div_term, int32_t batch, int32_t T, int32_t d_model, float* out, void* stream);
+/* ConformerProcessor.greedy_decode at token-id level (processing/processor.py:301-328), the step right after the
+ * path: ids = argmax over the vocabulary (first maximum), frames whose id is pad_id (the CTC blank,
+ * <PAD> = 0, processor.py:114) or unk_id (last vocabulary entry) are skipped WITHOUT resetting the previous id, an id is
+ * emitted when it differs from the previously emitted one.  Every row is decoded over the full padded length T, as the
+ * reference does.  logits fp32 [batch, T, vocab]; tokens int32 [batch, T] receives the collapsed ids followed by -1;
+ * counts int32 [batch] their number. */
+CFM_API int cfm_ctc_greedy_decode(const float* logits, int32_t batch, int32_t T, int32_t vocab, int32_t pad_id,
+                                  int32_t unk_id, int32_t* tokens, int32_t* counts, void* stream);
 /* Swish.forward / GLU.forward over the last dimension (model/utils/activation.py:4-17) */
 CFM_API int cfm_swish(const float* x, float* y, int64_t numel, void* stream);
 CFM_API int cfm_glu(const float* x, float* y, int64_t rows, int32_t d_out, void* stream);

@@ -144,6 +144,9 @@ def test_greedy_ctc_tokens_bit_exact_fp32():
     toks = O.greedy_ctc_batch(logits.cpu(), 0, c["vocab"] - 1)
     want = [[int(t) for t in row if t >= 0] for row in gold["tokens"]]
     assert toks == want
+    # the same through the device decode (no logits.cpu() round trip)
+    tok_dev, cnt_dev = cb.greedy_ctc_decode(logits)
+    assert [tok_dev[b, :cnt_dev[b]].tolist() for b in range(tok_dev.shape[0])] == want
     safe = gold["margin"] > 1e-3
     assert torch.equal(logits.cpu().argmax(-1)[safe], gold["ids"][safe])
 
@@ -373,3 +376,38 @@ def test_repeated_two_stream_forwards_do_not_hang_or_drift():
                 ref = s if ref is None else ref
                 assert abs(s - ref) <= 1e-3 * abs(ref), (i, s, ref)
     torch.cuda.synchronize()
+
+
+def _tokens_to_lists(tokens, counts):
+    tokens, counts = tokens.cpu(), counts.cpu()
+    for b in range(tokens.shape[0]):
+        assert (tokens[b, counts[b]:] == -1).all()
+    return [tokens[b, :counts[b]].tolist() for b in range(tokens.shape[0])]
+
+
+@pytest.mark.parametrize("B,T,V", [(1, 1, 5), (3, 33, 7), (4, 374, 370), (2, 1499, 370), (2, 64, 33), (5, 100, 2)])
+def test_greedy_ctc_decode_device_bit_exact(B, T, V):
+    """cfm_ctc_greedy_decode vs the oracle's restatement of processor.py:301-328: coarse logits force many argmax ties
+    (first maximum must win), long runs of pad / unk (skipped without resetting the previous id) and repeats."""
+    g = torch.Generator().manual_seed(1000 * B + T + V)
+    logits = torch.randint(0, 4, (B, T, V), generator=g).float()               # heavy ties
+    hot = torch.randint(0, V, (B, T), generator=g)
+    runs = torch.repeat_interleave(hot[:, ::3], 3, dim=1)[:, :T]                # repeated ids in runs of 3
+    boost = (torch.rand(B, T, generator=g) < 0.7).float() * 5.0
+    logits.scatter_add_(2, runs[..., None], boost[..., None])
+    got = _tokens_to_lists(*cb.greedy_ctc_decode(logits.to(DEV)))
+    want = O.greedy_ctc_batch(logits, 0, V - 1)
+    assert got == want
+    # explicit pad / unk ids
+    got2 = _tokens_to_lists(*cb.greedy_ctc_decode(logits.to(DEV), pad_id=1, unk_id=0))
+    assert got2 == O.greedy_ctc_batch(logits, 1, 0)
+
+
+def test_greedy_ctc_decode_device_matches_reference_golden_tokens():
+    """The reference Conformer's logits (golden fixture) decoded on the device give the reference's token ids."""
+    c = TOKEN_CASE
+    gold = golden("tokens")
+    logits = gold["logits"]
+    got = _tokens_to_lists(*cb.greedy_ctc_decode(logits.to(DEV)))
+    assert got == O.greedy_ctc_batch(logits, 0, c["vocab"] - 1)
+    assert got == [[int(t) for t in row if t >= 0] for row in gold["tokens"]]
