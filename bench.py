@@ -65,12 +65,13 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, None
 
     def start(self):
+        """Spawn the sampler (before the warm-up: nvidia-smi needs a few hundred ms to produce its first row)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -78,16 +79,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
+
+    def begin_timed(self):
+        """Call right before the first timed region: waits (bounded) for the sampler's first row."""
+        if self.proc is not None:
+            t0 = time.monotonic()
+            while not self.rows and time.monotonic() - t0 < 3.0:
+                time.sleep(0.01)
+        self.t_begin = time.monotonic()
 
     def stop(self):
+        """Call right after the last timed region; only rows sampled inside the timed regions are reported."""
+        t_end = time.monotonic()
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for t, r in self.rows if self.t_begin is not None and self.t_begin <= t <= t_end + 0.03]
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -277,18 +289,19 @@ def main():
             barrier()
             return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
 
-        warm = on_alternating_streams(step_dev)
-        for _ in range(2 * n_streams):
-            warm()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        warm = on_alternating_streams(step_dev)
+        for _ in range(2 * n_streams):
+            warm()
+        for _ in range(2):
+            step_e2e()
+        if rank == 0:
+            sampler.begin_timed()
         ms_dev_serial = timed(step_dev, args.steps)
         ms_dev = timed_two_streams(step_dev, args.steps)
         launches = enc.last_launch_count
-        clocks = sampler.stop() if rank == 0 else None
-        for _ in range(2):
-            step_e2e()
         ms_e2e_serial = timed(step_e2e, args.steps)
         # the same public call, issued the way a serving loop would: two streams and two pinned result buffers
         # alternate, so batch k's D2H / batch k+1's H2D overlap the other batch's kernels.  Every step still copies
@@ -304,6 +317,7 @@ def main():
         for _ in range(2 * n_streams):
             warm()
         ms_e2e = timed_two_streams(step_e2e_buffered, args.steps)
+        clocks = sampler.stop() if rank == 0 else None       # sampled across the four timed regions above
         # profiled pass (per-launch CUDA events on the launching stream), not part of the headline
         enc.profile(True)
         prof_steps = min(args.steps, 5)
