@@ -98,7 +98,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* acc1_full = xs_full + 1;      // [2]
   uint64_t* hs_full = acc1_full + 2;      // [2]
   uint64_t* acc2_full = hs_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_full + 1);
+  uint64_t* acc2_empty = acc2_full + 1;   // PRE: the epilogue warps have read acc2 of the previous item out of TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -119,6 +120,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       mbar_init(&hs_full[s], NUM_EPI_WARPS);
     }
     mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, NUM_EPI_WARPS);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -200,8 +202,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       }
       ++gc1;
     };
-    auto gemm2 = [&](bool first, bool last) {
+    auto gemm2 = [&](bool first, bool last, uint32_t n) {
       const int b = gc2 & 1;
+      if (PRE && first && n > 0) {                                 // the previous item's output has left the accumulator
+        mbar_wait(acc2_empty, (n - 1) & 1);
+        tc_fence_after();
+      }
       unsigned long long t0 = tr ? ffn_time_ns() : 0;
       mbar_wait(&hs_full[b], (gc2 >> 1) & 1);
       if (tr) w_hs += ffn_time_ns() - t0;
@@ -236,7 +242,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       gemm1();
       for (int c = w.cb; c < w.ce; ++c) {
         if (c + 1 < w.ce) gemm1();
-        gemm2(c == w.cb, c == w.ce - 1);
+        gemm2(c == w.cb, c == w.ce - 1, n);
       }
     }
     if (tr && lane == 0) {
@@ -257,16 +263,21 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const int row = q * 32 + lane;
     const int sw = row & 7;
     const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
-    for (uint32_t n = 0; items.next(w); ++n) {
-    const int m0 = w.tile * BM;
-    if (PRE) {
-      // ---- A operand: four [128 rows x 64] k-blocks straight into the swizzled MMA layout (rows past M arrive as zeros)
-      if (tid_e == 0) {
-        mbar_expect_tx(xs_full, XS_BYTES);
+    // PRE: A operand of an item = four [128 rows x 64] k-blocks straight into the swizzled MMA layout (rows past M arrive
+    // as zeros).  It is requested as soon as the previous item's last GEMM1 has finished reading xs, i.e. a chunk and a
+    // whole output epilogue ahead of its first use: the next item's first GEMM1s then run under this item's epilogue.
+    auto request_xs = [&](int tile) {
+      mbar_expect_tx(xs_full, XS_BYTES);
 #pragma unroll
-        for (int kb = 0; kb < D / KB; ++kb) tma_load_2d(xs + kb * (BM * 128), &tmA, xs_full, kb * KB, m0);
-      }
-    } else {
+      for (int kb = 0; kb < D / KB; ++kb) tma_load_2d(xs + kb * (BM * 128), &tmA, xs_full, kb * KB, tile * BM);
+    };
+    Item w_next;
+    bool have = items.next(w);
+    if (PRE && have && tid_e == 0) request_xs(w.tile);
+    for (uint32_t n = 0; have; ++n) {
+    const bool have_next = items.next(w_next);
+    const int m0 = w.tile * BM;
+    if (!PRE) {
     // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7; lane owns columns 8*lane .. 8*lane+7
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane);
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane + 1);
@@ -314,6 +325,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       for (int g = 0; g < 8; ++g) bc[g] = __ldg(b1v + c * (HC / 4) + g);
       mbar_wait(&acc1_full[b], (gc >> 1) & 1);
       tc_fence_after();
+      if (PRE && c == w.ce - 1 && have_next && tid_e == 0) request_xs(w_next.tile);   // every GEMM1 of this item is done
       uint32_t r[32];
       const uint32_t t_acc1 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32;
       tmem_ld_32x32(t_acc1, r);
@@ -341,6 +353,46 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     // ---- final epilogue: x += scale * (acc2 + b2) through a TMA reduction store
     mbar_wait(acc2_full, n & 1);
     tc_fence_after();
+    if (PRE) {
+      // xs already belongs to the next item: the tile is staged in two halves of 128 columns through the 64 KB that used
+      // to hold the hidden tile, and acc2 is handed back to the MMA warp as soon as the second half is in registers
+      uint8_t* stage_out = hs;
+      if (tid_e == 0) bulk_wait_read0();                         // second half of the previous item has left the staging
+      named_bar_sync(1, NUM_EPI_THREADS);
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        const int col = hh * 128 + cgrp * 32;
+        uint32_t r[32];
+        tmem_ld_32x32(tm_acc2 + (static_cast<uint32_t>(q * 32) << 16) + col, r);
+        tmem_ld_wait();
+        if (hh == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc2_empty);
+        }
+        uint8_t* blk = stage_out + cgrp * OUT_BLK_BYTES + row * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (w.cb == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);     // bias once per row tile
+          float4 o;
+          o.x = p.scale * (__uint_as_float(r[j * 4 + 0]) + b4.x);
+          o.y = p.scale * (__uint_as_float(r[j * 4 + 1]) + b4.y);
+          o.z = p.scale * (__uint_as_float(r[j * 4 + 2]) + b4.z);
+          o.w = p.scale * (__uint_as_float(r[j * 4 + 3]) + b4.w);
+          *reinterpret_cast<float4*>(blk + ((j ^ sw) << 4)) = o;
+        }
+        fence_proxy_async();
+        named_bar_sync(1, NUM_EPI_THREADS);
+        if (tid_e == 0) {
+          for (int blk4 = 0; blk4 < 4; ++blk4)
+            tma_reduce_add_2d(&tmX, stage_out + blk4 * OUT_BLK_BYTES, hh * 128 + blk4 * 32, m0);
+          bulk_commit();
+          if (hh == 0) bulk_wait_read0();                        // the first half has left the staging
+        }
+        if (hh == 0) named_bar_sync(1, NUM_EPI_THREADS);
+      }
+    } else {
     uint8_t* stage_out = smem;                                 // aliases xs/hs: every MMA has completed
 #pragma unroll 1
     for (int ch = 0; ch < 2; ++ch) {
@@ -371,6 +423,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     }
     named_bar_sync(1, NUM_EPI_THREADS);                        // staging (= the operand buffers) is free for the next item
     }
+    w = w_next;
+    have = have_next;
+    }
+    if (PRE && tid_e == 0) bulk_wait_read0();                   // the last half tile has left shared memory
   }
   tc_fence_before();
   __syncthreads();
