@@ -50,17 +50,25 @@ constexpr int ROT_BYTES = (D / 64) * Q_BYTES;         // 64 KB: rotation factors
 constexpr int KV_BYTES = BKV * 128;                   // 8 KB
 constexpr int E_BYTES = (D / 64) * KV_BYTES;          // 32 KB: E tile as 4 k-blocks of [64 keys x 64]
 constexpr int KP_BYTES = KV_BYTES + E_BYTES;          // K | E = 40 KB per stage
-constexpr int NS = 3;                                 // K | E ring stages
+constexpr int NS_RING = 3;                            // K | E stages with their own shared memory
+constexpr int NS = 4;                                 // K | E stages in all: the last one reuses the rotation-factor buffer,
+                                                      // dead after the prologue
+constexpr int WP_STAGE = 2;                           // stage whose first fill is the pos_proj slice of the prologue
+constexpr int NSB = 3;                                // S buffers in TMEM: S runs two tiles ahead of the softmax
 constexpr int NUM_SM_WARPS = 8, NUM_SM_THREADS = NUM_SM_WARPS * 32;
 constexpr int XCHG_BYTES = 3 * 2 * BQ * 4;            // tile-max exchange (double buffered) + row-sum exchange
-constexpr int SMEM_BYTES = 1024 + Q_BYTES + ROT_BYTES + NS * KP_BYTES + 2 * KV_BYTES + XCHG_BYTES + 256;
+constexpr int SMEM_BYTES = 1024 + Q_BYTES + ROT_BYTES + NS_RING * KP_BYTES + 2 * KV_BYTES + XCHG_BYTES + 256;
+static_assert(KP_BYTES <= ROT_BYTES, "the extra ring stage lives in the rotation-factor buffer");
 static_assert(SMEM_BYTES <= 227 * 1024, "attention shared memory budget");
 static_assert(D * 128 <= E_BYTES, "the pos_proj slice must fit the E region of a ring stage");
 constexpr int NUM_THREADS = 128 + NUM_SM_THREADS;     // warps 0,3: TMA; 1: MMA; 2: TMEM alloc; 4-11: softmax
-// TMEM columns.  Prologue: ab (256 fp32 columns).  Main loop, over the dead ab: S0 | S1 (64 each; each key half of P_j
-// overwrites, as bf16 pairs, the first 16 columns of its own half of S_j) and one O accumulator per key half (64 each).
-// Throughout: Q' (256 bf16 = 128 columns) and Qs (64 bf16 = 32).
-constexpr int TM_AB = 0, TM_S = 0, TM_O = 128, TM_QP = 256, TM_Q = 384;
+// TMEM columns.  Prologue: ab (256 fp32 columns).  Main loop, over the dead ab: S0 | S1 | S2 (64 each; each key half of
+// P_j overwrites, as bf16 pairs, the first 16 columns of its own half of S_j) and one O accumulator per key half (64
+// each).  Throughout: Q' (256 bf16 = 128 columns) and Qs (64 bf16 = 32).  480 of the 512 columns.
+// Three S buffers because P_j.V must precede S_{j+NSB} in the (in-order) tensor pipe: with two, S_{j+2} could only be
+// issued after P_j was ready and the softmax warps idled ~0.25 us per tile waiting for the next scores.
+constexpr int TM_AB = 0, TM_S = 0, TM_O = NSB * 64, TM_QP = TM_O + 128, TM_Q = TM_QP + 128;
+static_assert(TM_Q + 32 <= 512 && TM_QP >= 256, "TMEM budget; Q' must not alias ab");
 constexpr float RESCALE_THRESHOLD = 8.0f;             // log2 units: P stays below 2^8
 
 struct FactParams {
@@ -103,15 +111,15 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   uint8_t* q_s = smem;                                 // Qs tile as TMA delivers it
   uint8_t* rot_s = q_s + Q_BYTES;                      // rotation factors, laid out like a [128 x 256] K-major operand
   uint8_t* kp_ring = rot_s + ROT_BYTES;                // NS x (K | E)
-  uint8_t* v_ring = kp_ring + NS * KP_BYTES;           // 2 x V
+  uint8_t* v_ring = kp_ring + NS_RING * KP_BYTES;      // 2 x V
   float* xmax = reinterpret_cast<float*>(v_ring + 2 * KV_BYTES);    // [2 buffers][2 halves][128]
   float* xsum = xmax + 2 * 2 * BQ;                                   // [2 halves][128]
   uint64_t* kp_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xmax) + XCHG_BYTES);
   uint64_t* kp_empty = kp_full + NS;
   uint64_t* v_full = kp_empty + NS;
   uint64_t* v_empty = v_full + 2;
-  uint64_t* s_full = v_empty + 2;       // [2]
-  uint64_t* p_full = s_full + 2;
+  uint64_t* s_full = v_empty + 2;       // [NSB]
+  uint64_t* p_full = s_full + NSB;
   uint64_t* o_done = p_full + 1;
   uint64_t* q_full = o_done + 1;
   uint64_t* ab_full = q_full + 1;
@@ -136,10 +144,10 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       mbar_init(&kp_full[s], 1);
       mbar_init(&kp_empty[s], 1);
     }
+    for (int s = 0; s < NSB; ++s) mbar_init(&s_full[s], 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
     }
     mbar_init(p_full, NUM_SM_WARPS);
     mbar_init(o_done, 1);
@@ -156,8 +164,9 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot) + p.tmem_zero;
 
-  // the last ring stage is filled once more than the others: its first fill is the pos_proj slice of the prologue
-  auto fill_index = [](int j) { return j / NS + (j % NS == NS - 1 ? 1 : 0); };
+  // one ring stage is filled once more than the others: its first fill is the pos_proj slice of the prologue
+  auto fill_index = [](int j) { return j / NS + (j % NS == WP_STAGE ? 1 : 0); };
+  auto stage_ptr = [&](int st) { return st < NS_RING ? kp_ring + st * KP_BYTES : rot_s; };
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: pos_proj slice, then K + E tiles
@@ -165,8 +174,8 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       mbar_expect_tx(q_full, Q_BYTES);                                                 // rows past T arrive as zeros
       tma_load_3d(q_s, &tmQKV, q_full, h * DH, i0, b);
       tma_load_3d(q_s + KV_BYTES, &tmQKV, q_full, h * DH, i0 + BKV, b);
-      mbar_expect_tx(&kp_full[NS - 1], D * 128);
-      tma_load_2d(kp_ring + (NS - 1) * KP_BYTES + KV_BYTES, &tmWp, &kp_full[NS - 1], 0, h * D);   // [256 rows (m') x 64 (c)]
+      mbar_expect_tx(&kp_full[WP_STAGE], D * 128);
+      tma_load_2d(kp_ring + WP_STAGE * KP_BYTES + KV_BYTES, &tmWp, &kp_full[WP_STAGE], 0, h * D);   // [256 rows (m') x 64 (c)]
       // rotation factors of the 128 query rows (k-block kb = table columns 64*kb .. +63)
       mbar_expect_tx(rot_full, ROT_BYTES);
 #pragma unroll
@@ -175,9 +184,10 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     __syncwarp();
     for (int j = 0; j < ntiles; ++j) {
       const int s = j % NS, n = fill_index(j);
+      if (j == NS - 1) mbar_wait(qp_full, 0);              // the rotation factors have been consumed: their buffer is a stage now
       mbar_wait(&kp_empty[s], (n & 1) ^ 1);
       if (lane == 0) {
-        uint8_t* st = kp_ring + s * KP_BYTES;
+        uint8_t* st = stage_ptr(s);
         const int j0 = j * BKV;
         mbar_expect_tx(&kp_full[s], KP_BYTES);
         tma_load_3d(st, &tmQKV, &kp_full[s], d + h * DH, j0, b);                      // K rows j0..j0+63
@@ -204,14 +214,14 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     constexpr uint32_t idesc_pv = umma_idesc_bf16_bmn(BQ, DH);      // 128 x 64, B (=V) MN-major
     // ---- prologue: ab = Qs Wp_h   [128 x 256], K = 64 (both operands in shared memory: N = 256 amortises the A reads)
     mbar_wait(q_full, 0);
-    mbar_wait(&kp_full[NS - 1], 0);
+    mbar_wait(&kp_full[WP_STAGE], 0);
     tc_fence_after();
     if (elect_one()) {
-      const uint32_t sa = umma_desc_lo(smem_u32(q_s)), sb = umma_desc_lo(smem_u32(kp_ring + (NS - 1) * KP_BYTES + KV_BYTES));
+      const uint32_t sa = umma_desc_lo(smem_u32(q_s)), sb = umma_desc_lo(smem_u32(kp_ring + WP_STAGE * KP_BYTES + KV_BYTES));
 #pragma unroll
       for (int k = 0; k < 4; ++k) tc_mma_f16_lo(tmem_base + TM_AB, sa + k * 2, sb + k * 2, idesc_ab, k != 0 ? 1u : 0u);
       tc_commit(ab_full);
-      tc_commit(&kp_empty[NS - 1]);
+      tc_commit(&kp_empty[WP_STAGE]);
     }
     __syncwarp();
     auto issue_s = [&](int j) {
@@ -219,8 +229,8 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       mbar_wait(&kp_full[s], n & 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t sk = umma_desc_lo(smem_u32(kp_ring + s * KP_BYTES)), se = sk + (KV_BYTES >> 4);
-        const uint32_t ts = tmem_base + TM_S + (j & 1) * BKV;
+        const uint32_t sk = umma_desc_lo(smem_u32(stage_ptr(s))), se = sk + (KV_BYTES >> 4);
+        const uint32_t ts = tmem_base + TM_S + (j % NSB) * BKV;
 #pragma unroll
         for (int k = 0; k < 4; ++k) tc_mma_f16_ts(ts, tmem_base + TM_Q + k * 8, sk + k * 2, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
@@ -228,20 +238,21 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma_f16_ts(ts, tmem_base + TM_QP + (kb * 4 + k) * 8, se + kb * (KV_BYTES >> 4) + k * 2, idesc_s, 1u);
-        tc_commit(&s_full[j & 1]);
+        tc_commit(&s_full[j % NSB]);
         tc_commit(&kp_empty[s]);                                    // K + E may be refilled
       }
       __syncwarp();
     };
     mbar_wait(qp_full, 0);
     tc_fence_after();
-    issue_s(0);
+    // S runs NSB tiles ahead: S_0 .. S_{NSB-1} up front, then per tile  wait P_j -> P_j.V -> S_{j+NSB}.  P_j.V is issued
+    // the moment P_j is ready (the softmax warps' o_done handshake depends on it), and S_{j+NSB} goes to the buffer P_j
+    // has just vacated: the tensor pipe executes in issue order, so no further handshake is needed.  While the issuing
+    // thread is held up by the back-pressure of S_{j+NSB} (~0.45 us), the softmax warps work on S_{j+1}, complete long ago.
+    for (int j = 0; j < NSB && j < ntiles; ++j) issue_s(j);
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
-      // S_{j+1} goes to the buffer that held S_{j-1} / P_{j-1}: P_{j-1}.V was issued in the previous iteration and
-      // the tensor pipe executes in issue order, so no handshake is needed
       FTRACE(36 + 4 * j);
-      if (j + 1 < ntiles) issue_s(j + 1);
       FTRACE(37 + 4 * j);
       mbar_wait(p_full, j & 1);                                     // P_j in TMEM (and O rescaled where needed)
       FTRACE(38 + 4 * j);
@@ -249,7 +260,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       FTRACE(39 + 4 * j);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t tp = tmem_base + TM_S + s * BKV;
+        const uint32_t tp = tmem_base + TM_S + (j % NSB) * BKV;
         const uint32_t sv = umma_desc_lo(smem_u32(v_ring + s * KV_BYTES));
 #pragma unroll
         for (int g = 0; g < 2; ++g)                                 // key half g: keys 32g .. 32g+31 -> its own O
@@ -262,6 +273,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         if (j == ntiles - 1) tc_commit(o_final);
       }
       __syncwarp();
+      if (j + NSB < ntiles) issue_s(j + NSB);
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ softmax: thread = (query row, key half)
@@ -370,7 +382,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     // whenever a streamed tile meets a score far above the reference.
     auto exact_tile = [&](int j, uint32_t vm, uint32_t (&pk)[16], float& psum) {
       uint32_t sc[32];
-      tmem_ld_32x32(tlane + TM_S + (j & 1) * BKV + 32 * grp, sc);
+      tmem_ld_32x32(tlane + TM_S + (j % NSB) * BKV + 32 * grp, sc);
       tmem_ld_wait();
       if (vm != 0xffffffffu) {
 #pragma unroll
@@ -412,12 +424,12 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     float m_pend = m_ref;
     if (warp == 4) FTRACE(8);
     for (int j = 0; j < ntiles; ++j) {
-      const int buf = j & 1;
+      const int buf = j % NSB;
       const uint32_t vm = key_mask(j);
       const uint32_t t_s = tlane + TM_S + buf * BKV + 32 * grp;
       uint32_t pk[16];
       float psum;
-      mbar_wait(&s_full[buf], (j >> 1) & 1);
+      mbar_wait(&s_full[buf], (j / NSB) & 1);
       tc_fence_after();
       // (S_j complete implies P.V of tile j-2 complete - the tensor pipe runs in issue order - so the parity wait on
       // o_done for tile j-1 inside move_reference cannot alias an older phase, however far this warp has run ahead)

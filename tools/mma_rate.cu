@@ -76,17 +76,18 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int it
 
 // The attention kernel's S pattern: batches of 20 MMAs (N = 64, A in TMEM at 20 different column offsets, B = 5 blocks
 // of [64 x 64] x 4 K steps), each batch followed by a commit.  Reports clocks per MMA to ISSUE a batch and to COMPLETE it.
-template <int NB>
+template <int NB, bool DYN = false>
 __global__ void __launch_bounds__(128, 1) mma_batch_kernel(long long* out, int batches, uint32_t tmem_zero) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* b_s = smem;                 // 5 x [NB x 64] bf16
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 5 * NB * 128);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 6);
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 5 * NB * 128 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    for (int i = 2; i < 5; ++i) mbar_init(bar + i, 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(slot, 512);
@@ -101,13 +102,26 @@ __global__ void __launch_bounds__(128, 1) mma_batch_kernel(long long* out, int b
     long long t_issue = 0, t_done = 0;
     for (int bt = 0; bt < batches; ++bt) {
       const long long t0 = clock64();
+      // DYN: operand bases change from batch to batch (ring stage, accumulator buffer), as in the attention kernel,
+      // so every MMA carries its own uniform address arithmetic instead of loop-invariant registers
+      const uint32_t sbd = DYN ? sb + (bt % 3) * 64 * 0 + ((bt * 7) & 1) * 0 + (static_cast<uint32_t>(bt) % 3u) * 0u + (static_cast<uint32_t>(clock64()) & 0u) : sb;
+      const uint32_t tad = DYN ? tmem + 256 + (static_cast<uint32_t>(clock64()) & 0u) : tmem + 256;
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 5; ++kb)
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            tc_mma_f16_ts(tmem + (bt & 1) * NB, tmem + 256 + (kb * 4 + k) * 8, sb + kb * (NB * 128 >> 4) + k * 2, idesc,
+            tc_mma_f16_ts(tmem + (bt & 1) * NB, tad + (kb * 4 + k) * 8, sbd + kb * (NB * 128 >> 4) + k * 2, idesc,
                           (kb | k) != 0 ? 1u : 0u);
+        if (DYN) {                     // the attention kernel's commit pattern: 2 after S, 3 after P.V (dummy barriers here)
+          tc_commit(bar + 2);
+          tc_mma_f16_ts(tmem + 128, tad, sbd, idesc, 1u);
+          tc_mma_f16_ts(tmem + 128, tad + 8, sbd + 2, idesc, 1u);
+          tc_mma_f16_ts(tmem + 192, tad + 16, sbd + 4, idesc, 1u);
+          tc_mma_f16_ts(tmem + 192, tad + 24, sbd + 6, idesc, 1u);
+          tc_commit(bar + 3);
+          tc_commit(bar + 4);
+        }
         tc_commit(bar);
       }
       __syncwarp();
@@ -126,16 +140,17 @@ __global__ void __launch_bounds__(128, 1) mma_batch_kernel(long long* out, int b
   }
 }
 
-template <int NB>
+template <int NB, bool DYN = false>
 void run_batch(int grid, long long* d_out) {
-  const int batches = 65, smem = 1024 + 5 * NB * 128 + 64;
-  cudaFuncSetAttribute(mma_batch_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  mma_batch_kernel<NB><<<grid, 128, smem>>>(d_out, batches, 0u);
+  const int batches = 65, smem = 1024 + 5 * NB * 128 + 128;
+  cudaFuncSetAttribute(mma_batch_kernel<NB, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mma_batch_kernel<NB, DYN><<<grid, 128, smem>>>(d_out, batches, 0u);
   cudaError_t e = cudaDeviceSynchronize();
   long long r[2] = {0, 0};
   cudaMemcpy(r, d_out, 16, cudaMemcpyDeviceToHost);
-  printf("batch of 20 MMAs N=%d A tmem, grid %3d: issue %6.1f clk/MMA, issue+complete %6.1f clk/MMA (floor %d)%s\n", NB, grid,
-         r[0] / (64.0 * 20), r[1] / (64.0 * 20), NB / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
+  printf("batch of 20 MMAs N=%d A tmem%s, grid %3d: issue %6.1f clk/MMA, issue+complete %6.1f clk/MMA (floor %d)%s\n", NB,
+         DYN ? " (+4 MMAs, per-batch bases, 4 commits)" : "", grid,
+         r[0] / (64.0 * (DYN ? 24 : 20)), r[1] / (64.0 * (DYN ? 24 : 20)), NB / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
 
@@ -383,6 +398,7 @@ int main() {
   run_noise<false, 1>("A smem, 8 warps tcgen05.ld x32", d_out);
   run_noise<false, 2>("A smem, 8 warps ld.shared (8 x 16 B)", d_out);
   run_bmn(d_out);
+  run_batch<64, true>(1, d_out);
   run_batch<64>(1, d_out);
   run_batch<64>(148, d_out);
   run_batch<128>(1, d_out);
