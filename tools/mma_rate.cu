@@ -157,18 +157,19 @@ void run_batch(int grid, long long* d_out) {
 // Same batches while 8 other warps read TMEM continuously (tcgen05.ld, 32 columns each, as the softmax warps do), or,
 // with SMEM_NOISE, read shared memory instead: is the MMA slowed by TMEM-read or shared-memory-port contention?
 template <bool A_TMEM, int NOISE>     // NOISE: 0 none, 1 tcgen05.ld, 2 ld.shared, 3 tcgen05.st
-__global__ void __launch_bounds__(384, 1) mma_noise_kernel(long long* out, int batches, uint32_t tmem_zero) {
+__global__ void __launch_bounds__(384, 1) mma_noise_kernel(long long* out, int batches, uint32_t tmem_zero, const uint8_t* gsrc = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   uint8_t* b_s = smem;                 // 5 x [64 x 64] bf16
   uint8_t* a_s = smem + 5 * 8192;      // 5 x [128 x 64] bf16
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 5 * 8192 + 5 * 16384);
-  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 6);
   volatile int* stop = reinterpret_cast<volatile int*>(slot + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < (5 * 8192 + 5 * 16384) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    mbar_init(bar + 5, 1);
     fence_mbar_init();
     *stop = 0;
   }
@@ -199,7 +200,24 @@ __global__ void __launch_bounds__(384, 1) mma_noise_kernel(long long* out, int b
       if (bt > 0) t_done += clock64() - t0;
     }
     if (lane == 0) { *stop = 1; if (blockIdx.x == 0) out[0] = t_done; }
-  } else if (warp >= 4 && NOISE != 0) {
+  } else if (warp == 4 && NOISE == 5) {
+    // bulk async copies global -> shared (40 KB per round, the attention kernel's K|E tile) into the A region, back to back
+    uint64_t* cbar = bar + 5;
+    long long n = 0;
+    if (lane == 0) {
+      while (*stop == 0) {
+        mbar_expect_tx(cbar, 5 * 8192);
+        for (int i = 0; i < 5; ++i)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(a_s + i * 8192)), "l"(gsrc + ((n * 5 + i) % 64) * 8192), "r"(8192u), "r"(smem_u32(cbar))
+                       : "memory");
+        while (!mbar_try_wait(cbar, n & 1)) {
+        }
+        ++n;
+      }
+      if (blockIdx.x == 0) out[1] = n * 10;     // reported as "iterations" x 4096 B x 8 -> bytes = n * 40960
+    }
+  } else if (warp >= 4 && NOISE != 0 && NOISE != 5) {
     const uint32_t tl = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + 128;
     uint32_t acc = 0;
     long long n = 0;
@@ -246,10 +264,12 @@ __global__ void __launch_bounds__(384, 1) mma_noise_kernel(long long* out, int b
 }
 
 template <bool A_TMEM, int NOISE>
-void run_noise(const char* name, long long* d_out) {
-  const int batches = 65, smem = 1024 + 5 * 8192 + 5 * 16384 + 64;
+void run_noise(const char* name, long long* d_out, int grid = 1) {
+  const int batches = 65, smem = 1024 + 5 * 8192 + 5 * 16384 + 128;
+  static uint8_t* gsrc = nullptr;
+  if (gsrc == nullptr) { cudaMalloc(&gsrc, 64 * 8192); cudaMemset(gsrc, 0x3c, 64 * 8192); }
   cudaFuncSetAttribute(mma_noise_kernel<A_TMEM, NOISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  mma_noise_kernel<A_TMEM, NOISE><<<1, 384, smem>>>(d_out, batches, 0u);
+  mma_noise_kernel<A_TMEM, NOISE><<<grid, 384, smem>>>(d_out, batches, 0u, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
   long long r[2] = {0, 0};
   cudaMemcpy(r, d_out, 16, cudaMemcpyDeviceToHost);
@@ -394,6 +414,8 @@ int main() {
   run_noise<true, 3>("A tmem, 8 warps tcgen05.st x32", d_out);
   run_noise<true, 2>("A tmem, 8 warps ld.shared (8 x 16 B)", d_out);
   run_noise<true, 4>("A tmem, 8 warps ex2 + fma chains", d_out);
+  run_noise<true, 5>("A tmem, bulk copies global->smem (1 CTA)", d_out);
+  run_noise<true, 5>("A tmem, bulk copies global->smem (148 CTAs)", d_out, 148);
   run_noise<false, 0>("A smem, no noise", d_out);
   run_noise<false, 1>("A smem, 8 warps tcgen05.ld x32", d_out);
   run_noise<false, 2>("A smem, 8 warps ld.shared (8 x 16 B)", d_out);
