@@ -306,6 +306,14 @@ def main():
         # the same public call, issued the way a serving loop would: two streams and two pinned result buffers
         # alternate, so batch k's D2H / batch k+1's H2D overlap the other batch's kernels.  Every step still copies
         # its own input from pinned host memory and lands its own result on the host inside the timed region.
+        # The end-to-end loop keeps one more batch in flight than the device-resident loop (BENCH_E2E_STREAMS, default 3):
+        # a stream spends ~1 ms of its cycle in its own H2D / D2H copies, and with only two streams that leaves one
+        # stream computing alone for part of the time (measured 4.44 ms per step with 2, 4.31 ms with 3 or 4).
+        n_dev_streams = n_streams
+        n_streams = int(os.environ.get("BENCH_E2E_STREAMS", str(max(3, n_dev_streams)))) if n_dev_streams > 1 else 1
+        while len(streams) < n_streams:
+            streams.append(torch.cuda.Stream(device=dev))
+        del streams[n_streams:]
         y_hosts = [y_host] + [torch.empty_like(y_host).pin_memory() for _ in range(n_streams - 1)]
         lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() if lo_host is not None else None for _ in range(n_streams - 1)]
 
@@ -389,7 +397,7 @@ def main():
         "dtype": "bf16" if args.compute == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": desc, "per_gpu_batch": batch, "mel_frames": t_in, "frames_out": t_out,
                    "audio_seconds_per_gpu_step": secs_per_step, "parallelism": f"dp{world} (independent replicas)",
-                   "issue": "steps alternate two CUDA streams per GPU (independent batches overlap at kernel "
+                   "issue": f"steps rotate over {n_dev_streams} CUDA streams per GPU (independent batches overlap at kernel "
                             "boundaries); serial_ms_per_step is the single-stream time",
                    "l2": "no flush needed: one step streams ~1.3 GB of activations (conv1 output alone 958 MB) "
                          "through the 126 MB L2"},
@@ -398,8 +406,9 @@ def main():
                 "d2h_bytes_per_step": y_host.numel() * 4 + (lo_host.numel() * 8 if var_len else 0),
                 "serial_ms_per_step": ms_e2e_serial,
                 "api": "cfm_encoder_forward_host (Encoder.forward_host): pinned host mel -> device -> forward -> host; "
-                       "steps alternate two CUDA streams / result buffers (copies of one batch overlap the kernels of "
-                       "the next); serial_ms_per_step is the same call on a single stream"},
+                       f"steps rotate over {n_streams} CUDA streams / pinned result buffers (the copies of one batch overlap "
+                       "the kernels of the others); serial_ms_per_step is the same call on a single stream",
+                "streams": n_streams},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "algorithmic_tflops": flops / (ms_dev * 1e-3) / 1e12,
