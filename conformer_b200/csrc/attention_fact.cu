@@ -253,7 +253,6 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     for (int j = 0; j < ntiles; ++j) {
       const int s = j & 1;
       FTRACE(36 + 4 * j);
-      FTRACE(37 + 4 * j);
       mbar_wait(p_full, j & 1);                                     // P_j in TMEM (and O rescaled where needed)
       FTRACE(38 + 4 * j);
       mbar_wait(&v_full[s], (j >> 1) & 1);
@@ -273,6 +272,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
         if (j == ntiles - 1) tc_commit(o_final);
       }
       __syncwarp();
+      FTRACE(37 + 4 * j);
       if (j + NSB < ntiles) issue_s(j + NSB);
     }
   } else if (warp >= 4) {

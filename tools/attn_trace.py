@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline (ns) of CTA (0,0,0) of the tcgen05 attention kernel (debug).
+"""Timeline (ns) of one CTA of the tcgen05 attention kernels (debug; the stamps perturb the traced CTA).
 per tile j: MMA: [0] got TMEM buffer [1] K/V/window landed [2] P_j ready -> issue PV | softmax (warp 4):
 [3] top [4] O_{j-1} ready [5] S,PS_j ready [6] max exchanged [7] P_j published"""
 import ctypes as C
@@ -47,8 +47,8 @@ if os.environ.get("ATTN_POS", "none") == "none":
         r = t[36 + 4 * j: 40 + 4 * j]
         if int(r.max()) == 0:
             break
-        print(f"MMA warp, tile {j}: loop top {int(r[0]) - t0:6d}  S_{j + 1} issued (K|E landed) {int(r[1]) - t0:6d}  "
-              f"P_{j} ready {int(r[2]) - t0:6d}  V ready {int(r[3]) - t0:6d}")
+        print(f"MMA warp, tile {j}: loop top {int(r[0]) - t0:6d}  P_{j} ready {int(r[2]) - t0:6d}  V ready {int(r[3]) - t0:6d}  "
+              f"P_{j}.V issued {int(r[1]) - t0:6d}  (then S_{j + 3} is issued until the next loop top)")
 else:
     t0 = int(t[60])
     print("shift kernel: softmax warps start 0, Q staged %d, first tile top %d, end %d" % (int(t[61]) - t0, int(t[0]) - t0, int(t[62]) - t0))

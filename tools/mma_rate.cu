@@ -104,8 +104,9 @@ __global__ void __launch_bounds__(128, 1) mma_batch_kernel(long long* out, int b
       const long long t0 = clock64();
       // DYN: operand bases change from batch to batch (ring stage, accumulator buffer), as in the attention kernel,
       // so every MMA carries its own uniform address arithmetic instead of loop-invariant registers
-      const uint32_t sbd = DYN ? sb + (bt % 3) * 64 * 0 + ((bt * 7) & 1) * 0 + (static_cast<uint32_t>(bt) % 3u) * 0u + (static_cast<uint32_t>(clock64()) & 0u) : sb;
-      const uint32_t tad = DYN ? tmem + 256 + (static_cast<uint32_t>(clock64()) & 0u) : tmem + 256;
+      const uint32_t opaque_zero = static_cast<uint32_t>(clock64()) & 0u;      // a zero the compiler cannot fold
+      const uint32_t sbd = DYN ? sb + opaque_zero : sb;
+      const uint32_t tad = DYN ? tmem + 256 + opaque_zero : tmem + 256;
       if (elect_one()) {
 #pragma unroll
         for (int kb = 0; kb < 5; ++kb)
