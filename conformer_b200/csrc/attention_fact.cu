@@ -228,6 +228,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const int s = j % NS, n = fill_index(j);
       mbar_wait(&kp_full[s], n & 1);
       tc_fence_after();
+      if (j >= NSB) FTRACE(39 + 4 * (j - NSB));                  // K | E of tile j landed (stamped in the row of tile j-NSB)
       if (elect_one()) {
         const uint32_t sk = umma_desc_lo(smem_u32(stage_ptr(s))), se = sk + (KV_BYTES >> 4);
         const uint32_t ts = tmem_base + TM_S + (j % NSB) * BKV;
@@ -256,7 +257,6 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       mbar_wait(p_full, j & 1);                                     // P_j in TMEM (and O rescaled where needed)
       FTRACE(38 + 4 * j);
       mbar_wait(&v_full[s], (j >> 1) & 1);
-      FTRACE(39 + 4 * j);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t tp = tmem_base + TM_S + (j % NSB) * BKV;

@@ -47,8 +47,9 @@ if os.environ.get("ATTN_POS", "none") == "none":
         r = t[36 + 4 * j: 40 + 4 * j]
         if int(r.max()) == 0:
             break
-        print(f"MMA warp, tile {j}: loop top {int(r[0]) - t0:6d}  P_{j} ready {int(r[2]) - t0:6d}  V ready {int(r[3]) - t0:6d}  "
-              f"P_{j}.V issued {int(r[1]) - t0:6d}  (then S_{j + 3} is issued until the next loop top)")
+        landed = f"K|E_{j + 3} landed {int(r[3]) - t0:6d}" if int(r[3]) > 0 else "(no further S)"
+        print(f"MMA warp, tile {j}: loop top {int(r[0]) - t0:6d}  P_{j} ready {int(r[2]) - t0:6d}  P_{j}.V issued {int(r[1]) - t0:6d}  "
+              f"{landed}  (S_{j + 3} is then issued until the next loop top)")
 else:
     t0 = int(t[60])
     print("shift kernel: softmax warps start 0, Q staged %d, first tile top %d, end %d" % (int(t[61]) - t0, int(t[0]) - t0, int(t[62]) - t0))
