@@ -416,7 +416,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
     };
 
     // Key loop.  TMEM reads (64 B/clk) and the exponentials (MUFU) each take about 512 clocks per tile, so from the second
-    // tile on the scores are STREAMED in chunks of 8 columns against the reference maximum the half already has: the
+    // tile on the scores are STREAMED in two chunks of 16 columns against the reference maximum the half already has: the
     // next chunk's tcgen05.ld is in flight while the current one goes through ex2.  The tile maximum falls out of the
     // same pass and moves the reference (lazily, by the 2^8 rule) before the NEXT tile.  A score more than 2^60 above
     // the reference (P would overflow; also the case of a half that has seen no usable key yet) redoes the tile exactly.
@@ -443,35 +443,29 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       } else {
         const float m_use = (m_ref == -CUDART_INF_F) ? 0.f : m_ref;
         float ps0 = 0.f, ps1 = 0.f, t0 = -CUDART_INF_F, t1 = -CUDART_INF_F;
-        uint32_t ca[8], cb[8];
-        auto chunk = [&](const uint32_t (&cur)[8], int c) {
+        uint32_t ca[16], cb[16];
+        auto chunk = [&](const uint32_t (&cur)[16], int c) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 8; ++e) {
             float s0 = __uint_as_float(cur[2 * e]), s1 = __uint_as_float(cur[2 * e + 1]);
             if (vm != 0xffffffffu) {
-              if (((vm >> (8 * c + 2 * e)) & 1u) == 0) s0 = -CUDART_INF_F;
-              if (((vm >> (8 * c + 2 * e + 1)) & 1u) == 0) s1 = -CUDART_INF_F;
+              if (((vm >> (16 * c + 2 * e)) & 1u) == 0) s0 = -CUDART_INF_F;
+              if (((vm >> (16 * c + 2 * e + 1)) & 1u) == 0) s1 = -CUDART_INF_F;
             }
             t0 = fmaxf(t0, s0);
             t1 = fmaxf(t1, s1);
             const float p0 = ex2f(s0 - m_use), p1 = ex2f(s1 - m_use);
             ps0 += p0;
             ps1 += p1;
-            pk[4 * c + e] = pack_bf16x2(p0, p1);
+            pk[8 * c + e] = pack_bf16x2(p0, p1);
           }
         };
-        tmem_ld_32x8(t_s, ca);
-        tmem_ld_wait_for(ca);
-        tmem_ld_32x8(t_s + 8, cb);
+        tmem_ld_32x16(t_s, ca);
+        tmem_ld_wait_for16(ca);
+        tmem_ld_32x16(t_s + 16, cb);
         chunk(ca, 0);
-        tmem_ld_wait_for(cb);
-        tmem_ld_32x8(t_s + 16, ca);
+        tmem_ld_wait_for16(cb);
         chunk(cb, 1);
-        tmem_ld_wait_for(ca);
-        tmem_ld_32x8(t_s + 24, cb);
-        chunk(ca, 2);
-        tmem_ld_wait_for(cb);
-        chunk(cb, 3);
         const float tmax = fmaxf(t0, t1);
         psum = ps0 + ps1;
         if (__any_sync(0xffffffffu, tmax > m_ref + STREAM_GUARD)) {
