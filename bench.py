@@ -302,6 +302,18 @@ def main():
         ms_dev_serial = timed(step_dev, args.steps)
         ms_dev = timed_two_streams(step_dev, args.steps)
         launches = enc.last_launch_count
+        # informational: the same forward replayed from a CUDA graph on one stream (Encoder.capture).  Replay removes the
+        # per-kernel launch latency a single stream pays (4.30 vs 4.55 ms), but two overlapping graph replays pack worse
+        # than two streams of plain launches (4.12 vs 3.86 ms), so the headline loop stays on stream launches.
+        ms_graph_serial = None
+        try:
+            cap = enc.capture(x, lengths)
+            for _ in range(3):
+                cap.replay()
+            ms_graph_serial = timed(cap.replay, args.steps)
+            del cap
+        except Exception as e:  # noqa: BLE001 - optional measurement, never fatal
+            sys.stderr.write(f"[bench] CUDA-graph replay skipped: {e}\n")
         ms_e2e_serial = timed(step_e2e, args.steps)
         # the same public call, issued the way a serving loop would: two streams and two pinned result buffers
         # alternate, so batch k's D2H / batch k+1's H2D overlap the other batch's kernels.  Every step still copies
@@ -393,7 +405,7 @@ def main():
     line = {
         "metric": "encoder audio-seconds per second (RTFx)", "value": whole_job_rtfx(world, secs_per_step, ms_dev),
         "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
-        "serial_ms_per_step": ms_dev_serial, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "serial_ms_per_step": ms_dev_serial, "serial_cuda_graph_ms_per_step": ms_graph_serial, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.compute == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": desc, "per_gpu_batch": batch, "mel_frames": t_in, "frames_out": t_out,
                    "audio_seconds_per_gpu_step": secs_per_step, "parallelism": f"dp{world} (independent replicas)",

@@ -507,6 +507,27 @@ class Encoder(_Native):
                                         ws.data_ptr(), ws.numel(), _stream()))
         return y, lout
 
+    def capture(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> "CapturedEncoderForward":
+        """Capture one forward for this batch shape in a CUDA graph.  The forward is static - no host synchronisation, no
+        allocation, caller-owned workspace - so its ~130 kernel launches replay as one graph launch: the per-kernel launch
+        latency a single stream otherwise pays at every kernel boundary disappears.  Returns an object whose ``x`` /
+        ``lengths`` are the static input buffers (copy new batches into them), ``replay()`` enqueues the forward on the
+        current stream and ``y`` / ``out_lengths`` receive the result.  Re-capture after loading new weights."""
+        xin = _dev_f32(x, "x").clone()
+        lin = None if lengths is None else lengths.to(device=xin.device, dtype=torch.int64).clone()
+        cur = torch.cuda.current_stream(xin.device)
+        side = torch.cuda.Stream(device=xin.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                 # warm-up on the capture stream: weight packing, kernel attributes,
+            for _ in range(2):                        # and this stream's workspace all exist before the capture starts
+                self.forward(xin, lin)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(xin.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            y, lout = self.forward(xin, lin)
+        return CapturedEncoderForward(graph, xin, lin, y, lout)
+
     def forward_host(self, x_host: torch.Tensor, lengths_host: Optional[torch.Tensor], y_host: torch.Tensor,
                      lengths_out_host: Optional[torch.Tensor] = None, device=None) -> None:
         """End-to-end call with HOST (ideally pinned) buffers through cfm_encoder_forward_host: the
@@ -529,6 +550,17 @@ class Encoder(_Native):
             self._ws[key] = ws
         check(lib().cfm_encoder_forward_host(h, x_host.data_ptr(), _ptr(lengths_host), y_host.data_ptr(),
                                              _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream()))
+
+
+class CapturedEncoderForward:
+    """One Encoder.forward captured in a CUDA graph (Encoder.capture)."""
+
+    def __init__(self, graph, x, lengths, y, out_lengths) -> None:
+        self.graph, self.x, self.lengths, self.y, self.out_lengths = graph, x, lengths, y, out_lengths
+
+    def replay(self):
+        self.graph.replay()
+        return self.y, self.out_lengths
 
 
 class Decoder(nn.Module):
