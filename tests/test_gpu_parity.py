@@ -436,3 +436,32 @@ def test_encoder_cuda_graph_replay_matches_eager():
                 assert torch.allclose(y_g, y_e, rtol=1e-5, atol=1e-6)
             else:                                   # the residual stream is updated by L2 reduction adds: order may differ
                 assert ((y_g - y_e).norm() / y_e.norm()).item() < 2e-3
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("B,Tin,with_lengths", [(1, 7, False), (200, 99, True), (103, 50, True), (3, 4100, False),
+                                                 (5, 1541, True), (37, 389, True), (64, 771, False), (2, 9821, False),
+                                                 (149, 261, True), (12, 2053, True)])
+def test_encoder_bf16_shape_sweep_vs_fp32_path(B, Tin, with_lengths):
+    """Every shape-dependent schedule (FFN tile sharing for any tile count, attention ring / S-buffer rotation for 1..38
+    key tiles, conv-module tile edges, front-end odd/even lengths): the bf16 tensor-core path stays within 2e-2 of the
+    fp32 CUDA-core path, which the tests above pin to the reference."""
+    cfg = cb.EncoderConfig(80, 3, 256, 4, 31)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size),
+                synth_encoder_state_dict(cfg, 3))
+    from conformer_b200.synth import synth_logmel
+    x = synth_logmel(B, 80, Tin, seed=B + Tin).to(DEV)
+    lengths = None
+    if with_lengths:
+        g = torch.Generator().manual_seed(Tin)
+        ls = torch.randint(max(7, Tin // 4), Tin + 1, (B,), generator=g).sort(descending=True).values
+        ls[0] = Tin
+        lengths = ls.to(DEV)
+    y32, l32 = enc.set_compute("fp32")(x, lengths)
+    y16, l16 = enc.set_compute("bf16")(x, lengths)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y16).all()
+    if lengths is not None:
+        assert torch.equal(l32, l16)
+    rel = ((y16 - y32).norm() / y32.norm()).item()
+    assert rel < 2e-2, rel
