@@ -315,28 +315,47 @@ def main():
         except Exception as e:  # noqa: BLE001 - optional measurement, never fatal
             sys.stderr.write(f"[bench] CUDA-graph replay skipped: {e}\n")
         ms_e2e_serial = timed(step_e2e, args.steps)
-        # the same public call, issued the way a serving loop would: two streams and two pinned result buffers
-        # alternate, so batch k's D2H / batch k+1's H2D overlap the other batch's kernels.  Every step still copies
-        # its own input from pinned host memory and lands its own result on the host inside the timed region.
-        # The end-to-end loop keeps one more batch in flight than the device-resident loop (BENCH_E2E_STREAMS, default 3):
-        # a stream spends ~1 ms of its cycle in its own H2D / D2H copies, and with only two streams that leaves one
-        # stream computing alone for part of the time (measured 4.44 ms per step with 2, 4.31 ms with 3 or 4).
+        # The end-to-end loop through cfm_encoder_forward_host_pipelined: BENCH_E2E_SLOTS (default 4) in-flight batches
+        # rotate over the same two compute streams; each step's H2D copy goes to a copy-in stream and its D2H copy to a
+        # copy-out stream, ordered by the library's per-slot events, so the compute streams never wait for a copy
+        # (with forward_host on rotating streams every stream spent ~1 ms of its cycle in its own copies: 4.34 ms/step;
+        # pipelined: 4.01 ms with 3 slots, 3.94 ms with 4).
+        # Every step still copies its own input from pinned host memory and lands its own result on the host inside
+        # the timed region.
         n_dev_streams = n_streams
-        n_streams = int(os.environ.get("BENCH_E2E_STREAMS", str(max(3, n_dev_streams)))) if n_dev_streams > 1 else 1
-        while len(streams) < n_streams:
-            streams.append(torch.cuda.Stream(device=dev))
-        del streams[n_streams:]
-        y_hosts = [y_host] + [torch.empty_like(y_host).pin_memory() for _ in range(n_streams - 1)]
-        lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() if lo_host is not None else None for _ in range(n_streams - 1)]
+        n_slots = int(os.environ.get("BENCH_E2E_SLOTS", "4")) if n_dev_streams > 1 else 1
+        copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        y_hosts = [y_host] + [torch.empty_like(y_host).pin_memory() for _ in range(n_slots - 1)]
+        lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() if lo_host is not None else None for _ in range(n_slots - 1)]
+        e2e_count = [0]
 
-        def step_e2e_buffered():
-            i = counter[0] % n_streams    # the stream on_alternating_streams is about to pick
-            enc.forward_host(x_host, lengths_host, y_hosts[i], lo_hosts[i])
+        def step_e2e_pipelined():
+            k = e2e_count[0]
+            e2e_count[0] += 1
+            with torch.cuda.stream(streams[k % n_dev_streams]):
+                enc.forward_host_pipelined(x_host, lengths_host, y_hosts[k % n_slots], lo_hosts[k % n_slots], k % n_slots,
+                                           copy_in, copy_out)
 
-        warm = on_alternating_streams(step_e2e_buffered)
-        for _ in range(2 * n_streams):
-            warm()
-        ms_e2e = timed_two_streams(step_e2e_buffered, args.steps)
+        def timed_pipelined(steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            cur = torch.cuda.current_stream()
+            e0.record(cur)
+            for st in streams + [copy_in, copy_out]:
+                st.wait_event(e0)
+            for _ in range(steps):
+                step_e2e_pipelined()
+            for st in streams + [copy_in, copy_out]:
+                cur.wait_stream(st)
+            e1.record(cur)
+            barrier()
+            return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
+
+        for _ in range(2 * n_slots):
+            step_e2e_pipelined()
+        torch.cuda.synchronize()
+        ms_e2e = timed_pipelined(args.steps)
+        n_streams = n_slots
         clocks = sampler.stop() if rank == 0 else None       # sampled across the four timed regions above
         # profiled pass (per-launch CUDA events on the launching stream), not part of the headline
         enc.profile(True)
@@ -417,10 +436,11 @@ def main():
                 "h2d_bytes_per_step": x_host.numel() * 4 + (lengths_host.numel() * 8 if var_len else 0),
                 "d2h_bytes_per_step": y_host.numel() * 4 + (lo_host.numel() * 8 if var_len else 0),
                 "serial_ms_per_step": ms_e2e_serial,
-                "api": "cfm_encoder_forward_host (Encoder.forward_host): pinned host mel -> device -> forward -> host; "
-                       f"steps rotate over {n_streams} CUDA streams / pinned result buffers (the copies of one batch overlap "
-                       "the kernels of the others); serial_ms_per_step is the same call on a single stream",
-                "streams": n_streams},
+                "api": "cfm_encoder_forward_host_pipelined (Encoder.forward_host_pipelined): pinned host mel -> device -> "
+                       f"forward -> host; {n_slots} in-flight slots over {n_dev_streams} compute streams, copies on a copy-in and "
+                       "a copy-out stream ordered by the library's per-slot events; serial_ms_per_step is "
+                       "cfm_encoder_forward_host (copy, forward, copy) on a single stream",
+                "slots": n_slots, "compute_streams": n_dev_streams},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
         "algorithmic_tflops": flops / (ms_dev * 1e-3) / 1e12,

@@ -41,6 +41,7 @@ SIGNATURES = {
     "cfm_padding_mask": (C.c_int, [_p, _i32, _i32, _p, _p]),
     "cfm_rel_pos_encoding": (C.c_int, [_p, _i32, _i32, _i32, _p, _p]),
     "cfm_ctc_greedy_decode": (C.c_int, [_p, _i32, _i32, _i32, _i32, _i32, _p, _p, _p]),
+    "cfm_encoder_forward_host_pipelined": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p, _p, _p]),
     "cfm_swish": (C.c_int, [_p, _p, _i64, _p]),
     "cfm_glu": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "cfm_subsampled_lengths": (C.c_int, [_p, _p, _i32, _p]),

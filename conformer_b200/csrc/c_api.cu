@@ -166,6 +166,51 @@ int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, const int64_
   return 0;
 }
 
+int cfm_encoder_forward_host_pipelined(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host, float* y_host,
+                                       int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
+                                       int64_t workspace_bytes, void* stream, void* copy_in_stream, void* copy_out_stream) {
+  CFM_REQUIRE(m != nullptr && mel_host != nullptr && y_host != nullptr && workspace != nullptr, "null argument");
+  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
+  const size_t mel_b = static_cast<size_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
+  const size_t y_b = static_cast<size_t>(batch) * T2 * m->cfg.d_model * 4;
+  const size_t len_b = static_cast<size_t>(batch) * 8;
+  Workspace w;
+  w.init(workspace, static_cast<size_t>(workspace_bytes), false);
+  float* mel_d = static_cast<float*>(w.take(mel_b));
+  float* y_d = static_cast<float*>(w.take(y_b));
+  int64_t* li_d = static_cast<int64_t*>(w.take(len_b));
+  int64_t* lo_d = static_cast<int64_t*>(w.take(len_b));
+  char* rest = static_cast<char*>(w.take(256));
+  CFM_REQUIRE(mel_d && y_d && li_d && lo_d && rest, "workspace too small; query cfm_encoder_host_workspace_bytes");
+  const int64_t rest_bytes = workspace_bytes - (rest - static_cast<char*>(workspace));
+  // the slot's events (created at its first use; waiting on an event that was never recorded is a no-op)
+  Module::HostSlot& slot = m->host_slots[workspace];
+  if (slot.copied_in == nullptr) {
+    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.copied_in, cudaEventDisableTiming));
+    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.computed, cudaEventDisableTiming));
+    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.copied_out, cudaEventDisableTiming));
+  }
+  cudaStream_t s_in = S(copy_in_stream), s_fwd = S(stream), s_out = S(copy_out_stream);
+  // copy-in: after the slot's previous forward has finished reading its staged input
+  CFM_CUDA_OK(cudaStreamWaitEvent(s_in, slot.computed, 0));
+  CFM_CUDA_OK(cudaMemcpyAsync(mel_d, mel_host, mel_b, cudaMemcpyHostToDevice, s_in));
+  if (lengths_in_host) CFM_CUDA_OK(cudaMemcpyAsync(li_d, lengths_in_host, len_b, cudaMemcpyHostToDevice, s_in));
+  CFM_CUDA_OK(cudaEventRecord(slot.copied_in, s_in));
+  // forward: after the copy-in, and after the slot's previous result has left its staging buffer
+  CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot.copied_in, 0));
+  CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot.copied_out, 0));
+  CFM_TRY(run(m, CFM_KIND_ENCODER, mel_d, nullptr, nullptr, lengths_in_host ? li_d : nullptr, y_d,
+              lengths_in_host ? lo_d : nullptr, batch, Tin, rest, rest_bytes, stream));
+  CFM_CUDA_OK(cudaEventRecord(slot.computed, s_fwd));
+  // copy-out: after the forward
+  CFM_CUDA_OK(cudaStreamWaitEvent(s_out, slot.computed, 0));
+  CFM_CUDA_OK(cudaMemcpyAsync(y_host, y_d, y_b, cudaMemcpyDeviceToHost, s_out));
+  if (lengths_in_host && lengths_out_host)
+    CFM_CUDA_OK(cudaMemcpyAsync(lengths_out_host, lo_d, len_b, cudaMemcpyDeviceToHost, s_out));
+  CFM_CUDA_OK(cudaEventRecord(slot.copied_out, s_out));
+  return 0;
+}
+
 int64_t cfm_last_launch_count(cfm_module_t m) { return m ? m->last_launches : -1; }
 
 int cfm_profile_enable(cfm_module_t m, int32_t on) {

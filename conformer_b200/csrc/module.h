@@ -125,6 +125,16 @@ struct Module {
   int64_t last_launches = 0;
   Arena arena;
   Profiler prof;
+  // cfm_encoder_forward_host_pipelined: ordering events of each in-flight slot (a slot = its staging workspace)
+  struct HostSlot { cudaEvent_t copied_in = nullptr, computed = nullptr, copied_out = nullptr; };
+  std::unordered_map<void*, HostSlot> host_slots;
+  ~Module() {
+    for (auto& kv : host_slots) {
+      if (kv.second.copied_in) cudaEventDestroy(kv.second.copied_in);
+      if (kv.second.computed) cudaEventDestroy(kv.second.computed);
+      if (kv.second.copied_out) cudaEventDestroy(kv.second.copied_out);
+    }
+  }
   // packed weights (which members are populated depends on `kind`)
   FfnW ffn;
   AttnW attn;

@@ -552,6 +552,30 @@ class Encoder(_Native):
                                              _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream()))
 
 
+    def forward_host_pipelined(self, x_host: torch.Tensor, lengths_host: Optional[torch.Tensor], y_host: torch.Tensor,
+                               lengths_out_host: Optional[torch.Tensor], slot: int, copy_in_stream, copy_out_stream,
+                               device=None) -> None:
+        """cfm_encoder_forward_host_pipelined: like forward_host, but the H2D copy is enqueued on ``copy_in_stream``, the
+        forward on the current stream and the D2H copy on ``copy_out_stream``; the library orders them (and successive
+        uses of the same ``slot``, which owns the device staging workspace) with events.  Rotate more slots than compute
+        streams and the compute streams never wait for a copy.  The result is valid once ``copy_out_stream`` has drained."""
+        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
+        B, _, Tin = x_host.shape
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        h = self._native()
+        need = lib().cfm_encoder_host_workspace_bytes(h, B, Tin)
+        if need < 0:
+            check(1)
+        key = ("host-slot", device, int(slot))
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(int(need), device=device, dtype=torch.uint8)
+            self._ws[key] = ws
+        check(lib().cfm_encoder_forward_host_pipelined(h, x_host.data_ptr(), _ptr(lengths_host), y_host.data_ptr(),
+                                                       _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream(),
+                                                       copy_in_stream.cuda_stream, copy_out_stream.cuda_stream))
+
+
 class CapturedEncoderForward:
     """One Encoder.forward captured in a CUDA graph (Encoder.capture)."""
 

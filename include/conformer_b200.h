@@ -139,6 +139,16 @@ CFM_API int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, cons
                              int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
                              int64_t workspace_bytes, void* stream);
 CFM_API int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin);
+/* Pipelined form for serving loops: the copy-in runs on `copy_in_stream`, the forward on `stream`, the copy-out on
+ * `copy_out_stream`, ordered by events the handle keeps per SLOT (a slot is identified by its `workspace`, sized by
+ * cfm_encoder_host_workspace_bytes): a slot's copy-in waits for its previous forward, its forward for that copy-in and
+ * for its previous copy-out, its copy-out for the forward.  Rotating K slots over fewer compute streams keeps the
+ * compute streams free of copies (the reference's loop does .cuda() / .cpu() around every forward, test.py:145-149).
+ * y_host (and lengths_out_host) are valid once the work queued on `copy_out_stream` has completed. */
+CFM_API int cfm_encoder_forward_host_pipelined(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host,
+                                               float* y_host, int64_t* lengths_out_host, int32_t batch, int32_t Tin,
+                                               void* workspace, int64_t workspace_bytes, void* stream,
+                                               void* copy_in_stream, void* copy_out_stream);
 
 /* Which kernel evaluates the relative positional term of the bf16 attention when the caller did not supply a table
  * (the encoder's own RelativePositionalEncoding, position.py:11-28) and d_model = 256, head size 64:

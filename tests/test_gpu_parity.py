@@ -465,3 +465,37 @@ def test_encoder_bf16_shape_sweep_vs_fp32_path(B, Tin, with_lengths):
         assert torch.equal(l32, l16)
     rel = ((y16 - y32).norm() / y32.norm()).item()
     assert rel < 2e-2, rel
+
+
+def test_forward_host_pipelined_matches_forward():
+    """cfm_encoder_forward_host_pipelined: batches rotating over 3 slots / 2 compute streams with copies on their own
+    streams land the same results on the host as the device-resident forward of the same inputs (fp32 path)."""
+    cfg = cb.EncoderConfig(80, 2, 256, 4, 31)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size),
+                synth_encoder_state_dict(cfg, 17))
+    from conformer_b200.synth import synth_logmel
+    B, Tin, slots = 4, 401, 3
+    xs = [synth_logmel(B, 80, Tin, seed=50 + i).pin_memory() for i in range(7)]
+    lens = torch.tensor([401, 333, 200, 77]).pin_memory()
+    T2 = enc.output_frames(Tin)
+    y_hosts = [torch.empty(B, T2, 256).pin_memory() for _ in range(slots)]
+    l_hosts = [torch.empty(B, dtype=torch.int64).pin_memory() for _ in range(slots)]
+    compute = [torch.cuda.Stream(), torch.cuda.Stream()]
+    cin, cout = torch.cuda.Stream(), torch.cuda.Stream()
+    want = [enc(x.to(DEV), lens.to(DEV)) for x in xs]
+    torch.cuda.synchronize()
+    got = []
+    for k, x in enumerate(xs):
+        if k >= slots:                       # the slot's previous result must be consumed before it is overwritten
+            cout.synchronize()
+            got.append((y_hosts[k % slots].clone(), l_hosts[k % slots].clone())) if len(got) == k - slots else None
+        with torch.cuda.stream(compute[k % 2]):
+            enc.forward_host_pipelined(x, lens, y_hosts[k % slots], l_hosts[k % slots], k % slots, cin, cout)
+    torch.cuda.synchronize()
+    # results still sitting in the slots: the last `slots` batches
+    for k in range(len(xs) - slots, len(xs)):
+        got.append((y_hosts[k % slots].clone(), l_hosts[k % slots].clone()))
+    assert len(got) == len(xs)
+    for (y_g, l_g), (y_w, l_w) in zip(got, want):
+        assert torch.equal(l_g, l_w.cpu())
+        assert torch.allclose(y_g, y_w.cpu(), rtol=1e-5, atol=1e-6)
