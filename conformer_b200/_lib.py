@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libconformer_b200.so")
 
 COMPUTE_F32, COMPUTE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16 = 0, 1
 (KIND_ENCODER, KIND_BLOCK, KIND_FFN, KIND_MHSA, KIND_REL_ATTENTION, KIND_CONV_MODULE,
  KIND_SUBSAMPLING) = range(7)
 EPI_BIAS, EPI_BIAS_SWISH, EPI_BIAS_RELU, EPI_BIAS_RES, EPI_BIAS_F32 = range(5)
@@ -54,7 +55,8 @@ SIGNATURES = {
     "cfm_encoder_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_forward_host": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_host_workspace_bytes": (_i64, [_p, _i32, _i32]),
-    "cfm_set_attention_kernel": (C.c_int, [_i32]),
+    "cfm_encoder_forward_host_io": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i64, _p, _p, _p]),
+    "cfm_encoder_host_slot_release": (C.c_int, [_p, _p]),
     "cfm_last_launch_count": (_i64, [_p]),
     "cfm_profile_enable": (C.c_int, [_p, _i32]),
     "cfm_profile_collect": (C.c_int, [_p, C.POINTER(C.c_double), _i32]),

@@ -138,15 +138,9 @@ int rel_attention(const T* qkv, const T* pos, int ldp, const float* u, const flo
                   T* ctx, int B, int Tn, int H, int dh, cudaStream_t stream) {
   CFM_REQUIRE(dh >= 1 && dh <= DHMAX, "SIMT attention supports head size <= 64");
   CFM_REQUIRE(B > 0 && Tn > 0 && H > 0 && H <= 65535 && B <= 65535, "bad attention shape");
-  static bool attr_set = false;
   const size_t smem = ATT_SMEM_FLOATS * sizeof(float);
-  if (!attr_set) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_f32_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_f32_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(smem)));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};        // one per template instantiation
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_f32_kernel<T>), static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   rel_attention_f32_kernel<T><<<grid, 128, smem, stream>>>(qkv, pos, ldp, u, v, key_pad, ctx, Tn, H, dh);
   CFM_CUDA_OK(cudaGetLastError());

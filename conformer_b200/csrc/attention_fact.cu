@@ -655,11 +655,8 @@ int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, c
     cuuint32_t box[2] = {64, BQ};
     CFM_TRY(encode_tmap(&tmRot, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, r16, dims, strides, box, "attention rotation table"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_fact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_fact_kernel), SMEM_BYTES));
   FactParams p{pos_const, key_pad, ctx, Tn, H, 0u, g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   rel_attention_fact_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmE, tmWp, tmRot, p);

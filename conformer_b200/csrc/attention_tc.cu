@@ -388,11 +388,8 @@ int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float
     cuuint32_t box[2] = {DH, WIN};
     CFM_TRY(encode_tmap(&tmPos, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pos, dims, strides, box, "attention pos"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(rel_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_tc_kernel), SMEM_BYTES));
   AttnParams p{qkv, u, v, key_pad, ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   rel_attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);

@@ -9,7 +9,7 @@ static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 }  // namespace cfm
 
-namespace cfm { extern unsigned long long* g_gemm_trace; extern int g_attention_kernel; }
+namespace cfm { extern unsigned long long* g_gemm_trace; }
 using namespace cfm;
 
 namespace {
@@ -136,78 +136,109 @@ int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t 
   const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
   const int64_t mel = static_cast<int64_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
   const int64_t y = static_cast<int64_t>(batch) * T2 * m->cfg.d_model * 4;
-  return inner + mel + y + 2 * (static_cast<int64_t>(batch) * 8 + 256) + 1024;
+  // fp32 staging of both tensors + their bf16 transfer copies (cfm_encoder_forward_host_io) + lengths
+  return inner + mel + y + mel / 2 + y / 2 + 2 * (static_cast<int64_t>(batch) * 8 + 256) + 2048;
 }
+
+namespace {
+// One host-buffer forward: copy-in on s_in, forward on s_fwd, copy-out on s_out (all three may be the same stream, in
+// which case no events are needed).  bf16 transfer dtypes halve the PCIe bytes: a bf16 mel is widened on the device (the
+// bf16 compute path rounds the mel to bf16 in its first kernel anyway, so nothing is lost there), a bf16 result is
+// narrowed on the device before it leaves.
+int host_forward(cfm_module_t m, const void* mel_host, int mel_dtype, const int64_t* lengths_in_host, void* y_host, int y_dtype,
+                 int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace, int64_t workspace_bytes,
+                 cudaStream_t s_fwd, cudaStream_t s_in, cudaStream_t s_out) {
+  CFM_REQUIRE(m != nullptr && mel_host != nullptr && y_host != nullptr && workspace != nullptr, "null argument");
+  CFM_REQUIRE((mel_dtype == CFM_DTYPE_F32 || mel_dtype == CFM_DTYPE_BF16) && (y_dtype == CFM_DTYPE_F32 || y_dtype == CFM_DTYPE_BF16),
+              "host transfer dtype must be CFM_DTYPE_F32 or CFM_DTYPE_BF16");
+  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
+  const int64_t mel_n = static_cast<int64_t>(batch) * m->cfg.n_mel_channels * Tin;
+  const int64_t y_n = static_cast<int64_t>(batch) * T2 * m->cfg.d_model;
+  const size_t len_b = static_cast<size_t>(batch) * 8;
+  Workspace w;
+  w.init(workspace, static_cast<size_t>(workspace_bytes), false);
+  float* mel_d = static_cast<float*>(w.take(static_cast<size_t>(mel_n) * 4));
+  float* y_d = static_cast<float*>(w.take(static_cast<size_t>(y_n) * 4));
+  bf16* mel16_d = static_cast<bf16*>(w.take(static_cast<size_t>(mel_n) * 2));
+  bf16* y16_d = static_cast<bf16*>(w.take(static_cast<size_t>(y_n) * 2));
+  int64_t* li_d = static_cast<int64_t*>(w.take(len_b));
+  int64_t* lo_d = static_cast<int64_t*>(w.take(len_b));
+  char* rest = static_cast<char*>(w.take(256));
+  CFM_REQUIRE(mel_d && y_d && mel16_d && y16_d && li_d && lo_d && rest, "workspace too small; query cfm_encoder_host_workspace_bytes");
+  const int64_t rest_bytes = workspace_bytes - (rest - static_cast<char*>(workspace));
+  const bool piped = s_in != s_fwd || s_out != s_fwd;
+  Module::HostSlot* slot = nullptr;
+  if (piped) {
+    // the slot's events (created at its first use; waiting on an event that was never recorded is a no-op)
+    slot = &m->host_slots[workspace];
+    if (slot->copied_in == nullptr) {
+      CFM_CUDA_OK(cudaEventCreateWithFlags(&slot->copied_in, cudaEventDisableTiming));
+      CFM_CUDA_OK(cudaEventCreateWithFlags(&slot->computed, cudaEventDisableTiming));
+      CFM_CUDA_OK(cudaEventCreateWithFlags(&slot->copied_out, cudaEventDisableTiming));
+    }
+    // copy-in: after the slot's previous forward has finished reading its staged input
+    CFM_CUDA_OK(cudaStreamWaitEvent(s_in, slot->computed, 0));
+  }
+  if (mel_dtype == CFM_DTYPE_F32) CFM_CUDA_OK(cudaMemcpyAsync(mel_d, mel_host, static_cast<size_t>(mel_n) * 4, cudaMemcpyHostToDevice, s_in));
+  else CFM_CUDA_OK(cudaMemcpyAsync(mel16_d, mel_host, static_cast<size_t>(mel_n) * 2, cudaMemcpyHostToDevice, s_in));
+  if (lengths_in_host) CFM_CUDA_OK(cudaMemcpyAsync(li_d, lengths_in_host, len_b, cudaMemcpyHostToDevice, s_in));
+  if (piped) {
+    CFM_CUDA_OK(cudaEventRecord(slot->copied_in, s_in));
+    // forward: after the copy-in, and after the slot's previous result has left its staging buffer
+    CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot->copied_in, 0));
+    CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot->copied_out, 0));
+  }
+  if (mel_dtype == CFM_DTYPE_BF16) CFM_TRY(cast_bf16_to_f32(mel16_d, mel_d, mel_n, s_fwd));
+  CFM_TRY(m->forward(CFM_KIND_ENCODER, mel_d, nullptr, nullptr, lengths_in_host ? li_d : nullptr, y_d,
+                     lengths_in_host ? lo_d : nullptr, batch, Tin, rest, rest_bytes, s_fwd, nullptr));
+  if (y_dtype == CFM_DTYPE_BF16) CFM_TRY(cast_f32_to_bf16(y_d, y16_d, y_n, s_fwd));
+  if (piped) {
+    CFM_CUDA_OK(cudaEventRecord(slot->computed, s_fwd));
+    CFM_CUDA_OK(cudaStreamWaitEvent(s_out, slot->computed, 0));      // copy-out: after the forward
+  }
+  if (y_dtype == CFM_DTYPE_F32) CFM_CUDA_OK(cudaMemcpyAsync(y_host, y_d, static_cast<size_t>(y_n) * 4, cudaMemcpyDeviceToHost, s_out));
+  else CFM_CUDA_OK(cudaMemcpyAsync(y_host, y16_d, static_cast<size_t>(y_n) * 2, cudaMemcpyDeviceToHost, s_out));
+  if (lengths_in_host && lengths_out_host)
+    CFM_CUDA_OK(cudaMemcpyAsync(lengths_out_host, lo_d, len_b, cudaMemcpyDeviceToHost, s_out));
+  if (piped) CFM_CUDA_OK(cudaEventRecord(slot->copied_out, s_out));
+  return 0;
+}
+}  // namespace
 
 int cfm_encoder_forward_host(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host, float* y_host,
                              int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
                              int64_t workspace_bytes, void* stream) {
-  CFM_REQUIRE(m != nullptr && mel_host != nullptr && y_host != nullptr && workspace != nullptr, "null argument");
-  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
-  const size_t mel_b = static_cast<size_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
-  const size_t y_b = static_cast<size_t>(batch) * T2 * m->cfg.d_model * 4;
-  const size_t len_b = static_cast<size_t>(batch) * 8;
-  Workspace w;
-  w.init(workspace, static_cast<size_t>(workspace_bytes), false);
-  float* mel_d = static_cast<float*>(w.take(mel_b));
-  float* y_d = static_cast<float*>(w.take(y_b));
-  int64_t* li_d = static_cast<int64_t*>(w.take(len_b));
-  int64_t* lo_d = static_cast<int64_t*>(w.take(len_b));
-  char* rest = static_cast<char*>(w.take(256));
-  CFM_REQUIRE(mel_d && y_d && li_d && lo_d && rest, "workspace too small; query cfm_encoder_host_workspace_bytes");
-  const int64_t rest_bytes = workspace_bytes - (rest - static_cast<char*>(workspace));
-  CFM_CUDA_OK(cudaMemcpyAsync(mel_d, mel_host, mel_b, cudaMemcpyHostToDevice, S(stream)));
-  if (lengths_in_host) CFM_CUDA_OK(cudaMemcpyAsync(li_d, lengths_in_host, len_b, cudaMemcpyHostToDevice, S(stream)));
-  CFM_TRY(run(m, CFM_KIND_ENCODER, mel_d, nullptr, nullptr, lengths_in_host ? li_d : nullptr, y_d,
-              lengths_in_host ? lo_d : nullptr, batch, Tin, rest, rest_bytes, stream));
-  CFM_CUDA_OK(cudaMemcpyAsync(y_host, y_d, y_b, cudaMemcpyDeviceToHost, S(stream)));
-  if (lengths_in_host && lengths_out_host)
-    CFM_CUDA_OK(cudaMemcpyAsync(lengths_out_host, lo_d, len_b, cudaMemcpyDeviceToHost, S(stream)));
-  return 0;
+  return host_forward(m, mel_host, CFM_DTYPE_F32, lengths_in_host, y_host, CFM_DTYPE_F32, lengths_out_host, batch, Tin, workspace,
+                      workspace_bytes, S(stream), S(stream), S(stream));
 }
 
 int cfm_encoder_forward_host_pipelined(cfm_module_t m, const float* mel_host, const int64_t* lengths_in_host, float* y_host,
                                        int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
                                        int64_t workspace_bytes, void* stream, void* copy_in_stream, void* copy_out_stream) {
-  CFM_REQUIRE(m != nullptr && mel_host != nullptr && y_host != nullptr && workspace != nullptr, "null argument");
-  const int64_t T2 = ((Tin - 1) / 2 - 1) / 2;
-  const size_t mel_b = static_cast<size_t>(batch) * m->cfg.n_mel_channels * Tin * 4;
-  const size_t y_b = static_cast<size_t>(batch) * T2 * m->cfg.d_model * 4;
-  const size_t len_b = static_cast<size_t>(batch) * 8;
-  Workspace w;
-  w.init(workspace, static_cast<size_t>(workspace_bytes), false);
-  float* mel_d = static_cast<float*>(w.take(mel_b));
-  float* y_d = static_cast<float*>(w.take(y_b));
-  int64_t* li_d = static_cast<int64_t*>(w.take(len_b));
-  int64_t* lo_d = static_cast<int64_t*>(w.take(len_b));
-  char* rest = static_cast<char*>(w.take(256));
-  CFM_REQUIRE(mel_d && y_d && li_d && lo_d && rest, "workspace too small; query cfm_encoder_host_workspace_bytes");
-  const int64_t rest_bytes = workspace_bytes - (rest - static_cast<char*>(workspace));
-  // the slot's events (created at its first use; waiting on an event that was never recorded is a no-op)
-  Module::HostSlot& slot = m->host_slots[workspace];
-  if (slot.copied_in == nullptr) {
-    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.copied_in, cudaEventDisableTiming));
-    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.computed, cudaEventDisableTiming));
-    CFM_CUDA_OK(cudaEventCreateWithFlags(&slot.copied_out, cudaEventDisableTiming));
-  }
-  cudaStream_t s_in = S(copy_in_stream), s_fwd = S(stream), s_out = S(copy_out_stream);
-  // copy-in: after the slot's previous forward has finished reading its staged input
-  CFM_CUDA_OK(cudaStreamWaitEvent(s_in, slot.computed, 0));
-  CFM_CUDA_OK(cudaMemcpyAsync(mel_d, mel_host, mel_b, cudaMemcpyHostToDevice, s_in));
-  if (lengths_in_host) CFM_CUDA_OK(cudaMemcpyAsync(li_d, lengths_in_host, len_b, cudaMemcpyHostToDevice, s_in));
-  CFM_CUDA_OK(cudaEventRecord(slot.copied_in, s_in));
-  // forward: after the copy-in, and after the slot's previous result has left its staging buffer
-  CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot.copied_in, 0));
-  CFM_CUDA_OK(cudaStreamWaitEvent(s_fwd, slot.copied_out, 0));
-  CFM_TRY(run(m, CFM_KIND_ENCODER, mel_d, nullptr, nullptr, lengths_in_host ? li_d : nullptr, y_d,
-              lengths_in_host ? lo_d : nullptr, batch, Tin, rest, rest_bytes, stream));
-  CFM_CUDA_OK(cudaEventRecord(slot.computed, s_fwd));
-  // copy-out: after the forward
-  CFM_CUDA_OK(cudaStreamWaitEvent(s_out, slot.computed, 0));
-  CFM_CUDA_OK(cudaMemcpyAsync(y_host, y_d, y_b, cudaMemcpyDeviceToHost, s_out));
-  if (lengths_in_host && lengths_out_host)
-    CFM_CUDA_OK(cudaMemcpyAsync(lengths_out_host, lo_d, len_b, cudaMemcpyDeviceToHost, s_out));
-  CFM_CUDA_OK(cudaEventRecord(slot.copied_out, s_out));
+  return host_forward(m, mel_host, CFM_DTYPE_F32, lengths_in_host, y_host, CFM_DTYPE_F32, lengths_out_host, batch, Tin, workspace,
+                      workspace_bytes, S(stream), S(copy_in_stream), S(copy_out_stream));
+}
+
+int cfm_encoder_forward_host_io(cfm_module_t m, const void* mel_host, int32_t mel_dtype, const int64_t* lengths_in_host,
+                                void* y_host, int32_t y_dtype, int64_t* lengths_out_host, int32_t batch, int32_t Tin,
+                                void* workspace, int64_t workspace_bytes, void* stream, void* copy_in_stream,
+                                void* copy_out_stream) {
+  return host_forward(m, mel_host, mel_dtype, lengths_in_host, y_host, y_dtype, lengths_out_host, batch, Tin, workspace,
+                      workspace_bytes, S(stream), S(copy_in_stream ? copy_in_stream : stream),
+                      S(copy_out_stream ? copy_out_stream : stream));
+}
+
+int cfm_encoder_host_slot_release(cfm_module_t m, void* workspace) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  auto it = m->host_slots.find(workspace);
+  if (it == m->host_slots.end()) return 0;
+  // everything queued against the slot (copy-in, forward, copy-out) has finished once its last copy-out has
+  if (it->second.copied_out) CFM_CUDA_OK(cudaEventSynchronize(it->second.copied_out));
+  if (it->second.computed) CFM_CUDA_OK(cudaEventSynchronize(it->second.computed));
+  if (it->second.copied_in) { CFM_CUDA_OK(cudaEventSynchronize(it->second.copied_in)); cudaEventDestroy(it->second.copied_in); }
+  if (it->second.computed) cudaEventDestroy(it->second.computed);
+  if (it->second.copied_out) cudaEventDestroy(it->second.copied_out);
+  m->host_slots.erase(it);
   return 0;
 }
 
@@ -251,11 +282,6 @@ int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int3
   return gemm_bf16_tc(static_cast<const bf16*>(A), K, static_cast<const bf16*>(W), bias, C,
                       epi == EPI_BIAS_GLU ? N / 2 : N, M, N, K, static_cast<Epilogue>(epi), res, res_scale, nullptr, sms,
                       S(stream));
-}
-int cfm_set_attention_kernel(int32_t mode) {
-  CFM_REQUIRE(mode >= -1 && mode <= 1, "attention kernel mode must be -1, 0 or 1");
-  cfm::g_attention_kernel = mode;
-  return 0;
 }
 /* debug: device buffer receiving 8 globaltimer stamps per tile of CTA 0 of the next tcgen05 GEMMs (NULL = off) */
 __attribute__((visibility("default"))) int cfm_debug_set_gemm_trace(void* dev_buf) {

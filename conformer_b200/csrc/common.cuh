@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <string>
 
 namespace cfm {
@@ -37,6 +38,18 @@ void set_error(const std::string& msg);          // thread-local, read by cfm_la
   } while (0)
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel, device).  `done` is a
+// bit mask over device ordinals owned by the launcher (one static atomic per kernel); safe from any host thread.
+static inline int smem_attr_once(std::atomic<uint64_t>& done, const void* kernel, int bytes) {
+  int dev = 0;
+  CFM_CUDA_OK(cudaGetDevice(&dev));
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return 0;
+  CFM_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
 
 // ----------------------------------------------------------------------------- element access
 __device__ __forceinline__ float to_f32(float v) { return v; }

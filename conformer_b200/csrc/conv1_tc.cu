@@ -228,11 +228,8 @@ int subsample_conv1_tc(const float* mel, const bf16* w_packed, const float* bias
     cuuint32_t box[2] = {64, BM};
     CFM_TRY(encode_tmap(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides, box, "conv1 out"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(conv1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(conv1_tc_kernel), SMEM_BYTES));
   const int tiles = static_cast<int>(ceil_div(M, BM));
   Conv1Params p{mel, bias, n_mel, Tin, T1, T1p, F1, M, tiles};
   const int grid = tiles < num_sms ? tiles : num_sms;

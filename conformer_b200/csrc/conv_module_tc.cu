@@ -397,11 +397,8 @@ int conv_module_fused_bf16(const float* x, const float* res, float* out, const f
     cuuint32_t box[2] = {KB, 256};
     CFM_TRY(encode_tmap(&tmW2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W2, dims, strides, box, "conv module W2"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(conv_module_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(conv_module_fused_kernel), SMEM_BYTES));
   CFM_REQUIRE(a_out == nullptr || (ln2_g != nullptr && ln2_b != nullptr), "a_out needs the following LayerNorm's parameters");
   CFM_REQUIRE(((reinterpret_cast<uintptr_t>(a_out) | reinterpret_cast<uintptr_t>(ln2_g) | reinterpret_cast<uintptr_t>(ln2_b)) & 15) == 0,
               "fused conv module operands must be 16-byte aligned");

@@ -5,11 +5,10 @@ namespace cfm {
 namespace {
 
 // One warp per row; two-pass mean/variance in fp32 (rows are <= 4 KB and stay in L1).
+// (x and y may alias - the block-final LayerNorm runs in place - so neither is __restrict__.)
 template <typename TOut>
-__global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict__ x,
-                                                         const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, TOut* __restrict__ y,
-                                                         int64_t rows, int d) {
+__global__ void __launch_bounds__(256) layer_norm_kernel(const float* x, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, TOut* y, int64_t rows, int d) {
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -30,10 +29,8 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* __restrict
 // Vectorised variant for d = 128 * NV: each lane keeps its 4*NV values in registers (one pass over HBM),
 // loads them as float4 (coalesced 512 B per warp request) and stores 8-byte (bf16) or 16-byte (fp32) vectors.
 template <typename TOut, int NV>
-__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* __restrict__ x,
-                                                             const float* __restrict__ gamma,
-                                                             const float* __restrict__ beta, TOut* __restrict__ y,
-                                                             int64_t rows) {
+__global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, TOut* y, int64_t rows) {
   constexpr int D = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -71,8 +68,8 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* __rest
 // Two LayerNorms in one pass over a row of d = 256:  y = LN(x; g1, b1) (fp32: the block output, block.py:27) and
 // a = LN(y; g2, b2) (bf16: the normalised input of the NEXT block's first half-step FFN, ffn.py:16).  The fused FFN
 // kernel then starts from one TMA load of `a` instead of every CTA pulling 128 KB of fp32 rows and normalising them.
-__global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* __restrict__ x, const float* __restrict__ g1,
-                                                              const float* __restrict__ b1, float* __restrict__ y,
+__global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* x, const float* __restrict__ g1,
+                                                              const float* __restrict__ b1, float* y,
                                                               const float* __restrict__ g2, const float* __restrict__ b2,
                                                               bf16* __restrict__ a, int64_t rows) {
   constexpr int D = 256, RPW = 2;                                  // rows per warp: both rows' loads are in flight together
@@ -155,6 +152,25 @@ __global__ void lengths_mask_kernel(const int64_t* __restrict__ len_in, int64_t*
   if (threadIdx.x == 0 && len_out) len_out[b] = L;
   if (key_pad)
     for (int t = threadIdx.x; t < Tn; t += blockDim.x) key_pad[static_cast<int64_t>(b) * Tn + t] = ((t >= L) != mark_valid) ? 1 : 0;
+}
+
+// A sample whose keys are ALL masked: the reference fills every score with finfo.min, so its softmax is uniform over
+// all T keys (attention.py:60-66) and the context of every query is the mean of V.  The attention kernels give masked
+// keys weight exactly 0 (right whenever one key is valid), so such a sample is patched here: one block per sample, which
+// returns at once when it finds a valid key.
+template <typename T>
+__global__ void __launch_bounds__(256) all_masked_mean_v_kernel(const uint8_t* __restrict__ key_pad, const T* __restrict__ qkv,
+                                                                T* __restrict__ ctx, int Tn, int d) {
+  const int b = blockIdx.x;
+  int valid = 0;
+  for (int t = threadIdx.x; t < Tn; t += blockDim.x) valid |= key_pad[static_cast<int64_t>(b) * Tn + t] == 0;
+  if (__syncthreads_or(valid)) return;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float s = 0.f;
+    for (int t = 0; t < Tn; ++t) s += to_f32(qkv[(static_cast<int64_t>(b) * Tn + t) * 3 * d + 2 * d + c]);
+    const T m = from_f32<T>(s / static_cast<float>(Tn));
+    for (int t = 0; t < Tn; ++t) ctx[(static_cast<int64_t>(b) * Tn + t) * d + c] = m;
+  }
 }
 
 __global__ void swish_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
@@ -269,6 +285,16 @@ int lengths_and_mask(const int64_t* lengths_in, int64_t* lengths_out, uint8_t* k
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
+template <typename T>
+int all_masked_mean_v(const uint8_t* key_pad, const T* qkv, T* ctx, int B, int Tn, int d, cudaStream_t stream) {
+  CFM_REQUIRE(key_pad != nullptr && B > 0 && Tn > 0, "all_masked_mean_v needs a key mask");
+  all_masked_mean_v_kernel<T><<<B, 256, 0, stream>>>(key_pad, qkv, ctx, Tn, d);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+template int all_masked_mean_v<float>(const uint8_t*, const float*, float*, int, int, int, cudaStream_t);
+template int all_masked_mean_v<bf16>(const uint8_t*, const bf16*, bf16*, int, int, int, cudaStream_t);
+
 int swish_f32(const float* x, float* y, int64_t n, cudaStream_t stream) {
   swish_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, y, n);
   CFM_CUDA_OK(cudaGetLastError());

@@ -1,10 +1,12 @@
 // Fused FeedForwardModule half-step for d_model = 256 on tcgen05 tensor cores:
 //
-//     x[M,256] += scale * ( swish( LN(x) W1^T + b1 ) W2^T + b2 )      (ffn.py:15-23 + block.py:19,25)
+//     x[M,256] += scale * ( swish( A W1^T + b1 ) W2^T + b2 ),  A = LN(x) as bf16      (ffn.py:15-23 + block.py:19,25)
 //
-// One CTA owns 128 rows.  Nothing but x, the weights and the updated x touches global memory:
-//   prologue   16 warps LayerNorm their rows (fp32, two-pass in registers) and write the bf16 A operand
-//              straight into the 128B-swizzled K-major layout the MMA descriptors expect;
+// One CTA owns 128 rows.  Nothing but A, the weights and the updated x touches global memory:
+//   prologue   A arrives already normalised (the kernel that produced x also emitted LN(x) as bf16: the block-final
+//              dual LayerNorm, the fused conv module's epilogue, or a LayerNorm launch) and is TMA-loaded straight into
+//              the 128B-swizzled K-major layout the MMA descriptors expect.  The kernel never READS x, so x may be
+//              updated in place by any number of CTAs sharing a row tile;
 //   main loop  the 1024 hidden units are processed in 8 chunks of 128:
 //                GEMM1(c): acc1[c&1] (TMEM, 128 cols)  = LN(x) . W1[c]^T          (K = 256)
 //                epilogue: hidden = bf16(swish(acc1 + b1)) written IN PLACE over acc1[c&1] in tensor memory
@@ -17,8 +19,6 @@
 //   epilogue   scale*(acc2 + b2) is staged (aliasing the now-dead operand buffers) and leaves through a TMA
 //              reduction store, i.e. the residual add is executed by the L2 (x is never re-read).
 // TMEM: 2 x 128 (acc1 double buffer) + 256 (acc2) = 512 columns.
-#include <cstdlib>
-
 #include "ops.h"
 
 namespace cfm {
@@ -36,9 +36,6 @@ constexpr int OUT_BLK_BYTES = BM * 128;                    // staging block: 128
 static_assert((D / 32) * OUT_BLK_BYTES <= XS_BYTES + 2 * HS_BYTES, "output staging must fit the operand buffers");
 
 struct FfnParams {
-  const float* x;
-  const float* ln_g;
-  const float* ln_b;
   const float* b1;
   const float* b2;
   float scale;
@@ -81,9 +78,7 @@ struct ItemIter {
   }
 };
 
-// PRE: the A operand LN(x) arrives already normalised (bf16 [M,256], tensor map tmA) and is TMA-loaded into the
-// MMA layout; otherwise the 16 epilogue warps read x and normalise it.
-template <bool PRE>
+// The A operand LN(x) arrives already normalised (bf16 [M,256], tensor map tmA) and is TMA-loaded into the MMA layout.
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA, FfnParams p) {
@@ -98,7 +93,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* acc1_full = xs_full + 1;      // [2]
   uint64_t* hs_full = acc1_full + 2;      // [2]
   uint64_t* acc2_full = hs_full + 2;
-  uint64_t* acc2_empty = acc2_full + 1;   // PRE: the epilogue warps have read acc2 of the previous item out of TMEM
+  uint64_t* acc2_empty = acc2_full + 1;   // the epilogue warps have read acc2 of the previous item out of TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,14 +102,14 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmX);
-    if (PRE) tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(xs_full, PRE ? 1 : NUM_EPI_WARPS);
+    mbar_init(xs_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc1_full[s], 1);
       mbar_init(&hs_full[s], NUM_EPI_WARPS);
@@ -204,7 +199,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     };
     auto gemm2 = [&](bool first, bool last, uint32_t n) {
       const int b = gc2 & 1;
-      if (PRE && first && n > 0) {                                 // the previous item's output has left the accumulator
+      if (first && n > 0) {                                 // the previous item's output has left the accumulator
         mbar_wait(acc2_empty, (n - 1) & 1);
         tc_fence_after();
       }
@@ -253,7 +248,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       p.trace[4] = w_acc1;
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ LN prologue + epilogues (16 warps)
+    // ------------------------------------------------------------------ A-operand requests + epilogues (16 warps)
     const int ew = warp - 4;
     const int q = warp & 3, cgrp = ew >> 2;
     const int tid_e = threadIdx.x - 128;
@@ -263,7 +258,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const int row = q * 32 + lane;
     const int sw = row & 7;
     const float4* b1v = reinterpret_cast<const float4*>(p.b1 + cgrp * 32);
-    // PRE: A operand of an item = four [128 rows x 64] k-blocks straight into the swizzled MMA layout (rows past M arrive
+    // A operand of an item = four [128 rows x 64] k-blocks straight into the swizzled MMA layout (rows past M arrive
     // as zeros).  It is requested as soon as the previous item's last GEMM1 has finished reading xs, i.e. a chunk and a
     // whole output epilogue ahead of its first use: the next item's first GEMM1s then run under this item's epilogue.
     auto request_xs = [&](int tile) {
@@ -273,50 +268,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     };
     Item w_next;
     bool have = items.next(w);
-    if (PRE && have && tid_e == 0) request_xs(w.tile);
+    if (have && tid_e == 0) request_xs(w.tile);
     for (uint32_t n = 0; have; ++n) {
     const bool have_next = items.next(w_next);
     const int m0 = w.tile * BM;
-    if (!PRE) {
-    // ---- LayerNorm: warp ew normalises rows ew*8 .. ew*8+7; lane owns columns 8*lane .. 8*lane+7
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane);
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(p.ln_g) + 2 * lane + 1);
-      const float4 be0 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane);
-      const float4 be1 = __ldg(reinterpret_cast<const float4*>(p.ln_b) + 2 * lane + 1);
-      float4 a[8], b[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = m0 + ew * 8 + i;
-        if (row < p.M) {
-          const float4* xr = reinterpret_cast<const float4*>(p.x + static_cast<int64_t>(row) * D);
-          a[i] = xr[2 * lane];
-          b[i] = xr[2 * lane + 1];
-        } else {
-          a[i] = b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = ew * 8 + i;
-        float s = (a[i].x + a[i].y) + (a[i].z + a[i].w) + (b[i].x + b[i].y) + (b[i].z + b[i].w);
-        const float mean = warp_sum(s) * (1.0f / D);
-        a[i].x -= mean; a[i].y -= mean; a[i].z -= mean; a[i].w -= mean;
-        b[i].x -= mean; b[i].y -= mean; b[i].z -= mean; b[i].w -= mean;
-        float v = (a[i].x * a[i].x + a[i].y * a[i].y) + (a[i].z * a[i].z + a[i].w * a[i].w) +
-                  (b[i].x * b[i].x + b[i].y * b[i].y) + (b[i].z * b[i].z + b[i].w * b[i].w);
-        const float rstd = rsqrtf(warp_sum(v) * (1.0f / D) + 1e-5f);
-        uint4 o;
-        o.x = pack_bf16x2(a[i].x * rstd * g0.x + be0.x, a[i].y * rstd * g0.y + be0.y);
-        o.y = pack_bf16x2(a[i].z * rstd * g0.z + be0.z, a[i].w * rstd * g0.w + be0.w);
-        o.z = pack_bf16x2(b[i].x * rstd * g1.x + be1.x, b[i].y * rstd * g1.y + be1.y);
-        o.w = pack_bf16x2(b[i].z * rstd * g1.z + be1.z, b[i].w * rstd * g1.w + be1.w);
-        // column 8*lane -> k-block lane/8, 16-byte chunk lane%8 of row r (128B swizzle)
-        *reinterpret_cast<uint4*>(xs + (lane >> 3) * (BM * 128) + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = o;
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(xs_full);
-    }
     // ---- per-chunk epilogue: hidden = bf16(swish(acc1 + b1)) into the MMA A layout
     for (int c = w.cb; c < w.ce; ++c, ++gc) {
       const int b = gc & 1;
@@ -325,7 +280,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       for (int g = 0; g < 8; ++g) bc[g] = __ldg(b1v + c * (HC / 4) + g);
       mbar_wait(&acc1_full[b], (gc >> 1) & 1);
       tc_fence_after();
-      if (PRE && c == w.ce - 1 && have_next && tid_e == 0) request_xs(w_next.tile);   // every GEMM1 of this item is done
+      if (c == w.ce - 1 && have_next && tid_e == 0) request_xs(w_next.tile);   // every GEMM1 of this item is done
       uint32_t r[32];
       const uint32_t t_acc1 = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * HC + cgrp * 32;
       tmem_ld_32x32(t_acc1, r);
@@ -353,7 +308,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     // ---- final epilogue: x += scale * (acc2 + b2) through a TMA reduction store
     mbar_wait(acc2_full, n & 1);
     tc_fence_after();
-    if (PRE) {
+    {
       // xs already belongs to the next item: the tile is staged in two halves of 128 columns through the 64 KB that used
       // to hold the hidden tile, and acc2 is handed back to the MMA warp as soon as the second half is in registers
       uint8_t* stage_out = hs;
@@ -392,41 +347,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         }
         if (hh == 0) named_bar_sync(1, NUM_EPI_THREADS);
       }
-    } else {
-    uint8_t* stage_out = smem;                                 // aliases xs/hs: every MMA has completed
-#pragma unroll 1
-    for (int ch = 0; ch < 2; ++ch) {
-      const int col = cgrp * 64 + ch * 32;
-      uint32_t r[32];
-      tmem_ld_32x32(tm_acc2 + (static_cast<uint32_t>(q * 32) << 16) + col, r);
-      tmem_ld_wait();
-      uint8_t* blk = stage_out + (col >> 5) * OUT_BLK_BYTES + row * 128;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (w.cb == 0) b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + col) + j);       // bias once per row tile
-        float4 o;
-        o.x = p.scale * (__uint_as_float(r[j * 4 + 0]) + b4.x);
-        o.y = p.scale * (__uint_as_float(r[j * 4 + 1]) + b4.y);
-        o.z = p.scale * (__uint_as_float(r[j * 4 + 2]) + b4.z);
-        o.w = p.scale * (__uint_as_float(r[j * 4 + 3]) + b4.w);
-        *reinterpret_cast<float4*>(blk + ((j ^ sw) << 4)) = o;
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    named_bar_sync(1, NUM_EPI_THREADS);
-    if (tid_e == 0) {
-      for (int blk = 0; blk < D / 32; ++blk) tma_reduce_add_2d(&tmX, stage_out + blk * OUT_BLK_BYTES, blk * 32, m0);
-      bulk_commit();
-      bulk_wait_read0();                                       // smem may be released; the L2 finishes the adds
-    }
-    named_bar_sync(1, NUM_EPI_THREADS);                        // staging (= the operand buffers) is free for the next item
     }
     w = w_next;
     have = have_next;
     }
-    if (PRE && tid_e == 0) bulk_wait_read0();                   // the last half tile has left shared memory
+    if (tid_e == 0) bulk_wait_read0();                   // the last half tile has left shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -442,24 +367,21 @@ extern unsigned long long* g_gemm_trace;
 
 bool ffn_fused_supported(int d) { return d == D; }
 
-int ffn_fused_bf16(const float* x_in, const bf16* a_pre, float* x, const float* ln_g, const float* ln_b, const bf16* W1,
-                   const float* b1, const bf16* W2, const float* b2, float scale, int M, int d, int num_sms,
-                   cudaStream_t stream) {
+int ffn_fused_bf16(const bf16* a_pre, float* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float scale,
+                   int M, int d, int num_sms, cudaStream_t stream) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(d == D, "fused FFN kernel is specialised for d_model = 256");
   CFM_REQUIRE(M > 0, "empty FFN");
-  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_in) | reinterpret_cast<uintptr_t>(W1) | reinterpret_cast<uintptr_t>(W2) |
-                reinterpret_cast<uintptr_t>(ln_g) | reinterpret_cast<uintptr_t>(ln_b) | reinterpret_cast<uintptr_t>(b1) |
-                reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "fused FFN operands must be 16-byte aligned");
-  CFM_REQUIRE((reinterpret_cast<uintptr_t>(a_pre) & 15) == 0, "fused FFN operands must be 16-byte aligned");
+  CFM_REQUIRE(a_pre != nullptr && x != nullptr, "fused FFN needs the normalised input and the residual buffer");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a_pre) | reinterpret_cast<uintptr_t>(W1) |
+                reinterpret_cast<uintptr_t>(W2) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(b2)) & 15) == 0,
+              "fused FFN operands must be 16-byte aligned");
   CUtensorMap tmW1, tmW2, tmX, tmA;
-  if (a_pre != nullptr) {
+  {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(M)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(D) * 2};
     cuuint32_t box[2] = {KB, BM};
     CFM_TRY(encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a_pre, dims, strides, box, "ffn normalised input"));
-  } else {
-    tmA = CUtensorMap{};
   }
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(HID)};
@@ -479,22 +401,14 @@ int ffn_fused_bf16(const float* x_in, const bf16* a_pre, float* x, const float* 
     cuuint32_t box[2] = {32, BM};
     CFM_TRY(encode_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, x, dims, strides, box, "ffn x"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    CFM_CUDA_OK(cudaFuncSetAttribute(ffn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(ffn_fused_kernel), SMEM_BYTES));
   const int tiles = static_cast<int>(ceil_div(M, BM));
-  FfnParams p{x_in, ln_g, ln_b, b1, b2, scale, M, tiles, g_gemm_trace};
-  // Default: persistent CTAs, left-over row tiles shared along the hidden dimension (187 tiles on 148 SMs: the last wave
-  // is as full as the first).  With the pre-normalised A operand a share's prologue is one 64 KB TMA load, and the
-  // schedule wins on a single stream (4.66 vs 4.93 ms per C2 step) and ties with two streams in flight (4.01 vs 3.98).
-  // CFM_FFN_BALANCED=0 selects one CTA per row tile.
-  static const bool balanced = [] { const char* e = getenv("CFM_FFN_BALANCED"); return e == nullptr || e[0] != '0'; }();
-  const int grid = (!balanced || tiles < num_sms) ? tiles : num_sms;
-  if (a_pre != nullptr) ffn_fused_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, tmA, p);
-  else ffn_fused_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, tmA, p);
+  FfnParams p{b1, b2, scale, M, tiles, g_gemm_trace};
+  // Persistent CTAs, left-over row tiles shared along the hidden dimension (187 tiles on 148 SMs: the last wave is as full
+  // as the first); a share's prologue is one 64 KB TMA load.  Sharing is safe because the kernel only ever ADDS to x.
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  ffn_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, tmX, tmA, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -355,11 +355,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
            cudaStream_t stream) {
   using C_ = Cfg<BLOCK_N, EPI>;
   auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CFM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM_BYTES));
-    attr_done = true;
-  }
+  static std::atomic<uint64_t> attr_done{0};        // one per template instantiation
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);

@@ -4,12 +4,9 @@
 #include "module.h"
 
 #include <cmath>
-#include <cstdlib>
 #include <cstring>
 
 namespace cfm {
-
-int g_attention_kernel = 0;          // cfm_set_attention_kernel
 
 // =================================================================================== arena
 int Arena::reserve(size_t bytes) {
@@ -310,12 +307,7 @@ inline int attention_any(const float* qkv, const float* pos, int ldp, const floa
 }
 inline int attention_any(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* kp,
                          bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t st) {
-  if (dh == 64) {
-    // CFM_ATTN=mma selects the mma.sync kernel (kept for A/B comparison); default is the tcgen05 kernel
-    static const bool use_mma = [] { const char* e = getenv("CFM_ATTN"); return e != nullptr && e[0] == 'm'; }();
-    if (use_mma) return rel_attention_bf16_mma(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
-    return rel_attention_bf16_tc(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
-  }
+  if (dh == 64) return rel_attention_bf16_tc(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
   return rel_attention<bf16>(qkv, pos, ldp, u, v, kp, ctx, B, Tn, H, dh, st);
 }
 
@@ -340,22 +332,6 @@ template <typename TA> TA* ws_take(Ctx& c, int64_t n) { return static_cast<TA*>(
 #define WS_CHECK(ptr) CFM_REQUIRE((ptr) != nullptr || c.ws.measuring(), "workspace too small; query cfm_workspace_bytes")
 
 // out = res + scale * FFN(LN(x))      (ffn.py:15-23, block.py:19,25)
-// The LayerNorm-fused projection kernel is correct but, at one 128-row tile per CTA, not faster than
-// LayerNorm + GEMM on B200 (measured 31 us vs 11 + 20 us at M = 23936); opt in with CFM_LN_GEMM=1.
-inline bool ln_gemm_enabled() {
-  static const bool on = [] { const char* e = getenv("CFM_LN_GEMM"); return e != nullptr && e[0] == '1'; }();
-  return on;
-}
-inline bool ln_gemm_ok(const float*, int, int) { return false; }
-inline bool ln_gemm_ok(const bf16*, int d, int N) { return ln_gemm_enabled() && ln_gemm_supported(d, N); }
-inline int ln_gemm_any(const float*, const float*, const float*, const Linear&, float*, int, int, int, bool, cudaStream_t) {
-  set_error("ln_gemm is bf16 only");
-  return 1;
-}
-inline int ln_gemm_any(const float* x, const float* g, const float* b, const Linear& L, bf16* out, int ldc, int M, int d,
-                       bool glu, cudaStream_t st) {
-  return ln_gemm_bf16(x, g, b, L.w16, L.b, out, ldc, M, L.N, d, glu, st);
-}
 inline bool ffn_fast_ok(const float*, int) { return false; }
 inline bool ffn_fast_ok(const bf16*, int d) { return ffn_fused_supported(d); }
 
@@ -364,14 +340,26 @@ template <typename TA>
 int ffn_fwd(Ctx& c, const FfnW& w, const float* x, const float* res, float scale, float* out, int64_t M, int d,
             const bf16* a_pre = nullptr) {
   if (ffn_fast_ok(static_cast<const TA*>(nullptr), d)) {
-    // fused LN -> GEMM -> Swish -> GEMM -> residual kernel; `out` must hold the residual before it runs
-    if (c.ws.measuring()) return 0;
-    if (res == nullptr) CFM_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * d * 4, c.stream));
-    else if (res != out) CFM_CUDA_OK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
-    ++c.launches;
-    Timed t(c, KC_FFN_FUSED, 16.0 * M * d * d, 8.0 * M * d + 16.0 * d * d);
-    return ffn_fused_bf16(x, a_pre, out, w.ln_g, w.ln_b, w.hidden.w16, w.hidden.b, w.out.w16, w.out.b, scale,
-                          static_cast<int>(M), d, c.num_sms, c.stream);
+    // fused GEMM -> Swish -> GEMM -> residual kernel on the normalised input.  The kernel only ADDS into `out` (which
+    // must hold the residual before it runs) and never reads x, so out may alias x or res.
+    const size_t mark = c.ws.mark();
+    if (a_pre == nullptr) {
+      // no producer normalised x for us (block 0's ffn_1, the stand-alone module, an unfused conv module in front)
+      bf16* a = ws_take<bf16>(c, M * d);
+      WS_CHECK(a);
+      if (!c.ws.measuring())
+        KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, 2), layer_norm<bf16>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+      a_pre = a;
+    }
+    if (!c.ws.measuring()) {
+      if (res == nullptr) CFM_CUDA_OK(cudaMemsetAsync(out, 0, static_cast<size_t>(M) * d * 4, c.stream));
+      else if (res != out) CFM_CUDA_OK(cudaMemcpyAsync(out, res, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));
+      KRUN(KC_FFN_FUSED, 16.0 * M * d * d, 6.0 * M * d + 16.0 * d * d,
+           ffn_fused_bf16(a_pre, out, w.hidden.w16, w.hidden.b, w.out.w16, w.out.b, scale, static_cast<int>(M), d, c.num_sms,
+                          c.stream));
+    }
+    c.ws.reset(mark);
+    return 0;
   }
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
@@ -406,23 +394,12 @@ int pos_project(Ctx& c, const Linear& wp, const float* div_term, const float* po
 
 // sinusoid tables of the factorised positional term (bf16 path, d_model 256): cos|sin of t*w_k as bf16 and fp16
 struct FactPos { const bf16* e16 = nullptr; const void* r16 = nullptr; };
-// Which kernel computes the positional term when the table is the module's own sinusoids (bf16, d_model 256):
-// cfm_set_attention_kernel(1) forces the factorised kernel, (-1) the relative-shift kernel; by default the factorised
-// kernel takes every length (measured on B200 per layer: T=1499 194 us vs 233 us; T=374 72 us vs 80 us since its rotation
-// factors arrive by TMA).  CFM_ATTN=fact|skew|mma overrides (A/B runs).
-inline int fact_mode() {
-  static const int env_mode = [] {
-    const char* e = getenv("CFM_ATTN");
-    if (e == nullptr) return 0;
-    return e[0] == 'f' ? 1 : (e[0] == 's' || e[0] == 'm') ? -1 : 0;
-  }();
-  return env_mode != 0 ? env_mode : g_attention_kernel;
-}
-constexpr int FACT_MIN_FRAMES = 1;
+// The positional term of a module called WITHOUT a caller-supplied table (the encoder's own rel_pe sinusoids,
+// position.py:11-28) is evaluated by the factorised kernel where it exists (bf16, d_model 256, head size 64); a table the
+// caller passes in (any values) goes through pos_proj and the relative-shift kernel.  The choice follows from the inputs.
 inline bool fact_ok(const float*, const AttnW&, int, int, int) { return false; }
-inline bool fact_ok(const bf16*, const AttnW& w, int d, int H, int Tn) {
-  if (fact_mode() < 0 || w.wpT == nullptr || !rel_attention_fact_supported(d, d / H)) return false;
-  return fact_mode() > 0 || Tn >= FACT_MIN_FRAMES;
+inline bool fact_ok(const bf16*, const AttnW& w, int d, int H, int) {
+  return w.wpT != nullptr && rel_attention_fact_supported(d, d / H);
 }
 template <typename TA>
 int fact_tables(Ctx& c, const float* div_term, int Tn, int d, FactPos* fp) {
@@ -448,7 +425,7 @@ inline int attention_fact_any(const bf16* qkv, const AttnW& w, const FactPos& fp
 // given, from the factorised sinusoid form (the encoder's own rel_pe table).
 template <typename TA>
 int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_proj, int ldp, const FactPos* fp,
-             const uint8_t* key_pad, const float* res, float* out, int B, int Tn, int d, int H) {
+             const uint8_t* key_pad, const float* res, float* out, int B, int Tn, int d, int H, bool arbitrary_mask = true) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
   const size_t mark = c.ws.mark();
   TA* a = ws_take<TA>(c, M * d);
@@ -458,20 +435,14 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
   if (!c.ws.measuring()) {
     const TA* ain = a;
     const Linear& wqkv = fp != nullptr ? w.qkv_fact : w.qkv;      // the factorised kernel wants c (q + u) as its queries
-    if (pre_ln && ln_gemm_ok(static_cast<const TA*>(nullptr), d, 3 * d)) {
-      // LayerNorm fused into the q|k|v projection (A operand normalised on chip)
-      KRUN(KC_LN_GEMM, 2.0 * M * 3 * d * d, 4.0 * M * d + 2.0 * M * 3 * d + 6.0 * d * d,
-           ln_gemm_any(x, w.ln_g, w.ln_b, wqkv, qkv, 3 * d, static_cast<int>(M), d, false, c.stream));
+    if (pre_ln) {
+      KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    } else if (sizeof(TA) == 4) {
+      ain = reinterpret_cast<const TA*>(x);
     } else {
-      if (pre_ln) {
-        KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
-      } else if (sizeof(TA) == 4) {
-        ain = reinterpret_cast<const TA*>(x);
-      } else {
-        KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
-      }
-      CFM_TRY(Dispatch<TA>::gemm(c, ain, d, wqkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
+      KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(a), M * d, c.stream));
     }
+    CFM_TRY(Dispatch<TA>::gemm(c, ain, d, wqkv, qkv, 3 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
     // algorithmic work: content + positional + PV = 6*T*d FLOPs per token
     if (fp != nullptr) {
       KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
@@ -480,6 +451,9 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
       KRUN(KC_ATTENTION, 6.0 * M * Tn * d, static_cast<double>(M) * 4 * d * sizeof(TA),
            attention_any(qkv, pos_proj, ldp, w.u, w.v, key_pad, ctx, B, Tn, H, d / H, c.stream));
     }
+    // a caller-supplied mask may hide every key of a sample (the encoder's own length masks cannot: lengths' >= 1)
+    if (key_pad != nullptr && arbitrary_mask)
+      KRUN(KC_MISC, 0, static_cast<double>(M), all_masked_mean_v<TA>(key_pad, qkv, ctx, B, Tn, d, c.stream));
     CFM_TRY(Dispatch<TA>::gemm(c, ctx, d, w.out, out, d, static_cast<int>(M), res ? EPI_BIAS_RES : EPI_BIAS_F32, res, 1.f, nullptr));
   }
   c.ws.reset(mark);
@@ -489,8 +463,7 @@ int mhsa_fwd(Ctx& c, const AttnW& w, bool pre_ln, const float* x, const TA* pos_
 // out = res + ConvolutionModule(x)      (convolution.py:21-32; block.py:23)
 inline bool conv_fast_ok(const float*, const ConvW&, int) { return false; }
 inline bool conv_fast_ok(const bf16*, const ConvW& w, int d) {
-  static const bool off = [] { const char* e = getenv("CFM_CONV_FUSED"); return e != nullptr && e[0] == '0'; }();
-  return !off && w.glu_fused && conv_module_fused_supported(d, w.ksize);
+  return w.glu_fused && conv_module_fused_supported(d, w.ksize);
 }
 
 // next_ln / a_out (fused kernel only, nullable): also emit LN(out; next_ln) as bf16 for the FFN that follows.
@@ -513,18 +486,11 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
   TA* g = ws_take<TA>(c, M * d);
   WS_CHECK(a); WS_CHECK(u); WS_CHECK(g);
   if (!c.ws.measuring()) {
-    const bool ln_fused = w.glu_fused && ln_gemm_ok(static_cast<const TA*>(nullptr), d, 2 * d);
-    if (!ln_fused) KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
+    KRUN(KC_LAYERNORM, 0, LN_BYTES(M, d, sizeof(TA)), layer_norm<TA>(x, w.ln_g, w.ln_b, a, M, d, c.stream));
     // algorithmic bytes of the depthwise stage: input [M,d] + output [M,d] + taps
     const double dw_bytes = (2.0 * M * d + (w.ksize + 1.0) * d) * sizeof(TA);
     if (w.glu_fused) {
-      if (ln_fused) {
-        // LayerNorm -> pointwise_conv_1 -> GLU in one kernel
-        KRUN(KC_LN_GEMM, 2.0 * M * 2 * d * d, 4.0 * M * d + 2.0 * M * d + 4.0 * d * d,
-             ln_gemm_any(x, w.ln_g, w.ln_b, w.pw1, u, d, static_cast<int>(M), d, true, c.stream));
-      } else {
-        CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, d, static_cast<int>(M), EPI_BIAS_GLU, nullptr, 0.f, nullptr));
-      }
+      CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, d, static_cast<int>(M), EPI_BIAS_GLU, nullptr, 0.f, nullptr));
       KRUN(KC_DWCONV, 2.0 * w.ksize * M * d, dw_bytes, dwconv_fast(u, w.dw_w, w.dw_b, g, B, Tn, d, w.ksize, c.stream));
     } else {
       CFM_TRY(Dispatch<TA>::gemm(c, a, d, w.pw1, u, 2 * d, static_cast<int>(M), EPI_BIAS, nullptr, 0.f, nullptr));
@@ -545,10 +511,10 @@ int conv_fwd(Ctx& c, const ConvW& w, const float* x, const float* res, float* ou
 template <typename TA>
 int block_fwd(Ctx& c, const BlockW& w, const float* x, float* xw, float* y, const TA* pos_proj, int ldp, const FactPos* fp,
               const uint8_t* key_pad, int B, int Tn, int d, int H, const bf16* a1_pre = nullptr,
-              const FfnW* next_ffn1 = nullptr, bf16* a1_next = nullptr) {
+              const FfnW* next_ffn1 = nullptr, bf16* a1_next = nullptr, bool arbitrary_mask = true) {
   const int64_t M = static_cast<int64_t>(B) * Tn;
   CFM_TRY(ffn_fwd<TA>(c, w.ffn1, x, x, 0.5f, xw, M, d, a1_pre));
-  CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, fp, key_pad, xw, xw, B, Tn, d, H)));
+  CFM_TRY((mhsa_fwd<TA>(c, w.attn, true, xw, pos_proj, ldp, fp, key_pad, xw, xw, B, Tn, d, H, arbitrary_mask)));
   // the fused conv-module kernel reads a time halo, so it writes a second residual buffer instead of updating in place
   const size_t mark = c.ws.mark();
   float* xc = xw;
@@ -587,8 +553,7 @@ int front_fwd(Ctx& c, const Module& m, const float* mel, int B, int Tin, TA** h2
   WS_CHECK(out1); WS_CHECK(h2);
   *h2_out = h2;
   if (c.ws.measuring()) return 0;
-  static const bool conv1_simt = [] { const char* e = getenv("CFM_CONV1"); return e != nullptr && e[0] == 's'; }();
-  if (sizeof(TA) == 2 && m.front.c1_w16 != nullptr && !conv1_simt) {
+  if (sizeof(TA) == 2 && m.front.c1_w16 != nullptr) {
     KRUN(KC_CONV1, 18.0 * d * F1 * T1 * B, 4.0 * B * n_mel * Tin + static_cast<double>(B) * T1 * F1 * d * sizeof(TA),
          subsample_conv1_tc(mel, m.front.c1_w16, m.front.c1_b, reinterpret_cast<bf16*>(out1), B, n_mel, Tin, T1, T1p, F1, d,
                             c.num_sms, c.stream));
@@ -710,7 +675,7 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
         const bool to_next = a1 != nullptr && i + 1 < L;
         CFM_TRY(block_fwd<TA>(c, blocks[i], xw, xw, dst, fact ? nullptr : pp + static_cast<int64_t>(i) * d, L * d, fact ? &fp : nullptr,
                               kp, B, T2, d, H, (a1 != nullptr && i > 0) ? a1 : nullptr, to_next ? &blocks[i + 1].ffn1 : nullptr,
-                              to_next ? a1 : nullptr));
+                              to_next ? a1 : nullptr, /*arbitrary_mask=*/false));
       }
       if (L == 0 && !c.ws.measuring())
         CFM_CUDA_OK(cudaMemcpyAsync(y, xw, static_cast<size_t>(M) * d * 4, cudaMemcpyDeviceToDevice, c.stream));

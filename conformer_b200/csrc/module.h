@@ -43,7 +43,7 @@ class Workspace {                    // bump allocator over the caller's scratch
 };
 
 // kernel classes for the optional per-launch CUDA-event profile (bench.py's roofline numbers)
-enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_F32, KC_LAYERNORM, KC_ATTENTION, KC_DWCONV, KC_CONV1, KC_MISC, KC_FFN_FUSED, KC_LN_GEMM, KC_CONV_FUSED, KC_COUNT };
+enum KernelClass { KC_GEMM_TC = 0, KC_GEMM_F32, KC_LAYERNORM, KC_ATTENTION, KC_DWCONV, KC_CONV1, KC_MISC, KC_FFN_FUSED, KC_CONV_FUSED, KC_COUNT };
 
 struct ProfRec { int cls; double flops, bytes; cudaEvent_t e0, e1; };
 struct Profiler {

@@ -42,21 +42,13 @@ int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* b
                 const cuuint64_t* strides, const cuuint32_t* box, const char* what);
 
 // Fused FeedForwardModule half-step on the tensor cores (d_model = 256):
-//   x[M,256] += scale * (swish(LN(x_in) W1^T + b1) W2^T + b2)        (ffn.py:15-23, block.py:19,25)
-// LayerNorm in the prologue, the [M,1024] hidden activation never leaves the SM.  x_in may alias x (the
-// block's in-place residual update); x must already hold the residual (or zeros).
-// a_pre (nullable): LN(x_in) already normalised as bf16 [M,d] by the producer of x_in (layer_norm_dual or the fused conv
-// module); the kernel then TMA-loads it instead of reading and normalising x_in.
-int ffn_fused_bf16(const float* x_in, const bf16* a_pre, float* x, const float* ln_g, const float* ln_b, const bf16* W1,
-                   const float* b1, const bf16* W2, const float* b2, float scale, int M, int d, int num_sms,
-                   cudaStream_t stream);
+//   x[M,256] += scale * (swish(a_pre W1^T + b1) W2^T + b2)        (ffn.py:15-23, block.py:19,25)
+// a_pre = LN(x_in) as bf16 [M,d], normalised by the producer of x_in (layer_norm_dual, the fused conv module's epilogue,
+// or a layer_norm<bf16> launch).  The [M,1024] hidden activation never leaves the SM.  x must already hold the residual
+// (or zeros); the kernel only adds into it (TMA reduction stores) and never reads it.
+int ffn_fused_bf16(const bf16* a_pre, float* x, const bf16* W1, const float* b1, const bf16* W2, const float* b2, float scale,
+                   int M, int d, int num_sms, cudaStream_t stream);
 bool ffn_fused_supported(int d);
-
-// LayerNorm-fused projection (d_model = 256, N % 256 == 0): out = epi(LN(x) W^T + b), bf16 out.
-// glu = true applies the GLU epilogue on W packed by pack_glu_rows (out has N/2 columns).
-int ln_gemm_bf16(const float* x, const float* ln_g, const float* ln_b, const bf16* W, const float* bias, bf16* out,
-                 int ldc, int M, int N, int d, bool glu, cudaStream_t stream);
-bool ln_gemm_supported(int d, int N);
 
 // Fused ConvolutionModule on the tensor cores (d_model = 256, kernel size 31):
 //   out = res + pw2(swish(bn(dw(glu(pw1(LN(x)))))))        (convolution.py:21-32, block.py:23)
@@ -102,10 +94,6 @@ template <typename T>
 int rel_attention(const T* qkv, const T* pos, int ldp, const float* u, const float* v,
                   const uint8_t* key_pad, T* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
 
-// bf16 tensor-core (mma.sync) flash variant, head size 64 only
-int rel_attention_bf16_mma(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
-                           const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
-
 // bf16 tcgen05/TMEM flash variant (S, shifted positional scores and P.V on 5th-gen tensor cores), head size 64
 int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
                           const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream);
@@ -123,6 +111,12 @@ int pos_const_fact(const float* wp /*[d,d]*/, const float* u, const float* v, fl
 bool rel_attention_fact_supported(int d, int dh);
 int pos_fact_tables(const float* div_term, bf16* e16, void* r16, int Tn, int d, cudaStream_t stream);
 int pack_pos_fact(const float* wp /*[d,d]*/, bf16* out /*[H][d][dh]*/, int d, int dh, cudaStream_t stream);
+
+// samples whose keys are all masked get ctx = mean over time of V, as the reference's uniform softmax gives
+// (attention.py:60-66); a no-op for every sample with at least one valid key
+template <typename T>
+int all_masked_mean_v(const uint8_t* key_pad, const T* qkv /*[B,T,3d]*/, T* ctx /*[B,T,d]*/, int B, int Tn, int d,
+                      cudaStream_t stream);
 
 // sinusoid table [2T-1, d] (model/utils/position.py:11-25), row p <-> relative position T-1-p
 template <typename T>

@@ -33,8 +33,29 @@ __all__ = ["Swish", "GLU", "generate_padding_mask", "RelativePositionalEncoding"
            "ConvolutionSubsampling", "ConformerBlock", "Encoder", "Decoder", "Conformer"]
 
 
-def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None) -> int:
+    """The current stream OF THE TENSORS' DEVICE (the reference's ATen ops launch on the device their inputs live on)."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """Make ``device`` current around a native call: the library launches on (and its handles are tied to) the current
+    CUDA device, while PyTorch callers expect ``module(x)`` to work whatever device is current."""
+
+    def __init__(self, device) -> None:
+        self.device, self.prev = torch.device(device), None
+
+    def __enter__(self):
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        if idx != torch.cuda.current_device():
+            self.prev = torch.cuda.current_device()
+            torch.cuda.set_device(idx)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
 
 
 def _dev_f32(x: torch.Tensor, what: str) -> torch.Tensor:
@@ -57,7 +78,8 @@ class Swish(nn.Module):
         xin = _dev_f32(x, "x")
         y = torch.empty_like(xin)
         if xin.numel():
-            check(lib().cfm_swish(xin.data_ptr(), y.data_ptr(), xin.numel(), _stream()))
+            with _on_device(xin.device):
+                check(lib().cfm_swish(xin.data_ptr(), y.data_ptr(), xin.numel(), _stream(xin.device)))
         return y.to(x.dtype)
 
 
@@ -74,7 +96,8 @@ class GLU(nn.Module):
         y = torch.empty(xin.shape[:-1] + (half,), device=xin.device, dtype=torch.float32)
         rows = y.numel() // max(half, 1)
         if y.numel():
-            check(lib().cfm_glu(xin.data_ptr(), y.data_ptr(), rows, half, _stream()))
+            with _on_device(xin.device):
+                check(lib().cfm_glu(xin.data_ptr(), y.data_ptr(), rows, half, _stream(xin.device)))
         return y.movedim(-1, self.dim).to(x.dtype)
 
 
@@ -88,7 +111,8 @@ def generate_padding_mask(lengths: torch.Tensor, max_length: Optional[int] = Non
     l64 = lengths.to(torch.int64).contiguous()
     out = torch.empty((l64.numel(), max_length), device=lengths.device, dtype=torch.uint8)
     if out.numel():
-        check(lib().cfm_padding_mask(l64.data_ptr(), l64.numel(), max_length, out.data_ptr(), _stream()))
+        with _on_device(l64.device):
+            check(lib().cfm_padding_mask(l64.data_ptr(), l64.numel(), max_length, out.data_ptr(), _stream(l64.device)))
     return out.view(torch.bool)
 
 
@@ -106,8 +130,9 @@ def greedy_ctc_decode(logits: torch.Tensor, pad_id: int = 0, unk_id: Optional[in
     tokens = torch.empty((B, T), device=logits.device, dtype=torch.int32)
     counts = torch.zeros((B,), device=logits.device, dtype=torch.int32)
     if B and T:
-        check(lib().cfm_ctc_greedy_decode(lg.data_ptr(), B, T, V, int(pad_id), int(V - 1 if unk_id is None else unk_id),
-                                          tokens.data_ptr(), counts.data_ptr(), _stream()))
+        with _on_device(lg.device):
+            check(lib().cfm_ctc_greedy_decode(lg.data_ptr(), B, T, V, int(pad_id), int(V - 1 if unk_id is None else unk_id),
+                                              tokens.data_ptr(), counts.data_ptr(), _stream(lg.device)))
     return tokens, counts
 
 
@@ -120,7 +145,8 @@ class _Native(nn.Module):
     def __init__(self) -> None:
         super().__init__()
         object.__setattr__(self, "_handles", {})       # compute -> (handle, version_key)
-        object.__setattr__(self, "_ws", {})            # device -> uint8 workspace tensor
+        object.__setattr__(self, "_ws", {})            # (device, stream) -> uint8 workspace tensor
+        object.__setattr__(self, "_private_ws", None)  # set only while Encoder.capture records its graph
         self._compute_override: Optional[int] = None
 
     # -- configuration each subclass provides
@@ -153,6 +179,7 @@ class _Native(nn.Module):
         for h, _, _ in self._handles.values():
             lib().cfm_module_destroy(h)
         self._handles.clear()
+        self._ws.clear()
 
     def _apply(self, fn, *a, **k):                     # .to()/.cuda()/.float() move the parameters
         self._drop_handles()
@@ -166,7 +193,7 @@ class _Native(nn.Module):
 
     def __getstate__(self):                            # handles are process-local; never copy/pickle them
         state = dict(self.__dict__)
-        state["_handles"], state["_ws"] = {}, {}
+        state["_handles"], state["_ws"], state["_private_ws"] = {}, {}, None
         return state
 
     def _native(self) -> int:
@@ -174,19 +201,23 @@ class _Native(nn.Module):
             raise RuntimeError("conformer_b200: training-mode forward is not implemented (inference only); "
                                "call .eval()")
         compute = self._compute()
-        entry = self._handles.get(compute)
+        hkey = (compute, torch.cuda.current_device())
+        entry = self._handles.get(hkey)
         if entry is not None:
             h, tensors, key = entry
             if key == self._version_key(tensors):
                 return h
             lib().cfm_module_destroy(h)
-            del self._handles[compute]
+            del self._handles[hkey]
         named = self._tensors()
         staged = {}
         for name, t in named.items():
             if not t.is_cuda:
                 raise RuntimeError("conformer_b200: parameters must live on a CUDA device (there is no CPU path); "
                                    "call .cuda() on the module")
+            if t.device.index != torch.cuda.current_device():
+                raise RuntimeError(f"conformer_b200: parameter '{name}' is on {t.device} but the input is on "
+                                   f"cuda:{torch.cuda.current_device()}; move the module and its inputs to one device")
             staged[name] = t.detach().to(torch.float32).contiguous()
         h = C.c_void_p()
         cfg = self._config()
@@ -199,16 +230,22 @@ class _Native(nn.Module):
             lib().cfm_module_destroy(h)
             raise
         tensors = list(named.values())
-        self._handles[compute] = (h, tensors, self._version_key(tensors))
+        self._handles[hkey] = (h, tensors, self._version_key(tensors))
         return h
 
     def _workspace(self, h, batch: int, frames: int, device) -> torch.Tensor:
         need = lib().cfm_workspace_bytes(h, batch, frames)
         if need < 0:
             check(1)
-        key = (device, _stream())          # forwards on different streams may overlap on the device
+        if self._private_ws is not None:   # Encoder.capture: the graph owns its scratch (see CapturedEncoderForward)
+            assert self._private_ws.numel() >= need and self._private_ws.device == device
+            return self._private_ws
+        stream = torch.cuda.current_stream(device)
+        key = (device, stream.cuda_stream)  # forwards on different streams may overlap on the device
         ws = self._ws.get(key)
         if ws is None or ws.numel() < need:
+            if ws is not None:
+                ws.record_stream(stream)   # work already queued on this stream may still use the old block
             ws = torch.empty(int(need), device=device, dtype=torch.uint8)
             self._ws[key] = ws
         return ws
@@ -218,7 +255,7 @@ class _Native(nn.Module):
         """Kernel launches enqueued by the most recent forward (any compute mode)."""
         return max([int(lib().cfm_last_launch_count(h)) for h, _, _ in self._handles.values()] or [0])
 
-    KERNEL_CLASSES = ("gemm_tcgen05", "gemm_fp32", "layer_norm", "attention", "dwconv", "conv1", "misc", "ffn_fused", "ln_gemm", "conv_fused")
+    KERNEL_CLASSES = ("gemm_tcgen05", "gemm_fp32", "layer_norm", "attention", "dwconv", "conv1", "misc", "ffn_fused", "conv_fused")
 
     def profile(self, on: bool) -> None:
         """Bracket every kernel launch of subsequent forwards with CUDA events (see cfm_profile_enable)."""
@@ -281,7 +318,8 @@ class RelativePositionalEncoding(nn.Module):
         B, T = x.size(0), x.size(1)
         dt = _dev_f32(self.div_term.detach(), "div_term")
         out = torch.empty((B, 2 * T - 1, self.d_model), device=dt.device, dtype=torch.float32)
-        check(lib().cfm_rel_pos_encoding(dt.data_ptr(), B, T, self.d_model, out.data_ptr(), _stream()))
+        with _on_device(dt.device):
+            check(lib().cfm_rel_pos_encoding(dt.data_ptr(), B, T, self.d_model, out.data_ptr(), _stream()))
         return out
 
 
@@ -306,9 +344,10 @@ class FeedForwardModule(_Native):
         xin = _dev_f32(x, "x")
         rows, T = xin.numel() // self._dim // max(xin.shape[-2], 1), xin.shape[-2]
         y = torch.empty_like(xin)
-        h = self._native()
-        ws = self._workspace(h, rows, T, xin.device)
-        check(lib().cfm_ffn_forward(h, xin.data_ptr(), y.data_ptr(), rows, T, ws.data_ptr(), ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, rows, T, xin.device)
+            check(lib().cfm_ffn_forward(h, xin.data_ptr(), y.data_ptr(), rows, T, ws.data_ptr(), ws.numel(), _stream()))
         return y
 
 
@@ -344,10 +383,11 @@ class RelativeMultiHeadAttention(_Native):
         y = torch.empty_like(xin)
         pos = _pos_table(pos_embedding, T, d)
         kp = _key_pad(mask, B, T)
-        h = self._native()
-        ws = self._workspace(h, B, T, xin.device)
-        check(lib().cfm_mhsa_forward(h, xin.data_ptr(), _ptr(pos), _ptr(kp), y.data_ptr(), B, T, ws.data_ptr(),
-                                     ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, T, xin.device)
+            check(lib().cfm_mhsa_forward(h, xin.data_ptr(), _ptr(pos), _ptr(kp), y.data_ptr(), B, T, ws.data_ptr(),
+                                         ws.numel(), _stream()))
         return y
 
     def forward(self, q, k, v, pos_embedding, mask=None):
@@ -398,9 +438,10 @@ class ConvolutionModule(_Native):
         xin = _dev_f32(x, "x")
         B, T, _ = xin.shape
         y = torch.empty_like(xin)
-        h = self._native()
-        ws = self._workspace(h, B, T, xin.device)
-        check(lib().cfm_conv_module_forward(h, xin.data_ptr(), y.data_ptr(), B, T, ws.data_ptr(), ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, T, xin.device)
+            check(lib().cfm_conv_module_forward(h, xin.data_ptr(), y.data_ptr(), B, T, ws.data_ptr(), ws.numel(), _stream()))
         return y
 
 
@@ -433,10 +474,11 @@ class ConvolutionSubsampling(_Native):
         if lengths is not None:
             lin = lengths.to(device=xin.device, dtype=torch.int64).contiguous()
             lout = torch.empty_like(lin)
-        h = self._native()
-        ws = self._workspace(h, B, Tin, xin.device)
-        check(lib().cfm_subsampling_forward(h, xin.data_ptr(), _ptr(lin), y.data_ptr(), _ptr(lout), B, Tin,
-                                            ws.data_ptr(), ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, Tin, xin.device)
+            check(lib().cfm_subsampling_forward(h, xin.data_ptr(), _ptr(lin), y.data_ptr(), _ptr(lout), B, Tin,
+                                                ws.data_ptr(), ws.numel(), _stream()))
         return y, lout
 
 
@@ -463,10 +505,11 @@ class ConformerBlock(_Native):
         y = torch.empty_like(xin)
         pos = _pos_table(pos_embedding, T, d)
         kp = _key_pad(mask, B, T)
-        h = self._native()
-        ws = self._workspace(h, B, T, xin.device)
-        check(lib().cfm_block_forward(h, xin.data_ptr(), _ptr(pos), _ptr(kp), y.data_ptr(), B, T, ws.data_ptr(),
-                                      ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, T, xin.device)
+            check(lib().cfm_block_forward(h, xin.data_ptr(), _ptr(pos), _ptr(kp), y.data_ptr(), B, T, ws.data_ptr(),
+                                          ws.numel(), _stream()))
         return y
 
 
@@ -501,10 +544,11 @@ class Encoder(_Native):
         if lengths is not None:
             lin = lengths.to(device=xin.device, dtype=torch.int64).contiguous()
             lout = torch.empty_like(lin)
-        h = self._native()
-        ws = self._workspace(h, B, Tin, xin.device)
-        check(lib().cfm_encoder_forward(h, xin.data_ptr(), _ptr(lin), y.data_ptr(), _ptr(lout), B, Tin,
-                                        ws.data_ptr(), ws.numel(), _stream()))
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, Tin, xin.device)
+            check(lib().cfm_encoder_forward(h, xin.data_ptr(), _ptr(lin), y.data_ptr(), _ptr(lout), B, Tin,
+                                            ws.data_ptr(), ws.numel(), _stream()))
         return y, lout
 
     def capture(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> "CapturedEncoderForward":
@@ -515,72 +559,87 @@ class Encoder(_Native):
         current stream and ``y`` / ``out_lengths`` receive the result.  Re-capture after loading new weights."""
         xin = _dev_f32(x, "x").clone()
         lin = None if lengths is None else lengths.to(device=xin.device, dtype=torch.int64).clone()
-        cur = torch.cuda.current_stream(xin.device)
-        side = torch.cuda.Stream(device=xin.device)
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):                 # warm-up on the capture stream: weight packing, kernel attributes,
-            for _ in range(2):                        # and this stream's workspace all exist before the capture starts
-                self.forward(xin, lin)
-        cur.wait_stream(side)
-        torch.cuda.synchronize(xin.device)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
-            y, lout = self.forward(xin, lin)
-        return CapturedEncoderForward(graph, xin, lin, y, lout)
+        with _on_device(xin.device):
+            need = lib().cfm_workspace_bytes(self._native(), xin.shape[0], xin.shape[2])
+            if need < 0:
+                check(1)
+            # the graph bakes in the scratch pointer: give it a block of its own, kept alive by the returned object, so
+            # that no later forward (same stream id, larger shape, another thread) can free or share it
+            ws = torch.empty(int(need), device=xin.device, dtype=torch.uint8)
+            cur = torch.cuda.current_stream(xin.device)
+            side = torch.cuda.Stream(device=xin.device)
+            side.wait_stream(cur)
+            self._private_ws = ws
+            try:
+                with torch.cuda.stream(side):         # warm-up on the capture stream: weight packing and kernel
+                    for _ in range(2):                # attributes exist before the capture starts
+                        self.forward(xin, lin)
+                cur.wait_stream(side)
+                torch.cuda.synchronize(xin.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=side):
+                    y, lout = self.forward(xin, lin)
+            finally:
+                self._private_ws = None
+        return CapturedEncoderForward(graph, xin, lin, y, lout, ws)
+
+    def _host_call(self, x_host, lengths_host, y_host, lengths_out_host, ws_key, device, copy_in_stream, copy_out_stream):
+        if x_host.is_cuda or y_host.is_cuda or not x_host.is_contiguous() or not y_host.is_contiguous():
+            raise RuntimeError("conformer_b200: forward_host takes contiguous HOST tensors (pinned for asynchronous copies)")
+        dt = {torch.float32: _lib.DTYPE_F32, torch.bfloat16: _lib.DTYPE_BF16}
+        if x_host.dtype not in dt or y_host.dtype not in dt:
+            raise RuntimeError("conformer_b200: host buffers must be float32 or bfloat16")
+        B, _, Tin = x_host.shape
+        device = torch.device("cuda", torch.cuda.current_device() if device is None else torch.device(device).index or 0)
+        if tuple(y_host.shape) != (B, self.output_frames(Tin), self._cfg[2]):
+            raise RuntimeError(f"conformer_b200: y_host must be [B, T', d] = {(B, self.output_frames(Tin), self._cfg[2])}")
+        with _on_device(device):
+            h = self._native()
+            need = lib().cfm_encoder_host_workspace_bytes(h, B, Tin)
+            if need < 0:
+                check(1)
+            key = ws_key + (device,) if ws_key[0] == "host-slot" else ws_key + (device, _stream())
+            ws = self._ws.get(key)
+            if ws is None or ws.numel() < need:
+                if ws is not None:
+                    # copies and kernels queued against the old block (on up to three streams) must finish before it
+                    # is freed, and the library must forget the slot's events, which are keyed by its address
+                    for hh, _, _ in self._handles.values():
+                        check(lib().cfm_encoder_host_slot_release(hh, ws.data_ptr()))
+                    torch.cuda.current_stream(device).synchronize()
+                ws = torch.empty(int(need), device=device, dtype=torch.uint8)
+                self._ws[key] = ws
+            check(lib().cfm_encoder_forward_host_io(
+                h, x_host.data_ptr(), dt[x_host.dtype], _ptr(lengths_host), y_host.data_ptr(), dt[y_host.dtype],
+                _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream(),
+                None if copy_in_stream is None else copy_in_stream.cuda_stream,
+                None if copy_out_stream is None else copy_out_stream.cuda_stream))
 
     def forward_host(self, x_host: torch.Tensor, lengths_host: Optional[torch.Tensor], y_host: torch.Tensor,
                      lengths_out_host: Optional[torch.Tensor] = None, device=None) -> None:
-        """End-to-end call with HOST (ideally pinned) buffers through cfm_encoder_forward_host: the
-        H2D copy of the mel batch, the forward and the D2H copy of the result are enqueued on the
-        current stream.  ``y_host`` must be fp32 [B, T', d].  Everything is stream-ordered and asynchronous, so a
-        serving loop can alternate two streams (and two output buffers) to overlap one batch's copies with the
-        next batch's compute; each stream gets its own device staging workspace."""
-        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
-        B, _, Tin = x_host.shape
-        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        h = self._native()
-        need = lib().cfm_encoder_host_workspace_bytes(h, B, Tin)
-        if need < 0:
-            check(1)
-        # one staging workspace per (device, stream): calls on different streams may overlap on the device
-        key = ("host", device, _stream())
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(int(need), device=device, dtype=torch.uint8)
-            self._ws[key] = ws
-        check(lib().cfm_encoder_forward_host(h, x_host.data_ptr(), _ptr(lengths_host), y_host.data_ptr(),
-                                             _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream()))
-
+        """End-to-end call with HOST (ideally pinned) buffers through cfm_encoder_forward_host_io: the H2D copy of the mel
+        batch, the forward and the D2H copy of the result are enqueued on the current stream.  ``x_host`` / ``y_host`` are
+        float32 (the reference's tensors) or bfloat16 (half the PCIe bytes); ``y_host`` is [B, T', d].  Everything is
+        stream-ordered and asynchronous; each stream gets its own device staging workspace."""
+        self._host_call(x_host, lengths_host, y_host, lengths_out_host, ("host",), device, None, None)
 
     def forward_host_pipelined(self, x_host: torch.Tensor, lengths_host: Optional[torch.Tensor], y_host: torch.Tensor,
                                lengths_out_host: Optional[torch.Tensor], slot: int, copy_in_stream, copy_out_stream,
                                device=None) -> None:
-        """cfm_encoder_forward_host_pipelined: like forward_host, but the H2D copy is enqueued on ``copy_in_stream``, the
-        forward on the current stream and the D2H copy on ``copy_out_stream``; the library orders them (and successive
-        uses of the same ``slot``, which owns the device staging workspace) with events.  Rotate more slots than compute
-        streams and the compute streams never wait for a copy.  The result is valid once ``copy_out_stream`` has drained."""
-        assert not x_host.is_cuda and x_host.dtype == torch.float32 and x_host.is_contiguous()
-        B, _, Tin = x_host.shape
-        device = torch.device("cuda", torch.cuda.current_device()) if device is None else device
-        h = self._native()
-        need = lib().cfm_encoder_host_workspace_bytes(h, B, Tin)
-        if need < 0:
-            check(1)
-        key = ("host-slot", device, int(slot))
-        ws = self._ws.get(key)
-        if ws is None or ws.numel() < need:
-            ws = torch.empty(int(need), device=device, dtype=torch.uint8)
-            self._ws[key] = ws
-        check(lib().cfm_encoder_forward_host_pipelined(h, x_host.data_ptr(), _ptr(lengths_host), y_host.data_ptr(),
-                                                       _ptr(lengths_out_host), B, Tin, ws.data_ptr(), ws.numel(), _stream(),
-                                                       copy_in_stream.cuda_stream, copy_out_stream.cuda_stream))
+        """Like forward_host, but the H2D copy is enqueued on ``copy_in_stream``, the forward on the current stream and the
+        D2H copy on ``copy_out_stream``; the library orders them (and successive uses of the same ``slot``, which owns the
+        device staging workspace) with events.  Rotate more slots than compute streams and the compute streams never wait
+        for a copy.  The result is valid once ``copy_out_stream`` has drained."""
+        self._host_call(x_host, lengths_host, y_host, lengths_out_host, ("host-slot", int(slot)), device, copy_in_stream,
+                        copy_out_stream)
 
 
 class CapturedEncoderForward:
     """One Encoder.forward captured in a CUDA graph (Encoder.capture)."""
 
-    def __init__(self, graph, x, lengths, y, out_lengths) -> None:
+    def __init__(self, graph, x, lengths, y, out_lengths, workspace) -> None:
         self.graph, self.x, self.lengths, self.y, self.out_lengths = graph, x, lengths, y, out_lengths
+        self.workspace = workspace                    # scratch the captured kernels use; lives as long as the graph
 
     def replay(self):
         self.graph.replay()

@@ -131,3 +131,17 @@ def synth_lengths(batch: int, t_in: int, min_frac: float = 0.5) -> torch.Tensor:
     v = torch.linspace(float(t_in), float(t_in) * min_frac, batch).floor().long()
     v[0] = t_in
     return v
+
+
+def encoder_flops(batch: int, t_in: int, d: int, n_blocks: int, n_mel: int = 80, ksz: int = 31) -> float:
+    """Algorithmic FLOPs of one encoder forward (SURVEY.md section 8d / BASELINE.md section 3): per token per block
+    32d^2 (two FFNs) + 8d^2 (q,k,v,out) + 6d^2 + 2*ksz*d (conv module) + 6*T'*d (attention), pos_proj once per layer,
+    plus the two subsampling convs and Encoder.linear.  What bench.py's roofline figures are computed from."""
+    t1 = (t_in - 1) // 2
+    t2 = (t1 - 1) // 2
+    f1 = (n_mel - 1) // 2
+    f2 = (f1 - 1) // 2
+    front = 2 * 9 * d * f1 * t1 * batch + 2 * 9 * d * d * f2 * t2 * batch + 2 * f2 * d * d * t2 * batch
+    per_tok = 32 * d * d + 8 * d * d + (6 * d * d + 2 * ksz * d) + 6 * t2 * d
+    per_layer = per_tok * batch * t2 + 2 * d * d * (2 * t2 - 1)
+    return float(front + n_blocks * per_layer)

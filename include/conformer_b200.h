@@ -14,7 +14,16 @@
  *     (thread-local) describes it.  Nothing throws across the ABI, nothing allocates device
  *     memory inside a forward call (the caller supplies `workspace`), nothing synchronises;
  *   - a module handle owns device copies of its (packed) weights; it is tied to the CUDA device
- *     current at cfm_module_finalize and may be used from one host thread at a time.
+ *     current at cfm_module_finalize (which must also be current at every forward) and may be
+ *     used from one host thread at a time; different handles may be used from different threads
+ *     and on different devices of one process;
+ *   - aliasing: a forward's output `y` may alias its input `x` for cfm_ffn_forward only; every
+ *     other forward needs distinct buffers.  `workspace` must not overlap any argument;
+ *   - masks: key_pad marks padded KEYS (1 = masked).  A sample whose keys are all masked gets the
+ *     reference's result (uniform softmax = mean of V, attention.py:60-66) from the module-level
+ *     forwards (cfm_mhsa_forward, cfm_block_forward).  cfm_encoder_forward builds its masks from
+ *     `lengths` and requires every utterance to keep at least one output frame (lengths >= 7 mel
+ *     frames), which the reference's collate guarantees for real audio;
  *   - there is no CPU path: without a CUDA device every compute entry point fails.
  */
 #ifndef CONFORMER_B200_H_
@@ -27,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CFM_ABI_VERSION 1
+#define CFM_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CFM_API __attribute__((visibility("default")))
@@ -44,6 +53,9 @@ enum {
                         /* fp32 residual stream / LayerNorm / softmax (= the reference under        */
                         /* torch.autocast, train.py:232, with bf16 in place of fp16)                */
 };
+
+/* Element type of a HOST transfer buffer (cfm_encoder_forward_host_io). */
+enum { CFM_DTYPE_F32 = 0, CFM_DTYPE_BF16 = 1 };
 
 /* Which reference module a handle stands for (constructor arguments in cfm_config_t). */
 enum {
@@ -150,19 +162,24 @@ CFM_API int cfm_encoder_forward_host_pipelined(cfm_module_t m, const float* mel_
                                                void* workspace, int64_t workspace_bytes, void* stream,
                                                void* copy_in_stream, void* copy_out_stream);
 
-/* Which kernel evaluates the relative positional term of the bf16 attention when the caller did not supply a table
- * (the encoder's own RelativePositionalEncoding, position.py:11-28) and d_model = 256, head size 64:
- *   0 = automatic (by sequence length), 1 = factorised (rotated query x absolute sinusoid key table, no relative
- *   shift), -1 = relative-shift kernel on the projected table (attention.py:94-102 evaluated in-tile).
- * Both are implementations of the same reference arithmetic; process-wide, takes effect on the next forward. */
-CFM_API int cfm_set_attention_kernel(int32_t mode);
+/* General form of the two calls above.  mel_dtype / y_dtype select what crosses PCIe: CFM_DTYPE_F32 (the reference's
+ * tensors, test.py:145-149) or CFM_DTYPE_BF16 (half the bytes; the bf16 compute path rounds the mel to bf16 in its first
+ * kernel anyway, so a bf16 mel loses nothing there; a bf16 result is the fp32 result rounded once).  copy_in_stream /
+ * copy_out_stream may be NULL (= `stream`, i.e. the unpipelined form). */
+CFM_API int cfm_encoder_forward_host_io(cfm_module_t m, const void* mel_host, int32_t mel_dtype,
+                                        const int64_t* lengths_in_host, void* y_host, int32_t y_dtype,
+                                        int64_t* lengths_out_host, int32_t batch, int32_t Tin, void* workspace,
+                                        int64_t workspace_bytes, void* stream, void* copy_in_stream, void* copy_out_stream);
+/* Forget a pipelined slot before its workspace is freed or replaced: waits for the work queued against it and drops
+ * its events. */
+CFM_API int cfm_encoder_host_slot_release(cfm_module_t m, void* workspace);
 
 /* Number of kernel launches the last forward on `m` enqueued (for bench.py's gpu_launches). */
 CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 
 /* Optional per-launch profile: when enabled every kernel launch of a forward on `m` is bracketed by
  * CUDA events on the launching stream.  cfm_profile_collect waits for them and fills, per kernel class
- * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN, 8 LayerNorm-fused GEMM, 9 fused conv module), four
+ * (0 tcgen05 GEMM, 1 fp32 GEMM, 2 LayerNorm, 3 attention, 4 depthwise conv, 5 conv1, 6 misc, 7 fused FFN, 8 fused conv module), four
  * doubles: launches, total milliseconds, algorithmic FLOPs, algorithmic bytes. */
 CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
 CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);

@@ -16,9 +16,26 @@ ENCODER_CASES = [
     dict(name="M", cfg=CONFORMER_M, B=3, Tin=301, seed=22, with_lengths=True),       # T'=74
     dict(name="M_T150", cfg=CONFORMER_M, B=2, Tin=605, seed=23, with_lengths=True),  # T'=150 (>1 key tile)
     dict(name="L", cfg=CONFORMER_L, B=2, Tin=201, seed=24, with_lengths=True),       # T'=49
+    # BASELINE configs at their own shape: C1 in full (Conformer-S, 4 x 10 s, lengths all 1001) and one
+    # long-form utterance of C5 (Conformer-M, 60 s -> T'=1499)
+    dict(name="C1", cfg=CONFORMER_S, B=4, Tin=1001, seed=25, with_lengths="full"),   # T'=249
+    dict(name="C5_B1", cfg=CONFORMER_M, B=1, Tin=6001, seed=26, with_lengths="full"),  # T'=1499
 ]
+
+
+def case_lengths(case):
+    """lengths tensor of an encoder case: None, synth_lengths (sorted, first = Tin) or all = Tin ("full")."""
+    import torch
+    from conformer_b200.synth import synth_lengths
+    if not case["with_lengths"]:
+        return None
+    if case["with_lengths"] == "full":
+        return torch.full((case["B"],), case["Tin"], dtype=torch.long)
+    return synth_lengths(case["B"], case["Tin"])
 
 SUBMODULE_CFG = dict(cfg=EncoderConfig(80, 1, 64, 4, 31), B=3, T=41, seed=5, x_seed=6,
                      lengths=[41, 30, 1], Tin=171, mel_lengths=[171, 100, 9])
 
 TOKEN_CASE = dict(cfg=EncoderConfig(80, 4, 144, 4, 31), B=4, Tin=401, seed=31, vocab=370, peaky=8.0)
+# d_model 256 so that the bf16 tensor-core path takes it: the bf16 greedy-token gate (BASELINE.md section 5)
+TOKEN_CASE_BF16 = dict(cfg=EncoderConfig(80, 4, 256, 4, 31), B=4, Tin=401, seed=33, vocab=370, peaky=8.0, name="tokens_M")

@@ -24,7 +24,7 @@ sys.dont_write_bytecode = True
 
 from conformer_b200.synth import (EncoderConfig, synth_decoder_state_dict,   # noqa: E402
                                   synth_encoder_state_dict, synth_lengths, synth_logmel)
-from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE                  # noqa: E402
+from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE, TOKEN_CASE_BF16, case_lengths  # noqa: E402
 
 from model.conformer import Conformer                                        # noqa: E402
 from model.modules.encoder import Encoder                                    # noqa: E402
@@ -52,7 +52,7 @@ def reset_mask_value(m):
 def run_encoder_case(name, cfg: EncoderConfig, B, Tin, seed, with_lengths):
     sd = synth_encoder_state_dict(cfg, seed)
     x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=1000 + seed)
-    lengths = synth_lengths(B, Tin) if with_lengths else None
+    lengths = case_lengths(dict(B=B, Tin=Tin, with_lengths=with_lengths))
     enc = Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size).eval()
     enc.load_state_dict(sd, strict=True)
     y32, l32 = enc(x, lengths)
@@ -122,10 +122,10 @@ def run_submodules():
     print("submodules:", {k_: v.shape for k_, v in out.items()})
 
 
-def run_tokens():
-    cfg, B, Tin, seed, vocab = (TOKEN_CASE[k] for k in ("cfg", "B", "Tin", "seed", "vocab"))
+def run_tokens(case=TOKEN_CASE):
+    cfg, B, Tin, seed, vocab = (case[k] for k in ("cfg", "B", "Tin", "seed", "vocab"))
     sd = synth_encoder_state_dict(cfg, seed, prefix="encoder.")
-    sd.update(synth_decoder_state_dict(cfg.d_model, vocab, seed=seed + 1, peaky=TOKEN_CASE["peaky"]))
+    sd.update(synth_decoder_state_dict(cfg.d_model, vocab, seed=seed + 1, peaky=case["peaky"]))
     model = Conformer(vocab, cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size).eval()
     model.load_state_dict(sd, strict=True)
     x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=2000 + seed)
@@ -152,17 +152,23 @@ def run_tokens():
     flat = np.full((B, max(len(t) for t in toks)), -1, dtype=np.int64)
     for i, t in enumerate(toks):
         flat[i, :len(t)] = t
-    np.savez_compressed(os.path.join(HERE, "tokens.npz"), logits=logits.numpy(), ids=ids.numpy(),
+    np.savez_compressed(os.path.join(HERE, case.get("name", "tokens") + ".npz"), logits=logits.numpy(), ids=ids.numpy(),
                         tokens=flat, out_lengths=out_len.numpy(), margin=margin.numpy())
     print(f"tokens: logits {tuple(logits.shape)} median margin {margin.median():.4f} "
           f"min margin {margin.min():.5f} tokens/utt {[len(t) for t in toks]}")
 
 
 if __name__ == "__main__":
-    run_submodules()
+    only = set(sys.argv[1:])                       # optional: names of the fixtures to (re)generate
+    if not only or "submodules" in only:
+        run_submodules()
     for c in ENCODER_CASES:
-        run_encoder_case(**c)
-    run_tokens()
+        if not only or c["name"] in only:
+            run_encoder_case(**c)
+    if not only or "tokens" in only:
+        run_tokens()
+    if not only or "tokens_M" in only:
+        run_tokens(TOKEN_CASE_BF16)
 
 
 def dump_state_dict_keys():

@@ -46,3 +46,9 @@ def assert_close_bf16(a, b, what=""):
     r = bf16_report(a, b)
     assert r["rel_fro"] <= 2e-2 and r["frac_in_gate"] >= 0.99 and r["max_abs"] <= 0.15, f"{what}: {r}"
     return r
+
+
+def fp32_gate_ratio(a, b):
+    """max over elements of |a-b| / (1e-5 + 1e-4*|b|): <= 1 means inside the fp32 gate."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float(((a - b).abs() / (FP32_ATOL + FP32_RTOL * b.abs())).max())

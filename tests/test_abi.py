@@ -23,7 +23,7 @@ def test_library_builds_and_loads():
     from conformer_b200.build import build
     path = build()
     assert os.path.exists(path)
-    assert _lib.lib().cfm_abi_version() == 1
+    assert _lib.lib().cfm_abi_version() == 2
 
 
 def test_every_header_symbol_is_exported_and_bound():

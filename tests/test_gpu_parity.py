@@ -5,10 +5,10 @@ import pytest
 import torch
 
 import conformer_b200 as cb
-from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE
+from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE, TOKEN_CASE_BF16, case_lengths
 from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, synth_decoder_state_dict, synth_encoder_state_dict,
                                   synth_lengths, synth_logmel)
-from helpers import assert_close_bf16, assert_close_fp32, bf16_report, golden, sub
+from helpers import assert_close_bf16, assert_close_fp32, bf16_report, fp32_gate_ratio, golden, sub
 from oracle import conformer_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -81,7 +81,9 @@ def test_block_fp32(subcase, masked):
     cfg, sd, x, lengths, pos, gold = subcase
     m = _load(cb.ConformerBlock(cfg.d_model, cfg.n_heads, cfg.kernel_size), sub(sd, "layers.0."))
     mask = (~cb.generate_padding_mask(lengths))[:, None, None, :] if masked else None
-    assert_close_fp32(m(x, pos, mask), gold["block_mask" if masked else "block_nomask"], "block", scale=2.0)
+    y = m(x, pos, mask)
+    print("block fp32 gate ratio (<= 1 passes):", fp32_gate_ratio(y, gold["block_mask" if masked else "block_nomask"]))
+    assert_close_fp32(y, gold["block_mask" if masked else "block_nomask"], "block")
 
 
 def test_subsampling_fp32(subcase):
@@ -98,7 +100,8 @@ def _encoder_case(case):
     cfg = case["cfg"]
     sd = synth_encoder_state_dict(cfg, case["seed"])
     x = synth_logmel(case["B"], cfg.n_mel_channels, case["Tin"], seed=1000 + case["seed"]).to(DEV)
-    lengths = synth_lengths(case["B"], case["Tin"]).to(DEV) if case["with_lengths"] else None
+    lengths = case_lengths(case)
+    lengths = None if lengths is None else lengths.to(DEV)
     enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
     return enc, x, lengths, golden("encoder_" + case["name"])
 
@@ -107,8 +110,15 @@ def _encoder_case(case):
 def test_encoder_fp32_vs_reference_golden(case):
     enc, x, lengths, gold = _encoder_case(case)
     y, out_len = enc(x, lengths)
-    # two fp32 implementations with different summation orders: 4x the single-op gate over 16 layers
-    assert_close_fp32(y, gold["y"], "encoder fp32", scale=4.0)
+    # north_star: fp32 encoder outputs within rtol 1e-4 (gate |a-b| <= 1e-5 + 1e-4*|b|), asserted
+    # at 1x.  Where the fixture holds the reference's fp64 run, both fp32 implementations are also placed against it:
+    # the ratio is max |err| / gate, so <= 1 passes.
+    r = {"ours_vs_ref32": fp32_gate_ratio(y, gold["y"])}
+    if "y64" in gold:
+        r["ours_vs_ref64"] = fp32_gate_ratio(y, gold["y64"])
+        r["ref32_vs_ref64"] = fp32_gate_ratio(gold["y"], gold["y64"])
+    print("fp32 gate ratios", case["name"], {k: round(v, 4) for k, v in r.items()})
+    assert_close_fp32(y, gold["y"], "encoder fp32")
     if lengths is not None:
         assert torch.equal(out_len.cpu(), gold["out_lengths"])
     else:
@@ -168,18 +178,21 @@ def test_reload_weights_repacks():
     assert (y_other.cpu() - gold["y"]).abs().max() > 1e-2
     enc.load_state_dict(synth_encoder_state_dict(cfg, ENCODER_CASES[0]["seed"]))
     y, _ = enc(x, lengths)
-    assert_close_fp32(y, gold["y"], "reloaded", scale=4.0)
+    assert_close_fp32(y, gold["y"], "reloaded")
 
 
-@pytest.mark.parametrize("name,cfg,B,Tin", [("C2-M", CONFORMER_M, 8, 1501), ("C3-L", CONFORMER_L, 4, 2001)])
-def test_encoder_bf16_full_length_vs_oracle(name, cfg, B, Tin):
-    """Full utterance lengths of BASELINE configs 2/3 (reduced batch so the fp32 oracle stays quick);
-    oracle = the restated reference run in fp32 on the GPU with TF32 disabled."""
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("name,cfg,B,Tin,full", [("C2-M", CONFORMER_M, 64, 1501, True), ("C3-L", CONFORMER_L, 32, 2001, False),
+                                                 ("C5-M", CONFORMER_M, 16, 6001, True), ("C2-M-varlen", CONFORMER_M, 8, 1501, False)])
+def test_encoder_bf16_full_length_vs_oracle(name, cfg, B, Tin, full):
+    """BASELINE configs 2, 3 and 5 at their OWN shape (batch 64 x 15 s with lengths all 1501; batch 32 x 20 s with the
+    variable lengths of SURVEY 8d; batch 16 x 60 s, T' = 1499); oracle = the restated reference run in fp32 on the GPU
+    with TF32 disabled."""
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     sd = synth_encoder_state_dict(cfg, 7)
     x = synth_logmel(B, cfg.n_mel_channels, Tin, seed=8).to(DEV)
-    lengths = synth_lengths(B, Tin).to(DEV)
+    lengths = (torch.full((B,), Tin, dtype=torch.long) if full else synth_lengths(B, Tin)).to(DEV)
     enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
     y, out_len = enc.set_compute("bf16")(x, lengths)
     sd_dev = {k: v.to(DEV) for k, v in sd.items()}
@@ -252,12 +265,7 @@ def test_rel_attention_bf16_factorised_vs_oracle(T, masked):
     m = _load(cb.RelativeMultiHeadAttention(d, H), sd).set_compute("bf16")
     mask = key_is_pad[:, None, None, :].to(DEV) if masked else None
     xd = x.to(DEV)
-    from conformer_b200._lib import check, lib
-    check(lib().cfm_set_attention_kernel(1))
-    try:
-        got = m(xd, xd, xd, None, mask)
-    finally:
-        check(lib().cfm_set_attention_kernel(0))
+    got = m(xd, xd, xd, None, mask)              # no table: the module's own sinusoids -> factorised kernel
     assert torch.isfinite(got).all()
     rel = ((got.cpu() - want).norm() / want.norm()).item()
     # the relative-shift kernel on the same inputs (explicit table) is the yardstick
@@ -336,8 +344,9 @@ def test_ffn_module_bf16_fused_vs_oracle(rows):
 
 
 @pytest.mark.parametrize("B,T", [(1, 5), (2, 130), (4, 374)])
-def test_mhsa_module_bf16_ln_fused_vs_oracle(B, T):
-    """d_model = 256 in bf16 mode: LayerNorm is fused into the q|k|v projection kernel (ln_gemm)."""
+def test_mhsa_module_bf16_vs_oracle(B, T):
+    """MultiHeadSelfAttentionModule in bf16 at d_model = 256 with a caller-supplied table: LayerNorm -> fused q|k|v
+    projection -> relative-shift attention kernel -> out_proj."""
     d, H = 256, 4
     sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 70), "layers.0.attention.")
     g = torch.Generator().manual_seed(B * 100 + T)
@@ -499,3 +508,171 @@ def test_forward_host_pipelined_matches_forward():
     for (y_g, l_g), (y_w, l_w) in zip(got, want):
         assert torch.equal(l_g, l_w.cpu())
         assert torch.allclose(y_g, y_w.cpu(), rtol=1e-5, atol=1e-6)
+
+
+def test_greedy_ctc_tokens_bf16_gate():
+    """north_star: greedy CTC token ids bit-exact.  BASELINE.md section 5: on bf16 with the top-1/top-2 margin histogram
+    reported.  The reference Conformer (fp32, CPU) gives the golden logits, frame ids, margins and tokens; our bf16
+    tensor-core encoder feeds the same stock Decoder.  Frame ids must agree wherever the reference's own top-1/top-2
+    margin exceeds THR (a bf16 logit cannot be asked to resolve a tie finer than its own rounding noise - the measured
+    max logit error is printed next to THR), and the collapsed token lists must be IDENTICAL."""
+    c = TOKEN_CASE_BF16
+    cfg = c["cfg"]
+    gold = golden(c["name"])
+    sd = synth_encoder_state_dict(cfg, c["seed"], prefix="encoder.")
+    sd.update(synth_decoder_state_dict(cfg.d_model, c["vocab"], seed=c["seed"] + 1, peaky=c["peaky"]))
+    model = _load(cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size), sd)
+    x = synth_logmel(c["B"], cfg.n_mel_channels, c["Tin"], seed=2000 + c["seed"]).to(DEV)
+    lengths = synth_lengths(c["B"], c["Tin"]).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    model.encoder.set_compute("bf16")
+    logits, out_len = model(x, lengths)
+    assert torch.equal(out_len.cpu(), gold["out_lengths"])
+    margin = gold["margin"]
+    edges = [0.0, 0.01, 0.03, 0.1, 0.3, 1.0, 3.0, float("inf")]
+    hist = {f"[{a},{b})": int(((margin >= a) & (margin < b)).sum()) for a, b in zip(edges[:-1], edges[1:])}
+    err = (logits.cpu() - gold["logits"]).abs().max().item()
+    THR = 0.1
+    ids = logits.cpu().argmax(-1)
+    flips = ids != gold["ids"]
+    print(f"bf16 token gate: reference top-1/top-2 margin histogram {hist}; max |logit error| {err:.4f}; "
+          f"frames with margin <= {THR}: {int((margin <= THR).sum())}/{margin.numel()}; argmax flips {int(flips.sum())} "
+          f"(at margins {[round(float(v), 4) for v in margin[flips]]})")
+    assert err < THR / 2, "bf16 logit error must stay below half the margin threshold"
+    assert torch.equal(ids[margin > THR], gold["ids"][margin > THR])
+    want = [[int(t) for t in row if t >= 0] for row in gold["tokens"]]
+    tok_dev, cnt_dev = cb.greedy_ctc_decode(logits)
+    got = [tok_dev[b, :cnt_dev[b]].tolist() for b in range(tok_dev.shape[0])]
+    assert got == want, (got, want)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_all_keys_masked_sample_matches_reference_uniform_softmax(mode):
+    """A sample whose keys are ALL masked: the reference's masked_fill(finfo.min) + softmax is uniform over every key
+    (attention.py:60-66), i.e. the context is the mean of V.  Reachable through ConformerBlock / the attention modules
+    with a caller-supplied mask."""
+    B, T, d, H = 3, 70, 256, 4
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, H, 31), 53), "layers.0.")
+    g = torch.Generator().manual_seed(53)
+    x = torch.randn(B, T, d, generator=g)
+    pos = O.rel_pos_table(T, d)
+    pad = torch.zeros(B, T, dtype=torch.bool)
+    pad[1, :] = True                                   # sample 1: nothing valid
+    pad[2, 40:] = True
+    want = O.conformer_block(sd, "", x, pos, pad, H)
+    m = _load(cb.ConformerBlock(d, H, 31), sd).set_compute(mode)
+    got = m(x.to(DEV), pos[None].expand(B, -1, -1).to(DEV), pad[:, None, None, :].to(DEV))
+    if mode == "fp32":
+        assert_close_fp32(got, want, "block with an all-masked sample")
+    else:
+        print(assert_close_bf16(got, want, "block with an all-masked sample"))
+    att = _load(cb.MultiHeadSelfAttentionModule(d, H), sub(sd, "attention.")).set_compute(mode)
+    want_a = O.mhsa_module(sd, "attention.", x, pos, pad, H)
+    got_a = att(x.to(DEV), pos[None].expand(B, -1, -1).to(DEV), pad[:, None, None, :].to(DEV))
+    rel = ((got_a.cpu() - want_a).norm() / want_a.norm()).item()
+    assert rel < (1e-5 if mode == "fp32" else 2e-2), rel
+
+
+def test_ffn_shared_row_tiles_two_streams_match_single_tile_rows():
+    """Regression for the round-1 race: with more row tiles than SMs the left-over tiles are shared by several CTAs
+    which each ADD their part into the residual.  The kernel now never reads the buffer it updates, so the result must
+    not depend on CTA timing: many repeats on two streams, every row compared with a small-batch run of the same rows
+    (one tile per CTA, nothing shared)."""
+    d = 256
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 61), "layers.0.ffn_1.")
+    m = _load(cb.FeedForwardModule(d), sd).set_compute("bf16")
+    M = 148 * 128 + 39 * 128 + 17                       # 188 tiles: 40 of them shared
+    g = torch.Generator().manual_seed(61)
+    x = (torch.randn(1, M, d, generator=g) * 1.5 + 0.3).to(DEV)
+    ref = torch.cat([m(x[:, i:i + 64 * 128]) for i in range(0, M, 64 * 128)], dim=1)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = []
+    for i in range(24):
+        with torch.cuda.stream(streams[i & 1]):
+            outs.append(m(x))
+    torch.cuda.synchronize()
+    for y in outs:
+        # identical bf16 products; only the fp32 summation order of the shared tiles' partial sums may differ
+        assert (y - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-6
+
+
+def test_ffn_in_place_through_the_c_abi():
+    """include/conformer_b200.h: cfm_ffn_forward's y may alias x (bf16 and fp32 modes)."""
+    from conformer_b200._lib import check, lib
+    d = 256
+    sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 62), "layers.0.ffn_1.")
+    g = torch.Generator().manual_seed(62)
+    x = torch.randn(3, 50, d, generator=g).to(DEV)
+    for mode in ("fp32", "bf16"):
+        m = _load(cb.FeedForwardModule(d), sd).set_compute(mode)
+        want = m(x)
+        buf = x.clone()
+        h = m._native()
+        ws = m._workspace(h, 3, 50, buf.device)
+        check(lib().cfm_ffn_forward(h, buf.data_ptr(), buf.data_ptr(), 3, 50, ws.data_ptr(), ws.numel(),
+                                    torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.allclose(buf, want, rtol=1e-5, atol=1e-6), mode
+
+
+def test_captured_graph_owns_its_workspace():
+    """Encoder.capture: a later, LARGER forward on a stream with the same id must not free or share the scratch the
+    graph replays into."""
+    cfg = cb.EncoderConfig(80, 2, 256, 4, 31)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size),
+                synth_encoder_state_dict(cfg, 12)).set_compute("bf16")
+    x = synth_logmel(2, 80, 301, seed=31).to(DEV)
+    cap = enc.capture(x, None)
+    y0 = cap.replay()[0].clone()
+    big = synth_logmel(9, 80, 1201, seed=32).to(DEV)
+    for _ in range(3):
+        enc(big, None)                                  # regrows every cached per-stream workspace
+    torch.cuda.synchronize()
+    y1 = cap.replay()[0]
+    torch.cuda.synchronize()
+    assert ((y1 - y0).norm() / y0.norm()).item() < 2e-3
+    assert cap.workspace.numel() > 0
+
+
+def test_forward_host_bf16_transfer_dtypes():
+    """cfm_encoder_forward_host_io with bf16 host buffers: a bf16 mel gives the bf16 path's result for the rounded mel
+    (its first kernel rounds the mel anyway), a bf16 result is the fp32 result rounded once."""
+    cfg = cb.EncoderConfig(80, 2, 256, 4, 31)
+    enc = _load(cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size),
+                synth_encoder_state_dict(cfg, 18)).set_compute("bf16")
+    B, Tin = 3, 333
+    x = synth_logmel(B, 80, Tin, seed=40)
+    lens = torch.tensor([333, 200, 90])
+    T2 = enc.output_frames(Tin)
+    want, want_len = enc(x.bfloat16().float().to(DEV), lens.to(DEV))
+    xh = x.bfloat16().pin_memory()
+    yh16 = torch.empty(B, T2, 256, dtype=torch.bfloat16).pin_memory()
+    yh32 = torch.empty(B, T2, 256).pin_memory()
+    lo = torch.empty(B, dtype=torch.int64).pin_memory()
+    enc.forward_host(xh, lens.pin_memory(), yh32, lo)
+    torch.cuda.synchronize()
+    assert torch.equal(lo, want_len.cpu())
+    assert ((yh32 - want.cpu()).norm() / want.cpu().norm()).item() < 2e-3
+    cin, cout = torch.cuda.Stream(), torch.cuda.Stream()
+    enc.forward_host_pipelined(xh, lens.pin_memory(), yh16, lo, 0, cin, cout)
+    torch.cuda.synchronize()
+    assert ((yh16.float() - want.cpu()).norm() / want.cpu().norm()).item() < 5e-3
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_modules_follow_their_tensors_device():
+    """A module on cuda:1 called while cuda:0 is current (what PyTorch modules do transparently), and two devices used
+    from one process (per-device kernel attributes)."""
+    cfg = cb.EncoderConfig(80, 1, 256, 4, 31)
+    sd = synth_encoder_state_dict(cfg, 19)
+    x = synth_logmel(2, 80, 201, seed=41)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+        enc.load_state_dict(sd)
+        enc = enc.to(dev).eval().set_compute("bf16")
+        torch.cuda.set_device(0)
+        outs.append(enc(x.to(dev), None)[0].cpu())
+    assert ((outs[0] - outs[1]).norm() / outs[0].norm()).item() < 2e-3

@@ -63,9 +63,12 @@ def test_greedy_ctc_edge_cases():
 
 
 def test_flop_count_matches_baseline_md():
-    assert abs(O.encoder_flops(64, 1501, 256, 16) / 1e9 - 1986.9) < 0.5
-    assert abs(O.encoder_flops(32, 2001, 512, 17) / 1e9 - 5309.2) < 1.0      # C3
-    assert abs(O.encoder_flops(4, 1001, 144, 16) / 1e9 - 27.2) < 0.1         # C1
+    from conformer_b200.synth import encoder_flops
+    for f in (O.encoder_flops, encoder_flops):                               # the oracle's count and the product's agree
+        assert abs(f(64, 1501, 256, 16) / 1e9 - 1986.9) < 0.5
+        assert abs(f(32, 2001, 512, 17) / 1e9 - 5309.2) < 1.0                # C3
+        assert abs(f(4, 1001, 144, 16) / 1e9 - 27.2) < 0.1                   # C1
+        assert abs(f(16, 6001, 256, 16) / 1e9 - 2658.7) < 1.0                # C5, B = 16
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
