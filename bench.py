@@ -1,29 +1,33 @@
 #!/usr/bin/env python
 """Headline benchmark: Conformer-M encoder forward, audio-seconds per second (RTFx).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2|C3|C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C5]
 
 One "step" = one encoder forward over one synthetic batch of the named workload (BASELINE.json
-configs[1] = "C2": Conformer-M, d=256, 16 blocks, 4 heads, bf16, 64 x 15 s of 80-mel log-fbank).
+configs[1] = "C2": Conformer-M, d=256, 16 blocks, 4 heads, bf16, 64 x 15 s of 80-mel log-fbank,
+lengths all 1501 so the padding-mask path is inside the timed forward).
 For N > 1 launch under torchrun (one rank per GPU); each rank runs the same per-GPU batch
 (weak scaling, utterances are independent - no collective on the data path), and the time is the
 max over ranks of a CUDA-event interval bracketed by barriers.
 
 Printed JSON (rank 0, one line):
-  value          whole-job audio-s/s with the mel batch already resident in HBM
-  e2e            the same through cfm_encoder_forward_host: pinned HOST mel in, HOST result out,
-                 H2D/D2H copies inside the timed region
-  roofline       the dominant kernel class (tcgen05 GEMMs), timed per launch with CUDA events on the
-                 launching stream in a separate profiled pass of the same steps; `kernels` lists all
-  cpu_baseline   the oracle (a port of the reference's algorithm; the reference itself is a Python
-                 package that does not exist on the GPU box) on this box's host cores, bounded sample
-  --impl reference  times that CPU path alone, same metric/config.
+  value                whole-job audio-s/s with the mel batch already resident in HBM (K steps / total time)
+  ms_per_step_median   median over the K steps of the interval between consecutive step completions
+  e2e                  the same through the host-buffer entry point (cfm_encoder_forward_host_io): pinned HOST mel in,
+                       HOST result out, H2D/D2H copies inside the timed region
+  roofline             the dominant single kernel, timed per launch with CUDA events on the launching stream in a
+                       separate profiled pass of the same steps; `kernels` lists all classes
+  gpu_eager_baseline   the reference's own modules (baseline/_ref when it travelled, else the oracle port) run EAGERLY
+                       on this GPU under torch.autocast(bf16) at the same batch: the cuBLAS/cuDNN bar
+  configs              the other BASELINE configs (C1 fp32, C3, C5) at their own shape: ms_per_step, RTFx, dominant kernel
+  strong               strong scaling: the named batch split over the N ranks
+  cpu_baseline         the reference's CPU path on this box's host cores, bounded sample
+  --impl reference     times that CPU path alone, same metric/config.
 """
 from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import statistics
 import subprocess
@@ -36,18 +40,20 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, EncoderConfig, synth_encoder_state_dict,  # noqa: E402
-                                  synth_lengths, synth_logmel, subsampled_frames)
+from conformer_b200.synth import (CONFORMER_L, CONFORMER_M, CONFORMER_S, EncoderConfig, encoder_flops,  # noqa: E402
+                                  synth_encoder_state_dict, synth_lengths, synth_logmel, subsampled_frames)
 
 WORKLOADS = {
-    # name: (cfg, batch per GPU, mel frames, variable lengths, description)
-    "C2": (CONFORMER_M, 64, 1501, False, "Conformer-M encoder fwd, 64x15s, bf16 (BASELINE configs[1])"),
-    "C3": (CONFORMER_L, 32, 2001, True, "Conformer-L encoder fwd, 32x20s var-len, bf16 (BASELINE configs[2])"),
-    "C5": (CONFORMER_M, 16, 6001, False, "Conformer-M encoder fwd, 16x60s long-form, bf16 (BASELINE configs[4])"),
+    # name: (cfg, batch per GPU, mel frames, lengths: "full" | "var", compute, description)
+    "C1": (CONFORMER_S, 4, 1001, "full", "fp32", "Conformer-S encoder fwd, 4x10s, fp32 (BASELINE configs[0])"),
+    "C2": (CONFORMER_M, 64, 1501, "full", "bf16", "Conformer-M encoder fwd, 64x15s, bf16 (BASELINE configs[1])"),
+    "C3": (CONFORMER_L, 32, 2001, "var", "bf16", "Conformer-L encoder fwd, 32x20s var-len, bf16 (BASELINE configs[2])"),
+    "C5": (CONFORMER_M, 16, 6001, "full", "bf16", "Conformer-M encoder fwd, 16x60s long-form, bf16 (BASELINE configs[4])"),
     # tiny shape used only by the CPU multi-process tests of the harness itself
-    "T0": (EncoderConfig(80, 2, 64, 4, 31), 2, 101, True, "harness self-test (not a benchmark workload)"),
+    "T0": (EncoderConfig(80, 2, 64, 4, 31), 2, 101, "var", "fp32", "harness self-test (not a benchmark workload)"),
 }
 FRAME_SEC = 0.01   # hop 160 @ 16 kHz (train.py:105,109)
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
 def load_peaks():
@@ -130,59 +136,104 @@ def whole_job_rtfx(world: int, secs_per_rank_step: float, ms_per_step: float) ->
     return world * secs_per_rank_step / (ms_per_step * 1e-3)
 
 
+def strong_scaling_batches(batch: int, world: int):
+    """Strong scaling: the named batch split over the ranks (first ranks take the remainder)."""
+    return [batch // world + (1 if r < batch % world else 0) for r in range(world)]
+
+
+def make_lengths(mode: str, batch: int, t_in: int):
+    if mode == "full":
+        return torch.full((batch,), t_in, dtype=torch.long)
+    return synth_lengths(batch, t_in)
+
+
 def audio_seconds(lengths, batch, t_in):
     return float(lengths.sum().item() if lengths is not None else batch * t_in) * FRAME_SEC
 
 
-def cpu_reference_rtfx(cfg, t_in, var_len, budget_s=20.0, sample_batch=4):
-    """The reference's algorithm (oracle port) on the host cores: fp32, all threads, bounded sample."""
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            return next((l.split(":", 1)[1].strip() for l in fh if l.startswith("model name")), "?")
+    except OSError:
+        return "?"
+
+
+# ----------------------------------------------------------------------------------------- the reference itself
+def reference_encoder(cfg, sd):
+    """The reference's own Encoder (baseline/_ref, installed by baseline/install_ref.py; it does not exist in git and
+    /root/reference does not exist on the GPU box) with the seeded weights, or None when it did not travel."""
+    if not os.path.isdir(os.path.join(REF_DIR, "model")):
+        return None
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    sys.dont_write_bytecode = True
+    from model.modules.encoder import Encoder as RefEncoder
+    enc = RefEncoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size).eval()
+    enc.load_state_dict(sd, strict=True)
+    return enc
+
+
+def reference_forward_fn(cfg, sd, device):
+    """(callable(x, lengths) -> y, kind): the reference module when available, else the oracle port of it."""
+    enc = reference_encoder(cfg, sd)
+    if enc is not None:
+        enc = enc.to(device)
+
+        def run(x, lengths):
+            for m in enc.modules():                       # attention.py:60-61 caches a dtype-specific constant
+                if hasattr(m, "mask_value"):
+                    m.mask_value = None
+            return enc(x, lengths)[0]
+        return run, "reference"
     from oracle import conformer_oracle as O
+    sd_dev = {k: v.to(device) for k, v in sd.items()}
+    return (lambda x, lengths: O.encoder(sd_dev, x, lengths, cfg.n_heads)[0]), "port"
+
+
+def cpu_reference_rtfx(cfg, t_in, len_mode, budget_s=20.0, sample_batch=4):
+    """The reference's CPU path on the host cores: fp32, all threads, bounded sample."""
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth_encoder_state_dict(cfg, 0)
+    run, kind = reference_forward_fn(cfg, sd, "cpu")
     x = synth_logmel(sample_batch, cfg.n_mel_channels, t_in, seed=1234)
-    lengths = synth_lengths(sample_batch, t_in) if var_len else None
+    lengths = make_lengths(len_mode, sample_batch, t_in)
     secs = audio_seconds(lengths, sample_batch, t_in)
     times = []
     with torch.inference_mode():
         t0 = time.perf_counter()
-        O.encoder(sd, x, lengths, cfg.n_heads)                 # warm-up
+        run(x, lengths)                                          # warm-up
         first = time.perf_counter() - t0
         reps = max(1, min(5, int(budget_s / max(first, 1e-3)) - 1))
         for _ in range(reps):
             t0 = time.perf_counter()
-            O.encoder(sd, x, lengths, cfg.n_heads)
+            run(x, lengths)
             times.append(time.perf_counter() - t0)
     med = statistics.median(times) if times else first
-    model = "?"
-    try:
-        with open("/proc/cpuinfo") as fh:
-            model = next((l.split(":", 1)[1].strip() for l in fh if l.startswith("model name")), "?")
-    except OSError:
-        pass
-    return dict(value=secs / med, unit="audio-s/s", cores=torch.get_num_threads(), kind="port",
-                sample=f"oracle encoder fp32, batch {sample_batch} x {t_in} frames, median of {max(len(times), 1)} "
-                       f"after 1 warm-up, {med * 1e3:.0f} ms/forward, cpu '{model}'"), med
+    what = "reference Encoder (baseline/_ref)" if kind == "reference" else "oracle port of the reference Encoder"
+    return dict(value=secs / med, unit="audio-s/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"{what}, fp32, batch {sample_batch} x {t_in} frames, median of {max(len(times), 1)} "
+                       f"after 1 warm-up, {med * 1e3:.0f} ms/forward, cpu '{cpu_model_name()}'"), med
 
 
-def run_reference_arm(args, cfg, batch, t_in, var_len, desc):
+def run_reference_arm(args, cfg, batch, t_in, len_mode, desc):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, _ = cpu_reference_rtfx(cfg, t_in, var_len, budget_s=15.0)
-    # K timed "steps", each one bounded-sample forward
-    from oracle import conformer_oracle as O
+    base, _ = cpu_reference_rtfx(cfg, t_in, len_mode, budget_s=15.0)
     sd = synth_encoder_state_dict(cfg, 0)
+    run, kind = reference_forward_fn(cfg, sd, "cpu")
     sb = 4
     x = synth_logmel(sb, cfg.n_mel_channels, t_in, seed=1234)
-    lengths = synth_lengths(sb, t_in) if var_len else None
+    lengths = make_lengths(len_mode, sb, t_in)
     secs = audio_seconds(lengths, sb, t_in)
     steps = min(args.steps, 5)
     with torch.inference_mode():
         for _ in range(min(args.warmup, 1)):
-            O.encoder(sd, x, lengths, cfg.n_heads)
+            run(x, lengths)
         t0 = time.perf_counter()
         for _ in range(steps):
-            O.encoder(sd, x, lengths, cfg.n_heads)
+            run(x, lengths)
         dt = (time.perf_counter() - t0) / steps
     v = secs / dt
     base["value"] = v
@@ -195,6 +246,209 @@ def run_reference_arm(args, cfg, batch, t_in, var_len, desc):
     print(json.dumps(line), flush=True)
 
 
+def gpu_eager_baseline(cfg, batch, t_in, len_mode, dev, steps=5, warmup=2, seed=1234):
+    """The reference modules run eagerly on this GPU under bf16 autocast at the SAME batch (cuBLAS / cuDNN / ATen
+    sm_100 kernels): the kernel-for-kernel bar.  CUDA-event timed, median of `steps`."""
+    sd = synth_encoder_state_dict(cfg, 0)
+    run, kind = reference_forward_fn(cfg, sd, dev)
+    x = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=seed).to(dev)
+    lengths = make_lengths(len_mode, batch, t_in).to(dev)
+    secs = audio_seconds(lengths, batch, t_in)
+    out = {}
+    for name, ctx in (("bf16_autocast", lambda: torch.autocast("cuda", dtype=torch.bfloat16)),
+                      ("fp32_tf32_default", lambda: torch.autocast("cuda", enabled=False))):
+        times = []
+        try:
+            with torch.inference_mode(), ctx():
+                for _ in range(warmup):
+                    run(x, lengths)
+                torch.cuda.synchronize()
+                for _ in range(steps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    run(x, lengths)
+                    e1.record()
+                    e1.synchronize()
+                    times.append(e0.elapsed_time(e1))
+        except Exception as e:  # noqa: BLE001 - a reported baseline must never kill the bench line
+            out[name] = {"error": str(e)[:200]}
+            continue
+        ms = statistics.median(times)
+        out[name] = {"ms_per_step": ms, "value": secs / (ms * 1e-3), "unit": "audio-s/s", "steps": steps}
+        torch.cuda.empty_cache()
+    out["kind"] = kind
+    out["what"] = (("reference Encoder from baseline/_ref" if kind == "reference" else "oracle port of the reference Encoder")
+                   + f", eager PyTorch {torch.__version__} on this GPU, batch {batch} x {t_in} frames, median of {steps} "
+                   "CUDA-event-timed forwards after warm-up")
+    return out
+
+
+# ----------------------------------------------------------------------------------------- our arm
+class Bench:
+    """One workload on this rank's GPU: builds the encoder and the inputs, times device-resident steps."""
+
+    def __init__(self, cb, cfg, batch, t_in, len_mode, compute, dev, rank, dist):
+        self.cfg, self.batch, self.t_in, self.dev, self.dist = cfg, batch, t_in, dev, dist
+        sd = synth_encoder_state_dict(cfg, 0)
+        enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+        enc.load_state_dict(sd)
+        self.enc = enc.to(dev).eval().set_compute(compute)
+        self.x_host = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=rank_seed(rank)).pin_memory()
+        self.lengths_host = make_lengths(len_mode, batch, t_in).pin_memory()
+        self.x = self.x_host.to(dev)
+        self.lengths = self.lengths_host.to(dev)
+        self.t_out = subsampled_frames(t_in)
+        self.secs = audio_seconds(self.lengths_host, batch, t_in)
+        self.n_streams = int(os.environ.get("BENCH_STREAMS", "2"))
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(self.n_streams)]
+        self.count = 0
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(self):
+        self.enc(self.x, self.lengths)
+
+    def step_rotating(self):
+        i = self.count % self.n_streams
+        self.count += 1
+        with torch.cuda.stream(self.streams[i]):
+            self.step()
+        return i
+
+    def timed_serial(self, fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        return max_over_ranks(e0.elapsed_time(e1), self.dist, self.dev) / steps
+
+    def timed_rotating(self, steps, extra_streams=(), fn=None):
+        """K steps issued alternately on the compute streams (independent batches; the other stream's kernels fill the
+        SMs one forward leaves idle in partial waves and at kernel boundaries).  Returns (total/K, median of the
+        intervals between consecutive step completions), both max over ranks."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ends = []
+        self.barrier()
+        cur = torch.cuda.current_stream()
+        e0.record(cur)
+        every = list(self.streams) + list(extra_streams)
+        for st in every:
+            st.wait_event(e0)
+        for _ in range(steps):
+            st = (fn or self.step_rotating)()
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(st if not isinstance(st, int) else self.streams[st])
+            ends.append(ev)
+        for st in every:
+            cur.wait_stream(st)
+        e1.record(cur)
+        self.barrier()
+        t = sorted(e0.elapsed_time(ev) for ev in ends)
+        deltas = [b - a for a, b in zip([0.0] + t[:-1], t)]
+        # the first n_streams completions include the pipeline fill; the median ignores them by construction
+        med = statistics.median(deltas)
+        return (max_over_ranks(e0.elapsed_time(e1), self.dist, self.dev) / steps, max_over_ranks(med, self.dist, self.dev))
+
+    def profile(self, steps):
+        self.enc.profile(True)
+        for _ in range(steps):
+            self.step()
+        torch.cuda.synchronize()
+        prof = self.enc.collect_profile()
+        self.enc.profile(False)
+        return prof
+
+
+TENSOR_CLASSES = ("gemm_tcgen05", "attention", "gemm_fp32", "ffn_fused", "conv_fused")
+SINGLE_KERNEL_CLASSES = ("ffn_fused", "attention", "conv_fused", "conv1", "dwconv")
+
+
+def kernel_table(prof, prof_steps, peaks):
+    kernels = {}
+    for name, e in prof.items():
+        if e["launches"] == 0:
+            continue
+        ms = e["ms"] / prof_steps
+        k = {"launches_per_step": e["launches"] / prof_steps, "ms_per_step": ms}
+        if e["flops"] > 0:
+            k["tflops"] = e["flops"] / prof_steps / (ms * 1e-3) / 1e12
+        if e["bytes"] > 0:
+            k["gbs"] = e["bytes"] / prof_steps / (ms * 1e-3) / 1e9
+        kernels[name] = k
+    total = sum(k["ms_per_step"] for k in kernels.values())
+    for n, k in kernels.items():
+        k["share"] = k["ms_per_step"] / total if total else None
+        if "tflops" in k and n in TENSOR_CLASSES and n != "gemm_fp32":
+            k["tensor_frac"] = k["tflops"] / peaks["tensor"]
+        if "gbs" in k:
+            k["hbm_frac"] = k["gbs"] / peaks["hbm"]
+    return kernels
+
+
+def dominant_roofline(kernels, peaks):
+    """The roofline block describes ONE kernel (so does its ncu traffic figure): the most expensive class that is a single
+    kernel function; "gemm_tcgen05" aggregates several GEMM shapes and stays in `kernels`."""
+    single = [n for n in kernels if n in SINGLE_KERNEL_CLASSES]
+    dom_name = max(single or kernels, key=lambda n: kernels[n]["ms_per_step"])
+    dom = kernels[dom_name]
+    if "tflops" in dom and dom_name in TENSOR_CLASSES:
+        roof = {"kernel": dom_name, "bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tensor"],
+                "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tensor"], "traffic": None,
+                "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)"}
+    else:
+        roof = {"kernel": dom_name, "bound": "hbm", "achieved": dom.get("gbs"), "peak": peaks["hbm"], "unit": "GB/s",
+                "frac": (dom.get("gbs") or 0.0) / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} hbm_gbs"}
+    # roofline.traffic: DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        names = {"ffn_fused": ["ffn_fused_kernel"], "attention": ["rel_attention_fact_kernel", "rel_attention_tc_kernel"],
+                 "conv_fused": ["conv_module_fused_kernel"], "gemm_tcgen05": ["gemm_tc_kernel"], "conv1": ["conv1_tc_kernel"]}
+        for n in names.get(dom_name, []):
+            hit = [k for k in tr["kernels"] if k.startswith(n)]
+            if hit:
+                roof["traffic"] = tr["kernels"][hit[0]]["dram_bytes_per_launch"]
+                roof["traffic_source"] = "profiles/ncu_traffic.json (" + os.path.basename(tr["source"]) + "): " + hit[0]
+                break
+    except (OSError, ValueError, KeyError):
+        pass
+    return roof
+
+
+def side_config(cb, name, dev, rank, dist, world, steps, peaks):
+    """One of the other BASELINE configs at its own shape: device-resident two-stream time, single-stream time, dominant
+    kernel.  Fewer steps than the headline; same timing rules."""
+    cfg, batch, t_in, len_mode, compute, desc = WORKLOADS[name]
+    b = Bench(cb, cfg, batch, t_in, len_mode, compute, dev, rank, dist)
+    with torch.inference_mode():
+        for _ in range(3):
+            b.step()
+        for _ in range(2 * b.n_streams):
+            b.step_rotating()
+        ms_serial = b.timed_serial(b.step, steps)
+        ms, med = b.timed_rotating(steps)
+        prof = b.profile(min(steps, 3))
+    kernels = kernel_table(prof, min(steps, 3), peaks)
+    flops = encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
+    roof = dominant_roofline(kernels, peaks)
+    out = {"workload": desc, "dtype": "bf16" if compute == "bf16" else "f32", "per_gpu_batch": batch, "mel_frames": t_in,
+           "frames_out": b.t_out, "audio_seconds_per_gpu_step": b.secs, "steps": steps, "ms_per_step": ms,
+           "ms_per_step_median": med, "serial_ms_per_step": ms_serial, "value": whole_job_rtfx(world, b.secs, ms),
+           "unit": "audio-s/s", "algorithmic_tflops": flops / (ms * 1e-3) / 1e12,
+           "dominant_kernel": {k: roof[k] for k in ("kernel", "bound", "achieved", "unit", "frac")},
+           "kernels": {n: {kk: round(v, 4) for kk, v in k.items() if v is not None} for n, k in kernels.items()}}
+    if compute == "bf16":
+        out["tensor_frac_whole_step"] = out["algorithmic_tflops"] / peaks["tensor"]
+    del b
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -203,14 +457,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
-    ap.add_argument("--compute", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--compute", default=None, choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip gpu_eager_baseline, the other configs and strong scaling")
     args = ap.parse_args()
-    cfg, batch, t_in, var_len, desc = WORKLOADS[args.config]
+    cfg, batch, t_in, len_mode, compute, desc = WORKLOADS[args.config]
     if args.batch:
         batch = args.batch
+    if args.compute:
+        compute = args.compute
     if args.impl == "reference":
-        run_reference_arm(args, cfg, batch, t_in, var_len, desc)
+        run_reference_arm(args, cfg, batch, t_in, len_mode, desc)
         return
 
     import conformer_b200 as cb
@@ -225,146 +482,118 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     args.warmup = max(args.warmup, 3)
+    peaks = load_peaks()
 
-    sd = synth_encoder_state_dict(cfg, 0)
-    enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
-    enc.load_state_dict(sd)
-    enc = enc.to(dev).eval().set_compute(args.compute)
-    x_host = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=rank_seed(rank)).pin_memory()
-    lengths_host = synth_lengths(batch, t_in).pin_memory() if var_len else None
-    x = x_host.to(dev)
-    lengths = lengths_host.to(dev) if var_len else None
-    t_out = subsampled_frames(t_in)
+    b = Bench(cb, cfg, batch, t_in, len_mode, compute, dev, rank, dist)
+    enc, t_out = b.enc, b.t_out
+    n_dev_streams = b.n_streams
     y_host = torch.empty((batch, t_out, cfg.d_model), dtype=torch.float32).pin_memory()
-    lo_host = torch.empty(batch, dtype=torch.int64).pin_memory() if var_len else None
-    secs_per_step = audio_seconds(lengths_host, batch, t_in)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
+    lo_host = torch.empty(batch, dtype=torch.int64).pin_memory()
+    # end to end: the mel crosses PCIe as bf16 when the bf16 tensor-core front-end takes it (its first kernel rounds the
+    # mel to bf16, so the result is bit-identical to an fp32 transfer - tests/test_gpu_parity.py), the result as fp32
+    # (the reference's output dtype under autocast).  The fp32-in form is timed next to it.
+    bf16_in = compute == "bf16" and cfg.d_model == 256
+    x_e2e = b.x_host.bfloat16().pin_memory() if bf16_in else b.x_host
 
     with torch.inference_mode():
-        step_dev = lambda: enc(x, lengths)                                              # noqa: E731
-        step_e2e = lambda: enc.forward_host(x_host, lengths_host, y_host, lo_host)     # noqa: E731
         for _ in range(args.warmup):
-            step_dev()
-        n_streams = int(os.environ.get("BENCH_STREAMS", "2"))
-        streams = [torch.cuda.Stream(device=dev) for _ in range(n_streams)]
-        counter = [0]
-
-        def on_alternating_streams(fn):
-            def step():
-                i = counter[0] % n_streams
-                counter[0] += 1
-                with torch.cuda.stream(streams[i]):
-                    fn()
-            return step
-
-        def timed_two_streams(fn, steps):
-            """K steps issued alternately on two streams (independent batches; the second stream's kernels fill the
-            SMs the first one leaves idle in partial waves and during kernel ramp-up/tail)."""
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            step = on_alternating_streams(fn)
-            barrier()
-            cur = torch.cuda.current_stream()
-            e0.record(cur)
-            for st in streams:
-                st.wait_event(e0)
-            for _ in range(steps):
-                step()
-            for st in streams:
-                cur.wait_stream(st)
-            e1.record(cur)
-            barrier()
-            return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
-
+            b.step()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        warm = on_alternating_streams(step_dev)
-        for _ in range(2 * n_streams):
-            warm()
+        for _ in range(2 * n_dev_streams):
+            b.step_rotating()
+        step_e2e_serial = lambda: enc.forward_host(x_e2e, b.lengths_host, y_host, lo_host)     # noqa: E731
         for _ in range(2):
-            step_e2e()
+            step_e2e_serial()
         if rank == 0:
             sampler.begin_timed()
-        ms_dev_serial = timed(step_dev, args.steps)
-        ms_dev = timed_two_streams(step_dev, args.steps)
+        ms_dev_serial = b.timed_serial(b.step, args.steps)
+        ms_dev, ms_dev_median = b.timed_rotating(args.steps)
         launches = enc.last_launch_count
-        # informational: the same forward replayed from a CUDA graph on one stream (Encoder.capture).  Replay removes the
-        # per-kernel launch latency a single stream pays (4.30 vs 4.55 ms), but two overlapping graph replays pack worse
-        # than two streams of plain launches (4.12 vs 3.86 ms), so the headline loop stays on stream launches.
+        # informational: the same forward replayed from a CUDA graph on one stream (Encoder.capture)
         ms_graph_serial = None
         try:
-            cap = enc.capture(x, lengths)
+            cap = enc.capture(b.x, b.lengths)
             for _ in range(3):
                 cap.replay()
-            ms_graph_serial = timed(cap.replay, args.steps)
+            ms_graph_serial = b.timed_serial(cap.replay, args.steps)
             del cap
         except Exception as e:  # noqa: BLE001 - optional measurement, never fatal
             sys.stderr.write(f"[bench] CUDA-graph replay skipped: {e}\n")
-        ms_e2e_serial = timed(step_e2e, args.steps)
-        # The end-to-end loop through cfm_encoder_forward_host_pipelined: BENCH_E2E_SLOTS (default 4) in-flight batches
-        # rotate over the same two compute streams; each step's H2D copy goes to a copy-in stream and its D2H copy to a
-        # copy-out stream, ordered by the library's per-slot events, so the compute streams never wait for a copy
-        # (with forward_host on rotating streams every stream spent ~1 ms of its cycle in its own copies: 4.34 ms/step;
-        # pipelined: 4.01 ms with 3 slots, 3.94 ms with 4).
-        # Every step still copies its own input from pinned host memory and lands its own result on the host inside
-        # the timed region.
-        n_dev_streams = n_streams
+        ms_e2e_serial = b.timed_serial(step_e2e_serial, args.steps)
+        # The end-to-end loop through cfm_encoder_forward_host_io: BENCH_E2E_SLOTS (default 4) in-flight batches rotate over
+        # the same compute streams; each step's H2D copy goes to a copy-in stream and its D2H copy to a copy-out stream,
+        # ordered by the library's per-slot events, so the compute streams never wait for a copy.  Every step still copies
+        # its own input from pinned host memory and lands its own result on the host inside the timed region.
         n_slots = int(os.environ.get("BENCH_E2E_SLOTS", "4")) if n_dev_streams > 1 else 1
         copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         y_hosts = [y_host] + [torch.empty_like(y_host).pin_memory() for _ in range(n_slots - 1)]
-        lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() if lo_host is not None else None for _ in range(n_slots - 1)]
+        lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() for _ in range(n_slots - 1)]
         e2e_count = [0]
 
-        def step_e2e_pipelined():
-            k = e2e_count[0]
-            e2e_count[0] += 1
-            with torch.cuda.stream(streams[k % n_dev_streams]):
-                enc.forward_host_pipelined(x_host, lengths_host, y_hosts[k % n_slots], lo_hosts[k % n_slots], k % n_slots,
-                                           copy_in, copy_out)
+        def make_e2e_step(xh):
+            def step():
+                k = e2e_count[0]
+                e2e_count[0] += 1
+                st = b.streams[k % n_dev_streams]
+                with torch.cuda.stream(st):
+                    enc.forward_host_pipelined(xh, b.lengths_host, y_hosts[k % n_slots], lo_hosts[k % n_slots], k % n_slots,
+                                               copy_in, copy_out)
+                return copy_out                       # a step is complete when its result has landed on the host
+            return step
 
-        def timed_pipelined(steps):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            cur = torch.cuda.current_stream()
-            e0.record(cur)
-            for st in streams + [copy_in, copy_out]:
-                st.wait_event(e0)
-            for _ in range(steps):
-                step_e2e_pipelined()
-            for st in streams + [copy_in, copy_out]:
-                cur.wait_stream(st)
-            e1.record(cur)
-            barrier()
-            return max_over_ranks(e0.elapsed_time(e1), dist, dev) / steps
-
+        step_e2e = make_e2e_step(x_e2e)
         for _ in range(2 * n_slots):
-            step_e2e_pipelined()
+            step_e2e()
         torch.cuda.synchronize()
-        ms_e2e = timed_pipelined(args.steps)
-        n_streams = n_slots
-        clocks = sampler.stop() if rank == 0 else None       # sampled across the four timed regions above
+        ms_e2e, ms_e2e_median = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_e2e)
+        ms_e2e_fp32in = None
+        if bf16_in:
+            step_f32 = make_e2e_step(b.x_host)
+            for _ in range(n_slots):
+                step_f32()
+            torch.cuda.synchronize()
+            ms_e2e_fp32in, _ = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_f32)
+        clocks = sampler.stop() if rank == 0 else None       # sampled across the timed regions above
         # profiled pass (per-launch CUDA events on the launching stream), not part of the headline
-        enc.profile(True)
         prof_steps = min(args.steps, 5)
-        for _ in range(prof_steps):
-            step_dev()
-        torch.cuda.synchronize()
-        prof = enc.collect_profile()
-        enc.profile(False)
+        prof = b.profile(prof_steps)
+
+        # strong scaling (SURVEY.md 8e "alongside"): the named batch split over the ranks
+        strong = None
+        if not args.no_extras:
+            mine = strong_scaling_batches(batch, world)[rank]
+            if world == 1:
+                strong = {"per_rank_batches": [batch], "ms_per_step": ms_dev, "value": whole_job_rtfx(1, b.secs, ms_dev),
+                          "unit": "audio-s/s", "note": "N = 1: identical to the weak-scaling line"}
+            else:
+                sb = Bench(cb, cfg, max(mine, 1), t_in, len_mode, compute, dev, rank, dist)
+                for _ in range(3):
+                    sb.step()
+                for _ in range(2 * sb.n_streams):
+                    sb.step_rotating()
+                ms_s, med_s = sb.timed_rotating(args.steps)
+                total_secs = audio_seconds(make_lengths(len_mode, batch, t_in), batch, t_in)
+                strong = {"per_rank_batches": strong_scaling_batches(batch, world), "ms_per_step": ms_s,
+                          "ms_per_step_median": med_s, "value": total_secs / (ms_s * 1e-3), "unit": "audio-s/s",
+                          "note": f"the {batch}-utterance batch split over {world} ranks; max-over-ranks device time"}
+                del sb
+                torch.cuda.empty_cache()
+
+    # the other BASELINE configs at their own shape, and the eager-PyTorch bar, on rank 0's GPU after the headline numbers
+    # (every rank runs them so the barriers match; only rank 0 reports)
+    configs, eager = {}, None
+    if not args.no_extras and args.config == "C2":
+        del b
+        torch.cuda.empty_cache()
+        for name in ("C1", "C3", "C5"):
+            try:
+                configs[name] = side_config(cb, name, dev, rank, dist, world, max(5, args.steps // 2), peaks)
+            except Exception as e:  # noqa: BLE001
+                configs[name] = {"error": str(e)[:300]}
+        if rank == 0:
+            eager = gpu_eager_baseline(cfg, batch, t_in, len_mode, dev)
 
     if dist is not None:
         dist.barrier()
@@ -373,73 +602,36 @@ def main():
             dist.destroy_process_group()
         return
 
-    peaks = load_peaks()
-    kernels = {}
-    for name, e in prof.items():
-        if e["launches"] == 0:
-            continue
-        ms = e["ms"] / prof_steps
-        k = {"launches_per_step": e["launches"] / prof_steps, "ms_per_step": ms}
-        if e["flops"] > 0:
-            k["tflops"] = e["flops"] / prof_steps / (ms * 1e-3) / 1e12
-        if e["bytes"] > 0:
-            k["gbs"] = e["bytes"] / prof_steps / (ms * 1e-3) / 1e9
-        kernels[name] = k
-    prof_total = sum(k["ms_per_step"] for k in kernels.values())
-    for k in kernels.values():
-        k["share"] = k["ms_per_step"] / prof_total if prof_total else None
-    # the roofline block describes ONE kernel (so does its ncu traffic figure): the most expensive class that is a single
-    # kernel function; "gemm_tcgen05" aggregates four GEMM shapes (conv2, linear, q|k|v, out_proj) and stays in `kernels`
-    single = [n for n in kernels if n in ("ffn_fused", "attention", "conv_fused", "conv1", "dwconv", "ln_gemm")]
-    dom_name = max(single or kernels, key=lambda n: kernels[n]["ms_per_step"])
-    dom = kernels[dom_name]
-    if "tflops" in dom and dom_name in ("gemm_tcgen05", "attention", "gemm_fp32", "ffn_fused", "ln_gemm"):
-        roof = {"kernel": dom_name, "bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tensor"],
-                "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tensor"], "traffic": None,
-                "peak_source": f"{peaks['src']} bf16_tflops_sustained (kernel timed inside a long step)"}
-    else:
-        roof = {"kernel": dom_name, "bound": "hbm", "achieved": dom.get("gbs"), "peak": peaks["hbm"], "unit": "GB/s",
-                "frac": (dom.get("gbs") or 0.0) / peaks["hbm"], "traffic": None, "peak_source": f"{peaks['src']} hbm_gbs"}
-    # roofline.traffic: DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/)
-    try:
-        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
-        names = {"ffn_fused": ["ffn_fused_kernel<1>", "ffn_fused_kernel"], "attention": ["rel_attention_fact_kernel", "rel_attention_tc_kernel"],
-                 "conv_fused": ["conv_module_fused_kernel"], "gemm_tcgen05": ["gemm_tc_kernel"], "conv1": ["conv1_tc_kernel"]}
-        for n in names.get(dom_name, []):
-            hit = [k for k in tr["kernels"] if k.startswith(n)]
-            if hit:
-                roof["traffic"] = tr["kernels"][hit[0]]["dram_bytes_per_launch"]
-                roof["traffic_source"] = "profiles/ncu_traffic.json (" + os.path.basename(tr["source"]) + "): " + hit[0]
-                break
-    except (OSError, ValueError, KeyError):
-        pass
-    if "dwconv" in kernels and "gbs" in kernels["dwconv"]:
-        kernels["dwconv"]["hbm_frac"] = kernels["dwconv"]["gbs"] / peaks["hbm"]
-    for n in ("gemm_tcgen05", "attention", "ffn_fused", "ln_gemm"):
-        if n in kernels and "tflops" in kernels[n]:
-            kernels[n]["tensor_frac"] = kernels[n]["tflops"] / peaks["tensor"]
-
-    from oracle.conformer_oracle import encoder_flops
+    kernels = kernel_table(prof, prof_steps, peaks)
+    roof = dominant_roofline(kernels, peaks)
     flops = encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
+    secs_per_step = audio_seconds(make_lengths(len_mode, batch, t_in), batch, t_in)
+    h2d = x_e2e.numel() * x_e2e.element_size() + batch * 8
+    d2h = y_host.numel() * 4 + batch * 8
     line = {
         "metric": "encoder audio-seconds per second (RTFx)", "value": whole_job_rtfx(world, secs_per_step, ms_dev),
         "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
-        "serial_ms_per_step": ms_dev_serial, "serial_cuda_graph_ms_per_step": ms_graph_serial, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.compute == "bf16" else "f32", "data": "synthetic",
+        "ms_per_step_median": ms_dev_median, "serial_ms_per_step": ms_dev_serial,
+        "serial_cuda_graph_ms_per_step": ms_graph_serial, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if compute == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": desc, "per_gpu_batch": batch, "mel_frames": t_in, "frames_out": t_out,
+                   "lengths": "all = mel_frames (padding-mask path inside the timed forward)" if len_mode == "full"
+                              else "sorted descending, linspace(Tin, Tin/2)",
                    "audio_seconds_per_gpu_step": secs_per_step, "parallelism": f"dp{world} (independent replicas)",
                    "issue": f"steps rotate over {n_dev_streams} CUDA streams per GPU (independent batches overlap at kernel "
-                            "boundaries); serial_ms_per_step is the single-stream time",
+                            "boundaries); serial_ms_per_step is the single-stream time; ms_per_step = total / steps, "
+                            "ms_per_step_median = median interval between consecutive step completions",
                    "l2": "no flush needed: one step streams ~1.3 GB of activations (conv1 output alone 958 MB) "
                          "through the 126 MB L2"},
         "e2e": {"value": whole_job_rtfx(world, secs_per_step, ms_e2e), "unit": "audio-s/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": x_host.numel() * 4 + (lengths_host.numel() * 8 if var_len else 0),
-                "d2h_bytes_per_step": y_host.numel() * 4 + (lo_host.numel() * 8 if var_len else 0),
-                "serial_ms_per_step": ms_e2e_serial,
-                "api": "cfm_encoder_forward_host_pipelined (Encoder.forward_host_pipelined): pinned host mel -> device -> "
-                       f"forward -> host; {n_slots} in-flight slots over {n_dev_streams} compute streams, copies on a copy-in and "
-                       "a copy-out stream ordered by the library's per-slot events; serial_ms_per_step is "
-                       "cfm_encoder_forward_host (copy, forward, copy) on a single stream",
+                "ms_per_step_median": ms_e2e_median, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "pcie_gbs_per_rank": {"h2d": h2d / (ms_e2e * 1e-3) / 1e9, "d2h": d2h / (ms_e2e * 1e-3) / 1e9},
+                "host_dtypes": {"mel": "bf16" if bf16_in else "f32", "result": "f32"},
+                "fp32_mel_ms_per_step": ms_e2e_fp32in, "serial_ms_per_step": ms_e2e_serial,
+                "api": "cfm_encoder_forward_host_io (Encoder.forward_host_pipelined): pinned host mel -> device -> forward -> "
+                       f"host; {n_slots} in-flight slots over {n_dev_streams} compute streams, copies on a copy-in and a "
+                       "copy-out stream ordered by the library's per-slot events; serial_ms_per_step is the same call "
+                       "(copy, forward, copy) on a single stream",
                 "slots": n_slots, "compute_streams": n_dev_streams},
         "gpu_launches": int(launches) * args.steps,
         "clocks": clocks,
@@ -448,8 +640,18 @@ def main():
         "roofline": roof,
         "kernels": kernels,
     }
+    if strong is not None:
+        line["strong"] = strong
+    if configs:
+        line["configs"] = configs
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+        ours = ms_dev_serial
+        bf = eager.get("bf16_autocast", {})
+        if "ms_per_step" in bf:
+            eager["speedup_vs_bf16_autocast"] = {"single_stream": bf["ms_per_step"] / ours, "two_streams": bf["ms_per_step"] / ms_dev}
     if not args.no_cpu_baseline:
-        line["cpu_baseline"], _ = cpu_reference_rtfx(cfg, t_in, var_len)
+        line["cpu_baseline"], _ = cpu_reference_rtfx(cfg, t_in, len_mode)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

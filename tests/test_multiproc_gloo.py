@@ -46,6 +46,13 @@ def test_max_over_ranks_and_distinct_shards():
         assert abs(value - 2 * 9.6 / 0.015) < 1e-6       # whole-job aggregate, not per-GPU
 
 
+def test_strong_scaling_split_covers_the_batch():
+    import bench
+    for batch, world in ((64, 1), (64, 2), (64, 8), (32, 3), (5, 8)):
+        parts = bench.strong_scaling_batches(batch, world)
+        assert len(parts) == world and sum(parts) == batch and max(parts) - min(parts) <= 1
+
+
 def test_reference_arm_under_torchrun_rank0_only():
     port = 31500 + os.getpid() % 2000
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
@@ -56,5 +63,6 @@ def test_reference_arm_under_torchrun_rank0_only():
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
-    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] == "port"
+    # "reference" when baseline/_ref travelled with the repo (baseline/install_ref.py), else the oracle port
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
