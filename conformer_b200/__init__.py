@@ -7,9 +7,11 @@ any forward does.
 from .modules import (GLU, Conformer, ConformerBlock, ConvolutionModule, ConvolutionSubsampling, Decoder, Encoder,
                       FeedForwardModule, MultiHeadSelfAttentionModule, RelativeMultiHeadAttention,
                       RelativePositionalEncoding, Swish, generate_padding_mask, greedy_ctc_decode)
+from .frontend import LogMelFrontEnd
+from .checkpoint import CheckpointManager, load_checkpoint, load_model, save_checkpoint
 from .synth import CONFORMER_L, CONFORMER_M, CONFORMER_S, EncoderConfig
 
 __all__ = ["GLU", "Conformer", "ConformerBlock", "ConvolutionModule", "ConvolutionSubsampling", "Decoder", "Encoder",
            "FeedForwardModule", "MultiHeadSelfAttentionModule", "RelativeMultiHeadAttention",
            "RelativePositionalEncoding", "Swish", "generate_padding_mask", "greedy_ctc_decode", "EncoderConfig", "CONFORMER_S",
-           "CONFORMER_M", "CONFORMER_L"]
+           "CONFORMER_M", "CONFORMER_L", "LogMelFrontEnd", "CheckpointManager", "load_checkpoint", "load_model", "save_checkpoint"]

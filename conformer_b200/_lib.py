@@ -24,6 +24,12 @@ class Config(C.Structure):
                 ("n_heads", C.c_int32), ("kernel_size", C.c_int32)]
 
 
+class LogMelConfig(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("win_length", C.c_int32), ("hop_length", C.c_int32),
+                ("n_mels", C.c_int32), ("f_min", C.c_float), ("f_max", C.c_float), ("norm_slaney", C.c_int32),
+                ("mel_scale_slaney", C.c_int32), ("log_floor", C.c_float)]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -57,10 +63,16 @@ SIGNATURES = {
     "cfm_encoder_host_workspace_bytes": (_i64, [_p, _i32, _i32]),
     "cfm_encoder_forward_host_io": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i64, _p, _p, _p]),
     "cfm_encoder_host_slot_release": (C.c_int, [_p, _p]),
+    "cfm_logmel_create": (C.c_int, [C.POINTER(LogMelConfig), _p, _p, C.POINTER(_p)]),
+    "cfm_logmel_destroy": (C.c_int, [_p]),
+    "cfm_logmel_workspace_bytes": (_i64, [_p, _i32, _i32]),
+    "cfm_logmel_forward": (C.c_int, [_p, _p, _p, _i32, _i32, _p, _i64, _p]),
+    "cfm_logmel_lengths": (C.c_int, [_p, _p, _i32, _i32, _p]),
     "cfm_last_launch_count": (_i64, [_p]),
     "cfm_profile_enable": (C.c_int, [_p, _i32]),
     "cfm_profile_collect": (C.c_int, [_p, C.POINTER(C.c_double), _i32]),
     "cfm_gemm_bf16": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
+    "cfm_gemm_tf32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "cfm_gemm_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
     "cfm_dwconv_glu_bn_swish": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),
 }

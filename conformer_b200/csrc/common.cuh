@@ -271,6 +271,16 @@ __device__ __forceinline__ void tc_mma_f16_lo(uint32_t d_tmem, uint32_t a_lo, ui
       ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
       : "memory");
 }
+// kind::tf32: fp32 operands in shared memory, multiplied as TF32 (10-bit mantissa), K = 8 per instruction
+__device__ __forceinline__ void tc_mma_tf32_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
 // Same, with the A operand read from TENSOR MEMORY (row m of A in TMEM lane m; 16-bit elements packed two per 32-bit
 // column, element 2c in the low half of column c, so one K=16 step spans 8 columns).  Only B crosses the shared-memory
 // port: an M=128 MMA with both operands in shared memory needs (128+N)*32 bytes per 64*N/128 clocks - above the
@@ -398,6 +408,11 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
 // Instruction descriptor: bf16 x bf16 -> fp32, A K-major, B MN-major (e.g. V stored [key][dh] in P.V)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+// Instruction descriptor: tf32 x tf32 -> fp32 (a/b format 2), both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 // Instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, shape M x N

@@ -74,7 +74,9 @@ __device__ __forceinline__ unsigned long long gtime() {
     if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + (slot)] = gtime(); \
   } while (0)
 
-template <int BLOCK_N, int EPI, bool CONV>
+// TF32: A and W are fp32 in memory and multiplied as TF32 (kind::tf32, K = 8 per MMA, 32 elements per 128-byte row);
+// callers wanting fp32 accuracy pass operands split into TF32-exact high and low parts concatenated along K (3xTF32).
+template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmParams p) {
@@ -96,6 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  constexpr int BK = TF32 ? BLOCK_K / 2 : BLOCK_K;         // elements per 128-byte operand row
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -147,16 +150,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // dims: (c, f1, parity, pair, b); source time index 2*t2 + kw = 2*(t2 + (kw>>1)) + (kw&1)
             tma_load_5d(sa, &tmA, &full_bar[s], c0, 2 * cf + kh, kw & 1, ct * BLOCK_M + (kw >> 1), cb);
           } else {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m_tile * BLOCK_M);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * BLOCK_K, n_tile * BLOCK_N);
+          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_tile * BLOCK_N);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BLOCK_M, BLOCK_N) : umma_idesc_bf16(BLOCK_M, BLOCK_N);
     uint32_t it = 0, acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -175,8 +178,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = umma_desc_lo(smem_u32(smem + s * C_::STAGE_BYTES));
           const uint32_t sb = sa + (A_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // one MMA covers 32 bytes of K in either format
+            if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+            else tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+          }
           tc_commit(&empty_bar[s]);                            // smem slot free once these MMAs retire
           if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);   // accumulator complete
         }
@@ -418,6 +423,49 @@ int tc_init() {
 }
 
 unsigned long long* g_gemm_trace = nullptr;      // debug hook (cfm_debug_set_gemm_trace)
+
+int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+                 int num_sms, cudaStream_t stream) {
+  CFM_TRY(tc_init());
+  CFM_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
+  CFM_REQUIRE(lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0 && N % 4 == 0, "TF32 GEMM needs 16-byte aligned rows");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C) |
+                reinterpret_cast<uintptr_t>(bias)) & 15) == 0, "operands must be 16-byte aligned");
+  constexpr int BK = BLOCK_K / 2, BN = 128;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.res_scale = 1.f; p.trace = nullptr;
+  p.num_kb = static_cast<int>(ceil_div(K, BK));
+  p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
+  p.num_n_tiles = static_cast<int>(ceil_div(N, BN));
+  CUtensorMap tmA, tmB, tmC;
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(lda) * 4};
+    cuuint32_t box[2] = {BK, BLOCK_M};
+    CFM_TRY(encode_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, A, dims, strides, box, "tf32 A"));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldw) * 4};
+    cuuint32_t box[2] = {BK, BN};
+    CFM_TRY(encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dims, strides, box, "tf32 W"));
+  }
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * 4};
+    cuuint32_t box[2] = {32, BLOCK_M};
+    CFM_TRY(encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, "tf32 C"));
+  }
+  using C_ = Cfg<BN, EPI_BIAS_F32>;
+  auto kern = gemm_tc_kernel<BN, EPI_BIAS_F32, false, true>;
+  static std::atomic<uint64_t> attr_done{0};
+  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  kern<<<tiles < num_sms ? tiles : num_sms, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N, int K,
                  Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,

@@ -36,6 +36,10 @@ int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* 
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N,
                  int K, Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
                  cudaStream_t stream);
+// fp32 operands multiplied as TF32 on tcgen05 (kind::tf32), fp32 accumulate and output: C = A[M,K] W[N,K]^T + bias.
+// For fp32-grade accuracy pass TF32-exact high/low splits concatenated along K (A' = [Ahi|Alo|Ahi], W' = [Whi|Whi|Wlo]).
+int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
+                 int num_sms, cudaStream_t stream);
 int tc_init();   // resolves cuTensorMapEncodeTiled through the runtime; 0 when usable
 // 128-byte-swizzled tiled tensor map (call tc_init() first)
 int encode_tmap(CUtensorMap* tm, CUtensorMapDataType dt, int rank, const void* base, const cuuint64_t* dims,

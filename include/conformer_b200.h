@@ -184,12 +184,45 @@ CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
 CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);
 
+/* ---- log-mel front-end: the step right before the path ---------------------- */
+/* ConformerProcessor.mel_spectrogram (processing/processor.py:53-63,155-158):
+ *   log(clamp(torchaudio.transforms.MelSpectrogram(...)(signal), min=1e-5))
+ * i.e. centred reflect-padded STFT, periodic Hann window, power spectrum, triangular mel filterbank.  Both contractions
+ * (DFT, filterbank) run on the tcgen05 tensor cores as 3xTF32 GEMMs with fp32 accumulation.  The field defaults of the
+ * reference are {16000, 400, 400, 160, 80, 0.0, 8000.0, 1, 1, 1e-5}. */
+typedef struct {
+  int32_t sample_rate, n_fft, win_length, hop_length, n_mels;
+  float f_min, f_max;               /* f_max <= 0: sample_rate / 2 */
+  int32_t norm_slaney;              /* 1: norm="slaney" (area normalisation), 0: none */
+  int32_t mel_scale_slaney;         /* 1: mel_scale="slaney", 0: "htk" */
+  float log_floor;                  /* clamp before the log (1e-5, processor.py:157) */
+} cfm_logmel_config_t;
+typedef struct cfm_logmel* cfm_logmel_t;
+/* window_host [n_fft] and fb_host [n_fft/2+1, n_mels] (HOST pointers, nullable) are the module's constant buffers as
+ * torchaudio holds them (`spectrogram.window`, `mel_scale.fb`): torchaudio builds them in fp32, so a caller that wants
+ * the reference's exact filters passes its own; NULL = computed here in fp64 from the configuration. */
+CFM_API int cfm_logmel_create(const cfm_logmel_config_t* cfg, const float* window_host, const float* fb_host,
+                              cfm_logmel_t* out);
+CFM_API int cfm_logmel_destroy(cfm_logmel_t h);
+CFM_API int64_t cfm_logmel_workspace_bytes(cfm_logmel_t h, int32_t batch, int32_t samples);
+/* wave fp32 [batch, samples] (zero-padded to the longest utterance, processor.py:376-388) -> mel fp32
+ * [batch, n_mels, samples / hop_length + 1], the tensor Encoder.forward takes. */
+CFM_API int cfm_logmel_forward(cfm_logmel_t h, const float* wave, float* mel, int32_t batch, int32_t samples,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+/* frames = samples // hop_length + 1 (processor.py:392) */
+CFM_API int cfm_logmel_lengths(const int64_t* samples, int64_t* frames, int32_t batch, int32_t hop_length, void* stream);
+
 /* ---- low-level kernels exposed for unit tests and benchmarks -------------------------------- */
 /* bf16 tcgen05 GEMM: C = epi(A[M,K] W[N,K]^T + bias); epi: 0 bias, 1 bias+swish, 2 bias+relu,
  * 3 res + scale*(acc+bias), 4 acc+bias (C,res fp32; otherwise C bf16), 5 GLU: C is [M,N/2] and W's rows are
  * packed per 64-row group as 32 value rows followed by their 32 gate rows.  A,W bf16 (uint16 storage). */
 CFM_API int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
                   int32_t epi, const float* res, float res_scale, void* stream);
+/* TF32 tcgen05 GEMM (kind::tf32): C fp32 [M,N] = A fp32 [M,K] W fp32 [N,K]^T + bias; operands are read as TF32 (10-bit
+ * mantissa).  For fp32-grade accuracy pass operands split into a TF32-exact high part and the remainder, concatenated
+ * along K: A' = [Ah | Al | Ah], W' = [Wh | Wh | Wl] (the log-mel front-end does). */
+CFM_API int cfm_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
+                          void* stream);
 /* fp32 CUDA-core GEMM with the same epilogues (all fp32). */
 CFM_API int cfm_gemm_f32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K,
                  int32_t epi, const float* res, float res_scale, void* stream);

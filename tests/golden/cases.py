@@ -39,3 +39,13 @@ SUBMODULE_CFG = dict(cfg=EncoderConfig(80, 1, 64, 4, 31), B=3, T=41, seed=5, x_s
 TOKEN_CASE = dict(cfg=EncoderConfig(80, 4, 144, 4, 31), B=4, Tin=401, seed=31, vocab=370, peaky=8.0)
 # d_model 256 so that the bf16 tensor-core path takes it: the bf16 greedy-token gate
 TOKEN_CASE_BF16 = dict(cfg=EncoderConfig(80, 4, 256, 4, 31), B=4, Tin=401, seed=33, vocab=370, peaky=8.0, name="tokens_M")
+
+# tiny Conformer whose checkpoint file is written by the reference's own CheckpointManager (checkpoint interop, 8f-4)
+TINY_CKPT = dict(cfg=TINY, seed=41, vocab=37, hidden=48)
+
+# waveforms for the log-mel front-end (8f-3): [B, L] samples at 16 kHz
+LOGMEL_CASES = [
+    dict(name="short", B=2, L=4000, seed=51),                       # 26 frames
+    dict(name="odd", B=3, L=16001 + 77, seed=52, pad_from=9000),    # L not a multiple of hop; one zero-padded utterance
+    dict(name="sec3", B=2, L=48000, seed=53),                       # 301 frames
+]

@@ -24,7 +24,7 @@ sys.dont_write_bytecode = True
 
 from conformer_b200.synth import (EncoderConfig, synth_decoder_state_dict,   # noqa: E402
                                   synth_encoder_state_dict, synth_lengths, synth_logmel)
-from cases import ENCODER_CASES, SUBMODULE_CFG, TOKEN_CASE, TOKEN_CASE_BF16, case_lengths  # noqa: E402
+from cases import ENCODER_CASES, SUBMODULE_CFG, TINY_CKPT, TOKEN_CASE, TOKEN_CASE_BF16, case_lengths  # noqa: E402
 
 from model.conformer import Conformer                                        # noqa: E402
 from model.modules.encoder import Encoder                                    # noqa: E402
@@ -183,3 +183,63 @@ def dump_state_dict_keys():
 
 if __name__ == "__main__":
     dump_state_dict_keys()
+
+
+def dump_reference_checkpoint():
+    """A checkpoint file written by the REFERENCE's own CheckpointManager (manager.py:33-41) for a DDP-style wrapped tiny
+    Conformer: the fixture of the checkpoint-interop test (keys carry the 'module.' prefix, as train.py:185-186 produces)."""
+    import tempfile
+    from manager import CheckpointManager
+    cfg = TINY_CKPT["cfg"]
+    sd = synth_encoder_state_dict(cfg, TINY_CKPT["seed"], prefix="encoder.")
+    sd.update(synth_decoder_state_dict(cfg.d_model, TINY_CKPT["vocab"], hidden=TINY_CKPT["hidden"], seed=TINY_CKPT["seed"] + 1))
+    model = Conformer(TINY_CKPT["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size,
+                      TINY_CKPT["hidden"], 1)
+    model.load_state_dict(sd, strict=True)
+
+    class Wrapped(torch.nn.Module):                    # what DistributedDataParallel does to the key names
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    wrapped = Wrapped(model)
+    opt = torch.optim.Adam(wrapped.parameters(), lr=2e-5)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    with tempfile.TemporaryDirectory() as td:
+        CheckpointManager(td).save_checkpoint(wrapped, opt, sched, 7, 1)
+        with open(os.path.join(td, "7.pt"), "rb") as src, open(os.path.join(HERE, "ref_checkpoint_tiny_ddp.pt"), "wb") as dst:
+            dst.write(src.read())
+    x = synth_logmel(2, cfg.n_mel_channels, 83, seed=TINY_CKPT["seed"] + 2)
+    lengths = synth_lengths(2, 83)
+    logits, out_len = model.eval()(x, lengths)
+    np.savez_compressed(os.path.join(HERE, "ref_checkpoint_tiny_out.npz"), logits=logits.numpy(), out_lengths=out_len.numpy())
+    print("ref_checkpoint_tiny_ddp.pt:", os.path.getsize(os.path.join(HERE, "ref_checkpoint_tiny_ddp.pt")), "bytes")
+
+
+if __name__ == "__main__":
+    if not set(sys.argv[1:]) or "checkpoint" in sys.argv[1:]:
+        dump_reference_checkpoint()
+
+
+def run_logmel():
+    """torchaudio.transforms.MelSpectrogram with the reference's arguments (processing/processor.py:53-63) followed by the
+    reference's log-clamp (:155-158), in fp32 (what the reference runs) and fp64 (noise floor)."""
+    from torchaudio.transforms import MelSpectrogram
+    sys.path.insert(0, ROOT)
+    from oracle.logmel_oracle import synth_waveform
+    from cases import LOGMEL_CASES
+    out = {}
+    for c in LOGMEL_CASES:
+        x = synth_waveform(c["B"], c["L"], c["seed"])
+        if c.get("pad_from"):                               # a zero-padded shorter utterance, as the collate makes them
+            x[1, c["pad_from"]:] = 0.0
+        ms = MelSpectrogram(sample_rate=16000, n_fft=400, win_length=400, hop_length=160, f_min=0.0, f_max=8000.0, n_mels=80,
+                            norm="slaney", mel_scale="slaney")
+        out[c["name"]] = torch.log(torch.clamp(ms(x), min=1e-5)).numpy()
+        out[c["name"] + "_f64"] = torch.log(torch.clamp(ms.double()(x.double()), min=1e-5)).numpy()
+        print("logmel", c["name"], out[c["name"]].shape, "mean", out[c["name"]].mean())
+    np.savez_compressed(os.path.join(HERE, "logmel.npz"), **out)
+
+
+if __name__ == "__main__":
+    if not set(sys.argv[1:]) or "logmel" in sys.argv[1:]:
+        run_logmel()

@@ -676,3 +676,73 @@ def test_modules_follow_their_tensors_device():
         torch.cuda.set_device(0)
         outs.append(enc(x.to(dev), None)[0].cpu())
     assert ((outs[0] - outs[1]).norm() / outs[0].norm()).item() < 2e-3
+
+
+def test_reference_checkpoint_file_drives_the_drop_in_model():
+    """A checkpoint FILE written by the reference's CheckpointManager (DDP-prefixed keys) loaded with
+    conformer_b200.load_model gives the reference's logits (fp32 path, fp32 gate at 1x)."""
+    import os
+    from cases import TINY_CKPT
+    from helpers import GOLDEN_DIR
+    c = TINY_CKPT
+    cfg = c["cfg"]
+    model = cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, c["hidden"], 1)
+    cb.load_model(os.path.join(GOLDEN_DIR, "ref_checkpoint_tiny_ddp.pt"), model)
+    model = model.to(DEV).eval()
+    gold = golden("ref_checkpoint_tiny_out")
+    x = synth_logmel(2, cfg.n_mel_channels, 83, seed=c["seed"] + 2).to(DEV)
+    lengths = synth_lengths(2, 83).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    logits, out_len = model(x, lengths)
+    assert torch.equal(out_len.cpu(), gold["out_lengths"])
+    assert_close_fp32(logits, gold["logits"], "logits from the reference checkpoint", scale=2.0)   # + cuDNN LSTM vs CPU LSTM
+
+
+def test_logmel_front_end_vs_torchaudio_golden():
+    """cfm_logmel_forward (framing -> 3xTF32 tcgen05 DFT -> power -> 3xTF32 filterbank -> log-clamp) against the committed
+    output of torchaudio's MelSpectrogram with the reference's arguments (processor.py:53-63,155-158) and against the
+    fp64 oracle: the device result must be as close to the fp64 truth as torchaudio's own fp32 run is (within 2x)."""
+    from cases import LOGMEL_CASES
+    from oracle.logmel_oracle import log_mel, synth_waveform
+    gold = golden("logmel")
+    fe = cb.LogMelFrontEnd()
+    for c in LOGMEL_CASES:
+        x = synth_waveform(c["B"], c["L"], c["seed"])
+        if c.get("pad_from"):
+            x[1, c["pad_from"]:] = 0.0
+        y = fe.mel_spectrogram(x.to(DEV)).cpu()
+        g32, g64 = gold[c["name"]], gold[c["name"] + "_f64"]
+        assert y.shape == g32.shape
+        e_ref, e_ours = (g32.double() - g64).abs().max().item(), (y.double() - g64).abs().max().item()
+        print(f"logmel {c['name']}: ours vs torchaudio fp32 {(y - g32).abs().max():.2e}; vs fp64 truth: ours {e_ours:.2e}, "
+              f"torchaudio fp32 {e_ref:.2e}")
+        assert (y - g32).abs().max() < 2e-4
+        assert e_ours < max(2 * e_ref, 1e-4)
+    # the collate rule: zero-pad to the longest utterance, frames = samples // hop + 1 (processor.py:373-394)
+    a, b = synth_waveform(1, 9000, 60)[0].to(DEV), synth_waveform(1, 5000, 61)[0].to(DEV)
+    mels, lens = fe([a, b])
+    assert mels.shape == (2, 80, 9000 // 160 + 1) and lens.tolist() == [9000 // 160 + 1, 5000 // 160 + 1]
+    want = log_mel(torch.stack([a.cpu(), torch.nn.functional.pad(b.cpu(), (0, 4000))]))
+    assert (mels.cpu() - want).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 8, 8), (129, 80, 624), (300, 416, 1200), (1000, 256, 100)])
+def test_gemm_tf32x3_matches_fp64(M, N, K):
+    """The 3xTF32 tcgen05 GEMM behind the log-mel front-end: operands split on the host exactly as the kernels do, result
+    against an fp64 product - fp32-grade accuracy (error ~1e-6 of the row scale), including M/N/K tails."""
+    from conformer_b200._lib import check, lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g) * torch.logspace(-3, 0, K)[None, :]     # loud and quiet columns
+    W = torch.randn(N, K, generator=g)
+
+    def split(x, w_side):
+        hi = ((x.view(torch.int32) + 0x1000) & ~0x1fff).view(torch.float32)
+        lo = x - hi
+        return torch.cat([hi, hi, lo] if w_side else [hi, lo, hi], dim=1).contiguous()
+    A3, W3 = split(A, False).to(DEV), split(W, True).to(DEV)
+    C = torch.empty(M, N, device=DEV)
+    check(lib().cfm_gemm_tf32(A3.data_ptr(), W3.data_ptr(), None, C.data_ptr(), M, N, 3 * K, torch.cuda.current_stream().cuda_stream))
+    want = A.double() @ W.double().T
+    scale = (A.double().abs() @ W.double().abs().T)
+    assert ((C.cpu().double() - want).abs() / scale).max() < 2e-6

@@ -87,3 +87,51 @@ def test_oracle_is_not_imported_by_the_product():
     root = pathlib.Path(cb.__file__).parent
     for f in list(root.glob("*.py")) + list((root / "csrc").glob("*")):
         assert "oracle" not in f.read_text().replace("oracle/", "").replace("no oracle", ""), f
+
+
+def test_reference_written_checkpoint_loads_and_round_trips(tmp_path):
+    """tests/golden/ref_checkpoint_tiny_ddp.pt was written by the REFERENCE's CheckpointManager for a DDP-style wrapped
+    model (keys prefixed 'module.', manager.py:33-41 / train.py:185-186).  It must load strictly into the drop-in
+    Conformer (prefix stripped, checkpoint.py:27-35), into a DDP-style wrapper (prefix kept), and the encoder sub-tree into
+    a stand-alone Encoder; a checkpoint written here must read back identically."""
+    from cases import TINY_CKPT
+    from conformer_b200 import checkpoint as ck
+    c = TINY_CKPT
+    cfg = c["cfg"]
+    path = os.path.join(GOLDEN_DIR, "ref_checkpoint_tiny_ddp.pt")
+    want = synth_encoder_state_dict(cfg, c["seed"], prefix="encoder.")
+    want.update(synth_decoder_state_dict(cfg.d_model, c["vocab"], hidden=c["hidden"], seed=c["seed"] + 1))
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"model", "optimizer", "scheduler", "n_steps", "n_epochs"} and ck.is_ddp_state_dict(raw["model"])
+
+    model = cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, c["hidden"], 1)
+    ck.load_model(path, model)                                      # from a path, prefix stripped, strict
+    got = model.state_dict()
+    assert set(got) == set(want) and all(torch.equal(got[k], want[k]) for k in want)
+
+    class Wrapped(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.module = m
+    other = cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, c["hidden"], 1)
+    ck.load_model(ck.strip_ddp_prefix(raw["model"]), Wrapped(other), world_size=2)     # prefix added for a wrapped model
+    assert all(torch.equal(other.state_dict()[k], want[k]) for k in want)
+
+    enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+    ck.load_model(path, enc, prefix="encoder.")
+    assert all(torch.equal(v, want["encoder." + k]) for k, v in enc.state_dict().items())
+
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5)
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.9999)
+    assert ck.load_checkpoint(path, model, opt, sched) == (7, 1)    # optimizer/scheduler state of the reference file
+    mgr = ck.CheckpointManager(str(tmp_path), n_savings=2)
+    for step in (1, 2, 3):
+        mgr.save_checkpoint(model, opt, sched, step, 0)
+    assert sorted(os.listdir(tmp_path)) == ["2.pt", "3.pt"]         # rotation keeps the last n_savings
+    fresh = cb.Conformer(c["vocab"], cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, c["hidden"], 1)
+    assert ck.load_checkpoint(os.path.join(tmp_path, "3.pt"), fresh) == (3, 0)
+    assert all(torch.equal(fresh.state_dict()[k], want[k]) for k in want)
+    with pytest.raises(RuntimeError):                               # strict: a foreign key is an error, as in the reference
+        bad = dict(ck.strip_ddp_prefix(raw["model"]))
+        bad["encoder.extra"] = torch.zeros(1)
+        ck.load_model(bad, fresh)
