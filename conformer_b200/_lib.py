@@ -15,13 +15,14 @@ LIB_PATH = os.path.join(HERE, "lib", "libconformer_b200.so")
 COMPUTE_F32, COMPUTE_BF16 = 0, 1
 DTYPE_F32, DTYPE_BF16 = 0, 1
 (KIND_ENCODER, KIND_BLOCK, KIND_FFN, KIND_MHSA, KIND_REL_ATTENTION, KIND_CONV_MODULE,
- KIND_SUBSAMPLING) = range(7)
+ KIND_SUBSAMPLING, KIND_DECODER) = range(8)
 EPI_BIAS, EPI_BIAS_SWISH, EPI_BIAS_RELU, EPI_BIAS_RES, EPI_BIAS_F32 = range(5)
 
 
 class Config(C.Structure):
     _fields_ = [("n_mel_channels", C.c_int32), ("n_blocks", C.c_int32), ("d_model", C.c_int32),
-                ("n_heads", C.c_int32), ("kernel_size", C.c_int32)]
+                ("n_heads", C.c_int32), ("kernel_size", C.c_int32), ("vocab_size", C.c_int32),
+                ("lstm_hidden_dim", C.c_int32), ("n_lstm_layers", C.c_int32)]
 
 
 class LogMelConfig(C.Structure):
@@ -59,6 +60,7 @@ SIGNATURES = {
     "cfm_block_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_subsampling_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
+    "cfm_decoder_forward": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_forward_host": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _i64, _p]),
     "cfm_encoder_host_workspace_bytes": (_i64, [_p, _i32, _i32]),
     "cfm_encoder_forward_host_io": (C.c_int, [_p, _p, _i32, _p, _p, _i32, _p, _i32, _i32, _p, _i64, _p, _p, _p]),

@@ -39,7 +39,7 @@ int cfm_device_check(void) {
 
 int cfm_module_create(int kind, const cfm_config_t* cfg, cfm_module_t* out) {
   CFM_REQUIRE(cfg != nullptr && out != nullptr, "null argument");
-  CFM_REQUIRE(kind >= CFM_KIND_ENCODER && kind <= CFM_KIND_SUBSAMPLING, "unknown module kind");
+  CFM_REQUIRE(kind >= CFM_KIND_ENCODER && kind <= CFM_KIND_DECODER, "unknown module kind");
   cfm_module* m = new (std::nothrow) cfm_module();
   CFM_REQUIRE(m != nullptr, "out of host memory");
   m->kind = kind;
@@ -128,6 +128,11 @@ int cfm_subsampling_forward(cfm_module_t m, const float* mel, const int64_t* len
 int cfm_encoder_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y, int64_t* lengths_out,
                         int32_t batch, int32_t Tin, void* ws, int64_t wsb, void* stream) {
   return run(m, CFM_KIND_ENCODER, mel, nullptr, nullptr, lengths_in, y, lengths_out, batch, Tin, ws, wsb, stream);
+}
+
+int cfm_decoder_forward(cfm_module_t m, const float* x, const int64_t* lengths, float* logits, int32_t batch, int32_t T,
+                        void* ws, int64_t wsb, void* stream) {
+  return run(m, CFM_KIND_DECODER, x, nullptr, nullptr, lengths, logits, nullptr, batch, T, ws, wsb, stream);
 }
 
 int64_t cfm_encoder_host_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin) {

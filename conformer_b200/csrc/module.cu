@@ -168,6 +168,32 @@ struct Packer {
     w.ln_g = vec(pre + "layer_norm.weight", d);
     w.ln_b = vec(pre + "layer_norm.bias", d);
   }
+  // CTC head (decoder.py:10-13): nn.LSTM parameter names weight_ih_l{k}, weight_hh_l{k}, bias_ih_l{k}, bias_hh_l{k}
+  void decoder(DecW& w, int d, int V, int H, int L) {
+    w.V = V; w.H = H; w.Vp = (V + 7) & ~7;
+    w.layers.resize(L);
+    for (int l = 0; l < L && !status; ++l) {
+      const int in = l == 0 ? d : H;
+      const std::string sfx = "_l" + std::to_string(l);
+      float* wih = const_cast<float*>(vec("lstm.weight_ih" + sfx, 4LL * H * in));
+      const float* bih = param("lstm.bias_ih" + sfx, 4LL * H);
+      const float* bhh = param("lstm.bias_hh" + sfx, 4LL * H);
+      float* bsum = alloc_f32(4LL * H);
+      if (!status && add_vec(bih, bhh, bsum, 4 * H, stream)) status = 2;
+      finish_linear(w.layers[l].ih, wih, bsum, 4 * H, in);
+      w.layers[l].w_hh = vec("lstm.weight_hh" + sfx, 4LL * H * H);
+    }
+    const float* lw = param("linear.weight", static_cast<int64_t>(V) * H);
+    const float* lb = param("linear.bias", V);
+    const float* g = param("norm.weight", H);
+    const float* be = param("norm.bias", H);
+    const float* rm = param("norm.running_mean", H);
+    const float* rv = param("norm.running_var", H);
+    float* wo = alloc_f32(static_cast<int64_t>(w.Vp) * H);
+    float* bo = alloc_f32(w.Vp);
+    if (!status && fold_bn_linear(lw, lb, g, be, rm, rv, 1e-5f, wo, bo, V, w.Vp, H, stream)) status = 2;
+    finish_linear(w.out, wo, bo, w.Vp, H);
+  }
   void front(FrontW& w, const std::string& pre, int d) {
     w.c1_w = vec(pre + "conv_1.weight", static_cast<int64_t>(d) * 9);
     w.c1_b = vec(pre + "conv_1.bias", d);
@@ -198,7 +224,7 @@ int Module::finalize(int compute_mode, cudaStream_t stream) {
   CFM_REQUIRE(compute_mode == 0 || compute_mode == 1, "compute must be CFM_COMPUTE_F32 or CFM_COMPUTE_BF16");
   const int d = cfg.d_model, H = cfg.n_heads, k = cfg.kernel_size;
   CFM_REQUIRE(d > 0 && d % 4 == 0, "d_model must be a positive multiple of 4");
-  CFM_REQUIRE(kind == CFM_KIND_FFN || kind == CFM_KIND_CONV_MODULE || kind == CFM_KIND_SUBSAMPLING ||
+  CFM_REQUIRE(kind == CFM_KIND_FFN || kind == CFM_KIND_CONV_MODULE || kind == CFM_KIND_SUBSAMPLING || kind == CFM_KIND_DECODER ||
                   (H > 0 && d % H == 0),
               "d_model must be divisible by n_heads");
   int dev = 0;
@@ -222,6 +248,11 @@ int Module::finalize(int compute_mode, cudaStream_t stream) {
     case CFM_KIND_CONV_MODULE: P.conv(conv, "", d, k); break;
     case CFM_KIND_BLOCK: blocks.resize(1); P.block(blocks[0], "", d, H, k); break;
     case CFM_KIND_SUBSAMPLING: P.front(front, "", d); break;
+    case CFM_KIND_DECODER:
+      CFM_REQUIRE(cfg.vocab_size > 0 && cfg.lstm_hidden_dim > 0 && cfg.n_lstm_layers > 0, "decoder needs vocab_size, lstm_hidden_dim, n_lstm_layers");
+      CFM_REQUIRE(!bf16_mode || cfg.lstm_hidden_dim % 8 == 0, "bf16 mode needs lstm_hidden_dim to be a multiple of 8");
+      P.decoder(dec, d, cfg.vocab_size, cfg.lstm_hidden_dim, cfg.n_lstm_layers);
+      break;
     case CFM_KIND_ENCODER: {
       P.front(front, "downsampling_conv.", d);
       const int F2 = freq_bins();
@@ -252,7 +283,8 @@ int Module::finalize(int compute_mode, cudaStream_t stream) {
     default: set_error("unknown module kind"); return 1;
   }
   if (P.status) return P.status;
-  if (kind != CFM_KIND_ENCODER && kind != CFM_KIND_FFN && kind != CFM_KIND_CONV_MODULE && kind != CFM_KIND_SUBSAMPLING) {
+  if (kind != CFM_KIND_ENCODER && kind != CFM_KIND_FFN && kind != CFM_KIND_CONV_MODULE && kind != CFM_KIND_SUBSAMPLING &&
+      kind != CFM_KIND_DECODER) {
     // default sinusoid frequencies for a stand-alone attention/block handle called without `pos`
     std::vector<float> dt(d / 2);
     const float c = static_cast<float>(-(std::log(10000.0) / d));
@@ -634,6 +666,38 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
         ++c.launches;
         CFM_TRY(lengths_and_mask(len_in, len_out, nullptr, B, T2, true, false, c.stream));
       }
+      return 0;
+    }
+    case CFM_KIND_DECODER: {
+      // Decoder.forward (decoder.py:15-27): per layer the input projection of all frames as one GEMM, then the
+      // persistent recurrence; Swish fused into the last layer's output, BatchNorm folded into the vocabulary GEMM
+      const int Hd = dec.H, T = frames;
+      const int64_t M = static_cast<int64_t>(B) * T;
+      float* xin = ws_take<float>(c, M * 4 * Hd);
+      TA* seq_a = ws_take<TA>(c, M * (Hd > d ? Hd : d));
+      TA* seq_b = ws_take<TA>(c, M * Hd);
+      float* hst = ws_take<float>(c, 2LL * B * Hd);
+      float* cst = ws_take<float>(c, static_cast<int64_t>(B) * Hd);
+      float* lg = ws_take<float>(c, M * dec.Vp);
+      WS_CHECK(xin); WS_CHECK(seq_a); WS_CHECK(seq_b); WS_CHECK(hst); WS_CHECK(cst); WS_CHECK(lg);
+      if (c.ws.measuring()) return 0;
+      const TA* cur = reinterpret_cast<const TA*>(x);
+      if (sizeof(TA) == 2) {
+        KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(seq_a), M * d, c.stream));
+        cur = seq_a;
+      }
+      const int L = static_cast<int>(dec.layers.size());
+      for (int l = 0; l < L; ++l) {
+        const int in = l == 0 ? d : Hd;
+        CFM_TRY(Dispatch<TA>::gemm(c, cur, in, dec.layers[l].ih, xin, 4 * Hd, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
+        TA* dst = (cur == seq_b) ? seq_a : seq_b;
+        KRUN(KC_MISC, 8.0 * M * Hd * Hd, 4.0 * M * 5 * Hd,
+             lstm_layer_forward<TA>(xin, dec.layers[l].w_hh, len_in, hst, cst, dst, B, T, Hd, l == L - 1, c.num_sms, c.stream));
+        cur = dst;
+      }
+      CFM_TRY(Dispatch<TA>::gemm(c, cur, Hd, dec.out, lg, dec.Vp, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
+      CFM_CUDA_OK(cudaMemcpy2DAsync(y, static_cast<size_t>(dec.V) * 4, lg, static_cast<size_t>(dec.Vp) * 4,
+                                    static_cast<size_t>(dec.V) * 4, static_cast<size_t>(M), cudaMemcpyDeviceToDevice, c.stream));
       return 0;
     }
     case CFM_KIND_ENCODER: {

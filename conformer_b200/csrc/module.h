@@ -114,6 +114,13 @@ struct FrontW {
   Linear conv2;
 };
 
+struct LstmLayerW { Linear ih; const float* w_hh = nullptr; };   // ih: [4H, in] with bias b_ih + b_hh
+struct DecW {
+  std::vector<LstmLayerW> layers;
+  Linear out;                        // vocabulary projection with the eval-mode BatchNorm folded in, rows padded to a multiple of 8
+  int V = 0, Vp = 0, H = 0;
+};
+
 struct ParamRef { const float* data; int64_t numel; bool used; };
 
 struct Module {
@@ -143,6 +150,7 @@ struct Module {
   Linear lin, pos_all;
   const float* div_term = nullptr;
   std::vector<BlockW> blocks;
+  DecW dec;
 
   int freq_bins() const { return ((cfg.n_mel_channels - 1) / 2 - 1) / 2; }
   int finalize(int compute_mode, cudaStream_t stream);

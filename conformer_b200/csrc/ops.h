@@ -64,6 +64,16 @@ int conv_module_fused_bf16(const float* x, const float* res, float* out, const f
                            int B, int Tn, int d, int ksize, cudaStream_t stream);
 bool conv_module_fused_supported(int d, int ksize);
 
+// ---- CTC head (model/modules/decoder.py:15-27; decoder.cu) -------------------------------------
+// one LSTM layer over packed sequences: xin [B,T,4H] = x W_ih^T + b_ih + b_hh (gate order i|f|g|o), out [B,T,H] = h_t (or
+// swish(h_t) for the last layer), zeros at frames >= lengths[b]; h_state [2,B,H] and c_state [B,H] are scratch
+template <typename TOut>
+int lstm_layer_forward(const float* xin, const float* w_hh, const int64_t* lengths, float* h_state, float* c_state, TOut* out,
+                       int B, int T, int H, bool last_layer, int num_sms, cudaStream_t stream);
+int fold_bn_linear(const float* w, const float* b, const float* gamma, const float* beta, const float* mean, const float* var,
+                   float eps, float* w_out /*[Vp,H]*/, float* b_out /*[Vp]*/, int V, int Vp, int H, cudaStream_t stream);
+int add_vec(const float* a, const float* b, float* o, int n, cudaStream_t stream);
+
 // ---- greedy CTC decode (processing/processor.py:301-328, id level; ctc.cu) ----------------------
 // tokens int32 [B,T]: collapsed ids, -1 after counts[b] entries
 int ctc_greedy_decode(const float* logits /*[B,T,V]*/, int B, int T, int V, int pad_id, int unk_id, int32_t* tokens,

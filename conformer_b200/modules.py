@@ -646,27 +646,39 @@ class CapturedEncoderForward:
         return self.y, self.out_lengths
 
 
-class Decoder(nn.Module):
-    """CTC head, model/modules/decoder.py:7-27.  OUT of the hot path: it stays
-    stock PyTorch (cuDNN LSTM) exactly as in the reference; kept so that Conformer keeps its API and the
-    token-parity harness can run."""
+class Decoder(_Native):
+    """CTC head, model/modules/decoder.py:7-27: LSTM over packed sequences -> Swish -> BatchNorm1d -> Linear.  The step
+    right after the encoder path, on the device through cfm_decoder_forward: the input and
+    vocabulary projections are GEMMs, the recurrence one persistent cooperative kernel per layer (decoder.cu).  The
+    sub-modules are parameter containers with the reference's names (``lstm.weight_ih_l0`` ..., ``norm.*``,
+    ``linear.*``).  Unlike the reference there is no ``lengths.cpu()`` host synchronisation (decoder.py:17): the kernel
+    reads the lengths on the device; like the reference's ``pad_packed_sequence`` the output keeps all T frames when
+    ``max(lengths) == T``, which the encoder's collate contract guarantees."""
+    _KIND = _lib.KIND_DECODER
 
     def __init__(self, vocab_size: int, d_model: int, hidden_dim: int, n_layers: int) -> None:
         super().__init__()
         self.lstm = nn.LSTM(input_size=d_model, hidden_size=hidden_dim, num_layers=n_layers, batch_first=True)
-        self.activation = nn.SiLU()          # x * sigmoid(x); parameter-free, so no state_dict key
+        self.activation = Swish()
         self.norm = nn.BatchNorm1d(num_features=hidden_dim)
         self.linear = nn.Linear(in_features=hidden_dim, out_features=vocab_size)
+        self._dims = (vocab_size, d_model, hidden_dim, n_layers)
+
+    def _config(self) -> Config:
+        v, d, h, n = self._dims
+        return Config(0, 0, d, 1, 1, v, h, n)
 
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
-        packed = lengths is not None
-        if packed:
-            x = nn.utils.rnn.pack_padded_sequence(x, lengths.cpu(), batch_first=True, enforce_sorted=self.training)
-        x, _ = self.lstm(x)
-        if packed:
-            x, _ = nn.utils.rnn.pad_packed_sequence(x, batch_first=True)
-        x = self.norm(self.activation(x).transpose(1, 2)).transpose(1, 2)
-        return self.linear(x)
+        xin = _dev_f32(x, "x")
+        B, T, _ = xin.shape
+        lin = None if lengths is None else lengths.to(device=xin.device, dtype=torch.int64).contiguous()
+        y = torch.empty((B, T, self._dims[0]), device=xin.device, dtype=torch.float32)
+        with _on_device(xin.device):
+            h = self._native()
+            ws = self._workspace(h, B, T, xin.device)
+            check(lib().cfm_decoder_forward(h, xin.data_ptr(), _ptr(lin), y.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
+                                            _stream()))
+        return y
 
 
 class Conformer(nn.Module):
@@ -679,6 +691,12 @@ class Conformer(nn.Module):
         self.encoder = Encoder(n_mel_channels=n_mel_channels, n_blocks=n_conformer_blocks, d_model=d_model,
                                n_heads=n_heads, kernel_size=kernel_size, dropout_rate=dropout_rate)
         self.decoder = Decoder(vocab_size=vocab_size, d_model=d_model, hidden_dim=lstm_hidden_dim, n_layers=n_lstm_layers)
+
+    def set_compute(self, mode: Optional[str]) -> "Conformer":
+        """'fp32', 'bf16' or None (= follow torch.autocast) for the encoder and the CTC head."""
+        self.encoder.set_compute(mode)
+        self.decoder.set_compute(mode)
+        return self
 
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None):
         x, lengths = self.encoder(x, lengths)

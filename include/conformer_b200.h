@@ -65,7 +65,8 @@ enum {
   CFM_KIND_MHSA = 3,         /* MultiHeadSelfAttentionModule model/utils/attention.py:7-18      */
   CFM_KIND_REL_ATTENTION = 4,/* RelativeMultiHeadAttention   model/utils/attention.py:20-102    */
   CFM_KIND_CONV_MODULE = 5,  /* ConvolutionModule            model/utils/convolution.py:7-32    */
-  CFM_KIND_SUBSAMPLING = 6   /* ConvolutionSubsampling       model/utils/convolution.py:34-57   */
+  CFM_KIND_SUBSAMPLING = 6,  /* ConvolutionSubsampling       model/utils/convolution.py:34-57   */
+  CFM_KIND_DECODER = 7       /* Decoder (CTC head)           model/modules/decoder.py:7-27      */
 };
 
 typedef struct {
@@ -74,6 +75,9 @@ typedef struct {
   int32_t d_model;        /* d_model / dim / channels of every module             */
   int32_t n_heads;        /* n_heads                                              */
   int32_t kernel_size;    /* ConvolutionModule(kernel_size=...)  convolution.py:8 */
+  int32_t vocab_size;     /* Decoder(vocab_size, d_model, hidden_dim, n_layers)   decoder.py:8; 0 for the other kinds */
+  int32_t lstm_hidden_dim;
+  int32_t n_lstm_layers;
 } cfm_config_t;
 
 CFM_API int cfm_abi_version(void);
@@ -144,6 +148,12 @@ CFM_API int cfm_subsampling_forward(cfm_module_t m, const float* mel, const int6
 CFM_API int cfm_encoder_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y,
                         int64_t* lengths_out, int32_t batch, int32_t Tin, void* workspace,
                         int64_t workspace_bytes, void* stream);
+/* Decoder.forward(x, lengths) in eval mode (model/modules/decoder.py:15-27), the step right after the path: x fp32
+ * [B,T,d_model] (the encoder output), lengths int64 [B] or NULL (sorted or not; lengths[b] <= T, and like the
+ * reference's pad_packed_sequence the output keeps T frames when max(lengths) == T) -> logits fp32 [B,T,vocab].
+ * Frames at or beyond a sample's length carry the constant Linear(BatchNorm(0)), as pad_packed_sequence + the head give. */
+CFM_API int cfm_decoder_forward(cfm_module_t m, const float* x, const int64_t* lengths, float* logits, int32_t batch,
+                                int32_t T, void* workspace, int64_t workspace_bytes, void* stream);
 /* Same call with HOST buffers (pinned or pageable): copies mel/lengths in, runs the forward and
  * copies y/lengths' out on `stream`, using workspace for the device staging.  This is the
  * end-to-end entry point a non-torch caller would use. */

@@ -228,30 +228,36 @@ def decoder_head(sd: StateDict, x: torch.Tensor, lengths: Optional[torch.Tensor]
     an explicit time loop (gate order i,f,g,o as in nn.LSTM); frames at or beyond a
     sample's length produce zeros like pad_packed_sequence does (decoder.py:16-21)."""
     B, T, d = x.shape
-    w_ih = _p(sd, pre + "lstm.weight_ih_l0", x)
-    w_hh = _p(sd, pre + "lstm.weight_hh_l0", x)
-    b = _p(sd, pre + "lstm.bias_ih_l0", x) + _p(sd, pre + "lstm.bias_hh_l0", x)
-    Hd = w_hh.shape[1]
-    h = x.new_zeros(B, Hd)
-    c = x.new_zeros(B, Hd)
-    xin = x @ w_ih.T + b
     if lengths is not None:
         T = int(lengths.max())
-    outs = []
-    for t in range(T):
-        gates = xin[:, t] + h @ w_hh.T
-        i, f, g, o = gates.chunk(4, dim=-1)
-        c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-        h_new = torch.sigmoid(o) * torch.tanh(c_new)
-        if lengths is not None:
-            live = (lengths.to(x.device) > t)[:, None]
-            c = torch.where(live, c_new, c)
-            h = torch.where(live, h_new, h)
-            outs.append(torch.where(live, h_new, torch.zeros_like(h_new)))
-        else:
-            c, h = c_new, h_new
-            outs.append(h_new)
-    y = swish(torch.stack(outs, dim=1))                                      # decoder.py:22
+    seq = x[:, :T]
+    layer = 0
+    while pre + f"lstm.weight_ih_l{layer}" in sd:                            # nn.LSTM(num_layers=n), decoder.py:10
+        w_ih = _p(sd, pre + f"lstm.weight_ih_l{layer}", x)
+        w_hh = _p(sd, pre + f"lstm.weight_hh_l{layer}", x)
+        b = _p(sd, pre + f"lstm.bias_ih_l{layer}", x) + _p(sd, pre + f"lstm.bias_hh_l{layer}", x)
+        Hd = w_hh.shape[1]
+        h = x.new_zeros(B, Hd)
+        c = x.new_zeros(B, Hd)
+        xin = seq @ w_ih.T + b
+        outs = []
+        for t in range(T):
+            gates = xin[:, t] + h @ w_hh.T
+            i, f, g, o = gates.chunk(4, dim=-1)
+            c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+            h_new = torch.sigmoid(o) * torch.tanh(c_new)
+            if lengths is not None:
+                live = (lengths.to(x.device) > t)[:, None]
+                c = torch.where(live, c_new, c)
+                h = torch.where(live, h_new, h)
+                outs.append(torch.where(live, h_new, torch.zeros_like(h_new)))
+            else:
+                c, h = c_new, h_new
+                outs.append(h_new)
+        seq = torch.stack(outs, dim=1)
+        layer += 1
+    outs = None
+    y = swish(seq)                                                           # decoder.py:22
     rm = _p(sd, pre + "norm.running_mean", x)
     rv = _p(sd, pre + "norm.running_var", x)
     y = (y - rm) * torch.rsqrt(rv + BN_EPS) * _p(sd, pre + "norm.weight", x) + _p(sd, pre + "norm.bias", x)

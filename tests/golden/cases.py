@@ -49,3 +49,6 @@ LOGMEL_CASES = [
     dict(name="odd", B=3, L=16001 + 77, seed=52, pad_from=9000),    # L not a multiple of hop; one zero-padded utterance
     dict(name="sec3", B=2, L=48000, seed=53),                       # 301 frames
 ]
+
+# the reference Decoder alone: two LSTM layers, unsorted lengths with max == T (decoder.py:15-27)
+DECODER_CASE = dict(d=64, vocab=37, hidden=96, layers=2, B=5, T=33, lengths=[20, 33, 1, 33, 7], seed=71)

@@ -243,3 +243,29 @@ def run_logmel():
 if __name__ == "__main__":
     if not set(sys.argv[1:]) or "logmel" in sys.argv[1:]:
         run_logmel()
+
+
+def run_decoder():
+    """The reference Decoder (model/modules/decoder.py) with TWO LSTM layers and unsorted lengths, eval mode."""
+    from model.modules.decoder import Decoder
+    from cases import DECODER_CASE as c
+    sd = sub(synth_decoder_state_dict(c["d"], c["vocab"], hidden=c["hidden"], seed=c["seed"]), "decoder.")
+    g = torch.Generator().manual_seed(c["seed"] + 1)
+    for l in range(1, c["layers"]):                           # synth_decoder_state_dict makes layer 0 only
+        bound = 1.0 / c["hidden"] ** 0.5
+        for name, shape in (("weight_ih", (4 * c["hidden"], c["hidden"])), ("weight_hh", (4 * c["hidden"], c["hidden"])),
+                            ("bias_ih", (4 * c["hidden"],)), ("bias_hh", (4 * c["hidden"],))):
+            sd[f"lstm.{name}_l{l}"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+    dec = Decoder(c["vocab"], c["d"], c["hidden"], c["layers"]).eval()
+    dec.load_state_dict(sd, strict=True)
+    x = torch.randn(c["B"], c["T"], c["d"], generator=g)
+    lengths = torch.tensor(c["lengths"])
+    out = {"x": x.numpy(), "logits": dec(x, lengths).numpy(), "logits_nolen": dec(x, None).numpy()}
+    out.update({"sd." + k: v.numpy() for k, v in sd.items()})
+    np.savez_compressed(os.path.join(HERE, "decoder_2layer.npz"), **out)
+    print("decoder_2layer:", out["logits"].shape)
+
+
+if __name__ == "__main__":
+    if not set(sys.argv[1:]) or "decoder" in sys.argv[1:]:
+        run_decoder()

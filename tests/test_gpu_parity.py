@@ -513,7 +513,7 @@ def test_forward_host_pipelined_matches_forward():
 def test_greedy_ctc_tokens_bf16_gate():
     """north_star: greedy CTC token ids bit-exact.  BASELINE.md section 5: on bf16 with the top-1/top-2 margin histogram
     reported.  The reference Conformer (fp32, CPU) gives the golden logits, frame ids, margins and tokens; our bf16
-    tensor-core encoder feeds the same stock Decoder.  Frame ids must agree wherever the reference's own top-1/top-2
+    tensor-core encoder feeds the CTC head (fp32 recurrence on the device).  Frame ids must agree wherever the reference's own top-1/top-2
     margin exceeds THR (a bf16 logit cannot be asked to resolve a tie finer than its own rounding noise - the measured
     max logit error is printed next to THR), and the collapsed token lists must be IDENTICAL."""
     c = TOKEN_CASE_BF16
@@ -696,7 +696,7 @@ def test_reference_checkpoint_file_drives_the_drop_in_model():
     torch.backends.cuda.matmul.allow_tf32 = False
     logits, out_len = model(x, lengths)
     assert torch.equal(out_len.cpu(), gold["out_lengths"])
-    assert_close_fp32(logits, gold["logits"], "logits from the reference checkpoint", scale=2.0)   # + cuDNN LSTM vs CPU LSTM
+    assert_close_fp32(logits, gold["logits"], "logits from the reference checkpoint", scale=2.0)   # encoder + LSTM recurrence
 
 
 def test_logmel_front_end_vs_torchaudio_golden():
@@ -746,3 +746,57 @@ def test_gemm_tf32x3_matches_fp64(M, N, K):
     want = A.double() @ W.double().T
     scale = (A.double().abs() @ W.double().abs().T)
     assert ((C.cpu().double() - want).abs() / scale).max() < 5e-6   # measured 2.5e-6 (dropped low x low term + fp32 accumulation)
+
+
+def _decoder_from_golden():
+    from cases import DECODER_CASE as c
+    gold = golden("decoder_2layer")
+    sd = {k[3:]: v for k, v in gold.items() if k.startswith("sd.")}
+    sd["norm.num_batches_tracked"] = torch.tensor(100)
+    dec = cb.Decoder(c["vocab"], c["d"], c["hidden"], c["layers"])
+    dec.load_state_dict(sd, strict=True)
+    return dec.to(DEV).eval(), gold, c
+
+
+def test_decoder_head_on_device_vs_reference_golden():
+    """cfm_decoder_forward (input GEMM -> persistent cooperative LSTM kernel per layer -> Swish -> BatchNorm folded into
+    the vocabulary GEMM) against the real reference Decoder: two LSTM layers, UNSORTED lengths (the reference sorts
+    inside pack_padded_sequence in eval mode), frames beyond a sample's length, and no lengths at all."""
+    dec, gold, c = _decoder_from_golden()
+    x = gold["x"].to(DEV)
+    y = dec(x, torch.tensor(c["lengths"], device=DEV))
+    assert_close_fp32(y, gold["logits"], "decoder logits", scale=2.0)     # two chained recurrences of 33 steps
+    assert_close_fp32(dec(x, None), gold["logits_nolen"], "decoder logits without lengths", scale=2.0)
+    y16 = dec.set_compute("bf16")(x, torch.tensor(c["lengths"], device=DEV))
+    rel = ((y16.cpu() - gold["logits"]).norm() / gold["logits"].norm()).item()
+    print("decoder bf16 rel", rel)
+    assert rel < 2e-2
+
+
+@pytest.mark.parametrize("B,T,H", [(64, 374, 640), (7, 50, 48), (33, 20, 256)])
+def test_decoder_head_large_vs_oracle_and_timing(B, T, H):
+    """The head at the size it has behind Conformer-M (batch 64, T' = 374, LSTM(256 -> 640), vocab 370): against the
+    oracle's explicit time loop in fp32 on the GPU, with the device time of ours and of the stock cuDNN LSTM module
+    printed side by side."""
+    d, V = 256, 370
+    sd = sub(synth_decoder_state_dict(d, V, hidden=H, seed=72), "decoder.")
+    dec = cb.Decoder(V, d, H, 1)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.to(DEV).eval()
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, d, generator=g).to(DEV)
+    lengths = synth_lengths(B, T).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = O.decoder_head({"decoder." + k: v.to(DEV) for k, v in sd.items()}, x, lengths)
+    got = dec(x, lengths)
+    err = (got - want).abs().max().item()
+    assert err < 2e-4 * max(1.0, want.abs().max().item()), err
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record(); dec(x, lengths); ev[1].record()
+    ref = torch.nn.LSTM(d, H, 1, batch_first=True).to(DEV)
+    ref(x)
+    ev[2].record(); ref(x); ev[3].record()
+    torch.cuda.synchronize()
+    print(f"decoder head B={B} T={T} H={H}: ours (whole head) {ev[0].elapsed_time(ev[1]):.3f} ms, cuDNN LSTM alone "
+          f"{ev[2].elapsed_time(ev[3]):.3f} ms, max abs err vs oracle {err:.2e}")
