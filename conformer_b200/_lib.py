@@ -44,6 +44,12 @@ SIGNATURES = {
     "cfm_device_check": (C.c_int, []),
     "cfm_module_create": (C.c_int, [C.c_int, C.POINTER(Config), C.POINTER(_p)]),
     "cfm_module_set_param": (C.c_int, [_p, C.c_char_p, _p, _i64]),
+    "cfm_module_set_grad": (C.c_int, [_p, C.c_char_p, _p, _i64]),
+    "cfm_train_bind": (C.c_int, [_p, C.c_int]),
+    "cfm_train_refresh": (C.c_int, [_p, _p]),
+    "cfm_encoder_train_workspace_bytes": (_i64, [_p, _i32, _i32]),
+    "cfm_encoder_train_forward": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _f, C.c_uint64, _p, _i64, _p]),
+    "cfm_encoder_train_backward": (C.c_int, [_p, _p, _i32, _i32, _i32, _p, _i64, _p]),
     "cfm_module_finalize": (C.c_int, [_p, C.c_int, _p]),
     "cfm_module_destroy": (C.c_int, [_p]),
     "cfm_padding_mask": (C.c_int, [_p, _i32, _i32, _p, _p]),

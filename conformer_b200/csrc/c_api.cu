@@ -55,6 +55,35 @@ int cfm_module_set_param(cfm_module_t m, const char* name, const float* data, in
   return 0;
 }
 
+int cfm_module_set_grad(cfm_module_t m, const char* name, float* grad, int64_t numel) {
+  CFM_REQUIRE(m != nullptr && name != nullptr && grad != nullptr && numel > 0, "bad gradient registration");
+  m->grads[name] = ParamRef{grad, numel, false};
+  m->train.bound = false;
+  return 0;
+}
+int cfm_train_bind(cfm_module_t m, int compute) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  return m->train_bind(compute);
+}
+int cfm_train_refresh(cfm_module_t m, void* stream) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  return m->train_refresh(S(stream));
+}
+int64_t cfm_encoder_train_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin) {
+  if (m == nullptr) { set_error("null module handle"); return -1; }
+  return m->train_workspace_bytes(batch, Tin);
+}
+int cfm_encoder_train_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y, int64_t* lengths_out, int32_t batch,
+                              int32_t Tin, float dropout_p, uint64_t seed, void* workspace, int64_t workspace_bytes, void* stream) {
+  CFM_REQUIRE(m != nullptr, "null module handle");
+  return m->train_forward(mel, lengths_in, y, lengths_out, batch, Tin, workspace, workspace_bytes, dropout_p, seed, S(stream));
+}
+int cfm_encoder_train_backward(cfm_module_t m, const float* dy, int32_t block_hi, int32_t block_lo, int32_t front_end, void* workspace,
+                               int64_t workspace_bytes, void* stream) {
+  CFM_REQUIRE(m != nullptr && workspace != nullptr, "null argument");
+  return m->train_backward(dy, block_hi, block_lo, front_end != 0, workspace, workspace_bytes, S(stream));
+}
+
 int cfm_module_finalize(cfm_module_t m, int compute, void* stream) {
   CFM_REQUIRE(m != nullptr, "null module handle");
   return m->finalize(compute, S(stream));

@@ -56,6 +56,7 @@ template <int BLOCK_N, int EPI> struct Cfg {
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_kb;
+  int k_splits, kb_per_split;          // split-K (reduce-add epilogue only): tile = (split, m_tile, n_tile)
   const float* bias;
   float res_scale;
   // conv mode
@@ -97,7 +98,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   constexpr int BK = TF32 ? BLOCK_K / 2 : BLOCK_K;         // elements per 128-byte operand row
 
   if (warp == 0 && lane == 0) {
@@ -127,19 +128,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const int mn = tile % (p.num_m_tiles * p.num_n_tiles), ks = tile / (p.num_m_tiles * p.num_n_tiles);
+      const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
       int cb = 0, cf = 0, ct = 0;
       if (CONV) {
         ct = m_tile % p.TCH;
         cf = (m_tile / p.TCH) % p.F2;
         cb = m_tile / (p.TCH * p.F2);
       }
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
-        if (kb == 0) TRACE(0);
-        if (kb == p.num_kb - 1) TRACE(1);
+        if (kb == kb0) TRACE(0);
+        if (kb == kb1 - 1) TRACE(1);
         if (lane == 0) {
           uint8_t* sa = smem + s * C_::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
@@ -167,23 +170,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       TRACE(2);
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
+      const int ks = tile / (p.num_m_tiles * p.num_n_tiles);
+      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        if (kb == 0) TRACE(3);
-        if (kb == p.num_kb - 1) TRACE(4);
+        if (kb == kb0) TRACE(3);
+        if (kb == kb1 - 1) TRACE(4);
         if (elect_one()) {
           const uint32_t sa = umma_desc_lo(smem_u32(smem + s * C_::STAGE_BYTES));
           const uint32_t sb = sa + (A_STAGE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // one MMA covers 32 bytes of K in either format
-            if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
-            else tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, (kb | k) != 0 ? 1u : 0u);
+            if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            else tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);                            // smem slot free once these MMAs retire
-          if (kb == p.num_kb - 1) tc_commit(&tfull_bar[as]);   // accumulator complete
+          if (kb == kb1 - 1) tc_commit(&tfull_bar[as]);        // accumulator complete
         }
         __syncwarp();
       }
@@ -203,7 +208,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sw = row & 7;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
-      const int m_tile = tile / p.num_n_tiles, n_tile = tile - m_tile * p.num_n_tiles;
+      const int mn = tile % (p.num_m_tiles * p.num_n_tiles), ks = tile / (p.num_m_tiles * p.num_n_tiles);
+      const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BLOCK_N;                        // first GEMM column of the tile
       const int o0 = n_tile * C_::OUT_N;                      // first OUTPUT column of the tile
       const int out_n = GLU ? (p.N >> 1) : p.N;
@@ -213,7 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (leader) {
         if (C_::CBUF_COUNT == 2) bulk_wait_read1(); else bulk_wait_read0();
       }
-      if (tid_e < BLOCK_N) bias_s[tid_e] = (p.bias != nullptr && n0 + tid_e < p.N) ? __ldg(p.bias + n0 + tid_e) : 0.f;
+      if (tid_e < BLOCK_N) bias_s[tid_e] = (p.bias != nullptr && ks == 0 && n0 + tid_e < p.N) ? __ldg(p.bias + n0 + tid_e) : 0.f;
       named_bar_sync(1, NUM_EPI_THREADS);
       if (warp == 4) TRACE(5);
       mbar_wait(&tfull_bar[as], aph);
@@ -362,7 +368,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV>;
   static std::atomic<uint64_t> attr_done{0};        // one per template instantiation
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
-  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
   CFM_CUDA_OK(cudaGetLastError());
@@ -436,6 +442,8 @@ int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* 
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.res_scale = 1.f; p.trace = nullptr;
   p.num_kb = static_cast<int>(ceil_div(K, BK));
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
   p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
   p.num_n_tiles = static_cast<int>(ceil_div(N, BN));
   CUtensorMap tmA, tmB, tmC;
@@ -484,6 +492,8 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
   p.M = M; p.N = N; p.K = K;
   p.bias = bias; p.res_scale = res_scale; p.trace = g_gemm_trace;
   p.num_kb = static_cast<int>(ceil_div(K, BLOCK_K));
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
   CUtensorMap tmA, tmB, tmC;
   if (conv != nullptr) {
     CFM_REQUIRE(conv->C % BLOCK_K == 0, "implicit-GEMM conv needs channels to be a multiple of 64");
@@ -522,6 +532,19 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
   p.num_n_tiles = static_cast<int>(ceil_div(N, bn));
   CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
                          static_cast<uint32_t>(bn), "W"));
+  if (epi == EPI_BIAS_RES) {
+    // few output tiles and a long contraction (the weight-gradient GEMMs of the training step): split K over the idle SMs;
+    // every split reduce-adds its partial product into C, the bias enters with split 0
+    const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+    if (mn_tiles * 2 <= num_sms && p.num_kb >= 16) {
+      int splits = num_sms / mn_tiles;
+      if (splits > p.num_kb / 8) splits = p.num_kb / 8;
+      if (splits > 1) {
+        p.kb_per_split = static_cast<int>(ceil_div(p.num_kb, splits));
+        p.k_splits = static_cast<int>(ceil_div(p.num_kb, p.kb_per_split));
+      }
+    }
+  }
   if (out_f32) return launch_epi_f32(tmA, tmB, tmC, p, epi, num_sms, stream);
   if (conv != nullptr)
     return use256 ? launch_epi<256, true>(tmA, tmB, tmC, p, epi, num_sms, stream)

@@ -121,12 +121,59 @@ struct DecW {
   int V = 0, Vp = 0, H = 0;
 };
 
+// ---- training step (train.cu): pointers to the LIVE master parameters / gradient buffers + derived copies
+struct TrainLinear {
+  const float* w = nullptr;          // the parameter [N,K] (fp32 master)
+  const float* wg = nullptr;         // the [N,K] fp32 matrix the GEMMs use (w itself, or its packed form for conv_2 / linear)
+  const float* b = nullptr;
+  float *dw = nullptr, *db = nullptr;
+  bf16* w16 = nullptr;               // bf16 copy of wg (bf16 mode)
+  void* wT = nullptr;                // [K,N] transposed copy in the activation type (input-gradient GEMMs)
+  int N = 0, K = 0;
+};
+struct TrainNorm { const float *g = nullptr, *b = nullptr; float *dg = nullptr, *db = nullptr; };
+struct TrainBlock {
+  TrainNorm ffn1_ln, att_ln, conv_ln, ffn2_ln, out_ln;
+  TrainLinear ffn1_h, ffn1_o, q, k, v, pos, o, pw1, pw2, ffn2_h, ffn2_o;
+  const float *u = nullptr, *vb = nullptr, *dw_w = nullptr, *dw_b = nullptr, *bn_g = nullptr, *bn_b = nullptr;
+  float *du = nullptr, *dvb = nullptr, *ddw_w = nullptr, *ddw_b = nullptr, *dbn_g = nullptr, *dbn_b = nullptr;
+  float *bn_rm = nullptr, *bn_rv = nullptr;      // running statistics, updated in place by the training forward
+};
+struct BlockTape {                   // what one ConformerBlock's backward needs from its forward
+  const float* x = nullptr;
+  void *a1 = nullptr, *hp1 = nullptr, *a2 = nullptr, *qkv = nullptr, *pp = nullptr, *ctx = nullptr, *a3 = nullptr, *u = nullptr,
+       *g = nullptr, *a4 = nullptr, *hp4 = nullptr;
+  float *x1 = nullptr, *lse = nullptr, *x2 = nullptr, *z = nullptr, *bn = nullptr, *x3 = nullptr, *x4 = nullptr, *y = nullptr;
+};
+struct TrainTape {
+  bool valid = false;
+  int B = 0, Tin = 0, T2 = 0;
+  float p = 0.f;
+  uint64_t seed = 0;
+  const float* mel = nullptr;
+  void *out1 = nullptr, *h2 = nullptr, *pe = nullptr, *kp = nullptr;
+  float* x0 = nullptr;
+  size_t end_of_tape = 0;
+  std::vector<BlockTape> blocks;
+};
+struct TrainState {
+  bool bound = false;
+  TrainLinear conv2, lin;
+  float *conv2_packed = nullptr, *lin_packed = nullptr;
+  const float *c1_w = nullptr, *c1_b = nullptr, *div_term = nullptr;
+  float *dc1_w = nullptr, *dc1_b = nullptr;
+  std::vector<TrainBlock> blocks;
+  TrainTape tape;
+};
+
 struct ParamRef { const float* data; int64_t numel; bool used; };
 
 struct Module {
   int kind = 0;
   cfm_config_t cfg{};
   std::unordered_map<std::string, ParamRef> params;
+  std::unordered_map<std::string, ParamRef> grads;       // cfm_module_set_grad: fp32 gradient buffer of each parameter
+  TrainState train;
   bool finalized = false, bf16_mode = false;
   int num_sms = 148;
   int64_t last_launches = 0;
@@ -158,6 +205,18 @@ struct Module {
   int forward(int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in, float* y,
               int64_t* len_out, int B, int frames, void* workspace, int64_t ws_bytes, cudaStream_t stream,
               int64_t* needed);
+  // training step (train.cu)
+  int train_bind(int compute_mode);
+  int train_refresh(cudaStream_t stream);
+  int64_t train_workspace_bytes(int B, int Tin);
+  int train_forward(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, void* ws, int64_t ws_bytes,
+                    float p_drop, uint64_t seed, cudaStream_t stream);
+  int train_backward(const float* dy, int block_hi, int block_lo, bool front, void* ws, int64_t ws_bytes, cudaStream_t stream);
+  template <typename TA>
+  int train_forward_impl(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, Workspace& ws, float p_drop,
+                         uint64_t seed, cudaStream_t stream);
+  template <typename TA>
+  int train_backward_impl(const float* dy, int block_hi, int block_lo, bool front, void* ws, int64_t ws_bytes, cudaStream_t stream);
   template <typename TA>
   int forward_impl(Ctx& c, int op, const float* x, const float* pos, const uint8_t* key_pad, const int64_t* len_in,
                    float* y, int64_t* len_out, int B, int frames);

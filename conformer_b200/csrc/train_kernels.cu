@@ -1,0 +1,533 @@
+// Element-wise, normalisation and reduction kernels of the TRAINING step (BASELINE config 4; train.py:232-243 runs
+// forward -> CTC loss -> backward -> optimizer step over the modules of model/utils/*.py).  Everything dense goes through
+// the GEMM kernels (gemm_tc.cu / gemm_f32.cu); this file holds what surrounds them: dropout (nn.Dropout at ffn.py:19,21,
+// attention.py:12, convolution.py:19, encoder.py:14), LayerNorm backward, Swish / GLU backward, depthwise conv forward
+// and backward, training-mode BatchNorm1d (batch statistics over every frame of the batch, padded ones included, running
+// statistics updated with momentum 0.1, convolution.py:16,27), bias gradients, transposes for the weight-gradient GEMMs,
+// and the front-end's ReLU / im2col / col2im steps.
+//
+// Dropout masks are never stored: keep(seed, site, element) is a stateless hash, recomputed in the backward pass.
+// Activations are stored as TA (bf16 in CFM_COMPUTE_BF16, fp32 in CFM_COMPUTE_F32); the residual stream, every
+// gradient of it, LayerNorm / BatchNorm arithmetic and all parameter gradients are fp32.
+#include "train.h"
+
+namespace cfm {
+namespace {
+
+inline unsigned nblk(int64_t n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------- element-wise
+template <typename TOut>
+__global__ void cast_scale_drop_kernel(const float* __restrict__ in, TOut* __restrict__ out, int64_t n, float scale, Drop dr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<TOut>(in[i] * scale * dr.factor(i));
+}
+template <typename TA>
+__global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<TA>(swish_f(to_f32(hp[i])) * dr.factor(i));
+}
+template <typename TA>
+__global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = to_f32(hp[i]), s = sigmoid_f(x);
+  out[i] = from_f32<TA>(dh[i] * dr.factor(i) * (s + x * s * (1.f - s)));
+}
+__global__ void residual_drop_add_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ out, int64_t n,
+                                         float scale, Drop dr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = x[i] + scale * dr.factor(i) * t[i];
+}
+__global__ void drop_inplace_kernel(float* __restrict__ x, int64_t n, Drop dr) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) x[i] *= dr.factor(i);
+}
+template <typename TA>
+__global__ void glu_fwd_kernel(const TA* __restrict__ u, TA* __restrict__ g, int64_t rows, int d) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = static_cast<int>(i - r * d);
+  g[i] = from_f32<TA>(to_f32(u[r * 2 * d + c]) * sigmoid_f(to_f32(u[r * 2 * d + d + c])));     // activation.py:16-17
+}
+template <typename TA>
+__global__ void glu_bwd_kernel(const float* __restrict__ dg, const TA* __restrict__ u, TA* __restrict__ du, int64_t rows, int d) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * d) return;
+  const int64_t r = i / d;
+  const int c = static_cast<int>(i - r * d);
+  const float a = to_f32(u[r * 2 * d + c]), s = sigmoid_f(to_f32(u[r * 2 * d + d + c])), g = dg[i];
+  du[r * 2 * d + c] = from_f32<TA>(g * s);
+  du[r * 2 * d + d + c] = from_f32<TA>(g * a * s * (1.f - s));
+}
+template <typename TA>
+__global__ void relu_bwd_kernel(const float* __restrict__ dy, const TA* __restrict__ y, TA* __restrict__ out, int64_t n) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = from_f32<TA>(to_f32(y[i]) > 0.f ? dy[i] : 0.f);
+}
+
+// [M,N] (row stride ld) -> [N, Mp] with the columns M..Mp-1 zeroed: operands of the weight-gradient GEMMs, whose
+// contraction runs over the M rows
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ in, int ld, T* __restrict__ out, int M, int N, int Mp) {
+  __shared__ T tile[32][33];
+  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int m = m0 + r, n = n0 + tx;
+    tile[r][tx] = (m < M && n < N) ? in[static_cast<int64_t>(m) * ld + n] : from_f32<T>(0.f);
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, m = m0 + tx;
+    if (n < N && m < Mp) out[static_cast<int64_t>(n) * Mp + m] = tile[tx][r];
+  }
+}
+
+// column sums: out[n] += sum_m in[m, n]   (bias gradients)
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float acc = 0.f;
+  for (int m = m0; m < m1; ++m) acc += to_f32(in[static_cast<int64_t>(m) * ld + n]);
+  atomicAdd(out + n, acc);
+}
+
+// ------------------------------------------------------------------------------------------- LayerNorm backward
+// dx (+)= (rstd / d) * (d * gy - sum(gy) - xhat * sum(gy * xhat)),  gy = dy * gamma;  dgamma += dy * xhat, dbeta += dy.
+// One warp per row (row in registers); the parameter gradients are reduced per block in shared memory, then atomically.
+template <int NV>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                     const float* __restrict__ gamma, float* dx, int accumulate,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d,
+                                                     int rows_per_warp) {
+  extern __shared__ float red[];                                // [2][d]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float gsum[NV], bsum[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gsum[i] = bsum[i] = 0.f;
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * nwarps + warp) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int64_t row = r0 + rr;
+    if (row >= rows) break;
+    float xv[NV], gv[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] = c < d ? x[row * d + c] : 0.f;
+      s += xv[i];
+    }
+    const float mean = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] = c < d ? xv[i] - mean : 0.f;
+      q += xv[i] * xv[i];
+    }
+    const float rstd = rsqrtf(warp_sum(q) / d + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      xv[i] *= rstd;                                            // xhat
+      const float dyv = c < d ? dy[row * d + c] : 0.f;
+      gv[i] = c < d ? dyv * gamma[c] : 0.f;
+      s1 += gv[i];
+      s2 += gv[i] * xv[i];
+      gsum[i] += dyv * xv[i];
+      bsum[i] += dyv;
+    }
+    s1 = warp_sum(s1) / d;
+    s2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) {
+        const float v = rstd * (gv[i] - s1 - xv[i] * s2);
+        dx[row * d + c] = accumulate ? dx[row * d + c] + v : v;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d) {
+      atomicAdd(&red[c], gsum[i]);
+      atomicAdd(&red[d + c], bsum[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d; i += blockDim.x) {
+    atomicAdd(dgamma + i, red[i]);
+    atomicAdd(dbeta + i, red[d + i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- depthwise conv
+// z[b,t,c] = bias[c] + sum_j w[c,j] g[b,t+j-half,c]   (Conv1d groups = channels, zero padding at the tensor edges,
+// convolution.py:15,26); weights in the module's own layout [c][k]
+template <typename TA>
+__global__ void dwconv_fwd_kernel(const TA* __restrict__ g, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ z, int Tn, int d, int ks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
+  if (c >= d) return;
+  const int half = (ks - 1) / 2;
+  float acc = bias[c];
+  for (int j = 0; j < ks; ++j) {
+    const int tt = t + j - half;
+    if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ks + j], to_f32(g[(static_cast<int64_t>(b) * Tn + tt) * d + c]), acc);
+  }
+  z[(static_cast<int64_t>(b) * Tn + t) * d + c] = acc;
+}
+// dg[b,t,c] = sum_j w[c,j] dz[b,t-j+half,c]
+__global__ void dwconv_bwd_input_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* __restrict__ dg, int Tn, int d,
+                                        int ks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
+  if (c >= d) return;
+  const int half = (ks - 1) / 2;
+  float acc = 0.f;
+  for (int j = 0; j < ks; ++j) {
+    const int tt = t - j + half;
+    if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ks + j], dz[(static_cast<int64_t>(b) * Tn + tt) * d + c], acc);
+  }
+  dg[(static_cast<int64_t>(b) * Tn + t) * d + c] = acc;
+}
+// dw[c,j] += sum_{b,t} dz[b,t,c] g[b,t+j-half,c];  db[c] += sum dz.  grid (channel blocks, batch): one utterance per block row
+template <typename TA>
+__global__ void dwconv_bwd_weight_kernel(const float* __restrict__ dz, const TA* __restrict__ g, float* __restrict__ dw,
+                                         float* __restrict__ db, int Tn, int d, int ks) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (c >= d) return;
+  const int half = (ks - 1) / 2;
+  float bsum = 0.f;
+  for (int t = 0; t < Tn; ++t) bsum += dz[(static_cast<int64_t>(b) * Tn + t) * d + c];
+  atomicAdd(db + c, bsum);
+  for (int j = 0; j < ks; ++j) {
+    float acc = 0.f;
+    const int lo = max(0, half - j), hi = min(Tn, Tn + half - j);          // t with 0 <= t + j - half < Tn
+    for (int t = lo; t < hi; ++t)
+      acc = fmaf(dz[(static_cast<int64_t>(b) * Tn + t) * d + c], to_f32(g[(static_cast<int64_t>(b) * Tn + t + j - half) * d + c]), acc);
+    atomicAdd(dw + c * ks + j, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- BatchNorm1d, training mode
+// per-channel sums over all M = B*T rows: acc[c] += sum z, acc[d + c] += sum z^2 (fp32 partials, one atomic per block)
+__global__ void bn_sums_kernel(const float* __restrict__ z, float* __restrict__ acc, int M, int d, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  float s = 0.f, q = 0.f;
+  for (int m = m0; m < m1; ++m) {
+    const float v = z[static_cast<int64_t>(m) * d + c];
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  atomicAdd(acc + c, s);
+  atomicAdd(acc + d + c, q);
+}
+// mean / rstd of the batch (biased variance normalises, nn.BatchNorm1d), running statistics updated in place with the
+// unbiased variance and momentum 0.1
+__global__ void bn_finish_kernel(const float* __restrict__ acc, float* __restrict__ stats, float* running_mean, float* running_var,
+                                 int M, int d, float momentum, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const float mean = acc[c] / M;
+  const float var = fmaxf(acc[d + c] / M - mean * mean, 0.f);
+  stats[c] = mean;
+  stats[d + c] = rsqrtf(var + eps);
+  if (running_mean != nullptr) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * var * (M > 1 ? static_cast<float>(M) / (M - 1) : 1.f);
+  }
+}
+template <typename TA>
+__global__ void bn_swish_fwd_kernel(const float* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, TA* __restrict__ s, int64_t M, int d) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M * d) return;
+  const int c = static_cast<int>(i % d);
+  s[i] = from_f32<TA>(swish_f((z[i] - stats[c]) * stats[d + c] * gamma[c] + beta[c]));
+}
+// first backward pass: dzn = ds * swish'(zn) written over ds; acc[c] += sum dzn, acc[d+c] += sum dzn * zhat
+__global__ void bn_swish_bwd_reduce_kernel(float* ds, const float* __restrict__ z, const float* __restrict__ stats,
+                                           const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ acc, int M,
+                                           int d, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  const float mean = stats[c], rstd = stats[d + c], ga = gamma[c], be = beta[c];
+  float s1 = 0.f, s2 = 0.f;
+  for (int m = m0; m < m1; ++m) {
+    const int64_t i = static_cast<int64_t>(m) * d + c;
+    const float zh = (z[i] - mean) * rstd, zn = zh * ga + be, sg = sigmoid_f(zn);
+    const float dzn = ds[i] * (sg + zn * sg * (1.f - sg));
+    ds[i] = dzn;
+    s1 += dzn;
+    s2 = fmaf(dzn, zh, s2);
+  }
+  atomicAdd(acc + c, s1);
+  atomicAdd(acc + d + c, s2);
+}
+// second pass: dz = gamma * rstd * (dzn - mean(dzn) - zhat * mean(dzn * zhat)), in place; block row 0 adds dgamma, dbeta
+__global__ void bn_bwd_apply_kernel(float* dzn, const float* __restrict__ z, const float* __restrict__ stats,
+                                    const float* __restrict__ gamma, const float* __restrict__ acc, float* __restrict__ dgamma,
+                                    float* __restrict__ dbeta, int M, int d, int rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+  const float mean = stats[c], rstd = stats[d + c], k = gamma[c] * rstd, a1 = acc[c] / M, a2 = acc[d + c] / M;
+  for (int m = m0; m < m1; ++m) {
+    const int64_t i = static_cast<int64_t>(m) * d + c;
+    dzn[i] = k * (dzn[i] - a1 - (z[i] - mean) * rstd * a2);
+  }
+  if (blockIdx.y == 0) {
+    atomicAdd(dgamma + c, acc[d + c]);
+    atomicAdd(dbeta + c, acc[c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- front-end backward
+// colT[(kw*3+kh)*C + c][m] = out1[b][2 t2 + kw][2 f2 + kh][c], m = (b*T2 + t2)*F2 + f2: the transposed im2col operand of
+// conv_2's weight gradient (K order of pack_conv2_weight); columns m >= M2 are zero
+template <typename TA>
+__global__ void im2col_t_kernel(const TA* __restrict__ out1, TA* __restrict__ colT, ConvGeom g, int64_t M2, int64_t M2p) {
+  __shared__ TA tile[32][33];
+  const int tap = blockIdx.z, kw = tap / 3, kh = tap - kw * 3;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {                            // rows m, columns c (coalesced along c)
+    const int64_t m = m0 + r;
+    TA v = from_f32<TA>(0.f);
+    if (m < M2 && c0 + tx < g.C) {
+      const int f2 = static_cast<int>(m % g.F2), t2 = static_cast<int>((m / g.F2) % g.T2), b = static_cast<int>(m / (static_cast<int64_t>(g.F2) * g.T2));
+      v = out1[((static_cast<int64_t>(b) * g.T1p + 2 * t2 + kw) * g.F1 + 2 * f2 + kh) * g.C + c0 + tx];
+    }
+    tile[r][tx] = v;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r;
+    const int64_t m = m0 + tx;
+    if (c < g.C && m < M2p) colT[(static_cast<int64_t>(tap) * g.C + c) * M2p + m] = tile[tx][r];
+  }
+}
+// dOut1[b,t1,f1,c] = relu'(out1) * sum over the taps that read this input of dcol[m(t2,f2)][(kw*3+kh)*C + c]
+template <typename TA>
+__global__ void col2im_relu_kernel(const TA* __restrict__ dcol, const TA* __restrict__ out1, float* __restrict__ dout1, ConvGeom g) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t total = static_cast<int64_t>(g.B) * g.T1p * g.F1 * g.C;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % g.C), f1 = static_cast<int>((i / g.C) % g.F1), t1 = static_cast<int>((i / (static_cast<int64_t>(g.C) * g.F1)) % g.T1p);
+  const int b = static_cast<int>(i / (static_cast<int64_t>(g.C) * g.F1 * g.T1p));
+  float acc = 0.f;
+  if (to_f32(out1[i]) > 0.f) {
+    for (int kw = 0; kw < 3; ++kw) {
+      const int tt = t1 - kw;
+      if (tt < 0 || (tt & 1) || (tt >> 1) >= g.T2) continue;
+      for (int kh = 0; kh < 3; ++kh) {
+        const int ff = f1 - kh;
+        if (ff < 0 || (ff & 1) || (ff >> 1) >= g.F2) continue;
+        const int64_t m = (static_cast<int64_t>(b) * g.T2 + (tt >> 1)) * g.F2 + (ff >> 1);
+        acc += to_f32(dcol[m * 9 * g.C + (kw * 3 + kh) * g.C + c]);
+      }
+    }
+  }
+  dout1[i] = acc;
+}
+// conv_1 parameter gradients: dw[c][kh*3+kw] += sum_{b,t1,f1} dout1[b,t1,f1,c] mel[b][2 f1 + kh][2 t1 + kw]; db[c] += sum dout1.
+// block = (32 channels) x (a slab of t1 rows of one utterance)
+__global__ void conv1_wgrad_kernel(const float* __restrict__ dout1, const float* __restrict__ mel, float* __restrict__ dw, float* __restrict__ db,
+                                   int n_mel, int Tin, int T1, int T1p, int F1, int C, int t_per_block) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.z;
+  const int sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
+  const int t0 = blockIdx.y * t_per_block, t1e = min(T1, t0 + t_per_block);
+  float acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = 0.f;
+  if (c < C) {
+    for (int t1 = t0 + sub; t1 < t1e; t1 += nsub)
+      for (int f1 = 0; f1 < F1; ++f1) {
+        const float gsc = dout1[((static_cast<int64_t>(b) * T1p + t1) * F1 + f1) * C + c];
+        if (gsc == 0.f) continue;
+        acc[9] += gsc;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw)
+            acc[kh * 3 + kw] = fmaf(gsc, mel[(static_cast<int64_t>(b) * n_mel + 2 * f1 + kh) * Tin + 2 * t1 + kw], acc[kh * 3 + kw]);
+      }
+  }
+  __shared__ float red[8][32][10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) red[sub][threadIdx.x & 31][k] = acc[k];
+  __syncthreads();
+  if (sub == 0 && c < C) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      float t = 0.f;
+      for (int s = 0; s < nsub; ++s) t += red[s][threadIdx.x & 31][k];
+      if (k < 9) atomicAdd(dw + c * 9 + k, t);
+      else atomicAdd(db + c, t);
+    }
+  }
+}
+
+}  // namespace
+
+#define LAUNCH_OK()                    \
+  do {                                 \
+    CFM_CUDA_OK(cudaGetLastError());   \
+    return 0;                          \
+  } while (0)
+
+template <typename TOut>
+int cast_scale_drop(const float* in, TOut* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
+  cast_scale_drop_kernel<TOut><<<nblk(n, 256), 256, 0, st>>>(in, out, n, scale, dr);
+  LAUNCH_OK();
+}
+template <typename TA>
+int swish_drop_fwd(const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
+  swish_drop_fwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(hp, out, n, dr);
+  LAUNCH_OK();
+}
+template <typename TA>
+int swish_drop_bwd(const float* dh, const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
+  swish_drop_bwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(dh, hp, out, n, dr);
+  LAUNCH_OK();
+}
+int residual_drop_add(const float* x, const float* t, float* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
+  residual_drop_add_kernel<<<nblk(n, 256), 256, 0, st>>>(x, t, out, n, scale, dr);
+  LAUNCH_OK();
+}
+int drop_inplace(float* x, int64_t n, Drop dr, cudaStream_t st) {
+  if (dr.p <= 0.f) return 0;
+  drop_inplace_kernel<<<nblk(n, 256), 256, 0, st>>>(x, n, dr);
+  LAUNCH_OK();
+}
+template <typename TA>
+int glu_fwd(const TA* u, TA* g, int64_t rows, int d, cudaStream_t st) {
+  glu_fwd_kernel<TA><<<nblk(rows * d, 256), 256, 0, st>>>(u, g, rows, d);
+  LAUNCH_OK();
+}
+template <typename TA>
+int glu_bwd(const float* dg, const TA* u, TA* du, int64_t rows, int d, cudaStream_t st) {
+  glu_bwd_kernel<TA><<<nblk(rows * d, 256), 256, 0, st>>>(dg, u, du, rows, d);
+  LAUNCH_OK();
+}
+template <typename TA>
+int relu_bwd(const float* dy, const TA* y, TA* out, int64_t n, cudaStream_t st) {
+  relu_bwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(dy, y, out, n);
+  LAUNCH_OK();
+}
+template <typename T>
+int transpose_pad(const T* in, int ld, T* out, int M, int N, int Mp, cudaStream_t st) {
+  dim3 grid(nblk(Mp, 32), nblk(N, 32));
+  transpose_kernel<T><<<grid, 256, 0, st>>>(in, ld, out, M, N, Mp);
+  LAUNCH_OK();
+}
+template <typename T>
+int colsum_add(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
+  const int rpb = 256;
+  dim3 grid(nblk(N, 128), nblk(M, rpb));
+  colsum_kernel<T><<<grid, 128, 0, st>>>(in, ld, out, M, N, rpb);
+  LAUNCH_OK();
+}
+int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool accumulate, float* dgamma, float* dbeta, int64_t rows,
+           int d, cudaStream_t st) {
+  CFM_REQUIRE(d <= 1024, "LayerNorm backward supports d_model <= 1024");
+  const int rpw = 8, warps = 8;
+  const unsigned grid = nblk(rows, rpw * warps);
+  const size_t smem = static_cast<size_t>(2) * d * 4;
+  const int nv = (d + 31) / 32;
+  if (nv <= 8) ln_bwd_kernel<8><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
+  else if (nv <= 16) ln_bwd_kernel<16><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
+  else ln_bwd_kernel<32><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
+  LAUNCH_OK();
+}
+template <typename TA>
+int dwconv_fwd(const TA* g, const float* w, const float* bias, float* z, int B, int Tn, int d, int ks, cudaStream_t st) {
+  dim3 grid(nblk(d, 128), Tn, B);
+  dwconv_fwd_kernel<TA><<<grid, 128, 0, st>>>(g, w, bias, z, Tn, d, ks);
+  LAUNCH_OK();
+}
+int dwconv_bwd_input(const float* dz, const float* w, float* dg, int B, int Tn, int d, int ks, cudaStream_t st) {
+  dim3 grid(nblk(d, 128), Tn, B);
+  dwconv_bwd_input_kernel<<<grid, 128, 0, st>>>(dz, w, dg, Tn, d, ks);
+  LAUNCH_OK();
+}
+template <typename TA>
+int dwconv_bwd_weight(const float* dz, const TA* g, float* dw, float* db, int B, int Tn, int d, int ks, cudaStream_t st) {
+  dim3 grid(nblk(d, 64), B);
+  dwconv_bwd_weight_kernel<TA><<<grid, 64, 0, st>>>(dz, g, dw, db, Tn, d, ks);
+  LAUNCH_OK();
+}
+int bn_train_stats(const float* z, float* acc2d, float* stats2d, float* running_mean, float* running_var, int M, int d, float momentum,
+                   cudaStream_t st) {
+  CFM_CUDA_OK(cudaMemsetAsync(acc2d, 0, static_cast<size_t>(2) * d * 4, st));
+  const int rpb = 128;
+  dim3 grid(nblk(d, 128), nblk(M, rpb));
+  bn_sums_kernel<<<grid, 128, 0, st>>>(z, acc2d, M, d, rpb);
+  bn_finish_kernel<<<nblk(d, 128), 128, 0, st>>>(acc2d, stats2d, running_mean, running_var, M, d, momentum, 1e-5f);
+  LAUNCH_OK();
+}
+template <typename TA>
+int bn_swish_fwd(const float* z, const float* stats, const float* gamma, const float* beta, TA* s, int64_t M, int d, cudaStream_t st) {
+  bn_swish_fwd_kernel<TA><<<nblk(M * d, 256), 256, 0, st>>>(z, stats, gamma, beta, s, M, d);
+  LAUNCH_OK();
+}
+int bn_swish_bwd(float* ds_to_dz, const float* z, const float* stats, const float* gamma, const float* beta, float* acc2d, float* dgamma,
+                 float* dbeta, int M, int d, cudaStream_t st) {
+  CFM_CUDA_OK(cudaMemsetAsync(acc2d, 0, static_cast<size_t>(2) * d * 4, st));
+  const int rpb = 128;
+  dim3 grid(nblk(d, 128), nblk(M, rpb));
+  bn_swish_bwd_reduce_kernel<<<grid, 128, 0, st>>>(ds_to_dz, z, stats, gamma, beta, acc2d, M, d, rpb);
+  bn_bwd_apply_kernel<<<grid, 128, 0, st>>>(ds_to_dz, z, stats, gamma, acc2d, dgamma, dbeta, M, d, rpb);
+  LAUNCH_OK();
+}
+template <typename TA>
+int im2col_t(const TA* out1, TA* colT, const ConvGeom& g, int64_t M2, int64_t M2p, cudaStream_t st) {
+  dim3 grid(nblk(M2p, 32), nblk(g.C, 32), 9);
+  im2col_t_kernel<TA><<<grid, 256, 0, st>>>(out1, colT, g, M2, M2p);
+  LAUNCH_OK();
+}
+template <typename TA>
+int col2im_relu(const TA* dcol, const TA* out1, float* dout1, const ConvGeom& g, cudaStream_t st) {
+  const int64_t total = static_cast<int64_t>(g.B) * g.T1p * g.F1 * g.C;
+  col2im_relu_kernel<TA><<<nblk(total, 256), 256, 0, st>>>(dcol, out1, dout1, g);
+  LAUNCH_OK();
+}
+int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int B, int n_mel, int Tin, int T1, int T1p, int F1, int C,
+                cudaStream_t st) {
+  const int tpb = 16;
+  dim3 grid(nblk(C, 32), nblk(T1, tpb), B);
+  conv1_wgrad_kernel<<<grid, 256, 0, st>>>(dout1, mel, dw, db, n_mel, Tin, T1, T1p, F1, C, tpb);
+  LAUNCH_OK();
+}
+
+#define INST_TA(T)                                                                                                   \
+  template int swish_drop_fwd<T>(const T*, T*, int64_t, Drop, cudaStream_t);                                          \
+  template int swish_drop_bwd<T>(const float*, const T*, T*, int64_t, Drop, cudaStream_t);                            \
+  template int glu_fwd<T>(const T*, T*, int64_t, int, cudaStream_t);                                                  \
+  template int glu_bwd<T>(const float*, const T*, T*, int64_t, int, cudaStream_t);                                    \
+  template int relu_bwd<T>(const float*, const T*, T*, int64_t, cudaStream_t);                                        \
+  template int transpose_pad<T>(const T*, int, T*, int, int, int, cudaStream_t);                                      \
+  template int colsum_add<T>(const T*, int, float*, int, int, cudaStream_t);                                          \
+  template int dwconv_fwd<T>(const T*, const float*, const float*, float*, int, int, int, int, cudaStream_t);         \
+  template int dwconv_bwd_weight<T>(const float*, const T*, float*, float*, int, int, int, int, cudaStream_t);        \
+  template int bn_swish_fwd<T>(const float*, const float*, const float*, const float*, T*, int64_t, int, cudaStream_t); \
+  template int im2col_t<T>(const T*, T*, const ConvGeom&, int64_t, int64_t, cudaStream_t);                            \
+  template int col2im_relu<T>(const T*, const T*, float*, const ConvGeom&, cudaStream_t);                             \
+  template int cast_scale_drop<T>(const float*, T*, int64_t, float, Drop, cudaStream_t);
+INST_TA(float)
+INST_TA(bf16)
+
+}  // namespace cfm

@@ -194,6 +194,8 @@ class _Native(nn.Module):
     def __getstate__(self):                            # handles are process-local; never copy/pickle them
         state = dict(self.__dict__)
         state["_handles"], state["_ws"], state["_private_ws"] = {}, {}, None
+        if "_train_state" in state:
+            state["_train_state"] = None
         return state
 
     def _native(self) -> int:
@@ -527,6 +529,8 @@ class Encoder(_Native):
         self.layers = nn.ModuleList([ConformerBlock(d_model=d_model, n_heads=n_heads, kernel_size=kernel_size,
                                                     dropout_rate=dropout_rate) for _ in range(n_blocks)])
         self._cfg = (n_mel_channels, n_blocks, d_model, n_heads, kernel_size)
+        self._dropout_rate = float(dropout_rate)
+        object.__setattr__(self, "_train_state", None)     # conformer_b200.training.TrainState, built lazily
 
     def _config(self) -> Config:
         return Config(*self._cfg)
@@ -539,6 +543,9 @@ class Encoder(_Native):
         B, n_mel, Tin = xin.shape
         if n_mel != self._cfg[0]:
             raise RuntimeError(f"conformer_b200: expected {self._cfg[0]} mel channels, got {n_mel}")
+        if self.training:
+            from .training import encoder_train_forward
+            return encoder_train_forward(self, xin, lengths)
         y = torch.empty((B, self.output_frames(Tin), self._cfg[2]), device=xin.device, dtype=torch.float32)
         lin = lout = None
         if lengths is not None:
@@ -669,6 +676,17 @@ class Decoder(_Native):
         return Config(0, 0, d, 1, 1, v, h, n)
 
     def forward(self, x: torch.Tensor, lengths: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if self.training:
+            # Training mode: the head is outside the path and is differentiated by autograd, so
+            # it runs the reference's own torch ops (cuDNN LSTM, batch-statistics BatchNorm), decoder.py:15-27.
+            packed = lengths is not None
+            if packed:
+                x = nn.utils.rnn.pack_padded_sequence(x, lengths.cpu(), batch_first=True, enforce_sorted=True)
+            x, _ = self.lstm(x)
+            if packed:
+                x, _ = nn.utils.rnn.pad_packed_sequence(x, batch_first=True)
+            x = x * torch.sigmoid(x)
+            return self.linear(self.norm(x.transpose(1, 2)).transpose(1, 2))
         xin = _dev_f32(x, "x")
         B, T, _ = xin.shape
         lin = None if lengths is None else lengths.to(device=xin.device, dtype=torch.int64).contiguous()

@@ -194,6 +194,30 @@ CFM_API int64_t cfm_last_launch_count(cfm_module_t m);
 CFM_API int cfm_profile_enable(cfm_module_t m, int32_t on);
 CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_classes);
 
+/* ---- training step of the encoder (BASELINE config 4; train.py:232-243) ---------------------- */
+/* The handle keeps POINTERS to the live fp32 master parameters (cfm_module_set_param, which must then stay valid) and to
+ * one fp32 gradient buffer per parameter (cfm_module_set_grad; the backward ACCUMULATES into them, the caller zeroes
+ * them).  cfm_train_bind checks the reference's state_dict contract and allocates the derived copies; cfm_train_refresh
+ * re-derives them (bf16 / transposed / packed) and must be called after every optimizer step, before the next forward.
+ * Buffers (running_mean / running_var) are registered like parameters and are UPDATED IN PLACE by the training forward
+ * (momentum 0.1, unbiased variance), as nn.BatchNorm1d does; num_batches_tracked stays with the caller. */
+CFM_API int cfm_module_set_grad(cfm_module_t m, const char* name, float* grad, int64_t numel);
+CFM_API int cfm_train_bind(cfm_module_t m, int compute);
+CFM_API int cfm_train_refresh(cfm_module_t m, void* stream);
+/* One buffer holds the tape (activations kept for the backward) followed by scratch. */
+CFM_API int64_t cfm_encoder_train_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin);
+/* Encoder.forward(x, lengths) in TRAINING mode: dropout with rate dropout_p at every nn.Dropout of the path (stateless
+ * masks from `seed`, recomputed by the backward), BatchNorm1d with batch statistics over all B*T' frames. */
+CFM_API int cfm_encoder_train_forward(cfm_module_t m, const float* mel, const int64_t* lengths_in, float* y, int64_t* lengths_out,
+                                      int32_t batch, int32_t Tin, float dropout_p, uint64_t seed, void* workspace,
+                                      int64_t workspace_bytes, void* stream);
+/* Backward of the blocks [block_lo, block_hi) in reverse order, then (front_end != 0, block_lo == 0) of Encoder.linear and
+ * the two subsampling convolutions.  dy fp32 [B,T',d] = gradient of the encoder output, passed with the FIRST call of a
+ * step (block_hi == n_blocks) and NULL afterwards: the gradient of the residual stream stays in the workspace between
+ * calls, so a caller can all-reduce the gradients of finished blocks while the next call computes. */
+CFM_API int cfm_encoder_train_backward(cfm_module_t m, const float* dy, int32_t block_hi, int32_t block_lo, int32_t front_end,
+                                       void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- log-mel front-end: the step right before the path ---------------------- */
 /* ConformerProcessor.mel_spectrogram (processing/processor.py:53-63,155-158):
  *   log(clamp(torchaudio.transforms.MelSpectrogram(...)(signal), min=1e-5))

@@ -52,3 +52,10 @@ LOGMEL_CASES = [
 
 # the reference Decoder alone: two LSTM layers, unsorted lengths with max == T (decoder.py:15-27)
 DECODER_CASE = dict(d=64, vocab=37, hidden=96, layers=2, B=5, T=33, lengths=[20, 33, 1, 33, 7], seed=71)
+
+# training-step gradients from the reference's own autograd (config 4): Encoder in train mode, dropout 0,
+# loss = sum(y * R) with a seeded cotangent R
+TRAIN_CASES = [
+    dict(name="train_tiny", cfg=TINY, B=3, Tin=83, seed=81, with_lengths=True),
+    dict(name="train_k31", cfg=EncoderConfig(80, 1, 64, 4, 31), B=2, Tin=131, seed=82, with_lengths=False),
+]

@@ -269,3 +269,38 @@ def run_decoder():
 if __name__ == "__main__":
     if not set(sys.argv[1:]) or "decoder" in sys.argv[1:]:
         run_decoder()
+
+
+def run_train_grads():
+    """Reference Encoder in TRAINING mode (batch-statistics BatchNorm, dropout 0) under autograd, CPU fp32 and fp64."""
+    from cases import TRAIN_CASES
+    torch.set_grad_enabled(True)
+    for c in TRAIN_CASES:
+        cfg = c["cfg"]
+        out = {}
+        for dt, tag in ((torch.float32, ""), (torch.float64, "64")):
+            sd = synth_encoder_state_dict(cfg, c["seed"])
+            enc = Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, dropout_rate=0.0)
+            enc.load_state_dict(sd, strict=True)
+            enc = enc.to(dt).train()
+            x = synth_logmel(c["B"], cfg.n_mel_channels, c["Tin"], seed=1000 + c["seed"]).to(dt)
+            lengths = case_lengths(c)
+            y, _ = enc(x, lengths)
+            R = torch.randn(y.shape, generator=torch.Generator().manual_seed(c["seed"] + 7)).to(dt)
+            (y * R).sum().backward()
+            out["y" + tag] = y.detach().numpy()
+            for n, p in enc.named_parameters():
+                if p.requires_grad:
+                    out[f"grad{tag}." + n] = p.grad.numpy()
+            if not tag:
+                for n, b in enc.named_buffers():
+                    if "running" in n:
+                        out["buf." + n] = b.numpy()
+        np.savez_compressed(os.path.join(HERE, c["name"] + ".npz"), **out)
+        print(c["name"], "y", out["y"].shape, "grads", sum(1 for k in out if k.startswith("grad.")))
+    torch.set_grad_enabled(False)
+
+
+if __name__ == "__main__":
+    if not set(sys.argv[1:]) or "train" in sys.argv[1:]:
+        run_train_grads()
