@@ -49,6 +49,8 @@ WORKLOADS = {
     "C2": (CONFORMER_M, 64, 1501, "full", "bf16", "Conformer-M encoder fwd, 64x15s, bf16 (BASELINE configs[1])"),
     "C3": (CONFORMER_L, 32, 2001, "var", "bf16", "Conformer-L encoder fwd, 32x20s var-len, bf16 (BASELINE configs[2])"),
     "C5": (CONFORMER_M, 16, 6001, "full", "bf16", "Conformer-M encoder fwd, 16x60s long-form, bf16 (BASELINE configs[4])"),
+    # training step: Conformer(370, M) fwd + CTC + bwd + Adam, 32 x 15 s per GPU, gradient all-reduce over NCCL
+    "C4": (CONFORMER_M, 32, 1501, "full", "bf16", "Conformer-M CTC training step, 32x15s per GPU, bf16, DP all-reduce (BASELINE configs[3])"),
     # tiny shape used only by the CPU multi-process tests of the harness itself
     "T0": (EncoderConfig(80, 2, 64, 4, 31), 2, 101, "var", "fp32", "harness self-test (not a benchmark workload)"),
 }
@@ -449,6 +451,173 @@ def side_config(cb, name, dev, rank, dist, world, steps, peaks):
     return out
 
 
+# ----------------------------------------------------------------------------------------- config 4: the training step
+VOCAB = 370            # tokenizer/vi.json (train.py:115)
+
+
+def train_batch(cfg, batch, t_in, seed, dev):
+    g = torch.Generator().manual_seed(seed)
+    x = synth_logmel(batch, cfg.n_mel_channels, t_in, seed=seed).to(dev)
+    xl = torch.full((batch,), t_in, dtype=torch.long, device=dev)
+    yl = torch.randint(40, 81, (batch,), generator=g)
+    y = torch.randint(1, VOCAB - 1, (batch, 80), generator=g).to(dev)
+    return x, xl, y, yl.to(dev)
+
+
+def ctc_loss_fn(outputs, targets, in_lens, tgt_lens):
+    """evaluation.py:10-16"""
+    return torch.nn.functional.ctc_loss(outputs.float().log_softmax(-1).transpose(0, 1), targets, in_lens, tgt_lens, blank=0,
+                                        zero_infinity=True)
+
+
+def run_train_bench(args, cfg, batch, t_in, desc):
+    """One step = forward (training mode, dropout 0.1) + CTC loss + backward + gradient all-reduce + Adam, as train.py:232-243."""
+    import conformer_b200 as cb
+    from conformer_b200.synth import synth_decoder_state_dict
+    from conformer_b200.training import GradientAllReducer
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    args.warmup = max(args.warmup, 3)
+    sd = synth_encoder_state_dict(cfg, 0, prefix="encoder.")
+    sd.update(synth_decoder_state_dict(cfg.d_model, VOCAB, seed=1))
+    model = cb.Conformer(VOCAB, cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, dropout_rate=0.1)
+    model.load_state_dict(sd)
+    model = model.to(dev).train().set_compute("bf16")
+    opt = torch.optim.Adam(model.parameters(), lr=2e-5)
+    reducer = GradientAllReducer(model)
+    x, xl, y, yl = train_batch(cfg, batch, t_in, rank_seed(rank), dev)
+    secs = audio_seconds(xl.cpu(), batch, t_in)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out, ol = model(x, xl)
+        loss = ctc_loss_fn(out, y, ol, yl)
+        opt.zero_grad()
+        reducer.arm()
+        loss.backward()
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss = step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        sampler.begin_timed()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dist, dev) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    loss_v = float(loss.item())
+    # forward-only and forward+backward-only splits, and the all-reduce alone (bus bandwidth against NVLink)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    barrier()
+    ev[0].record()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        out, ol = model(x, xl)
+    ev[1].record()
+    l2 = ctc_loss_fn(out, y, ol, yl)
+    opt.zero_grad()
+    l2.backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    fwd_ms, bwd_ms = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+    allreduce = None
+    n_params = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    if dist is not None:
+        flat = torch.zeros(n_params, device=dev)
+        for _ in range(3):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        barrier()
+        ev[0].record()
+        for _ in range(5):
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        ev[1].record()
+        barrier()
+        t = max_over_ranks(ev[0].elapsed_time(ev[1]), dist, dev) / 5
+        allreduce = {"bytes_per_step": n_params * 4, "ms_alone": t, "bus_gbs": 2 * (world - 1) / world * n_params * 4 / (t * 1e-3) / 1e9,
+                     "nvlink_ref_gbs": 725.0, "overlap": "per-block slices of the flat fp32 gradient buffer are all-reduced "
+                     "(NCCL, async) while the backward of the earlier blocks runs; exposed cost = step time at N minus step time at 1"}
+    eager = None
+    if rank == 0 and not args.no_extras:
+        eager = gpu_eager_train_baseline(cfg, batch, t_in, dev)
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    fl = 3.0 * encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
+    line = {"metric": "training-step audio-seconds per second", "value": world * secs / (ms * 1e-3), "unit": "audio-s/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": desc, "per_gpu_batch": batch, "mel_frames": t_in, "vocab": VOCAB, "dropout": 0.1,
+                       "optimizer": "Adam lr 2e-5 (train.py:188), fp32 master weights", "targets": "80 ids per utterance, lengths 40-80",
+                       "parallelism": f"dp{world}: one process per GPU, gradient all-reduce (AVG) over NCCL, no SyncBN (as the reference)",
+                       "step": "encoder fwd/bwd in the native library (training-mode BatchNorm, dropout), CTC head + CTC loss + Adam in PyTorch (outside the path)"},
+            "forward_ms": fwd_ms, "backward_ms": bwd_ms, "final_loss": loss_v,
+            "algorithmic_tflops_encoder": fl / (ms * 1e-3) / 1e12, "allreduce": allreduce, "clocks": clocks,
+            "gpu_launches": None}
+    if eager is not None:
+        line["gpu_eager_baseline"] = eager
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def gpu_eager_train_baseline(cfg, batch, t_in, dev, steps=3):
+    """The reference Conformer (baseline/_ref) training step eagerly on this GPU under bf16 autocast, same batch."""
+    if not os.path.isdir(os.path.join(REF_DIR, "model")):
+        return {"unavailable": "baseline/_ref did not travel"}
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    try:
+        from conformer_b200.synth import synth_decoder_state_dict
+        from model.conformer import Conformer as RefConformer
+        sd = synth_encoder_state_dict(cfg, 0, prefix="encoder.")
+        sd.update(synth_decoder_state_dict(cfg.d_model, VOCAB, seed=1))
+        m = RefConformer(VOCAB, cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size, dropout_rate=0.1)
+        m.load_state_dict(sd)
+        m = m.to(dev).train()
+        opt = torch.optim.Adam(m.parameters(), lr=2e-5)
+        x, xl, y, yl = train_batch(cfg, batch, t_in, 1234, dev)
+        times = []
+        for i in range(steps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out, ol = m(x, xl)
+            loss = ctc_loss_fn(out, y, ol, yl)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            e1.record()
+            e1.synchronize()
+            if i >= 2:
+                times.append(e0.elapsed_time(e1))
+        ms = statistics.median(times)
+        return {"ms_per_step": ms, "value": batch * t_in * FRAME_SEC / (ms * 1e-3), "unit": "audio-s/s", "kind": "reference",
+                "what": f"reference Conformer training step, eager PyTorch {torch.__version__} bf16 autocast, batch {batch}, median of {steps}"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:300]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -468,6 +637,9 @@ def main():
         compute = args.compute
     if args.impl == "reference":
         run_reference_arm(args, cfg, batch, t_in, len_mode, desc)
+        return
+    if args.config == "C4":
+        run_train_bench(args, cfg, batch, t_in, desc)
         return
 
     import conformer_b200 as cb

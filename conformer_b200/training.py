@@ -49,18 +49,25 @@ class TrainState:
         sel = [v for k, v in self.offsets.items() if (k.startswith(pre) if pre else not k.startswith("layers."))]
         return min(a for a, _ in sel), max(b for _, b in sel)
 
-    def attach_grads(self) -> None:
-        """param.grad := its view of the flat buffer.  A parameter whose .grad is None (zero_grad(set_to_none=True), the
-        optimizer default) starts a fresh step: its slice is zeroed; an attached view keeps accumulating, like autograd."""
-        fresh = [v for (_, p), v in zip(self.params, self.views) if p.grad is None or p.grad.data_ptr() != v.data_ptr()]
-        if len(fresh) == len(self.views):
+    def begin_backward(self) -> None:
+        """The native backward ACCUMULATES into the flat buffer.  A parameter whose .grad is None (the optimizer's
+        zero_grad(set_to_none=True), which the reference calls between forward and backward, train.py:238) or a foreign
+        tensor starts from a zeroed slice; a parameter whose .grad already is its slice keeps accumulating, like autograd."""
+        self._fresh = [i for i, ((_, p), v) in enumerate(zip(self.params, self.views))
+                       if p.grad is None or p.grad.data_ptr() != v.data_ptr()]
+        if len(self._fresh) == len(self.views):
             self.flat_grad.zero_()
         else:
-            for v in fresh:
-                v.zero_()
-        for (_, p), v in zip(self.params, self.views):
-            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                p.grad = v
+            for i in self._fresh:
+                self.views[i].zero_()
+
+    def end_backward(self) -> None:
+        for i in self._fresh:
+            p, v = self.params[i][1], self.views[i]
+            if p.grad is None:
+                p.grad = v                       # .grad now aliases the flat buffer (what the all-reduce works on)
+            else:
+                p.grad.add_(v)                   # a gradient tensor someone else installed: add ours into it
 
     def bind(self, enc, compute: int) -> None:
         named = {k: v for k, v in enc.state_dict(keep_vars=True).items() if v.is_floating_point()}
@@ -126,6 +133,7 @@ class _EncoderTrainFn(torch.autograd.Function):
         L = enc._cfg[1]
         dy = dy.to(torch.float32).contiguous()
         ws = state.workspace
+        state.begin_backward()
         with _on_device(dy.device):
             # block by block, last to first: after each call that block's parameter gradients are final
             for i in range(L - 1, -1, -1):
@@ -137,6 +145,7 @@ class _EncoderTrainFn(torch.autograd.Function):
                                                    ws.numel(), _stream()))
             if state.on_block_done is not None:
                 state.on_block_done(-1, *state.block_slice(-1))
+        state.end_backward()
         return None, None, None, None, None
 
 
@@ -150,7 +159,6 @@ def encoder_train_forward(enc, x: torch.Tensor, lengths: Optional[torch.Tensor])
     compute = enc._compute()
     with _on_device(dev):
         st.bind(enc, compute)
-    st.attach_grads()
     if not hasattr(st, "hook") or st.hook.device != dev:
         st.hook = torch.zeros(1, device=dev, requires_grad=True)     # makes autograd call our backward
     out = _EncoderTrainFn.apply(st.hook, enc, st, x, lengths)
