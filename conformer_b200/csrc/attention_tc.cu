@@ -21,7 +21,7 @@
 // Masked keys (and keys past T) get weight exactly 0.
 #include <math_constants.h>
 
-#include "ops.h"
+#include "train.h"
 
 namespace cfm {
 namespace {
@@ -56,6 +56,8 @@ struct AttnParams {
   int Tn, H;
   float scale_log2e;
   unsigned long long* trace;     // debug: globaltimer stamps of CTA (0,0,0)
+  float* lse;                    // TRAIN: natural-log softmax normaliser of every query row, [B,H,T] (for the backward pass)
+  Drop dr;                       // TRAIN: attention-weight dropout (attention.py:67), element ((b*H+h)*T+i)*T+j
 };
 __device__ __forceinline__ unsigned long long atime_ns() {
   unsigned long long t;
@@ -74,6 +76,8 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// TRAIN: also writes the softmax normaliser and applies attention-weight dropout to P (the row sums stay undropped)
+template <bool TRAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPos, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -320,7 +324,12 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
         for (int e = 0; e < 4; ++e) {
           const float p0 = ex2f(sc[c4 * 8 + 2 * e] - m_use), p1 = ex2f(sc[c4 * 8 + 2 * e + 1] - m_use);
           psum += p0 + p1;
-          o[e] = pack_bf16x2(p0, p1);
+          if (TRAIN) {
+            const int64_t e0 = (static_cast<int64_t>(b * p.H + h) * Tn + qi) * Tn + j * BKV + 32 * grp + c4 * 8 + 2 * e;
+            o[e] = pack_bf16x2(p0 * p.dr.factor(e0), p1 * p.dr.factor(e0 + 1));
+          } else {
+            o[e] = pack_bf16x2(p0, p1);
+          }
         }
         *reinterpret_cast<uint4*>(prow + (((grp * 4 + c4) ^ sw) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
       }
@@ -341,6 +350,8 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     named_bar_sync(1 + w, 64);
     const float l_tot = l_part + xsum[(grp ^ 1) * BQ + row];
     const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+    if (TRAIN && grp == 0 && qi < Tn)                    // scores are in log2 units: ln sum e^s = m ln2 + ln l
+      p.lse[(static_cast<int64_t>(b) * p.H + h) * Tn + qi] = (m_ref == -CUDART_INF_F ? 0.f : m_ref) * 0.6931471805599453f + __logf(fmaxf(l_tot, 1e-30f));
     if (qi < Tn) {
       bf16* orow = p.ctx + (static_cast<int64_t>(b) * Tn + qi) * d + h * DH + 32 * grp;
 #pragma unroll
@@ -367,8 +378,8 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
 
 extern unsigned long long* g_gemm_trace;
 
-int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
-                          const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream) {
+static int launch_attention_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* key_pad, bf16* ctx,
+                               float* lse, Drop dr, bool train, int B, int Tn, int H, int dh, cudaStream_t stream) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(dh == DH, "tcgen05 attention is specialised for head size 64");
   CFM_REQUIRE(B > 0 && Tn > 0 && H > 0 && H <= 65535 && B <= 65535, "bad attention shape");
@@ -388,13 +399,29 @@ int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float
     cuuint32_t box[2] = {DH, WIN};
     CFM_TRY(encode_tmap(&tmPos, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, pos, dims, strides, box, "attention pos"));
   }
-  static std::atomic<uint64_t> attr_done{0};
-  CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_tc_kernel), SMEM_BYTES));
-  AttnParams p{qkv, u, v, key_pad, ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace};
+  static std::atomic<uint64_t> attr_done{0}, attr_done_t{0};
+  AttnParams p{qkv, u, v, key_pad, ctx, Tn, H, 1.4426950408889634f / sqrtf(static_cast<float>(dh)), g_gemm_trace, lse, dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  rel_attention_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
+  if (train) {
+    CFM_TRY(smem_attr_once(attr_done_t, reinterpret_cast<const void*>(rel_attention_tc_kernel<true>), SMEM_BYTES));
+    rel_attention_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
+  } else {
+    CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_tc_kernel<false>), SMEM_BYTES));
+    rel_attention_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
+  }
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int rel_attention_bf16_tc(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v,
+                          const uint8_t* key_pad, bf16* ctx, int B, int Tn, int H, int dh, cudaStream_t stream) {
+  return launch_attention_tc(qkv, pos, ldp, u, v, key_pad, ctx, nullptr, Drop{}, false, B, Tn, H, dh, stream);
+}
+// training forward: the same kernel, also emitting the log-sum-exp of every row and applying attention-weight dropout
+int rel_attention_bf16_tc_train(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* key_pad,
+                                bf16* ctx, float* lse, Drop dr, int B, int Tn, int H, int dh, cudaStream_t stream) {
+  CFM_REQUIRE(lse != nullptr, "training attention needs the log-sum-exp buffer");
+  return launch_attention_tc(qkv, pos, ldp, u, v, key_pad, ctx, lse, dr, true, B, Tn, H, dh, stream);
 }
 
 }  // namespace cfm

@@ -65,6 +65,56 @@ __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* x, con
   }
 }
 
+// Same, RPW rows per warp with every row's loads issued before the first reduction: 4 x 1 KB in flight per warp keeps
+// the HBM pipe fuller than one row at a time (measured on B200 at [23936, 256]: 8.4 -> see DESIGN.md).
+template <typename TOut, int NV, int RPW>
+__global__ void __launch_bounds__(256) layer_norm_vec_rows_kernel(const float* x, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, TOut* y, int64_t rows) {
+  constexpr int D = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= rows) return;
+  float4 v[RPW][NV];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const bool ok = row0 + r < rows;
+    const float4* xr = reinterpret_cast<const float4*>(x + (row0 + (ok ? r : 0)) * D);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[r][i] = xr[i * 32 + lane];
+  }
+  float4 g4[NV], b4[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    g4[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+    b4[i] = __ldg(reinterpret_cast<const float4*>(beta) + i * 32 + lane);
+  }
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    if (row0 + r >= rows) break;                                 // warp-uniform
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      v[r][i].x -= mean; v[r][i].y -= mean; v[r][i].z -= mean; v[r][i].w -= mean;
+      q += (v[r][i].x * v[r][i].x + v[r][i].y * v[r][i].y) + (v[r][i].z * v[r][i].z + v[r][i].w * v[r][i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const float o0 = v[r][i].x * rstd * g4[i].x + b4[i].x, o1 = v[r][i].y * rstd * g4[i].y + b4[i].y;
+      const float o2 = v[r][i].z * rstd * g4[i].z + b4[i].z, o3 = v[r][i].w * rstd * g4[i].w + b4[i].w;
+      if (sizeof(TOut) == 4) {
+        reinterpret_cast<float4*>(y + (row0 + r) * D)[i * 32 + lane] = make_float4(o0, o1, o2, o3);
+      } else {
+        reinterpret_cast<uint2*>(y + (row0 + r) * D)[i * 32 + lane] = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+      }
+    }
+  }
+}
+
 // Two LayerNorms in one pass over a row of d = 256:  y = LN(x; g1, b1) (fp32: the block output, block.py:27) and
 // a = LN(y; g2, b2) (bf16: the normalised input of the NEXT block's first half-step FFN, ffn.py:16).  The fused FFN
 // kernel then starts from one TMA load of `a` instead of every CTA pulling 128 KB of fp32 rows and normalising them.
@@ -72,7 +122,7 @@ __global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* x, co
                                                               const float* __restrict__ b1, float* y,
                                                               const float* __restrict__ g2, const float* __restrict__ b2,
                                                               bf16* __restrict__ a, int64_t rows) {
-  constexpr int D = 256, RPW = 2;                                  // rows per warp: both rows' loads are in flight together
+  constexpr int D = 256, RPW = 4;                                  // rows per warp: all rows' loads are in flight together
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
@@ -242,7 +292,9 @@ int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, i
   CFM_REQUIRE(rows > 0 && d > 0, "empty layer_norm");
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                          reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
-  if (aligned && d == 256)
+  if (aligned && d == 256 && rows >= 4096)
+    layer_norm_vec_rows_kernel<TOut, 2, 4><<<blocks_for(rows, 32), 256, 0, stream>>>(x, gamma, beta, y, rows);
+  else if (aligned && d == 256)
     layer_norm_vec_kernel<TOut, 2><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
   else if (aligned && d == 512)
     layer_norm_vec_kernel<TOut, 4><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
@@ -260,7 +312,7 @@ int layer_norm_dual(const float* x, const float* g1, const float* b1, float* y, 
                 reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(g2) |
                 reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "layer_norm_dual operands must be 16-byte aligned");
   if (rows <= 0) return 0;
-  layer_norm_dual_kernel<<<blocks_for(rows, 16), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
+  layer_norm_dual_kernel<<<blocks_for(rows, 32), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

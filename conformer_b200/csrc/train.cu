@@ -58,6 +58,17 @@ template <typename T> T* take(const TC& c, int64_t n) { return static_cast<T*>(c
   T* var = take<T>(c, (n));                                                                                      \
   CFM_REQUIRE(var != nullptr || c.ws->measuring(), "training workspace too small; query cfm_encoder_train_workspace_bytes")
 
+// training forward of the attention core: the tcgen05 kernel where it exists (bf16, head size 64), else the CUDA-core one
+inline int attn_fwd_any(const float* qkv, const float* pp, const float* u, const float* v, const uint8_t* kp, float* ctx, float* lse, int B,
+                        int Tn, int H, int dh, Drop dr, cudaStream_t st) {
+  return attn_train_fwd<float>(qkv, pp, u, v, kp, ctx, lse, B, Tn, H, dh, dr, st);
+}
+inline int attn_fwd_any(const bf16* qkv, const bf16* pp, const float* u, const float* v, const uint8_t* kp, bf16* ctx, float* lse, int B,
+                        int Tn, int H, int dh, Drop dr, cudaStream_t st) {
+  if (dh == 64) return rel_attention_bf16_tc_train(qkv, pp, H * dh, u, v, kp, ctx, lse, dr, B, Tn, H, dh, st);
+  return attn_train_fwd<bf16>(qkv, pp, u, v, kp, ctx, lse, B, Tn, H, dh, dr, st);
+}
+
 inline int round8(int64_t v) { return static_cast<int>((v + 7) & ~static_cast<int64_t>(7)); }
 
 // dW[N_w, K_w] += dY[M, N_w]^T X[M, K_w]  and  db[N_w] += colsum(dY):  the weight-gradient GEMM contracts over the M rows
@@ -97,6 +108,7 @@ int Module::train_bind(int compute_mode) {
   CFM_REQUIRE(compute_mode == 0 || compute_mode == 1, "compute must be CFM_COMPUTE_F32 or CFM_COMPUTE_BF16");
   const int d = cfg.d_model, H = cfg.n_heads, k = cfg.kernel_size, L = cfg.n_blocks, F2 = freq_bins();
   CFM_REQUIRE(d % 8 == 0 && H > 0 && d % H == 0 && (d / H) % 4 == 0 && d / H <= 64, "training needs d_model % 8 == 0 and head size % 4 == 0, <= 64");
+  CFM_REQUIRE(k % 2 == 1 && k <= 63, "training needs an odd depthwise kernel size up to 63 (the reference uses 31)");
   int dev = 0;
   CFM_CUDA_OK(cudaGetDevice(&dev));
   CFM_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
@@ -296,7 +308,7 @@ int Module::train_forward_impl(const float* mel, const int64_t* len_in, float* y
     CFM_TRY(gemm_any(c, a2, d, WSel<TA>::w(w.k), w.k.b, qkv + d, 3 * d, Mi, d, d, EPI_BIAS, nullptr, 0.f));
     CFM_TRY(gemm_any(c, a2, d, WSel<TA>::w(w.v), w.v.b, qkv + 2 * d, 3 * d, Mi, d, d, EPI_BIAS, nullptr, 0.f));
     CFM_TRY(gemm_any(c, static_cast<const TA*>(pe), d, WSel<TA>::w(w.pos), w.pos.b, pp, d, R, d, d, EPI_BIAS, nullptr, 0.f));
-    CFM_TRY(attn_train_fwd<TA>(qkv, pp, w.u, w.vb, kp, ctx, bt.lse, B, T2, H, dh, c.drop(i, SITE_ATTN_P), st));
+    CFM_TRY(attn_fwd_any(qkv, pp, w.u, w.vb, kp, ctx, bt.lse, B, T2, H, dh, c.drop(i, SITE_ATTN_P), st));
     CFM_TRY(gemm_any(c, static_cast<const TA*>(ctx), d, WSel<TA>::w(w.o), w.o.b, tmp, d, Mi, d, d, EPI_BIAS_F32, nullptr, 0.f));
     CFM_TRY(residual_drop_add(bt.x1, tmp, bt.x2, M * d, 1.f, c.drop(i, SITE_ATTN_O), st));
     // x3 = x2 + Conv(x2)                                                                        (block.py:23, convolution.py:21-32)

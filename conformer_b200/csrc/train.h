@@ -67,4 +67,8 @@ int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
                    const float* dctx, TA* dqkv, float* dpp, float* du, float* dv, float* scratch, int B, int Tn, int H, int dh, Drop dr,
                    cudaStream_t st);
 
+// attention_tc.cu: the tcgen05 forward kernel in training form (head size 64, bf16)
+int rel_attention_bf16_tc_train(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* key_pad,
+                                bf16* ctx, float* lse, Drop dr, int B, int Tn, int H, int dh, cudaStream_t stream);
+
 }  // namespace cfm

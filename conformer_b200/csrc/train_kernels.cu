@@ -17,27 +17,65 @@ namespace {
 inline unsigned nblk(int64_t n, int t) { return static_cast<unsigned>((n + t - 1) / t); }
 
 // ------------------------------------------------------------------------------------------- element-wise
+// 4 consecutive elements per thread (n % 4 == 0 and 16-byte aligned buffers: every caller passes [rows, multiple of 8])
+__device__ __forceinline__ void ld4(const float* p, float (&v)[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
+  const uint2 t = *reinterpret_cast<const uint2*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+__device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+__device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
 template <typename TOut>
 __global__ void cast_scale_drop_kernel(const float* __restrict__ in, TOut* __restrict__ out, int64_t n, float scale, Drop dr) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = from_f32<TOut>(in[i] * scale * dr.factor(i));
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float v[4];
+  ld4(in + i, v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] *= scale * dr.factor(i + e);
+  st4(out + i, v);
 }
 template <typename TA>
 __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = from_f32<TA>(swish_f(to_f32(hp[i])) * dr.factor(i));
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float v[4];
+  ld4(hp + i, v);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = swish_f(v[e]) * dr.factor(i + e);
+  st4(out + i, v);
 }
 template <typename TA>
 __global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
-  const float x = to_f32(hp[i]), s = sigmoid_f(x);
-  out[i] = from_f32<TA>(dh[i] * dr.factor(i) * (s + x * s * (1.f - s)));
+  float x[4], g[4];
+  ld4(hp + i, x);
+  ld4(dh + i, g);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float s = sigmoid_f(x[e]);
+    g[e] *= dr.factor(i + e) * (s + x[e] * s * (1.f - s));
+  }
+  st4(out + i, g);
 }
 __global__ void residual_drop_add_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ out, int64_t n,
                                          float scale, Drop dr) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = x[i] + scale * dr.factor(i) * t[i];
+  const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i >= n) return;
+  float a[4], b[4];
+  ld4(x + i, a);
+  ld4(t + i, b);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) a[e] += scale * dr.factor(i + e) * b[e];
+  st4(out + i, a);
 }
 __global__ void drop_inplace_kernel(float* __restrict__ x, int64_t n, Drop dr) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -92,6 +130,7 @@ __global__ void colsum_kernel(const T* __restrict__ in, int ld, float* __restric
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
   float acc = 0.f;
+#pragma unroll 8
   for (int m = m0; m < m1; ++m) acc += to_f32(in[static_cast<int64_t>(m) * ld + n]);
   atomicAdd(out + n, acc);
 }
@@ -172,49 +211,69 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
 
 // ------------------------------------------------------------------------------------------- depthwise conv
 // z[b,t,c] = bias[c] + sum_j w[c,j] g[b,t+j-half,c]   (Conv1d groups = channels, zero padding at the tensor edges,
-// convolution.py:15,26); weights in the module's own layout [c][k]
-template <typename TA>
-__global__ void dwconv_fwd_kernel(const TA* __restrict__ g, const float* __restrict__ w, const float* __restrict__ bias,
-                                  float* __restrict__ z, int Tn, int d, int ks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
-  if (c >= d) return;
-  const int half = (ks - 1) / 2;
-  float acc = bias[c];
-  for (int j = 0; j < ks; ++j) {
-    const int tt = t + j - half;
-    if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ks + j], to_f32(g[(static_cast<int64_t>(b) * Tn + tt) * d + c]), acc);
+// convolution.py:15,26); weights in the module's own layout [c][k].  FLIP = true computes the input gradient
+// dg[b,t,c] = sum_j w[c,j] dz[b,t-j+half,c] with the same code (taps reversed, no bias).
+// One block = 32 channels x 64 frames of one utterance, input rows staged in shared memory; thread = (channel, 8 frames).
+template <typename TIn, bool FLIP>
+__global__ void __launch_bounds__(256) dwconv_tile_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
+                                                          float* __restrict__ out, int Tn, int d, int ks) {
+  constexpr int TT = 64, KMAX = 64;
+  __shared__ float in_s[TT + KMAX][32];
+  __shared__ float w_s[KMAX][33];
+  const int c0 = blockIdx.x * 32, t0 = blockIdx.y * TT, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int half = (ks - 1) / 2, c = c0 + lane;
+  for (int r = wp; r < TT + ks - 1; r += 8) {
+    const int t = t0 + r - half;
+    in_s[r][lane] = (t >= 0 && t < Tn && c < d) ? to_f32(in[(static_cast<int64_t>(b) * Tn + t) * d + c]) : 0.f;
   }
-  z[(static_cast<int64_t>(b) * Tn + t) * d + c] = acc;
-}
-// dg[b,t,c] = sum_j w[c,j] dz[b,t-j+half,c]
-__global__ void dwconv_bwd_input_kernel(const float* __restrict__ dz, const float* __restrict__ w, float* __restrict__ dg, int Tn, int d,
-                                        int ks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y, b = blockIdx.z;
-  if (c >= d) return;
-  const int half = (ks - 1) / 2;
-  float acc = 0.f;
-  for (int j = 0; j < ks; ++j) {
-    const int tt = t - j + half;
-    if (tt >= 0 && tt < Tn) acc = fmaf(w[c * ks + j], dz[(static_cast<int64_t>(b) * Tn + tt) * d + c], acc);
+  for (int i = threadIdx.x; i < 32 * ks; i += 256) {
+    const int cc = i / ks, j = i - cc * ks;
+    w_s[FLIP ? ks - 1 - j : j][cc] = (c0 + cc < d) ? w[(c0 + cc) * ks + j] : 0.f;
   }
-  dg[(static_cast<int64_t>(b) * Tn + t) * d + c] = acc;
-}
-// dw[c,j] += sum_{b,t} dz[b,t,c] g[b,t+j-half,c];  db[c] += sum dz.  grid (channel blocks, batch): one utterance per block row
-template <typename TA>
-__global__ void dwconv_bwd_weight_kernel(const float* __restrict__ dz, const TA* __restrict__ g, float* __restrict__ dw,
-                                         float* __restrict__ db, int Tn, int d, int ks) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  __syncthreads();
   if (c >= d) return;
-  const int half = (ks - 1) / 2;
-  float bsum = 0.f;
-  for (int t = 0; t < Tn; ++t) bsum += dz[(static_cast<int64_t>(b) * Tn + t) * d + c];
-  atomicAdd(db + c, bsum);
-  for (int j = 0; j < ks; ++j) {
+  const float bc = FLIP ? 0.f : bias[c];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = wp * 8 + i, t = t0 + r;
+    if (t >= Tn) break;
+    float acc = bc;
+    for (int j = 0; j < ks; ++j) acc = fmaf(w_s[j][lane], in_s[r + j][lane], acc);
+    out[(static_cast<int64_t>(b) * Tn + t) * d + c] = acc;
+  }
+}
+// dw[c,j] += sum_{b,t} dz[b,t,c] g[b,t+j-half,c];  db[c] += sum dz.  One block = 32 channels x 64 frames of one utterance:
+// the dz rows and the g rows they touch (64 + ks - 1) are staged in shared memory, thread = (channel, taps j0, j0+8, ...)
+template <typename TA>
+__global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ dz, const TA* __restrict__ g, float* __restrict__ dw,
+                                                                float* __restrict__ db, int Tn, int d, int ks) {
+  constexpr int TT = 64, KMAX = 64;
+  __shared__ float dz_s[TT][32];
+  __shared__ float g_s[TT + KMAX][32];
+  const int c0 = blockIdx.x * 32, t0 = blockIdx.y * TT, b = blockIdx.z;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int half = (ks - 1) / 2, c = c0 + lane;
+  for (int r = w; r < TT; r += 8) {
+    const int t = t0 + r;
+    dz_s[r][lane] = (t < Tn && c < d) ? dz[(static_cast<int64_t>(b) * Tn + t) * d + c] : 0.f;
+  }
+  for (int r = w; r < TT + ks - 1; r += 8) {
+    const int t = t0 + r - half;
+    g_s[r][lane] = (t >= 0 && t < Tn && c < d) ? to_f32(g[(static_cast<int64_t>(b) * Tn + t) * d + c]) : 0.f;
+  }
+  __syncthreads();
+  if (c >= d) return;
+  for (int j = w; j < ks; j += 8) {
     float acc = 0.f;
-    const int lo = max(0, half - j), hi = min(Tn, Tn + half - j);          // t with 0 <= t + j - half < Tn
-    for (int t = lo; t < hi; ++t)
-      acc = fmaf(dz[(static_cast<int64_t>(b) * Tn + t) * d + c], to_f32(g[(static_cast<int64_t>(b) * Tn + t + j - half) * d + c]), acc);
+#pragma unroll 8
+    for (int r = 0; r < TT; ++r) acc = fmaf(dz_s[r][lane], g_s[r + j][lane], acc);
     atomicAdd(dw + c * ks + j, acc);
+  }
+  if (w == 0) {
+    float bs = 0.f;
+    for (int r = 0; r < TT; ++r) bs += dz_s[r][lane];
+    atomicAdd(db + c, bs);
   }
 }
 
@@ -391,21 +450,22 @@ __global__ void conv1_wgrad_kernel(const float* __restrict__ dout1, const float*
 
 template <typename TOut>
 int cast_scale_drop(const float* in, TOut* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
-  cast_scale_drop_kernel<TOut><<<nblk(n, 256), 256, 0, st>>>(in, out, n, scale, dr);
+  CFM_REQUIRE(n % 4 == 0, "element count must be a multiple of 4");
+  cast_scale_drop_kernel<TOut><<<nblk(n, 1024), 256, 0, st>>>(in, out, n, scale, dr);
   LAUNCH_OK();
 }
 template <typename TA>
 int swish_drop_fwd(const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
-  swish_drop_fwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(hp, out, n, dr);
+  swish_drop_fwd_kernel<TA><<<nblk(n, 1024), 256, 0, st>>>(hp, out, n, dr);
   LAUNCH_OK();
 }
 template <typename TA>
 int swish_drop_bwd(const float* dh, const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
-  swish_drop_bwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(dh, hp, out, n, dr);
+  swish_drop_bwd_kernel<TA><<<nblk(n, 1024), 256, 0, st>>>(dh, hp, out, n, dr);
   LAUNCH_OK();
 }
 int residual_drop_add(const float* x, const float* t, float* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
-  residual_drop_add_kernel<<<nblk(n, 256), 256, 0, st>>>(x, t, out, n, scale, dr);
+  residual_drop_add_kernel<<<nblk(n, 1024), 256, 0, st>>>(x, t, out, n, scale, dr);
   LAUNCH_OK();
 }
 int drop_inplace(float* x, int64_t n, Drop dr, cudaStream_t st) {
@@ -436,7 +496,7 @@ int transpose_pad(const T* in, int ld, T* out, int M, int N, int Mp, cudaStream_
 }
 template <typename T>
 int colsum_add(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
-  const int rpb = 256;
+  const int rpb = 32;
   dim3 grid(nblk(N, 128), nblk(M, rpb));
   colsum_kernel<T><<<grid, 128, 0, st>>>(in, ld, out, M, N, rpb);
   LAUNCH_OK();
@@ -444,7 +504,7 @@ int colsum_add(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool accumulate, float* dgamma, float* dbeta, int64_t rows,
            int d, cudaStream_t st) {
   CFM_REQUIRE(d <= 1024, "LayerNorm backward supports d_model <= 1024");
-  const int rpw = 8, warps = 8;
+  const int rpw = 2, warps = 8;
   const unsigned grid = nblk(rows, rpw * warps);
   const size_t smem = static_cast<size_t>(2) * d * 4;
   const int nv = (d + 31) / 32;
@@ -455,19 +515,22 @@ int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool 
 }
 template <typename TA>
 int dwconv_fwd(const TA* g, const float* w, const float* bias, float* z, int B, int Tn, int d, int ks, cudaStream_t st) {
-  dim3 grid(nblk(d, 128), Tn, B);
-  dwconv_fwd_kernel<TA><<<grid, 128, 0, st>>>(g, w, bias, z, Tn, d, ks);
+  CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
+  dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
+  dwconv_tile_kernel<TA, false><<<grid, 256, 0, st>>>(g, w, bias, z, Tn, d, ks);
   LAUNCH_OK();
 }
 int dwconv_bwd_input(const float* dz, const float* w, float* dg, int B, int Tn, int d, int ks, cudaStream_t st) {
-  dim3 grid(nblk(d, 128), Tn, B);
-  dwconv_bwd_input_kernel<<<grid, 128, 0, st>>>(dz, w, dg, Tn, d, ks);
+  CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
+  dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
+  dwconv_tile_kernel<float, true><<<grid, 256, 0, st>>>(dz, w, nullptr, dg, Tn, d, ks);
   LAUNCH_OK();
 }
 template <typename TA>
 int dwconv_bwd_weight(const float* dz, const TA* g, float* dw, float* db, int B, int Tn, int d, int ks, cudaStream_t st) {
-  dim3 grid(nblk(d, 64), B);
-  dwconv_bwd_weight_kernel<TA><<<grid, 64, 0, st>>>(dz, g, dw, db, Tn, d, ks);
+  CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
+  dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
+  dwconv_bwd_weight_kernel<TA><<<grid, 256, 0, st>>>(dz, g, dw, db, Tn, d, ks);
   LAUNCH_OK();
 }
 int bn_train_stats(const float* z, float* acc2d, float* stats2d, float* running_mean, float* running_var, int M, int d, float momentum,

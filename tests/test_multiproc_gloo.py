@@ -66,3 +66,54 @@ def test_reference_arm_under_torchrun_rank0_only():
     # "reference" when baseline/_ref travelled with the repo (baseline/install_ref.py), else the oracle port
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["cpu_baseline"]["kind"] in ("port", "reference")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def _reducer_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import conformer_b200 as cb
+    from conformer_b200.training import GradientAllReducer, TrainState
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        model = cb.Conformer(11, 80, 2, 32, 2, 7, 16, 1)
+        enc = model.encoder
+        st = TrainState(enc, torch.device("cpu"))
+        object.__setattr__(enc, "_train_state", st)
+        # what the native backward leaves behind: per-rank gradients in the flat buffer, .grad aliasing its slices
+        st.flat_grad.copy_(torch.arange(st.flat_grad.numel(), dtype=torch.float32) * (rank + 1))
+        st.begin_backward.__func__  # noqa: B018 - the attribute exists
+        for (_, p), v in zip(st.params, st.views):
+            p.grad = v
+        for p in model.decoder.parameters():
+            p.grad = torch.full_like(p, float(rank + 1))
+        red = GradientAllReducer(model)
+        red.arm()
+        for i in (1, 0, -1):                               # the order the backward finishes them in
+            st.on_block_done(i, *st.block_slice(i))
+        red.finish()
+        want = torch.arange(st.flat_grad.numel(), dtype=torch.float32) * (sum(range(1, world + 1)) / world)
+        ok_enc = torch.allclose(st.flat_grad, want)
+        ok_dec = all(torch.allclose(p.grad, torch.full_like(p, sum(range(1, world + 1)) / world)) for p in model.decoder.parameters())
+        slices = [st.block_slice(-1), st.block_slice(0), st.block_slice(1)]
+        out.put((rank, ok_enc, ok_dec, slices, st.flat_grad.numel(), red.bytes_reduced))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reducer_averages_block_slices_and_head():
+    """World-size-2 gloo run of the data-parallel gradient exchange of config 4: per-block slices of the encoder's flat
+    gradient buffer (in the order the backward finishes them) and the CTC head's gradients are averaged over the ranks;
+    the slices partition the buffer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_reducer_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_enc, ok_dec, slices, total, nbytes in res:
+        assert ok_enc and ok_dec
+        assert slices[0][0] == 0 and slices[0][1] == slices[1][0] and slices[1][1] == slices[2][0] and slices[2][1] == total
+        assert nbytes >= total * 4
