@@ -477,7 +477,7 @@ int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* 
 
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N, int K,
                  Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, bool split_k) {
   CFM_TRY(tc_init());
   CFM_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
   CFM_REQUIRE(K % 8 == 0 && N % 8 == 0 && ldc % 8 == 0, "tensor-core GEMM needs K, N, ldc multiples of 8");
@@ -532,7 +532,7 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
   p.num_n_tiles = static_cast<int>(ceil_div(N, bn));
   CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
                          static_cast<uint32_t>(bn), "W"));
-  if (epi == EPI_BIAS_RES) {
+  if (epi == EPI_BIAS_RES && split_k) {
     // few output tiles and a long contraction (the weight-gradient GEMMs of the training step): split K over the idle SMs;
     // every split reduce-adds its partial product into C, the bias enters with split 0
     const int mn_tiles = p.num_m_tiles * p.num_n_tiles;

@@ -35,7 +35,10 @@ int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* 
 // output rows are ordered (b, t2, f2).
 int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N,
                  int K, Epilogue epi, const float* res, float res_scale, const ConvGeom* conv, int num_sms,
-                 cudaStream_t stream);
+                 cudaStream_t stream, bool split_k = false);
+// split_k (EPI_BIAS_RES only): when the output has few tiles and K is long - the weight-gradient GEMMs of the training
+// step - the contraction is split over the idle SMs, every split reduce-adding its partial product into C (summation
+// order then varies from run to run, so the inference path keeps it off)
 // fp32 operands multiplied as TF32 on tcgen05 (kind::tf32), fp32 accumulate and output: C = A[M,K] W[N,K]^T + bias.
 // For fp32-grade accuracy pass TF32-exact high/low splits concatenated along K (A' = [Ahi|Alo|Ahi], W' = [Whi|Whi|Wlo]).
 int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,

@@ -50,7 +50,7 @@ inline int gemm_any(const TC& c, const float* A, int lda, const float* W, const 
 }
 inline int gemm_any(const TC& c, const bf16* A, int lda, const bf16* W, const float* bias, void* C, int ldc, int M, int N, int K,
                     Epilogue e, const float* res, float scale, const ConvGeom* g = nullptr) {
-  return gemm_bf16_tc(A, lda, W, bias, C, ldc, M, N, K, e, res, scale, g, c.num_sms, c.st);
+  return gemm_bf16_tc(A, lda, W, bias, C, ldc, M, N, K, e, res, scale, g, c.num_sms, c.st, /*split_k=*/true);
 }
 
 template <typename T> T* take(const TC& c, int64_t n) { return static_cast<T*>(c.ws->take(static_cast<size_t>(n) * sizeof(T))); }
