@@ -351,10 +351,13 @@ class Bench:
             cur.wait_stream(st)
         e1.record(cur)
         self.barrier()
-        t = sorted(e0.elapsed_time(ev) for ev in ends)
-        deltas = [b - a for a, b in zip([0.0] + t[:-1], t)]
-        # the first n_streams completions include the pipeline fill; the median ignores them by construction
-        med = statistics.median(deltas)
+        # step k runs on stream k % n: the interval between consecutive completions ON THE SAME STREAM covers n steps of
+        # the whole pipeline, so interval / n is a per-step time that does not depend on how completions of different
+        # streams bunch together
+        t = [e0.elapsed_time(ev) for ev in ends]
+        n = max(1, len(self.streams)) if fn is None else max(1, getattr(self, "e2e_lanes", len(self.streams)))
+        deltas = [(t[k] - t[k - n]) / n for k in range(n, len(t))]
+        med = statistics.median(deltas) if deltas else e0.elapsed_time(e1) / steps
         return (max_over_ranks(e0.elapsed_time(e1), self.dist, self.dev) / steps, max_over_ranks(med, self.dist, self.dev))
 
     def profile(self, steps):
@@ -715,6 +718,7 @@ def main():
                 return copy_out                       # a step is complete when its result has landed on the host
             return step
 
+        b.e2e_lanes = n_slots                         # a slot's results complete in order; n_slots steps per slot cycle
         step_e2e = make_e2e_step(x_e2e)
         for _ in range(2 * n_slots):
             step_e2e()

@@ -165,9 +165,11 @@ def test_cpu_tensors_and_training_mode_fail_loudly():
     enc = cb.Encoder(80, 1, 64, 4, 7).to(DEV).eval()
     with pytest.raises(RuntimeError):
         enc(torch.zeros(1, 80, 64))
-    enc.train()
+    # training mode: the Encoder has its native training step (tests/test_gpu_training.py); the stand-alone sub-modules
+    # are inference-only and say so
+    ffn = cb.FeedForwardModule(64).to(DEV).train()
     with pytest.raises(RuntimeError):
-        enc(torch.zeros(1, 80, 64, device=DEV))
+        ffn(torch.zeros(1, 4, 64, device=DEV))
 
 
 def test_reload_weights_repacks():
