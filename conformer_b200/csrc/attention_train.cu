@@ -14,7 +14,8 @@
 // positional operand of entry (i, j) is row j - i + 63 of a 127-row window of the projected table, so no shifted copy
 // exists); the "P x something" products re-read the score tile from shared memory with each thread accumulating a
 // [4 rows x 4 channels] block.  fp32 arithmetic on the CUDA cores throughout: this is the first, correctness-first
-// version of the training path (the inference path has the tcgen05 kernels); its cost is reported next to the GEMMs'.
+// version of the backward (the forward of the training step at head size 64 is the tcgen05 kernel of attention_tc.cu, the
+// forward kernel here serves the other head sizes and the fp32 mode); its cost is reported next to the GEMMs'.
 #include <math_constants.h>
 
 #include "train.h"
@@ -24,6 +25,27 @@ namespace {
 
 constexpr int TQ = 64, TK = 64, DHP = 64, LDS_ = DHP + 4, WIN = TQ + TK - 1;      // 127-row positional window
 constexpr int THREADS = 256;
+// Operand tiles (q+u, q+v, dctx, k, v, positional window) are held in shared memory in the ACTIVATION type: fp32 in the
+// gradient-parity mode, bf16 in bf16 mode, where they halve the footprint (2 CTAs per SM instead of 1: the second CTA's
+// FMAs hide the first one's shared-memory latency).  Score tiles (P, ds) stay fp32.  Row pitch: 68 floats / 72 bf16 -
+// both conflict-free for the 4-element accesses of consecutive rows.
+template <typename TS> struct Tile;
+template <> struct Tile<float> {
+  static constexpr int LD = DHP + 4;
+  static __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Tile<bf16> {
+  static constexpr int LD = DHP + 8;
+  static __device__ __forceinline__ float4 ld4(const bf16* p) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    return make_float4(__uint_as_float(t.x << 16), __uint_as_float(t.x & 0xffff0000u), __uint_as_float(t.y << 16),
+                       __uint_as_float(t.y & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void st4(bf16* p, float4 v) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+};
 
 struct AttnArgs {
   const void* qkv;
@@ -36,8 +58,8 @@ struct AttnArgs {
   Drop dr;
 };
 
-template <typename TA>
-__device__ __forceinline__ void load_rows(float* dst, const TA* src, int64_t row_stride, int row0, int nrows_valid_lo, int nrows_valid_hi,
+template <typename TA, typename TS>
+__device__ __forceinline__ void load_rows(TS* dst, const TA* src, int64_t row_stride, int row0, int nrows_valid_lo, int nrows_valid_hi,
                                           int rows, int dh, const float* add) {
   // dst[r][c] = src[(row0 + r) * row_stride + c] (+ add[c]) for row0 + r in [lo, hi), zeros elsewhere and for c >= dh
   for (int idx = threadIdx.x; idx < rows * (DHP / 4); idx += THREADS) {
@@ -49,16 +71,17 @@ __device__ __forceinline__ void load_rows(float* dst, const TA* src, int64_t row
       o = make_float4(to_f32(p[0]), to_f32(p[1]), to_f32(p[2]), to_f32(p[3]));
       if (add != nullptr) { o.x += add[c4]; o.y += add[c4 + 1]; o.z += add[c4 + 2]; o.w += add[c4 + 3]; }
     }
-    *reinterpret_cast<float4*>(dst + r * LDS_ + c4) = o;
+    Tile<TS>::st4(dst + r * Tile<TS>::LD + c4, o);
   }
 }
-__device__ __forceinline__ void load_rows_f32(float* dst, const float* src, int64_t row_stride, int row0, int hi, int rows, int dh) {
+template <typename TS>
+__device__ __forceinline__ void load_rows_f32(TS* dst, const float* src, int64_t row_stride, int row0, int hi, int rows, int dh) {
   for (int idx = threadIdx.x; idx < rows * (DHP / 4); idx += THREADS) {
     const int r = idx / (DHP / 4), c4 = (idx - r * (DHP / 4)) * 4;
     const int row = row0 + r;
     float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
     if (row < hi && c4 < dh) o = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * row_stride + c4);
-    *reinterpret_cast<float4*>(dst + r * LDS_ + c4) = o;
+    Tile<TS>::st4(dst + r * Tile<TS>::LD + c4, o);
   }
 }
 
@@ -67,8 +90,10 @@ __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
 }
 
 // s[a][e] = scale * (Qc_i . K_j + Qp_i . Pw_{j-i+63}), i = ti + 16a, j = tj + 16e
-__device__ __forceinline__ void score_tile(const float* Qc, const float* Qp, const float* Kt, const float* Pw, int ti, int tj, float scale,
+template <typename TS>
+__device__ __forceinline__ void score_tile(const TS* Qc, const TS* Qp, const TS* Kt, const TS* Pw, int ti, int tj, float scale,
                                            float (&s)[4][4]) {
+  constexpr int LD = Tile<TS>::LD;
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -79,12 +104,12 @@ __device__ __forceinline__ void score_tile(const float* Qc, const float* Qp, con
     float4 qc[4], qp[4], kk[4], pw[7];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      qc[a] = *reinterpret_cast<const float4*>(Qc + (ti + 16 * a) * LDS_ + c4);
-      qp[a] = *reinterpret_cast<const float4*>(Qp + (ti + 16 * a) * LDS_ + c4);
-      kk[a] = *reinterpret_cast<const float4*>(Kt + (tj + 16 * a) * LDS_ + c4);
+      qc[a] = Tile<TS>::ld4(Qc + (ti + 16 * a) * LD + c4);
+      qp[a] = Tile<TS>::ld4(Qp + (ti + 16 * a) * LD + c4);
+      kk[a] = Tile<TS>::ld4(Kt + (tj + 16 * a) * LD + c4);
     }
 #pragma unroll
-    for (int dlt = 0; dlt < 7; ++dlt) pw[dlt] = *reinterpret_cast<const float4*>(Pw + (wbase + 16 * (dlt - 3)) * LDS_ + c4);
+    for (int dlt = 0; dlt < 7; ++dlt) pw[dlt] = Tile<TS>::ld4(Pw + (wbase + 16 * (dlt - 3)) * LD + c4);
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -96,7 +121,9 @@ __device__ __forceinline__ void score_tile(const float* Qc, const float* Qp, con
     for (int e = 0; e < 4; ++e) s[a][e] *= scale;
 }
 // plain [4][4] block of A_i . B_j
-__device__ __forceinline__ void dot_tile(const float* A, const float* Bm, int ti, int tj, float (&s)[4][4]) {
+template <typename TS>
+__device__ __forceinline__ void dot_tile(const TS* A, const TS* Bm, int ti, int tj, float (&s)[4][4]) {
+  constexpr int LD = Tile<TS>::LD;
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -106,8 +133,8 @@ __device__ __forceinline__ void dot_tile(const float* A, const float* Bm, int ti
     float4 av[4], bv[4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      av[a] = *reinterpret_cast<const float4*>(A + (ti + 16 * a) * LDS_ + c4);
-      bv[a] = *reinterpret_cast<const float4*>(Bm + (tj + 16 * a) * LDS_ + c4);
+      av[a] = Tile<TS>::ld4(A + (ti + 16 * a) * LD + c4);
+      bv[a] = Tile<TS>::ld4(Bm + (tj + 16 * a) * LD + c4);
     }
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -116,23 +143,26 @@ __device__ __forceinline__ void dot_tile(const float* A, const float* Bm, int ti
   }
 }
 // acc[a][0..3] += sum_j S[i][j] * Bm[row(j)][4 tj ..], i = ti + 16a; row(j) = j + row_shift(i) (0 for K/V, j - i + 63 for the window)
-template <bool WINDOW>
-__device__ __forceinline__ void row_matmul(const float* S, const float* Bm, int ti, int tj, float (&acc)[4][4]) {
+template <bool WINDOW, typename TS>
+__device__ __forceinline__ void row_matmul(const float* S, const TS* Bm, int ti, int tj, float (&acc)[4][4]) {
+  constexpr int LD = Tile<TS>::LD;
   for (int j = 0; j < TK; ++j) {
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const int i = ti + 16 * a;
       const float sv = S[i * LDS_ + j];
-      const float4 b4 = *reinterpret_cast<const float4*>(Bm + (WINDOW ? (j - i + TQ - 1) : j) * LDS_ + 4 * tj);
+      const float4 b4 = Tile<TS>::ld4(Bm + (WINDOW ? (j - i + TQ - 1) : j) * LD + 4 * tj);
       acc[a][0] = fmaf(sv, b4.x, acc[a][0]); acc[a][1] = fmaf(sv, b4.y, acc[a][1]);
       acc[a][2] = fmaf(sv, b4.z, acc[a][2]); acc[a][3] = fmaf(sv, b4.w, acc[a][3]);
     }
   }
 }
 // acc[a][0..3] += sum_i S[i][j] * A[i][4 tj ..], j = ti + 16a   (the transposed product of the key-side kernel)
-__device__ __forceinline__ void col_matmul(const float* S, const float* A, int ti, int tj, float (&acc)[4][4]) {
+template <typename TS>
+__device__ __forceinline__ void col_matmul(const float* S, const TS* A, int ti, int tj, float (&acc)[4][4]) {
+  constexpr int LD = Tile<TS>::LD;
   for (int i = 0; i < TQ; ++i) {
-    const float4 a4 = *reinterpret_cast<const float4*>(A + i * LDS_ + 4 * tj);
+    const float4 a4 = Tile<TS>::ld4(A + i * LD + 4 * tj);
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
       const float sv = S[i * LDS_ + ti + 16 * a];
@@ -155,13 +185,14 @@ __device__ __forceinline__ float group16_sum(float v) {
 // ------------------------------------------------------------------------------------------------ forward
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(AttnArgs p, TA* __restrict__ ctx, float* __restrict__ lse) {
-  extern __shared__ float sm[];
-  float* Qc = sm;
-  float* Qp = Qc + TQ * LDS_;
-  float* Kt = Qp + TQ * LDS_;
-  float* Vt = Kt + TK * LDS_;
-  float* Pw = Vt + TK * LDS_;                                    // [WIN + 1][LDS_]
-  float* Ps = Pw + (WIN + 1) * LDS_;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  constexpr int LD = Tile<TA>::LD;
+  float* Ps = reinterpret_cast<float*>(sm_raw);                  // [TQ][LDS_] fp32
+  TA* Qc = reinterpret_cast<TA*>(Ps + TQ * LDS_);
+  TA* Qp = Qc + TQ * LD;
+  TA* Kt = Qp + TQ * LD;
+  TA* Vt = Kt + TK * LD;
+  TA* Pw = Vt + TK * LD;                                         // [WIN + 1][LD]
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
   const int Tn = p.Tn, dh = p.dh, d = p.H * dh;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
@@ -275,21 +306,22 @@ __device__ __forceinline__ void bwd_entries(const AttnArgs& p, const float (&s)[
 // ------------------------------------------------------------------------------------------------ backward, query side
 // one CTA = 64 queries of one (b, h): dq (content + positional parts), the window gradient of the projected table, du, dv
 template <typename TA>
-__global__ void __launch_bounds__(THREADS) attn_bwd_q_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
+__global__ void __launch_bounds__(THREADS, 2) attn_bwd_q_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
                                                              const float* __restrict__ dctx, TA* __restrict__ dqkv, float* __restrict__ dpp,
                                                              float* __restrict__ du, float* __restrict__ dv) {
-  extern __shared__ float sm[];
-  float* Qc = sm;
-  float* Qp = Qc + TQ * LDS_;
-  float* dO = Qp + TQ * LDS_;
-  float* Kt = dO + TQ * LDS_;
-  float* Vt = Kt + TK * LDS_;
-  float* Pw = Vt + TK * LDS_;                                    // [WIN + 1][LDS_]
-  float* Ps = Pw + (WIN + 1) * LDS_;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  constexpr int LD = Tile<TA>::LD;
+  float* Ps = reinterpret_cast<float*>(sm_raw);                  // fp32 score tiles and small vectors first
   float* DSs = Ps + TQ * LDS_;
   float* lse_s = DSs + TQ * LDS_;                                // [TQ]
   float* D_s = lse_s + TQ;
   float* red = D_s + TQ;                                         // [2][DHP]
+  TA* Qc = reinterpret_cast<TA*>(red + 2 * DHP);
+  TA* Qp = Qc + TQ * LD;
+  TA* dO = Qp + TQ * LD;
+  TA* Kt = dO + TQ * LD;
+  TA* Vt = Kt + TK * LD;
+  TA* Pw = Vt + TK * LD;                                         // [WIN + 1][LD]
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
   const int Tn = p.Tn, dh = p.dh, d = p.H * dh;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
@@ -337,7 +369,7 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_q_kernel(AttnArgs p, const f
       const int ilo = max(0, (TQ - 1) - w), ihi = min(TQ, TK + (TQ - 1) - w);      // 0 <= i + w - 63 < 64
       for (int i = ilo; i < ihi; ++i) {
         const float sv = DSs[i * LDS_ + i + w - (TQ - 1)];
-        const float4 q4 = *reinterpret_cast<const float4*>(Qp + i * LDS_ + 4 * tj);
+        const float4 q4 = Tile<TA>::ld4(Qp + i * LD + 4 * tj);
         dw[mm][0] = fmaf(sv, q4.x, dw[mm][0]); dw[mm][1] = fmaf(sv, q4.y, dw[mm][1]);
         dw[mm][2] = fmaf(sv, q4.z, dw[mm][2]); dw[mm][3] = fmaf(sv, q4.w, dw[mm][3]);
       }
@@ -394,19 +426,20 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_q_kernel(AttnArgs p, const f
 // ------------------------------------------------------------------------------------------------ backward, key side
 // one CTA = 64 keys of one (b, h): dk and dv
 template <typename TA>
-__global__ void __launch_bounds__(THREADS) attn_bwd_kv_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
+__global__ void __launch_bounds__(THREADS, 2) attn_bwd_kv_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
                                                               const float* __restrict__ dctx, TA* __restrict__ dqkv) {
-  extern __shared__ float sm[];
-  float* Qc = sm;
-  float* Qp = Qc + TQ * LDS_;
-  float* dO = Qp + TQ * LDS_;
-  float* Kt = dO + TQ * LDS_;
-  float* Vt = Kt + TK * LDS_;
-  float* Pw = Vt + TK * LDS_;
-  float* Ps = Pw + (WIN + 1) * LDS_;
+  extern __shared__ __align__(16) uint8_t sm_raw[];
+  constexpr int LD = Tile<TA>::LD;
+  float* Ps = reinterpret_cast<float*>(sm_raw);
   float* DSs = Ps + TQ * LDS_;
   float* lse_s = DSs + TQ * LDS_;
   float* D_s = lse_s + TQ;
+  TA* Qc = reinterpret_cast<TA*>(D_s + TQ);
+  TA* Qp = Qc + TQ * LD;
+  TA* dO = Qp + TQ * LD;
+  TA* Kt = dO + TQ * LD;
+  TA* Vt = Kt + TK * LD;
+  TA* Pw = Vt + TK * LD;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TK;
   const int Tn = p.Tn, dh = p.dh, d = p.H * dh;
   const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
@@ -452,8 +485,10 @@ __global__ void __launch_bounds__(THREADS) attn_bwd_kv_kernel(AttnArgs p, const 
   }
 }
 
-constexpr int FWD_SMEM = (4 * TQ + (WIN + 1) + TQ) * LDS_ * 4;
-constexpr int BWD_SMEM = ((5 * TQ + (WIN + 1) + 2 * TQ) * LDS_ + 2 * TQ + 2 * DHP) * 4;
+template <typename TA> constexpr int fwd_smem() { return TQ * LDS_ * 4 + (4 * TQ + WIN + 1) * Tile<TA>::LD * static_cast<int>(sizeof(TA)); }
+template <typename TA> constexpr int bwd_smem() {
+  return (2 * TQ * LDS_ + 2 * TQ + 2 * DHP) * 4 + (5 * TQ + WIN + 1) * Tile<TA>::LD * static_cast<int>(sizeof(TA));
+}
 
 }  // namespace
 
@@ -463,10 +498,10 @@ int attn_train_fwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
   CFM_REQUIRE(dh >= 4 && dh <= DHP && dh % 4 == 0, "training attention supports head sizes that are multiples of 4 up to 64");
   CFM_REQUIRE(B > 0 && Tn > 0 && H > 0 && H <= 65535 && B <= 65535, "bad attention shape");
   static std::atomic<uint64_t> done{0};
-  CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(attn_fwd_kernel<TA>), FWD_SMEM));
+  CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(attn_fwd_kernel<TA>), fwd_smem<TA>()));
   AttnArgs a{qkv, pp, u, v, key_pad, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
-  attn_fwd_kernel<TA><<<grid, THREADS, FWD_SMEM, st>>>(a, ctx, lse);
+  attn_fwd_kernel<TA><<<grid, THREADS, fwd_smem<TA>(), st>>>(a, ctx, lse);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -477,16 +512,16 @@ int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
                    cudaStream_t st) {
   CFM_REQUIRE(dh >= 4 && dh <= DHP && dh % 4 == 0, "training attention supports head sizes that are multiples of 4 up to 64");
   static std::atomic<uint64_t> done_q{0}, done_kv{0};
-  CFM_TRY(smem_attr_once(done_q, reinterpret_cast<const void*>(attn_bwd_q_kernel<TA>), BWD_SMEM));
-  CFM_TRY(smem_attr_once(done_kv, reinterpret_cast<const void*>(attn_bwd_kv_kernel<TA>), BWD_SMEM));
+  CFM_TRY(smem_attr_once(done_q, reinterpret_cast<const void*>(attn_bwd_q_kernel<TA>), bwd_smem<TA>()));
+  CFM_TRY(smem_attr_once(done_kv, reinterpret_cast<const void*>(attn_bwd_kv_kernel<TA>), bwd_smem<TA>()));
   const int64_t rows = static_cast<int64_t>(B) * Tn * H;
   attn_delta_kernel<TA><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(dctx, ctx, scratch, B, Tn, H, dh);
   CFM_CUDA_OK(cudaGetLastError());
   AttnArgs a{qkv, pp, u, v, key_pad, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
-  attn_bwd_q_kernel<TA><<<grid, THREADS, BWD_SMEM, st>>>(a, lse, scratch, dctx, dqkv, dpp, du, dv);
+  attn_bwd_q_kernel<TA><<<grid, THREADS, bwd_smem<TA>(), st>>>(a, lse, scratch, dctx, dqkv, dpp, du, dv);
   CFM_CUDA_OK(cudaGetLastError());
-  attn_bwd_kv_kernel<TA><<<grid, THREADS, BWD_SMEM, st>>>(a, lse, scratch, dctx, dqkv);
+  attn_bwd_kv_kernel<TA><<<grid, THREADS, bwd_smem<TA>(), st>>>(a, lse, scratch, dctx, dqkv);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
