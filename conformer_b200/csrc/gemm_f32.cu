@@ -98,6 +98,86 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(ARows a, const float* __r
   }
 }
 
+// Larger tile for the shapes that matter (M, N >= 128): 128 x 128 outputs per block, 8 x 8 per thread as four 4 x 4
+// quadrants, K in steps of 16 through a double-buffered shared-memory tile with the next step's global loads in flight
+// under the FMAs.  Every output is still ONE fmaf chain over k = 0 .. K-1, so results are bit-identical to the small kernel.
+constexpr int GBM = 128, GBN = 128, GBK = 16;
+
+template <int EPI>
+__global__ void __launch_bounds__(256) gemm_f32_big_kernel(ARows a, const float* __restrict__ W, const float* __restrict__ bias,
+                                                           float* __restrict__ C, int ldc, int M, int N, int K,
+                                                           const float* __restrict__ res, float res_scale) {
+  __shared__ float As[2][GBK][GBM + 4];
+  __shared__ float Ws[2][GBK][GBN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+  const int lr = tid >> 1, lk = (tid & 1) * 8;        // loader: row 0..127, k offset 0 or 8 (two float4 each)
+  const int ty = tid >> 4, tx = tid & 15;
+  const int am = m0 + lr, wn = n0 + lr;
+  const int64_t a_off = (am < M) ? a_row_offset(a, am) : 0;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float4 ra[2], rw[2];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int k = k0 + lk + 4 * h;
+      ra[h] = (am < M && k < K) ? *reinterpret_cast<const float4*>(a.base + a_off + a_col_offset(a, k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rw[h] = (wn < N && k < K) ? *reinterpret_cast<const float4*>(W + static_cast<int64_t>(wn) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int kk = lk + 4 * h;
+      As[buf][kk + 0][lr] = ra[h].x; As[buf][kk + 1][lr] = ra[h].y; As[buf][kk + 2][lr] = ra[h].z; As[buf][kk + 3][lr] = ra[h].w;
+      Ws[buf][kk + 0][lr] = rw[h].x; Ws[buf][kk + 1][lr] = rw[h].y; Ws[buf][kk + 2][lr] = rw[h].z; Ws[buf][kk + 3][lr] = rw[h].w;
+    }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += GBK) {
+    const bool more = k0 + GBK < K;
+    if (more) gload(k0 + GBK);
+#pragma unroll
+    for (int kk = 0; kk < GBK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * 4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&Ws[buf][kk][64 + tx * 4]);
+      const float ar[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+    }
+    if (more) sstore(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (EPI == EPI_BIAS_SWISH) v = swish_f(v);
+      if (EPI == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+      if (EPI == EPI_BIAS_RES) v = res[static_cast<int64_t>(m) * ldc + n] + res_scale * v;
+      C[static_cast<int64_t>(m) * ldc + n] = v;
+    }
+  }
+}
+
 }  // namespace
 
 int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* C, int ldc, int M, int N,
@@ -119,6 +199,17 @@ int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* 
                        mm, N, K, epi, res ? res + static_cast<int64_t>(m) * ldc : nullptr, res_scale, nullptr,
                        stream));
     }
+    return 0;
+  }
+  if (M >= 256 && N >= 128) {
+    dim3 gb(static_cast<unsigned>(ceil_div(N, GBN)), static_cast<unsigned>(ceil_div(M, GBM)));
+    switch (epi) {
+      case EPI_BIAS_SWISH: gemm_f32_big_kernel<EPI_BIAS_SWISH><<<gb, 256, 0, stream>>>(a, W, bias, C, ldc, M, N, K, res, res_scale); break;
+      case EPI_BIAS_RELU: gemm_f32_big_kernel<EPI_BIAS_RELU><<<gb, 256, 0, stream>>>(a, W, bias, C, ldc, M, N, K, res, res_scale); break;
+      case EPI_BIAS_RES: gemm_f32_big_kernel<EPI_BIAS_RES><<<gb, 256, 0, stream>>>(a, W, bias, C, ldc, M, N, K, res, res_scale); break;
+      default: gemm_f32_big_kernel<EPI_BIAS><<<gb, 256, 0, stream>>>(a, W, bias, C, ldc, M, N, K, res, res_scale); break;
+    }
+    CFM_CUDA_OK(cudaGetLastError());
     return 0;
   }
   switch (epi) {
