@@ -201,7 +201,7 @@ int gemm_f32(const float* A, int lda, const float* W, const float* bias, float* 
     }
     return 0;
   }
-  if (M >= 256 && N >= 128) {
+  if (ceil_div(M, GBM) * ceil_div(N, GBN) >= 256) {       // at least ~2 waves of 128 x 128 tiles; smaller problems keep 64 x 64
     dim3 gb(static_cast<unsigned>(ceil_div(N, GBN)), static_cast<unsigned>(ceil_div(M, GBM)));
     switch (epi) {
       case EPI_BIAS_SWISH: gemm_f32_big_kernel<EPI_BIAS_SWISH><<<gb, 256, 0, stream>>>(a, W, bias, C, ldc, M, N, K, res, res_scale); break;

@@ -77,7 +77,9 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 // TF32: A and W are fp32 in memory and multiplied as TF32 (kind::tf32, K = 8 per MMA, 32 elements per 128-byte row);
 // callers wanting fp32 accuracy pass operands split into TF32-exact high and low parts concatenated along K (3xTF32).
-template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false>
+// SPLITK (reduce-add epilogue only): the tile index gets a third component, the K split; off for every inference GEMM so
+// that their tile loops stay free of the extra index arithmetic.
+template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false, bool SPLITK = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmParams p) {
@@ -98,7 +100,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles * (SPLITK ? p.k_splits : 1);
   constexpr int BK = TF32 ? BLOCK_K / 2 : BLOCK_K;         // elements per 128-byte operand row
 
   if (warp == 0 && lane == 0) {
@@ -128,9 +130,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------------ TMA producer
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mn = tile % (p.num_m_tiles * p.num_n_tiles), ks = tile / (p.num_m_tiles * p.num_n_tiles);
+      const int mn = SPLITK ? tile % (p.num_m_tiles * p.num_n_tiles) : tile, ks = SPLITK ? tile / (p.num_m_tiles * p.num_n_tiles) : 0;
       const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
-      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      const int kb0 = SPLITK ? ks * p.kb_per_split : 0, kb1 = SPLITK ? min(p.num_kb, kb0 + p.kb_per_split) : p.num_kb;
       int cb = 0, cf = 0, ct = 0;
       if (CONV) {
         ct = m_tile % p.TCH;
@@ -170,8 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       TRACE(2);
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-      const int ks = tile / (p.num_m_tiles * p.num_n_tiles);
-      const int kb0 = ks * p.kb_per_split, kb1 = min(p.num_kb, kb0 + p.kb_per_split);
+      const int ks = SPLITK ? tile / (p.num_m_tiles * p.num_n_tiles) : 0;
+      const int kb0 = SPLITK ? ks * p.kb_per_split : 0, kb1 = SPLITK ? min(p.num_kb, kb0 + p.kb_per_split) : p.num_kb;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (it / STAGES) & 1;
@@ -208,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int sw = row & 7;
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
-      const int mn = tile % (p.num_m_tiles * p.num_n_tiles), ks = tile / (p.num_m_tiles * p.num_n_tiles);
+      const int mn = SPLITK ? tile % (p.num_m_tiles * p.num_n_tiles) : tile, ks = SPLITK ? tile / (p.num_m_tiles * p.num_n_tiles) : 0;
       const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
       const int n0 = n_tile * BLOCK_N;                        // first GEMM column of the tile
       const int o0 = n_tile * C_::OUT_N;                      // first OUTPUT column of the tile
@@ -361,11 +363,11 @@ int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
   return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, "conv A");
 }
 
-template <int BLOCK_N, int EPI, bool CONV>
+template <int BLOCK_N, int EPI, bool CONV, bool SPLITK = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int num_sms,
            cudaStream_t stream) {
   using C_ = Cfg<BLOCK_N, EPI>;
-  auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV>;
+  auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV, false, SPLITK>;
   static std::atomic<uint64_t> attr_done{0};        // one per template instantiation
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
@@ -392,6 +394,7 @@ int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
 }
 int launch_epi_f32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
                    Epilogue epi, int num_sms, cudaStream_t stream) {
+  if (epi == EPI_BIAS_RES && p.k_splits > 1) return launch<128, EPI_BIAS_RES, false, true>(tmA, tmB, tmC, p, num_sms, stream);
   if (epi == EPI_BIAS_RES) return launch<128, EPI_BIAS_RES, false>(tmA, tmB, tmC, p, num_sms, stream);
   return launch<128, EPI_BIAS_F32, false>(tmA, tmB, tmC, p, num_sms, stream);
 }
