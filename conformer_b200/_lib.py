@@ -80,6 +80,7 @@ SIGNATURES = {
     "cfm_profile_enable": (C.c_int, [_p, _i32]),
     "cfm_profile_collect": (C.c_int, [_p, C.POINTER(C.c_double), _i32]),
     "cfm_gemm_bf16": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
+    "cfm_gemm_bf16_tn": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _p]),
     "cfm_gemm_tf32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "cfm_gemm_f32": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p, _f, _p]),
     "cfm_dwconv_glu_bn_swish": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -323,6 +323,14 @@ __attribute__((visibility("default"))) int cfm_debug_set_gemm_trace(void* dev_bu
   return 0;
 }
 
+int cfm_gemm_bf16_tn(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
+  CFM_REQUIRE(A && B && C, "bad GEMM arguments");
+  int dev = 0, sms = 0;
+  CFM_CUDA_OK(cudaGetDevice(&dev));
+  CFM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return gemm_bf16_tn(static_cast<const bf16*>(A), M, static_cast<const bf16*>(B), N, C, N, M, N, K, sms, S(stream));
+}
+
 int cfm_gemm_tf32(const float* A, const float* W, const float* bias, float* C, int32_t M, int32_t N, int32_t K, void* stream) {
   CFM_REQUIRE(A && W && C, "bad GEMM arguments");
   int dev = 0, sms = 0;

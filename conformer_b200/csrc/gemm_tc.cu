@@ -79,7 +79,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 // callers wanting fp32 accuracy pass operands split into TF32-exact high and low parts concatenated along K (3xTF32).
 // SPLITK (reduce-add epilogue only): the tile index gets a third component, the K split; off for every inference GEMM so
 // that their tile loops stay free of the extra index arithmetic.
-template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false, bool SPLITK = false>
+// TN: C[M,N] = A^T B with A [K rows, M cols] and B [K rows, N cols] row-major (the weight-gradient form dW = dY^T X, whose
+// contraction runs over the rows).  Both operands are then MN-major: a stage holds [64 k-rows][64 mn] slabs of 8 KB
+// (128-byte rows, one swizzle atom along MN), consecutive slabs = consecutive 64-wide MN atoms (descriptor LBO = 8 KB,
+// SBO = 1 KB = 8 k-rows), and one K = 16 MMA step advances the start address by 16 rows = 2 KB.
+template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false, bool SPLITK = false, bool TN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmParams p) {
@@ -154,17 +158,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int kw = tap / 3, kh = tap - kw * 3;
             // dims: (c, f1, parity, pair, b); source time index 2*t2 + kw = 2*(t2 + (kw>>1)) + (kw&1)
             tma_load_5d(sa, &tmA, &full_bar[s], c0, 2 * cf + kh, kw & 1, ct * BLOCK_M + (kw >> 1), cb);
+          } else if (TN) {
+#pragma unroll
+            for (int sl = 0; sl < BLOCK_M / 64; ++sl) tma_load_2d(sa + sl * 8192, &tmA, &full_bar[s], m_tile * BLOCK_M + sl * 64, kb * BLOCK_K);
           } else {
             tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m_tile * BLOCK_M);
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_tile * BLOCK_N);
+          if (TN) {
+#pragma unroll
+            for (int sl = 0; sl < BLOCK_N / 64; ++sl) tma_load_2d(sb + sl * 8192, &tmB, &full_bar[s], n_tile * BLOCK_N + sl * 64, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_tile * BLOCK_N);
+          }
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BLOCK_M, BLOCK_N) : umma_idesc_bf16(BLOCK_M, BLOCK_N);
+    constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BLOCK_M, BLOCK_N)
+                                    : (TN ? (umma_idesc_bf16(BLOCK_M, BLOCK_N) | (1u << 15) | (1u << 16)) : umma_idesc_bf16(BLOCK_M, BLOCK_N));
     uint32_t it = 0, acc_it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
@@ -182,11 +195,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kb == kb0) TRACE(3);
         if (kb == kb1 - 1) TRACE(4);
         if (elect_one()) {
-          const uint32_t sa = umma_desc_lo(smem_u32(smem + s * C_::STAGE_BYTES));
+          // descriptor low word = (address >> 4) | LBO field; MN-major operands: LBO = 8 KB between 64-wide MN atoms
+          const uint32_t sa = TN ? (((smem_u32(smem + s * C_::STAGE_BYTES) & 0x3FFFFu) >> 4) | ((8192u >> 4) << 16))
+                                 : umma_desc_lo(smem_u32(smem + s * C_::STAGE_BYTES));
           const uint32_t sb = sa + (A_STAGE_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // one MMA covers 32 bytes of K in either format
-            if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // one MMA covers 32 bytes of K (K-major) or 16 k-rows = 2 KB (MN-major)
+            if (TN) tc_mma_f16_lo(d_tmem, sa + k * (2048 >> 4), sb + k * (2048 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            else if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
           tc_commit(&empty_bar[s]);                            // smem slot free once these MMAs retire
@@ -432,6 +448,58 @@ int tc_init() {
 }
 
 unsigned long long* g_gemm_trace = nullptr;      // debug hook (cfm_debug_set_gemm_trace)
+
+int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, float* C, int ldc, int M, int N, int K, int num_sms,
+                 cudaStream_t stream) {
+  CFM_TRY(tc_init());
+  CFM_REQUIRE(M > 0 && N > 0 && K > 0, "empty GEMM");
+  CFM_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "TN GEMM needs 16-byte aligned rows");
+  CFM_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15) == 0,
+              "operands must be 16-byte aligned");
+  constexpr int BN = 128;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = nullptr; p.res_scale = 1.f; p.trace = nullptr;
+  p.num_kb = static_cast<int>(ceil_div(K, BLOCK_K));
+  p.k_splits = 1;
+  p.kb_per_split = p.num_kb;
+  p.num_m_tiles = static_cast<int>(ceil_div(M, BLOCK_M));
+  p.num_n_tiles = static_cast<int>(ceil_div(N, BN));
+  const int mn_tiles = p.num_m_tiles * p.num_n_tiles;
+  if (mn_tiles * 2 <= num_sms && p.num_kb >= 16) {
+    int splits = num_sms / mn_tiles;
+    if (splits > p.num_kb / 8) splits = p.num_kb / 8;
+    if (splits > 1) {
+      p.kb_per_split = static_cast<int>(ceil_div(p.num_kb, splits));
+      p.k_splits = static_cast<int>(ceil_div(p.num_kb, p.kb_per_split));
+    }
+  }
+  CUtensorMap tmA, tmB, tmC;
+  CFM_TRY(encode_2d_bf16(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), 64, BLOCK_K, "TN A"));
+  CFM_TRY(encode_2d_bf16(&tmB, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), 64, BLOCK_K, "TN B"));
+  {
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(N), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ldc) * 4};
+    cuuint32_t box[2] = {32, BLOCK_M};
+    CFM_TRY(encode_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dims, strides, box, "TN C"));
+  }
+  using C_ = Cfg<BN, EPI_BIAS_RES>;
+  const int tiles = mn_tiles * p.k_splits;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  if (p.k_splits > 1) {
+    auto kern = gemm_tc_kernel<BN, EPI_BIAS_RES, false, false, true, true>;
+    static std::atomic<uint64_t> done{0};
+    CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
+    kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  } else {
+    auto kern = gemm_tc_kernel<BN, EPI_BIAS_RES, false, false, false, true>;
+    static std::atomic<uint64_t> done{0};
+    CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
+    kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+  }
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,
                  int num_sms, cudaStream_t stream) {

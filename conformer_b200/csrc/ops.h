@@ -39,6 +39,11 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
 // split_k (EPI_BIAS_RES only): when the output has few tiles and K is long - the weight-gradient GEMMs of the training
 // step - the contraction is split over the idle SMs, every split reduce-adding its partial product into C (summation
 // order then varies from run to run, so the inference path keeps it off)
+// C[M,N] (fp32) += A^T B with A [K rows, M cols] (lda) and B [K rows, N cols] (ldb) bf16 row-major: the weight-gradient
+// form dW += dY^T X, contraction over the rows, operands consumed in place as MN-major tiles (no transposed copies);
+// split over K when the output has few tiles
+int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, float* C, int ldc, int M, int N, int K, int num_sms,
+                 cudaStream_t stream);
 // fp32 operands multiplied as TF32 on tcgen05 (kind::tf32), fp32 accumulate and output: C = A[M,K] W[N,K]^T + bias.
 // For fp32-grade accuracy pass TF32-exact high/low splits concatenated along K (A' = [Ahi|Alo|Ahi], W' = [Whi|Whi|Wlo]).
 int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N, int K,

@@ -71,13 +71,22 @@ inline int attn_fwd_any(const bf16* qkv, const bf16* pp, const float* u, const f
 
 inline int round8(int64_t v) { return static_cast<int>((v + 7) & ~static_cast<int64_t>(7)); }
 
-// dW[N_w, K_w] += dY[M, N_w]^T X[M, K_w]  and  db[N_w] += colsum(dY):  the weight-gradient GEMM contracts over the M rows
+// dW[N_w, K_w] += dY[M, N_w]^T X[M, K_w]  and  db[N_w] += colsum(dY):  the weight-gradient GEMM contracts over the M rows.
+// bf16: the tcgen05 GEMM reads both operands in place as MN-major tiles (gemm_bf16_tn); fp32: transposed copies + the
+// CUDA-core GEMM.
+inline int wgrad_gemm(const TC& c, const bf16* dY, int ld_dy, const bf16* X, int ld_x, float* dW, int M, int Nw, int Kw, bf16*, bf16*) {
+  return gemm_bf16_tn(dY, ld_dy, X, ld_x, dW, Kw, Nw, Kw, M, c.num_sms, c.st);
+}
+inline int wgrad_gemm(const TC& c, const float* dY, int ld_dy, const float* X, int ld_x, float* dW, int M, int Nw, int Kw, float* tA,
+                      float* tB) {
+  const int Mp = round8(M);
+  CFM_TRY(transpose_pad<float>(dY, ld_dy, tA, M, Nw, Mp, c.st));
+  CFM_TRY(transpose_pad<float>(X, ld_x, tB, M, Kw, Mp, c.st));
+  return gemm_any(c, static_cast<const float*>(tA), Mp, static_cast<const float*>(tB), nullptr, dW, Kw, Nw, Kw, Mp, EPI_BIAS_RES, dW, 1.f);
+}
 template <typename TA>
 int wgrad(const TC& c, const TA* dY, int ld_dy, const TA* X, int ld_x, float* dW, float* db, int M, int Nw, int Kw, TA* tA, TA* tB) {
-  const int Mp = round8(M);
-  CFM_TRY(transpose_pad<TA>(dY, ld_dy, tA, M, Nw, Mp, c.st));
-  CFM_TRY(transpose_pad<TA>(X, ld_x, tB, M, Kw, Mp, c.st));
-  CFM_TRY(gemm_any(c, tA, Mp, tB, nullptr, dW, Kw, Nw, Kw, Mp, EPI_BIAS_RES, dW, 1.f));
+  CFM_TRY(wgrad_gemm(c, dY, ld_dy, X, ld_x, dW, M, Nw, Kw, tA, tB));
   if (db != nullptr) CFM_TRY(colsum_add<TA>(dY, ld_dy, db, M, Nw, c.st));
   return 0;
 }
@@ -447,12 +456,8 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
   // Encoder.linear on the channels-last flatten: gradient in the packed column order, then scattered to the parameter's
   {
     const int K = F2 * d;
-    TA* tAx = big2;                                              // dxl^T [d, Mp]
-    TA* tBx = big2 + static_cast<int64_t>(d) * Mp;               // h2flat^T [K, Mp]
     CFM_CUDA_OK(cudaMemsetAsync(gpack, 0, static_cast<size_t>(d) * K * 4, st));
-    CFM_TRY(transpose_pad<TA>(dxl, d, tAx, Mi, d, Mp, st));
-    CFM_TRY(transpose_pad<TA>(h2, K, tBx, Mi, K, Mp, st));
-    CFM_TRY(gemm_any(c, static_cast<const TA*>(tAx), Mp, static_cast<const TA*>(tBx), nullptr, gpack, K, d, K, Mp, EPI_BIAS_RES, gpack, 1.f));
+    CFM_TRY(wgrad_gemm(c, static_cast<const TA*>(dxl), d, h2, K, gpack, Mi, d, K, big2, big2 + static_cast<int64_t>(d) * Mp));
     const int64_t n = static_cast<int64_t>(d) * K;
     unpack_linear_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(gpack, t.lin.dw, d, d, F2);
     CFM_CUDA_OK(cudaGetLastError());

@@ -252,6 +252,9 @@ CFM_API int cfm_logmel_lengths(const int64_t* samples, int64_t* frames, int32_t 
  * packed per 64-row group as 32 value rows followed by their 32 gate rows.  A,W bf16 (uint16 storage). */
 CFM_API int cfm_gemm_bf16(const void* A, const void* W, const float* bias, void* C, int32_t M, int32_t N, int32_t K,
                   int32_t epi, const float* res, float res_scale, void* stream);
+/* bf16 tcgen05 GEMM in the weight-gradient form: C fp32 [M,N] += A[K,M]^T B[K,N] (row-major bf16 operands read in place as
+ * MN-major tiles; split over K when the output has few tiles, so the summation order may vary between runs). */
+CFM_API int cfm_gemm_bf16_tn(const void* A, const void* B, float* C, int32_t M, int32_t N, int32_t K, void* stream);
 /* TF32 tcgen05 GEMM (kind::tf32): C fp32 [M,N] = A fp32 [M,K] W fp32 [N,K]^T + bias; operands are read as TF32 (10-bit
  * mantissa).  For fp32-grade accuracy pass operands split into a TF32-exact high part and the remainder, concatenated
  * along K: A' = [Ah | Al | Ah], W' = [Wh | Wh | Wl] (the log-mel front-end does). */

@@ -98,3 +98,19 @@ def test_gemm_bf16_glu_epilogue(M, d, K):
     acc = A.double() @ W.double().T + bias.double()
     want = acc[:, :d] * torch.sigmoid(acc[:, d:])
     torch.testing.assert_close(out.double(), want, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("K,M,N", [(64, 128, 128), (200, 64, 256), (11968, 256, 1024), (747, 256, 256), (1000, 40, 72)])
+def test_gemm_bf16_tn_weight_gradient_form(K, M, N):
+    """cfm_gemm_bf16_tn: C += A^T B with row-major A [K,M], B [K,N] consumed in place as MN-major tcgen05 operands
+    (the dW = dY^T X form of the training step), K / M / N tails, split-K for tall contractions, accumulation into C."""
+    from conformer_b200._lib import check, lib
+    g = torch.Generator().manual_seed(K + M + N)
+    A = torch.randn(K, M, generator=g).bfloat16().to("cuda")
+    B = torch.randn(K, N, generator=g).bfloat16().to("cuda")
+    C0 = torch.randn(M, N, generator=g).to("cuda")
+    C = C0.clone()
+    check(lib().cfm_gemm_bf16_tn(A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, torch.cuda.current_stream().cuda_stream))
+    want = C0.double() + A.double().T @ B.double()
+    err = (C.double() - want).abs().max().item()
+    assert err < 2e-3 * (K ** 0.5), err
