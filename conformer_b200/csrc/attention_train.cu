@@ -506,10 +506,25 @@ int attn_train_fwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
   return 0;
 }
 
+// bf16 mode with a head size that is a multiple of 8: the products run as warp-level tensor-core MMAs
+// (attention_train_mma.cu); the fp32 gradient-parity mode (and odd head sizes) use the CUDA-core kernels above
+inline bool bwd_on_tensor_cores(const float*, const float*, const float*, const float*, const uint8_t*, const float*, const float*, float*,
+                                float*, float*, float*, const float*, int, int, int, int, Drop, cudaStream_t, int*) {
+  return false;
+}
+inline bool bwd_on_tensor_cores(const bf16* qkv, const bf16* pp, const float* u, const float* v, const uint8_t* key_pad, const float* lse,
+                                const float* dctx, bf16* dqkv, float* dpp, float* du, float* dv, const float* D, int B, int Tn, int H, int dh,
+                                Drop dr, cudaStream_t st, int* status) {
+  if (dh % 8 != 0) return false;
+  *status = attn_train_bwd_mma(qkv, pp, u, v, key_pad, lse, dctx, dqkv, dpp, du, dv, D, B, Tn, H, dh, dr, st);
+  return true;
+}
+
 template <typename TA>
 int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, const uint8_t* key_pad, const TA* ctx, const float* lse,
                    const float* dctx, TA* dqkv, float* dpp, float* du, float* dv, float* scratch, int B, int Tn, int H, int dh, Drop dr,
                    cudaStream_t st) {
+  int status = 0;
   CFM_REQUIRE(dh >= 4 && dh <= DHP && dh % 4 == 0, "training attention supports head sizes that are multiples of 4 up to 64");
   static std::atomic<uint64_t> done_q{0}, done_kv{0};
   CFM_TRY(smem_attr_once(done_q, reinterpret_cast<const void*>(attn_bwd_q_kernel<TA>), bwd_smem<TA>()));
@@ -517,6 +532,7 @@ int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
   const int64_t rows = static_cast<int64_t>(B) * Tn * H;
   attn_delta_kernel<TA><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(dctx, ctx, scratch, B, Tn, H, dh);
   CFM_CUDA_OK(cudaGetLastError());
+  if (bwd_on_tensor_cores(qkv, pp, u, v, key_pad, lse, dctx, dqkv, dpp, du, dv, scratch, B, Tn, H, dh, dr, st, &status)) return status;
   AttnArgs a{qkv, pp, u, v, key_pad, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
   attn_bwd_q_kernel<TA><<<grid, THREADS, bwd_smem<TA>(), st>>>(a, lse, scratch, dctx, dqkv, dpp, du, dv);

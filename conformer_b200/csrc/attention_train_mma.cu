@@ -1,0 +1,403 @@
+// Attention backward of the training step with the matrix products on the tensor cores (bf16 mode).
+//
+// Same mathematics and the same flash-style tiling as attention_train.cu (nothing of size T x T is stored; 64 x 64
+// (query x key) tiles; the relative shift is an index into a 127-row window of the projected table), but every product of
+// a tile is a warp-level bf16 MMA with fp32 accumulation on shared-memory operands instead of CUDA-core dot products:
+//
+//   query-side kernel, one CTA = 64 queries of one (b, h), loop over key tiles:
+//     S  = Qc K^T            [64 x 64]      U = Qp Pw^T  [64 x 128] (all window rows; s_ij = S_ij + U[i][j - i + 63])
+//     dP = dO V^T            [64 x 64]
+//     element-wise: P = exp(s - lse), ds = P (f dP - D) / sqrt(dh)  ->  ds as a bf16 tile, and "unshifted" into a
+//     [64 x 128] tile dsu[i][j - i + 63] (the transpose of what the shift does to U)
+//     dQc += ds K,  dQp += dsu Pw,  dPw[128 x 64] += dsu^T Qp    (window gradient: rows < 64 leave through atomics after
+//                                                                  each tile, rows >= 64 carry over to the next window)
+//   key-side kernel, one CTA = 64 keys, loop over query tiles: the same S / U / dP / element-wise stage, then
+//     dV += Pd^T dO,  dK += ds^T Qc
+//
+// This is the interim tensor-core form (the nvcuda::wmma interface, i.e. the warp-level MMA path): it takes the backward
+// from the fp32 FMA pipe to the tensor pipe with fragments the compiler lays out; a tcgen05 version with the
+// accumulators in tensor memory is the next step.  The fp32 gradient-parity mode keeps the
+// CUDA-core kernels of attention_train.cu.
+#include <mma.h>
+
+#include "train.h"
+
+namespace cfm {
+namespace {
+
+using namespace nvcuda;
+
+constexpr int TQ = 64, TK = 64, DHP = 64, WINR = 128;             // 127 window rows used, 128 stored
+constexpr int LDB = DHP + 8;                                       // bf16 operand tiles: 72 elements = 144 B per row
+constexpr int LDU = WINR + 8;                                      // bf16 dsu tile: 136 elements
+constexpr int LDF = TK + 4;                                        // fp32 score tiles: 68 floats
+constexpr int LDUF = WINR + 4;                                     // fp32 U tile: 132 floats
+constexpr int THREADS = 256;
+
+struct MmaArgs {
+  const bf16* qkv;
+  const bf16* pp;
+  const float* u;
+  const float* v;
+  const uint8_t* key_pad;
+  const float* lse;
+  const float* D;
+  const float* dctx;
+  int Tn, H, dh;
+  float scale;
+  Drop dr;
+};
+
+typedef wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> FragA;
+typedef wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> FragAT;
+typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> FragB;     // B[k][n] stored [k][n]
+typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> FragBT;    // B[k][n] stored [n][k]
+typedef wmma::fragment<wmma::accumulator, 16, 16, 16, float> FragC;
+
+// dst[r][c] (bf16, pitch LDB) = src[(row0 + r) * stride + c] (+ add[c]) for row0 + r in [lo, hi), zeros elsewhere / c >= dh
+__device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t stride, int row0, int lo, int hi, int rows, int dh,
+                                          const float* add) {
+  for (int idx = threadIdx.x; idx < rows * (DHP / 8); idx += THREADS) {
+    const int r = idx >> 3, c8 = (idx & 7) * 8, row = row0 + r;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (row >= lo && row < hi && c8 < dh) {
+      o = *reinterpret_cast<const uint4*>(src + static_cast<int64_t>(row) * stride + c8);
+      if (add != nullptr) {
+        uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          w[e] = pack_bf16x2(__uint_as_float(w[e] << 16) + add[c8 + 2 * e], __uint_as_float(w[e] & 0xffff0000u) + add[c8 + 2 * e + 1]);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + r * LDB + c8) = o;
+  }
+}
+__device__ __forceinline__ void load_tile_f32(bf16* dst, const float* src, int64_t stride, int row0, int hi, int rows, int dh) {
+  for (int idx = threadIdx.x; idx < rows * (DHP / 8); idx += THREADS) {
+    const int r = idx >> 3, c8 = (idx & 7) * 8, row = row0 + r;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (row < hi && c8 < dh) {
+      const float4 a = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * stride + c8);
+      const float4 b = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(row) * stride + c8 + 4);
+      o = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+    *reinterpret_cast<uint4*>(dst + r * LDB + c8) = o;
+  }
+}
+
+// C[16 rb .. , 16 cb ..] = A[rows 16 rb][K] . B^T, A row-major (pitch lda), B stored [n][k] (pitch ldb): K = 64
+__device__ __forceinline__ void mma_abt(const bf16* A, int lda, const bf16* Bm, int ldb, int rb, int cb, float* out, int ldo) {
+  FragC c;
+  wmma::fill_fragment(c, 0.f);
+#pragma unroll
+  for (int k = 0; k < DHP; k += 16) {
+    FragA a;
+    FragBT b;
+    wmma::load_matrix_sync(a, A + rb * 16 * lda + k, lda);
+    wmma::load_matrix_sync(b, Bm + cb * 16 * ldb + k, ldb);
+    wmma::mma_sync(c, a, b, c);
+  }
+  wmma::store_matrix_sync(out + rb * 16 * ldo + cb * 16, c, ldo, wmma::mem_row_major);
+}
+
+// the shared first half of both kernels: S, U, dP on the tensor cores, then the per-entry stage.
+// Writes Pd (bf16, nullable), ds (bf16) and, if dsu != nullptr, the unshifted ds (bf16 [64][LDU], zeroed first).
+__device__ __forceinline__ void scores_and_grads(const MmaArgs& p, const bf16* Qc, const bf16* Qp, const bf16* dO, const bf16* Kt, const bf16* Vt,
+                                                 const bf16* Pw, float* Ss, float* Us, float* DPs, const float* lse_s, const float* D_s,
+                                                 bf16* Pd_b, bf16* dS_b, bf16* dSu_b, int b, int h, int i0, int j0) {
+  const int warp = threadIdx.x >> 5;
+  const int rb = warp >> 1;
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int cb = (warp & 1) * 2 + e;
+    mma_abt(Qc, LDB, Kt, LDB, rb, cb, Ss, LDF);
+    mma_abt(dO, LDB, Vt, LDB, rb, cb, DPs, LDF);
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) mma_abt(Qp, LDB, Pw, LDB, rb, (warp & 1) * 4 + e, Us, LDUF);
+  if (dSu_b != nullptr)
+    for (int idx = threadIdx.x; idx < TQ * (LDU / 8); idx += THREADS) reinterpret_cast<uint4*>(dSu_b)[idx] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  // per-entry stage: thread = (row i, 16 consecutive keys)
+  const int il = threadIdx.x >> 2, jl0 = (threadIdx.x & 3) * 16, i = i0 + il, Tn = p.Tn;
+  const float lse = lse_s[il], Dv = D_s[il];
+  uint32_t pk_p[8], pk_s[8];
+#pragma unroll
+  for (int e2 = 0; e2 < 8; ++e2) {
+    float pd2[2], ds2[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int jl = jl0 + 2 * e2 + q, j = j0 + jl;
+      const bool dead = j >= Tn || i >= Tn || (p.key_pad != nullptr && p.key_pad[static_cast<int64_t>(b) * Tn + j] != 0);
+      float pd = 0.f, ds = 0.f;
+      if (!dead) {
+        const float s = p.scale * (Ss[il * LDF + jl] + Us[il * LDUF + jl - il + (TQ - 1)]);
+        const float pv = __expf(s - lse);
+        const float f = p.dr.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
+        pd = pv * f;
+        ds = pv * (f * DPs[il * LDF + jl] - Dv) * p.scale;
+      }
+      pd2[q] = pd;
+      ds2[q] = ds;
+      if (dSu_b != nullptr) dSu_b[il * LDU + jl - il + (TQ - 1)] = __float2bfloat16_rn(ds);
+    }
+    pk_p[e2] = pack_bf16x2(pd2[0], pd2[1]);
+    pk_s[e2] = pack_bf16x2(ds2[0], ds2[1]);
+  }
+  if (Pd_b != nullptr) {
+    *reinterpret_cast<uint4*>(Pd_b + il * LDB + jl0) = make_uint4(pk_p[0], pk_p[1], pk_p[2], pk_p[3]);
+    *reinterpret_cast<uint4*>(Pd_b + il * LDB + jl0 + 8) = make_uint4(pk_p[4], pk_p[5], pk_p[6], pk_p[7]);
+  }
+  *reinterpret_cast<uint4*>(dS_b + il * LDB + jl0) = make_uint4(pk_s[0], pk_s[1], pk_s[2], pk_s[3]);
+  *reinterpret_cast<uint4*>(dS_b + il * LDB + jl0 + 8) = make_uint4(pk_s[4], pk_s[5], pk_s[6], pk_s[7]);
+  __syncthreads();
+}
+
+struct SmemQ {
+  static constexpr int TILES_B16 = (5 * TQ + WINR) * LDB + TQ * LDB + TQ * LDU;              // Qc Qp dO K V | Pw | ds | dsu
+  static constexpr int F32 = 2 * TQ * LDF + TQ * LDUF + WINR * LDF + 2 * TQ + 2 * DHP;       // S dP | U | dPw accumulator | lse D | red
+  static constexpr int BYTES = TILES_B16 * 2 + F32 * 4;
+};
+struct SmemKV {
+  static constexpr int TILES_B16 = (5 * TQ + WINR) * LDB + 2 * TQ * LDB;                      // ... | Pd | ds
+  static constexpr int F32 = 2 * TQ * LDF + TQ * LDUF + 2 * TQ;
+  static constexpr int BYTES = TILES_B16 * 2 + F32 * 4;
+};
+
+// ------------------------------------------------------------------------------------------------ query side
+__global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, bf16* __restrict__ dqkv, float* __restrict__ dpp,
+                                                                    float* __restrict__ du, float* __restrict__ dv) {
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  float* Ss = reinterpret_cast<float*>(sm_raw);
+  float* DPs = Ss + TQ * LDF;
+  float* Us = DPs + TQ * LDF;
+  float* Wacc = Us + TQ * LDUF;                                   // [128][LDF] window gradient of this query tile
+  float* lse_s = Wacc + WINR * LDF;
+  float* D_s = lse_s + TQ;
+  float* red = D_s + TQ;
+  bf16* Qc = reinterpret_cast<bf16*>(red + 2 * DHP);
+  bf16* Qp = Qc + TQ * LDB;
+  bf16* dO = Qp + TQ * LDB;
+  bf16* Kt = dO + TQ * LDB;
+  bf16* Vt = Kt + TK * LDB;
+  bf16* Pw = Vt + TK * LDB;
+  bf16* dS_b = Pw + WINR * LDB;
+  bf16* dSu_b = dS_b + TQ * LDB;
+  const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * TQ;
+  const int Tn = p.Tn, dh = p.dh, d = p.H * dh;
+  const int warp = threadIdx.x >> 5;
+  const bf16* qkv = p.qkv + static_cast<int64_t>(b) * Tn * 3 * d + h * dh;
+  const bf16* pp = p.pp + h * dh;
+  load_tile(Qc, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.u + h * dh);
+  load_tile(Qp, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.v + h * dh);
+  load_tile_f32(dO, p.dctx + static_cast<int64_t>(b) * Tn * d + h * dh, d, i0, Tn, TQ, dh);
+  for (int i = threadIdx.x; i < TQ; i += THREADS) {
+    const bool ok = i0 + i < Tn;
+    lse_s[i] = ok ? p.lse[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
+    D_s[i] = ok ? p.D[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < WINR * LDF; i += THREADS) Wacc[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * DHP; i += THREADS) red[i] = 0.f;
+  // dQ accumulators: warp -> row block rb = warp / 2, column blocks (warp & 1) * 2 + {0, 1}; content and positional parts
+  FragC dqc[2], dqp[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    wmma::fill_fragment(dqc[e], 0.f);
+    wmma::fill_fragment(dqp[e], 0.f);
+  }
+  const int rb = warp >> 1;
+  for (int j0 = 0; j0 < Tn; j0 += TK) {
+    __syncthreads();
+    const int r0 = (Tn - 1) + j0 - i0 - (TQ - 1);
+    load_tile(Kt, qkv + d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
+    load_tile(Vt, qkv + 2 * d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
+    load_tile(Pw, pp, d, r0, 0, 2 * Tn - 1, WINR, dh, nullptr);
+    __syncthreads();
+    scores_and_grads(p, Qc, Qp, dO, Kt, Vt, Pw, Ss, Us, DPs, lse_s, D_s, nullptr, dS_b, dSu_b, b, h, i0, j0);
+    // dQc += ds K   (A = ds [i][j], B[k = j][n = d] = K[j][d]);   dQp += dsu Pw   (K = 128 window rows)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cb = (warp & 1) * 2 + e;
+#pragma unroll
+      for (int k = 0; k < TK; k += 16) {
+        FragA a;
+        FragB bm;
+        wmma::load_matrix_sync(a, dS_b + rb * 16 * LDB + k, LDB);
+        wmma::load_matrix_sync(bm, Kt + k * LDB + cb * 16, LDB);
+        wmma::mma_sync(dqc[e], a, bm, dqc[e]);
+      }
+#pragma unroll
+      for (int k = 0; k < WINR; k += 16) {
+        FragA a;
+        FragB bm;
+        wmma::load_matrix_sync(a, dSu_b + rb * 16 * LDU + k, LDU);
+        wmma::load_matrix_sync(bm, Pw + k * LDB + cb * 16, LDB);
+        wmma::mma_sync(dqp[e], a, bm, dqp[e]);
+      }
+    }
+    // dPw[w][d] += sum_i dsu[i][w] Qp[i][d]: warp = 16 window rows, all four column blocks; accumulator lives in shared memory
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      FragC c;
+      wmma::load_matrix_sync(c, Wacc + warp * 16 * LDF + cb * 16, LDF, wmma::mem_row_major);
+#pragma unroll
+      for (int k = 0; k < TQ; k += 16) {
+        FragAT a;                                                  // A[m = w][k = i] stored at dsu[i][w]
+        FragB bm;
+        wmma::load_matrix_sync(a, dSu_b + k * LDU + warp * 16, LDU);
+        wmma::load_matrix_sync(bm, Qp + k * LDB + cb * 16, LDB);
+        wmma::mma_sync(c, a, bm, c);
+      }
+      wmma::store_matrix_sync(Wacc + warp * 16 * LDF + cb * 16, c, LDF, wmma::mem_row_major);
+    }
+    __syncthreads();
+    // window rows < 64 are complete: add them to the table gradient; rows >= 64 become rows - 64 of the next window
+    const bool last = j0 + TK >= Tn;
+    for (int idx = threadIdx.x; idx < (last ? WINR : TK) * (DHP / 4); idx += THREADS) {
+      const int w = idx / (DHP / 4), c4 = (idx - w * (DHP / 4)) * 4, r = r0 + w;
+      if (r >= 0 && r < 2 * Tn - 1 && c4 < dh) {
+        float* dst = dpp + static_cast<int64_t>(r) * d + h * dh + c4;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(dst + c, Wacc[w * LDF + c4 + c]);
+      }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TK * DHP; idx += THREADS) {
+      const int w = idx >> 6, c = idx & 63;
+      Wacc[w * LDF + c] = Wacc[(w + TK) * LDF + c];
+      Wacc[(w + TK) * LDF + c] = 0.f;
+    }
+  }
+  __syncthreads();
+  // dq = dQc + dQp (bf16), du += column sums of dQc, dv += column sums of dQp (valid rows only)
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int cb = (warp & 1) * 2 + e;
+    wmma::store_matrix_sync(Ss + rb * 16 * LDF + cb * 16, dqc[e], LDF, wmma::mem_row_major);
+    wmma::store_matrix_sync(DPs + rb * 16 * LDF + cb * 16, dqp[e], LDF, wmma::mem_row_major);
+  }
+  __syncthreads();
+  {
+    const int il = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, i = i0 + il;
+    if (i < Tn) {
+      bf16* dst = dqkv + (static_cast<int64_t>(b) * Tn + i) * 3 * d + h * dh;
+#pragma unroll
+      for (int c = 0; c < 16; c += 2) {
+        const float a0 = Ss[il * LDF + c0 + c], a1 = Ss[il * LDF + c0 + c + 1];
+        const float b0 = DPs[il * LDF + c0 + c], b1 = DPs[il * LDF + c0 + c + 1];
+        if (c0 + c < dh) {
+          *reinterpret_cast<uint32_t*>(dst + c0 + c) = pack_bf16x2(a0 + b0, a1 + b1);
+          atomicAdd(&red[c0 + c], a0);
+          atomicAdd(&red[c0 + c + 1], a1);
+          atomicAdd(&red[DHP + c0 + c], b0);
+          atomicAdd(&red[DHP + c0 + c + 1], b1);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < dh; c += THREADS) {
+    atomicAdd(du + h * dh + c, red[c]);
+    atomicAdd(dv + h * dh + c, red[DHP + c]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ key side
+__global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, bf16* __restrict__ dqkv) {
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  float* Ss = reinterpret_cast<float*>(sm_raw);
+  float* DPs = Ss + TQ * LDF;
+  float* Us = DPs + TQ * LDF;
+  float* lse_s = Us + TQ * LDUF;
+  float* D_s = lse_s + TQ;
+  bf16* Qc = reinterpret_cast<bf16*>(D_s + TQ);
+  bf16* Qp = Qc + TQ * LDB;
+  bf16* dO = Qp + TQ * LDB;
+  bf16* Kt = dO + TQ * LDB;
+  bf16* Vt = Kt + TK * LDB;
+  bf16* Pw = Vt + TK * LDB;
+  bf16* Pd_b = Pw + WINR * LDB;
+  bf16* dS_b = Pd_b + TQ * LDB;
+  const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * TK;
+  const int Tn = p.Tn, dh = p.dh, d = p.H * dh;
+  const int warp = threadIdx.x >> 5, rb = warp >> 1;
+  const bf16* qkv = p.qkv + static_cast<int64_t>(b) * Tn * 3 * d + h * dh;
+  const bf16* pp = p.pp + h * dh;
+  load_tile(Kt, qkv + d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
+  load_tile(Vt, qkv + 2 * d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
+  FragC dvv[2], dk[2];                                             // rows = keys 16 rb .., column blocks (warp & 1) * 2 + {0, 1}
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    wmma::fill_fragment(dvv[e], 0.f);
+    wmma::fill_fragment(dk[e], 0.f);
+  }
+  for (int i0 = 0; i0 < Tn; i0 += TQ) {
+    __syncthreads();
+    load_tile(Qc, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.u + h * dh);
+    load_tile(Qp, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.v + h * dh);
+    load_tile_f32(dO, p.dctx + static_cast<int64_t>(b) * Tn * d + h * dh, d, i0, Tn, TQ, dh);
+    load_tile(Pw, pp, d, (Tn - 1) + j0 - i0 - (TQ - 1), 0, 2 * Tn - 1, WINR, dh, nullptr);
+    for (int i = threadIdx.x; i < TQ; i += THREADS) {
+      const bool ok = i0 + i < Tn;
+      lse_s[i] = ok ? p.lse[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
+      D_s[i] = ok ? p.D[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
+    }
+    __syncthreads();
+    scores_and_grads(p, Qc, Qp, dO, Kt, Vt, Pw, Ss, Us, DPs, lse_s, D_s, Pd_b, dS_b, nullptr, b, h, i0, j0);
+    // dV[j][d] += sum_i Pd[i][j] dO[i][d],  dK[j][d] += sum_i ds[i][j] Qc[i][d]    (A[m = j][k = i] stored at [i][j])
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cb = (warp & 1) * 2 + e;
+#pragma unroll
+      for (int k = 0; k < TQ; k += 16) {
+        FragAT a;
+        FragB bm;
+        wmma::load_matrix_sync(a, Pd_b + k * LDB + rb * 16, LDB);
+        wmma::load_matrix_sync(bm, dO + k * LDB + cb * 16, LDB);
+        wmma::mma_sync(dvv[e], a, bm, dvv[e]);
+        wmma::load_matrix_sync(a, dS_b + k * LDB + rb * 16, LDB);
+        wmma::load_matrix_sync(bm, Qc + k * LDB + cb * 16, LDB);
+        wmma::mma_sync(dk[e], a, bm, dk[e]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int cb = (warp & 1) * 2 + e;
+    wmma::store_matrix_sync(Ss + rb * 16 * LDF + cb * 16, dk[e], LDF, wmma::mem_row_major);
+    wmma::store_matrix_sync(DPs + rb * 16 * LDF + cb * 16, dvv[e], LDF, wmma::mem_row_major);
+  }
+  __syncthreads();
+  const int jl = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, j = j0 + jl;
+  if (j < Tn) {
+    bf16* dst = dqkv + (static_cast<int64_t>(b) * Tn + j) * 3 * d + h * dh;
+#pragma unroll
+    for (int c = 0; c < 16; c += 2)
+      if (c0 + c < dh) {
+        *reinterpret_cast<uint32_t*>(dst + d + c0 + c) = pack_bf16x2(Ss[jl * LDF + c0 + c], Ss[jl * LDF + c0 + c + 1]);
+        *reinterpret_cast<uint32_t*>(dst + 2 * d + c0 + c) = pack_bf16x2(DPs[jl * LDF + c0 + c], DPs[jl * LDF + c0 + c + 1]);
+      }
+  }
+}
+
+}  // namespace
+
+// D (row term) must already be in `scratch` (attn_train_bwd computes it for both paths)
+int attn_train_bwd_mma(const bf16* qkv, const bf16* pp, const float* u, const float* v, const uint8_t* key_pad, const float* lse,
+                       const float* dctx, bf16* dqkv, float* dpp, float* du, float* dv, const float* scratch_D, int B, int Tn, int H, int dh,
+                       Drop dr, cudaStream_t st) {
+  CFM_REQUIRE(dh % 8 == 0 && dh <= DHP, "tensor-core attention backward needs a head size that is a multiple of 8, <= 64");
+  static std::atomic<uint64_t> done_q{0}, done_kv{0};
+  CFM_TRY(smem_attr_once(done_q, reinterpret_cast<const void*>(attn_bwd_q_mma_kernel), SmemQ::BYTES));
+  CFM_TRY(smem_attr_once(done_kv, reinterpret_cast<const void*>(attn_bwd_kv_mma_kernel), SmemKV::BYTES));
+  MmaArgs a{qkv, pp, u, v, key_pad, lse, scratch_D, dctx, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
+  dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
+  attn_bwd_q_mma_kernel<<<grid, THREADS, SmemQ::BYTES, st>>>(a, dqkv, dpp, du, dv);
+  CFM_CUDA_OK(cudaGetLastError());
+  attn_bwd_kv_mma_kernel<<<grid, THREADS, SmemKV::BYTES, st>>>(a, dqkv);
+  CFM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cfm

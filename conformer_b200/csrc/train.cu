@@ -91,6 +91,20 @@ int wgrad(const TC& c, const TA* dY, int ld_dy, const TA* X, int ld_x, float* dW
   return 0;
 }
 
+// conv_2 weight gradient in the packed layout: gpack[C, 9C] += dy2[M2, C]^T im2col(out1)[M2, 9C]
+inline int conv2_wgrad(const TC& c, const bf16* dy2, const bf16* out1, float* gpack, const ConvGeom& g, int64_t M2, int64_t, bf16* big1, bf16*) {
+  CFM_TRY(im2col_rows(out1, big1, g, M2, c.st));                  // row-major im2col, read in place by the TN GEMM
+  return gemm_bf16_tn(dy2, g.C, big1, 9 * g.C, gpack, 9 * g.C, g.C, 9 * g.C, static_cast<int>(M2), c.num_sms, c.st);
+}
+inline int conv2_wgrad(const TC& c, const float* dy2, const float* out1, float* gpack, const ConvGeom& g, int64_t M2, int64_t M2p, float* big1,
+                       float* big2) {
+  const int d = g.C, M2i = static_cast<int>(M2), M2pi = static_cast<int>(M2p);
+  CFM_TRY(transpose_pad<float>(dy2, d, big2, M2i, d, M2pi, c.st));                              // dy2^T [C, M2p]
+  CFM_TRY(im2col_t<float>(out1, big1, g, M2, M2p, c.st));                                       // im2col^T [9C, M2p]
+  return gemm_any(c, static_cast<const float*>(big2), M2pi, static_cast<const float*>(big1), nullptr, gpack, 9 * d, d, 9 * d, M2pi,
+                  EPI_BIAS_RES, gpack, 1.f);
+}
+
 __global__ void unpack_conv2_grad_kernel(const float* __restrict__ gp, float* __restrict__ g, int C) {
   // gp[n][(kw*3+kh)*C + c] -> g[n][c][kh][kw] (+=)
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -469,12 +483,8 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
   {
     ConvGeom g{B, T1p, F1, d, T2, F2};
     const int M2i = static_cast<int>(M2), M2pi = static_cast<int>(M2p);
-    TA* dy2T = big2;                                             // [C, M2p]
-    CFM_TRY(transpose_pad<TA>(dy2, d, dy2T, M2i, d, M2pi, st));
-    CFM_TRY(im2col_t<TA>(out1, big1, g, M2, M2p, st));
     CFM_CUDA_OK(cudaMemsetAsync(gpack, 0, static_cast<size_t>(d) * 9 * d * 4, st));
-    CFM_TRY(gemm_any(c, static_cast<const TA*>(dy2T), M2pi, static_cast<const TA*>(big1), nullptr, gpack, 9 * d, d, 9 * d, M2pi, EPI_BIAS_RES,
-                     gpack, 1.f));
+    CFM_TRY(conv2_wgrad(c, dy2, out1, gpack, g, M2, M2p, big1, big2));
     const int64_t n = static_cast<int64_t>(d) * d * 9;
     unpack_conv2_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(gpack, t.conv2.dw, d);
     CFM_CUDA_OK(cudaGetLastError());

@@ -49,6 +49,7 @@ template <typename TA> int bn_swish_fwd(const float* z, const float* stats, cons
 int bn_swish_bwd(float* ds_to_dz, const float* z, const float* stats, const float* gamma, const float* beta, float* acc2d, float* dgamma,
                  float* dbeta, int M, int d, cudaStream_t st);
 template <typename TA> int im2col_t(const TA* out1, TA* colT, const ConvGeom& g, int64_t M2, int64_t M2p, cudaStream_t st);
+int im2col_rows(const bf16* out1, bf16* col /*[M2, 9C]*/, const ConvGeom& g, int64_t M2, cudaStream_t st);
 template <typename TA> int col2im_relu(const TA* dcol, const TA* out1, float* dout1, const ConvGeom& g, cudaStream_t st);
 int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int B, int n_mel, int Tin, int T1, int T1p, int F1, int C,
                 cudaStream_t st);
@@ -67,6 +68,10 @@ int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
                    const float* dctx, TA* dqkv, float* dpp, float* du, float* dv, float* scratch, int B, int Tn, int H, int dh, Drop dr,
                    cudaStream_t st);
 
+// attention_train_mma.cu: the backward with tensor-core products (bf16); D = the row term computed by attn_train_bwd
+int attn_train_bwd_mma(const bf16* qkv, const bf16* pp, const float* u, const float* v, const uint8_t* key_pad, const float* lse,
+                       const float* dctx, bf16* dqkv, float* dpp, float* du, float* dv, const float* scratch_D, int B, int Tn, int H, int dh,
+                       Drop dr, cudaStream_t st);
 // attention_tc.cu: the tcgen05 forward kernel in training form (head size 64, bf16)
 int rel_attention_bf16_tc_train(const bf16* qkv, const bf16* pos, int ldp, const float* u, const float* v, const uint8_t* key_pad,
                                 bf16* ctx, float* lse, Drop dr, int B, int Tn, int H, int dh, cudaStream_t stream);

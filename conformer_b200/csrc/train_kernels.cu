@@ -379,6 +379,20 @@ __global__ void im2col_t_kernel(const TA* __restrict__ out1, TA* __restrict__ co
     if (c < g.C && m < M2p) colT[(static_cast<int64_t>(tap) * g.C + c) * M2p + m] = tile[tx][r];
   }
 }
+// col[m][(kw*3+kh)*C + c] = out1[b][2 t2 + kw][2 f2 + kh][c], m = (b*T2 + t2)*F2 + f2: the im2col operand of conv_2's weight
+// gradient in the row-major form the TN GEMM reads in place (8 channels = 16 bytes per thread, fully coalesced)
+__global__ void im2col_rows_kernel(const bf16* __restrict__ out1, bf16* __restrict__ col, ConvGeom g, int64_t M2) {
+  const int C8 = g.C / 8;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= M2 * 9 * C8) return;
+  const int c8 = static_cast<int>(i % C8), tap = static_cast<int>((i / C8) % 9);
+  const int64_t m = i / (9 * static_cast<int64_t>(C8));
+  const int kw = tap / 3, kh = tap - kw * 3;
+  const int f2 = static_cast<int>(m % g.F2), t2 = static_cast<int>((m / g.F2) % g.T2), b = static_cast<int>(m / (static_cast<int64_t>(g.F2) * g.T2));
+  const uint4 v = *reinterpret_cast<const uint4*>(out1 + ((static_cast<int64_t>(b) * g.T1p + 2 * t2 + kw) * g.F1 + 2 * f2 + kh) * g.C + c8 * 8);
+  *reinterpret_cast<uint4*>(col + (m * 9 + tap) * g.C + c8 * 8) = v;
+}
+
 // dOut1[b,t1,f1,c] = relu'(out1) * sum over the taps that read this input of dcol[m(t2,f2)][(kw*3+kh)*C + c]
 template <typename TA>
 __global__ void col2im_relu_kernel(const TA* __restrict__ dcol, const TA* __restrict__ out1, float* __restrict__ dout1, ConvGeom g) {
@@ -560,6 +574,12 @@ template <typename TA>
 int im2col_t(const TA* out1, TA* colT, const ConvGeom& g, int64_t M2, int64_t M2p, cudaStream_t st) {
   dim3 grid(nblk(M2p, 32), nblk(g.C, 32), 9);
   im2col_t_kernel<TA><<<grid, 256, 0, st>>>(out1, colT, g, M2, M2p);
+  LAUNCH_OK();
+}
+int im2col_rows(const bf16* out1, bf16* col, const ConvGeom& g, int64_t M2, cudaStream_t st) {
+  CFM_REQUIRE(g.C % 8 == 0, "im2col needs channels to be a multiple of 8");
+  const int64_t n = M2 * 9 * (g.C / 8);
+  im2col_rows_kernel<<<nblk(n, 256), 256, 0, st>>>(out1, col, g, M2);
   LAUNCH_OK();
 }
 template <typename TA>
