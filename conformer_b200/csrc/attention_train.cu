@@ -381,9 +381,13 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_q_kernel(AttnArgs p, cons
       if (mm >= 4 && !last) break;
       const int r = r0 + ti + 16 * mm;
       if (r >= 0 && r < 2 * Tn - 1 && 4 * tj < dh) {
-        float* dst = dpp + static_cast<int64_t>(r) * d + h * dh + 4 * tj;
+        if ((d & 3) == 0 && (dh & 3) == 0) {                       // one 16-byte vector reduction per 4 channels
+          atomicAdd(reinterpret_cast<float4*>(dpp + static_cast<int64_t>(r) * d + h * dh + 4 * tj), make_float4(dw[mm][0], dw[mm][1], dw[mm][2], dw[mm][3]));
+        } else {
+          float* dst = dpp + static_cast<int64_t>(r) * d + h * dh + 4 * tj;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(dst + c, dw[mm][c]);
+          for (int c = 0; c < 4; ++c) atomicAdd(dst + c, dw[mm][c]);
+        }
       }
     }
 #pragma unroll

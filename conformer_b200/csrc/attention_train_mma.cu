@@ -255,10 +255,9 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
     const bool last = j0 + TK >= Tn;
     for (int idx = threadIdx.x; idx < (last ? WINR : TK) * (DHP / 4); idx += THREADS) {
       const int w = idx / (DHP / 4), c4 = (idx - w * (DHP / 4)) * 4, r = r0 + w;
-      if (r >= 0 && r < 2 * Tn - 1 && c4 < dh) {
-        float* dst = dpp + static_cast<int64_t>(r) * d + h * dh + c4;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(dst + c, Wacc[w * LDF + c4 + c]);
+      if (r >= 0 && r < 2 * Tn - 1 && c4 < dh) {                   // one 16-byte vector reduction per 4 channels
+        float4* dst = reinterpret_cast<float4*>(dpp + static_cast<int64_t>(r) * d + h * dh + c4);
+        atomicAdd(dst, *reinterpret_cast<const float4*>(Wacc + w * LDF + c4));
       }
     }
     __syncthreads();
