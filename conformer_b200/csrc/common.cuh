@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -195,6 +196,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* tm, const v
                ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
@@ -211,6 +217,41 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {      // every thread of every CTA in the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// ---- CTA pairs (tcgen05 cta_group::2): the two CTAs of a cluster of 2 sit on the SMs of one TPC; the even-ranked one
+// (the leader) issues every MMA for both.  Barriers the leader waits on live in ITS shared memory; the peer reaches them
+// through the cluster address of the same offset.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// (default semantics - release at CTA scope - as for a local arrive: the data the leader's MMA consumes is in tensor
+// memory, ordered by tcgen05.fence::before_thread_sync; a cluster-scope release costs ~0.8 us per arrive, measured)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes complete on a barrier of either CTA of the pair (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {   // one full warp of each CTA
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrive on the barrier at this offset in both CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+
 // TMA load multicast to the CTAs in `mask`: same smem offset and same mbarrier offset in each of them
 __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
                                                uint16_t mask) {
@@ -291,6 +332,27 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
       "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
       "mov.b64 db, {%2, %5};\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+// CTA-pair forms (issued by the leader only): D is [256 x N], rows 0-127 in the leader's TMEM, 128-255 in the peer's, at
+// the same columns; A = each CTA's own 128 rows (same shared-memory offset / same TMEM columns in both); B is split along
+// N: the leader's shared memory holds rows [0, N/2) of B at the descriptor's offset, the peer's rows [N/2, N).
+__device__ __forceinline__ void tc_mma_f16_lo_pair(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 da, {%1, %5};\n\tmov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc,
+                                                   uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(UMMA_DESC_HI_SW128)
       : "memory");
 }

@@ -29,5 +29,9 @@ m(x)
 torch.cuda.synchronize()
 fn(None)
 t = trace.cpu()
-print("MMA warp of CTA 0: total %d ns; waiting for LN(x) %d, weights (full_bar) %d, hidden (hs_full) %d, acc1 drained %d"
+print("MMA warp of pair 0's leader: total %d ns; waiting for LN(x) %d, weights (full_bar) %d, hidden (hs_full) %d, acc2 drained %d"
       % tuple(int(v) for v in t[:5]))
+t0 = int(t[8])
+print("G2 issued      ", [int(v) for v in t[16:40]])
+print("epilogue done  ", [int(v) - t0 if v else 0 for v in t[48:72]])
+print("final start", [int(v) - t0 if v else 0 for v in t[80:84]], "end", [int(v) - t0 if v else 0 for v in t[84:88]])
