@@ -491,9 +491,15 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
     CFM_TRY(colsum_add<TA>(dy2, d, t.conv2.db, M2i, d, st));
     // dcol = dy2 W2p  ([M2, C] x [9C, C]^T), gathered back onto conv_1's output grid through its ReLU
     CFM_TRY(gemm_any(c, static_cast<const TA*>(dy2), d, WSel<TA>::wT(t.conv2), nullptr, big1, 9 * d, M2i, 9 * d, d, EPI_BIAS, nullptr, 0.f));
-    CFM_TRY(col2im_relu<TA>(big1, out1, dout1, g, st));
+    // conv_1's parameter gradients straight from dcol: its output gradient (relu' * col2im(dcol), [B,T1,F1,C] fp32 - 0.96 GB
+    // at C4) is gathered on the fly and never written
+    if (d % 8 == 0 && d / 8 <= 256) {
+      CFM_TRY(conv1_wgrad_fused<TA>(big1, out1, tp.mel, t.dc1_w, t.dc1_b, g, n_mel, Tin, T1, c.num_sms, st));
+    } else {
+      CFM_TRY(col2im_relu<TA>(big1, out1, dout1, g, st));
+      CFM_TRY(conv1_wgrad(dout1, tp.mel, t.dc1_w, t.dc1_b, B, n_mel, Tin, T1, T1p, F1, d, st));
+    }
   }
-  CFM_TRY(conv1_wgrad(dout1, tp.mel, t.dc1_w, t.dc1_b, B, n_mel, Tin, T1, T1p, F1, d, st));
   return 0;
 }
 

@@ -9,12 +9,16 @@ namespace cfm {
 struct Drop {
   float p = 0.f, inv_keep = 1.f;
   uint32_t seed_lo = 0, seed_hi = 0, site = 0;
+  // one 32-bit hash per PAIR of elements, 16 bits each (kernels handle 4 consecutive elements per thread, so the hash
+  // of a pair is computed once)
   __host__ __device__ __forceinline__ float factor(int64_t i) const {
     if (p <= 0.f) return 1.f;
-    uint32_t h = seed_lo ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(i) ^ (static_cast<uint32_t>(static_cast<uint64_t>(i) >> 32) * 0x85EBCA6Bu);
+    const uint64_t j = static_cast<uint64_t>(i) >> 1;
+    uint32_t h = seed_lo ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(j >> 32) * 0x85EBCA6Bu);
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
     h ^= seed_hi; h *= 0x9E3779B1u; h ^= h >> 15;
-    return (static_cast<float>(h >> 8) * (1.0f / 16777216.0f)) >= p ? inv_keep : 0.f;
+    const uint32_t u = (i & 1) ? (h >> 16) : (h & 0xFFFFu);
+    return (static_cast<float>(u) * (1.0f / 65536.0f)) >= p ? inv_keep : 0.f;
   }
 };
 inline Drop make_drop(float p, uint64_t seed, uint32_t site) {
@@ -51,6 +55,9 @@ int bn_swish_bwd(float* ds_to_dz, const float* z, const float* stats, const floa
 template <typename TA> int im2col_t(const TA* out1, TA* colT, const ConvGeom& g, int64_t M2, int64_t M2p, cudaStream_t st);
 int im2col_rows(const bf16* out1, bf16* col /*[M2, 9C]*/, const ConvGeom& g, int64_t M2, cudaStream_t st);
 template <typename TA> int col2im_relu(const TA* dcol, const TA* out1, float* dout1, const ConvGeom& g, cudaStream_t st);
+template <typename TA>
+int conv1_wgrad_fused(const TA* dcol, const TA* out1, const float* mel, float* dw, float* db, const ConvGeom& g, int n_mel, int Tin, int T1,
+                      int num_sms, cudaStream_t st);
 int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int B, int n_mel, int Tin, int T1, int T1p, int F1, int C,
                 cudaStream_t st);
 

@@ -27,6 +27,17 @@ __device__ __forceinline__ void ld4(const bf16* p, float (&v)[4]) {
   v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
   v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
 }
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const bf16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+  v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  v[4] = __uint_as_float(t.z << 16); v[5] = __uint_as_float(t.z & 0xffff0000u);
+  v[6] = __uint_as_float(t.w << 16); v[7] = __uint_as_float(t.w & 0xffff0000u);
+}
 __device__ __forceinline__ void st4(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
   *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
@@ -42,6 +53,16 @@ __global__ void cast_scale_drop_kernel(const float* __restrict__ in, TOut* __res
   for (int e = 0; e < 4; ++e) v[e] *= scale * dr.factor(i + e);
   st4(out + i, v);
 }
+// bf16 activations: the result is rounded to bf16, so the one-MUFU forms (tanh.approx, error ~5e-4) are exact enough;
+// fp32 activations (the gradient-parity mode) keep expf and a true division.
+template <typename TA> __device__ __forceinline__ float swish_act(float x) {
+  if constexpr (sizeof(TA) == 2) return swish_tanh(x);
+  else return swish_f(x);
+}
+template <typename TA> __device__ __forceinline__ float sigmoid_act(float x) {
+  if constexpr (sizeof(TA) == 2) return sigmoid_tanh(x);
+  else return sigmoid_f(x);
+}
 template <typename TA>
 __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -49,7 +70,7 @@ __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict_
   float v[4];
   ld4(hp + i, v);
 #pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = swish_f(v[e]) * dr.factor(i + e);
+  for (int e = 0; e < 4; ++e) v[e] = swish_act<TA>(v[e]) * dr.factor(i + e);
   st4(out + i, v);
 }
 template <typename TA>
@@ -61,7 +82,7 @@ __global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __
   ld4(dh + i, g);
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
-    const float s = sigmoid_f(x[e]);
+    const float s = sigmoid_act<TA>(x[e]);
     g[e] *= dr.factor(i + e) * (s + x[e] * s * (1.f - s));
   }
   st4(out + i, g);
@@ -203,9 +224,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < d; i += blockDim.x) {
-    atomicAdd(dgamma + i, red[i]);
-    atomicAdd(dbeta + i, red[d + i]);
+  if ((d & 3) == 0 && ((reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0) {
+    for (int i = threadIdx.x * 4; i < 2 * d; i += blockDim.x * 4) {       // 16-byte vector reductions: 4x fewer L2 atomics
+      float* dst = i < d ? dgamma + i : dbeta + (i - d);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(red[i]), "f"(red[i + 1]), "f"(red[i + 2]),
+                   "f"(red[i + 3])
+                   : "memory");
+    }
+  } else {
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+      atomicAdd(dgamma + i, red[i]);
+      atomicAdd(dbeta + i, red[d + i]);
+    }
   }
 }
 
@@ -416,6 +446,84 @@ __global__ void col2im_relu_kernel(const TA* __restrict__ dcol, const TA* __rest
   }
   dout1[i] = acc;
 }
+// Fused front-end tail of the backward: dOut1 = relu'(out1) * col2im(dcol) is never written - each thread gathers it for
+// 8 channels of one (b, t1, f1) position (<= 4 taps of dcol, 16-byte loads) and immediately accumulates conv_1's
+// parameter gradients  dw[c][kh*3+kw] += dOut1 * mel[b][2 f1 + kh][2 t1 + kw],  db[c] += dOut1  in registers; a block
+// walks positions grid-stride, reduces in shared memory and adds once to global memory.
+template <typename TA>
+__global__ void __launch_bounds__(256) conv1_wgrad_fused_kernel(const TA* __restrict__ dcol, const TA* __restrict__ out1,
+                                                               const float* __restrict__ mel, float* __restrict__ dw,
+                                                               float* __restrict__ db, ConvGeom g, int n_mel, int Tin, int T1, int py) {
+  extern __shared__ float red[];                                // [C][10]
+  const int cg = g.C >> 3;                                      // groups of 8 channels
+  const int c8 = threadIdx.x % cg, pl = threadIdx.x / cg;
+  for (int i = threadIdx.x; i < g.C * 10; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float acc[9][8], accb[8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) accb[e] = 0.f;
+  const int64_t npos = static_cast<int64_t>(g.B) * T1 * g.F1;
+  if (pl < py) {
+    for (int64_t pos = static_cast<int64_t>(blockIdx.x) * py + pl; pos < npos; pos += static_cast<int64_t>(gridDim.x) * py) {
+      const int f1 = static_cast<int>(pos % g.F1), t1 = static_cast<int>((pos / g.F1) % T1), b = static_cast<int>(pos / (static_cast<int64_t>(g.F1) * T1));
+      float o[8], gsum[8];
+      ld8(out1 + ((static_cast<int64_t>(b) * g.T1p + t1) * g.F1 + f1) * g.C + c8 * 8, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) gsum[e] = 0.f;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tt = t1 - kw;
+        if (tt < 0 || (tt & 1) || (tt >> 1) >= g.T2) continue;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ff = f1 - kh;
+          if (ff < 0 || (ff & 1) || (ff >> 1) >= g.F2) continue;
+          const int64_t m = (static_cast<int64_t>(b) * g.T2 + (tt >> 1)) * g.F2 + (ff >> 1);
+          float v[8];
+          ld8(dcol + (m * 9 + (kw * 3 + kh)) * g.C + c8 * 8, v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) gsum[e] += v[e];
+        }
+      }
+      bool any = false;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        gsum[e] = o[e] > 0.f ? gsum[e] : 0.f;
+        any |= gsum[e] != 0.f;
+      }
+      if (!any) continue;
+      const float* mrow = mel + (static_cast<int64_t>(b) * n_mel + 2 * f1) * Tin + 2 * t1;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const float mv = __ldg(mrow + static_cast<int64_t>(kh) * Tin + kw);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[kh * 3 + kw][e] = fmaf(gsum[e], mv, acc[kh * 3 + kw][e]);
+        }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) accb[e] += gsum[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float* r = red + (c8 * 8 + e) * 10;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) atomicAdd(r + k, acc[k][e]);
+      atomicAdd(r + 9, accb[e]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < g.C * 10; i += blockDim.x) {
+    const int c = i / 10, k = i - c * 10;
+    if (k < 9) atomicAdd(dw + c * 9 + k, red[i]);
+    else atomicAdd(db + c, red[i]);
+  }
+}
+
 // conv_1 parameter gradients: dw[c][kh*3+kw] += sum_{b,t1,f1} dout1[b,t1,f1,c] mel[b][2 f1 + kh][2 t1 + kw]; db[c] += sum dout1.
 // block = (32 channels) x (a slab of t1 rows of one utterance)
 __global__ void conv1_wgrad_kernel(const float* __restrict__ dout1, const float* __restrict__ mel, float* __restrict__ dw, float* __restrict__ db,
@@ -518,7 +626,10 @@ int colsum_add(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool accumulate, float* dgamma, float* dbeta, int64_t rows,
            int d, cudaStream_t st) {
   CFM_REQUIRE(d <= 1024, "LayerNorm backward supports d_model <= 1024");
-  const int rpw = 2, warps = 8;
+  // about two blocks per SM: every block ends with 2*d atomics on the same addresses, which serialise in the L2
+  const int warps = 8;
+  int rpw = static_cast<int>((rows + 296 * warps - 1) / (296 * warps));
+  if (rpw < 2) rpw = 2;
   const unsigned grid = nblk(rows, rpw * warps);
   const size_t smem = static_cast<size_t>(2) * d * 4;
   const int nv = (d + 31) / 32;
@@ -596,6 +707,15 @@ int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int 
   LAUNCH_OK();
 }
 
+template <typename TA>
+int conv1_wgrad_fused(const TA* dcol, const TA* out1, const float* mel, float* dw, float* db, const ConvGeom& g, int n_mel, int Tin, int T1,
+                      int num_sms, cudaStream_t st) {
+  CFM_REQUIRE(g.C % 8 == 0 && g.C / 8 <= 256, "fused conv_1 weight gradient needs a channel count that is a multiple of 8 (<= 2048)");
+  const int cg = g.C / 8, py = 256 / cg;
+  conv1_wgrad_fused_kernel<TA><<<2 * num_sms, cg * py, static_cast<size_t>(g.C) * 10 * 4, st>>>(dcol, out1, mel, dw, db, g, n_mel, Tin, T1, py);
+  LAUNCH_OK();
+}
+
 #define INST_TA(T)                                                                                                   \
   template int swish_drop_fwd<T>(const T*, T*, int64_t, Drop, cudaStream_t);                                          \
   template int swish_drop_bwd<T>(const float*, const T*, T*, int64_t, Drop, cudaStream_t);                            \
@@ -609,6 +729,7 @@ int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int 
   template int bn_swish_fwd<T>(const float*, const float*, const float*, const float*, T*, int64_t, int, cudaStream_t); \
   template int im2col_t<T>(const T*, T*, const ConvGeom&, int64_t, int64_t, cudaStream_t);                            \
   template int col2im_relu<T>(const T*, const T*, float*, const ConvGeom&, cudaStream_t);                             \
+  template int conv1_wgrad_fused<T>(const T*, const T*, const float*, float*, float*, const ConvGeom&, int, int, int, int, cudaStream_t); \
   template int cast_scale_drop<T>(const float*, T*, int64_t, float, Drop, cudaStream_t);
 INST_TA(float)
 INST_TA(bf16)

@@ -173,7 +173,9 @@ class _Native(nn.Module):
         return {k: v for k, v in self.state_dict(keep_vars=True).items() if v.is_floating_point()}
 
     def _version_key(self, tensors) -> Tuple:
-        return tuple((t.data_ptr(), t._version) for t in tensors)
+        # (address, autograd version) per tensor: an in-place update or a re-assignment triggers a re-pack.  Tensors
+        # created under torch.inference_mode() carry no version counter; for those only a new address is noticed.
+        return tuple((t.data_ptr(), 0 if t.is_inference() else t._version) for t in tensors)
 
     def _drop_handles(self) -> None:
         for h, _, _ in self._handles.values():

@@ -183,6 +183,22 @@ def test_reload_weights_repacks():
     assert_close_fp32(y, gold["y"], "reloaded")
 
 
+def test_module_built_under_inference_mode():
+    """Parameters created inside torch.inference_mode() carry no version counter (bench.py builds its strong-scaling
+    replica that way at N > 1): the handle cache must still work, and a reload must still re-pack."""
+    case = ENCODER_CASES[0]
+    cfg = case["cfg"]
+    with torch.inference_mode():
+        enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+        enc.load_state_dict(synth_encoder_state_dict(cfg, case["seed"]))
+        enc = enc.to(DEV).eval()
+        _, x, lengths, gold = _encoder_case(case)
+        y, _ = enc(x, lengths)
+        y2, _ = enc(x, lengths)
+    assert_close_fp32(y, gold["y"], "inference-mode module")
+    assert torch.equal(y, y2)
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("name,cfg,B,Tin,full", [("C2-M", CONFORMER_M, 64, 1501, True), ("C3-L", CONFORMER_L, 32, 2001, False),
                                                  ("C5-M", CONFORMER_M, 16, 6001, True), ("C2-M-varlen", CONFORMER_M, 8, 1501, False)])
@@ -327,11 +343,13 @@ def test_block_bf16_fused_conv_residual(T):
     print(assert_close_bf16(got, want, "block bf16"))
 
 
-@pytest.mark.parametrize("rows", [(1, 1), (2, 100), (3, 374), (5, 128), (64, 374), (40, 500), (149, 128), (300, 127)])
+@pytest.mark.parametrize("rows", [(1, 1), (1, 127), (1, 128), (1, 129), (1, 255), (1, 256), (1, 257), (2, 100), (3, 374),
+                                  (5, 128), (64, 374), (40, 500), (149, 128), (300, 127), (75, 256), (37, 513)])
 def test_ffn_module_bf16_fused_vs_oracle(rows):
-    """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel.  More than 148
-    row tiles (one per SM) exercises the balanced schedule: left-over tiles are split along the hidden dimension
-    across CTAs and summed by the reduction store."""
+    """d_model = 256 in bf16 mode routes FeedForwardModule to the fused LN->GEMM->Swish->GEMM kernel, which runs on CTA
+    pairs: a pair owns a 256-row tile, each CTA 128 rows of it (row counts around 128 / 256 leave the peer CTA with no
+    or partial rows).  More than 74 pair tiles (one per pair of SMs) exercises the balanced schedule: left-over tiles are
+    split along the hidden dimension across pairs and summed by the reduction store."""
     B, T = rows
     d = 256
     sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 60), "layers.0.ffn_1.")
@@ -584,7 +602,7 @@ def test_ffn_shared_row_tiles_two_streams_match_single_tile_rows():
     d = 256
     sd = sub(synth_encoder_state_dict(cb.EncoderConfig(80, 1, d, 4, 31), 61), "layers.0.ffn_1.")
     m = _load(cb.FeedForwardModule(d), sd).set_compute("bf16")
-    M = 148 * 128 + 39 * 128 + 17                       # 188 tiles: 40 of them shared
+    M = 148 * 128 + 39 * 128 + 17                       # 94 tiles of 256 rows on 74 CTA pairs: 20 of them shared
     g = torch.Generator().manual_seed(61)
     x = (torch.randn(1, M, d, generator=g) * 1.5 + 0.3).to(DEV)
     ref = torch.cat([m(x[:, i:i + 64 * 128]) for i in range(0, M, 64 * 128)], dim=1)
