@@ -567,6 +567,9 @@ def run_train_bench(args, cfg, batch, t_in, desc):
             dist.destroy_process_group()
         return
     fl = 3.0 * encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
+    from conformer_b200.training import encoder_train_state
+    enc_mod = next(m for m in model.modules() if hasattr(m, "_train_state"))
+    graph_stats = encoder_train_state(enc_mod).graph_stats()       # native calls launched directly / captured / replayed
     line = {"metric": "training-step audio-seconds per second", "value": world * secs / (ms * 1e-3), "unit": "audio-s/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
@@ -576,7 +579,7 @@ def run_train_bench(args, cfg, batch, t_in, desc):
                        "step": "encoder fwd/bwd in the native library (training-mode BatchNorm, dropout), CTC head + CTC loss + Adam in PyTorch (outside the path)"},
             "forward_ms": fwd_ms, "backward_ms": bwd_ms, "final_loss": loss_v,
             "algorithmic_tflops_encoder": fl / (ms * 1e-3) / 1e12, "allreduce": allreduce, "clocks": clocks,
-            "gpu_launches": None}
+            "cuda_graphs": graph_stats, "gpu_launches": None}
     if eager is not None:
         line["gpu_eager_baseline"] = eager
     print(json.dumps(line), flush=True)

@@ -65,6 +65,20 @@ int cfm_train_bind(cfm_module_t m, int compute) {
   CFM_REQUIRE(m != nullptr, "null module handle");
   return m->train_bind(compute);
 }
+int cfm_train_set_graphs(cfm_module_t m, int32_t enable) {
+  if (m == nullptr) return 1;
+  m->train.graphs_on = enable != 0;
+  if (!m->train.graphs_on) m->train_drop_graphs();
+  return 0;
+}
+int cfm_train_graph_stats(cfm_module_t m, int64_t* out4) {
+  if (m == nullptr || out4 == nullptr) return 1;
+  out4[0] = m->train.n_direct;
+  out4[1] = m->train.n_captured;
+  out4[2] = m->train.n_replayed;
+  out4[3] = m->train.n_failed;
+  return 0;
+}
 int cfm_train_refresh(cfm_module_t m, void* stream) {
   CFM_REQUIRE(m != nullptr, "null module handle");
   return m->train_refresh(S(stream));

@@ -149,15 +149,28 @@ struct TrainTape {
   bool valid = false;
   int B = 0, Tin = 0, T2 = 0;
   float p = 0.f;
-  uint64_t seed = 0;
   const float* mel = nullptr;
   void *out1 = nullptr, *h2 = nullptr, *pe = nullptr, *kp = nullptr;
   float* x0 = nullptr;
   size_t end_of_tape = 0;
   std::vector<BlockTape> blocks;
 };
+// One captured launch sequence of the training step (a whole forward, one block range of the backward, the weight
+// refresh): the second call with the same key captures it on a private stream, later calls replay it.
+struct TrainGraph {
+  uint64_t key[10] = {};
+  int seen = 0;
+  bool dead = false;                   // capture failed once: this key always launches directly
+  cudaGraphExec_t exec = nullptr;
+  TrainTape tape;                      // forward graphs: the tape the captured run laid out
+};
 struct TrainState {
   bool bound = false;
+  bool graphs_on = true;
+  uint32_t* seed_dev = nullptr;        // {lo, hi} of the step's dropout seed
+  cudaStream_t cap_stream = nullptr;
+  std::vector<TrainGraph> graphs;
+  int64_t n_direct = 0, n_captured = 0, n_replayed = 0, n_failed = 0;   // cfm_train_graph_stats
   TrainLinear conv2, lin;
   float *conv2_packed = nullptr, *lin_packed = nullptr;
   const float *c1_w = nullptr, *c1_b = nullptr, *div_term = nullptr;
@@ -183,6 +196,8 @@ struct Module {
   struct HostSlot { cudaEvent_t copied_in = nullptr, computed = nullptr, copied_out = nullptr; };
   std::unordered_map<void*, HostSlot> host_slots;
   ~Module() {
+    train_drop_graphs();
+    if (train.cap_stream != nullptr) cudaStreamDestroy(train.cap_stream);
     for (auto& kv : host_slots) {
       if (kv.second.copied_in) cudaEventDestroy(kv.second.copied_in);
       if (kv.second.computed) cudaEventDestroy(kv.second.computed);
@@ -212,9 +227,10 @@ struct Module {
   int train_forward(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, void* ws, int64_t ws_bytes,
                     float p_drop, uint64_t seed, cudaStream_t stream);
   int train_backward(const float* dy, int block_hi, int block_lo, bool front, void* ws, int64_t ws_bytes, cudaStream_t stream);
+  void train_drop_graphs();
   template <typename TA>
   int train_forward_impl(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, Workspace& ws, float p_drop,
-                         uint64_t seed, cudaStream_t stream);
+                         cudaStream_t stream);
   template <typename TA>
   int train_backward_impl(const float* dy, int block_hi, int block_lo, bool front, void* ws, int64_t ws_bytes, cudaStream_t stream);
   template <typename TA>

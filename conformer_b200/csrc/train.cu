@@ -40,7 +40,7 @@ struct TC {                               // per-call context
   int num_sms;
   Workspace* ws;
   float p;
-  uint64_t seed;
+  const uint32_t* seed;                   // device
   Drop drop(int block, int site) const { return make_drop(p, seed, static_cast<uint32_t>(1 + block * SITES_PER_BLOCK + site)); }
 };
 
@@ -179,6 +179,9 @@ int Module::train_bind(int compute_mode) {
     n.dg = Gp(pre + ".weight", d); n.db = Gp(pre + ".bias", d);
   };
   TrainState& t = train;
+  train_drop_graphs();                                       // every pointer below is baked into the captured launches
+  t.seed_dev = static_cast<uint32_t*>(arena.take(256));
+  if (t.seed_dev == nullptr) { set_error("weight arena exhausted"); return 4; }
   t.blocks.assign(L, TrainBlock{});
   lin(t.conv2, "downsampling_conv.conv_2", d, 9 * d);
   t.conv2_packed = static_cast<float*>(arena.take(static_cast<size_t>(d) * 9 * d * 4));
@@ -238,10 +241,17 @@ static int refresh_linear(const TrainLinear& l, const float* src, bool bf16_mode
   }
   return 0;
 }
+static int train_graphed_refresh(Module& m, cudaStream_t st);
+
 int Module::train_refresh(cudaStream_t st) {
   CFM_REQUIRE(train.bound, "call cfm_train_bind first");
-  const int d = cfg.d_model, F2 = freq_bins();
-  TrainState& t = train;
+  return train_graphed_refresh(*this, st);
+}
+
+static int train_refresh_body(Module& m, cudaStream_t st) {
+  const bool bf16_mode = m.bf16_mode;
+  const int d = m.cfg.d_model, F2 = m.freq_bins();
+  TrainState& t = m.train;
   CFM_TRY(pack_conv2_weight(t.conv2.w, t.conv2_packed, d, st));
   CFM_TRY(pack_linear_weight(t.lin.w, t.lin_packed, d, d, F2, st));
   CFM_TRY(refresh_linear<float>(t.conv2, t.conv2_packed, bf16_mode, st));
@@ -256,18 +266,18 @@ int Module::train_refresh(cudaStream_t st) {
 // =================================================================================== forward
 template <typename TA>
 int Module::train_forward_impl(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, Workspace& ws,
-                               float p_drop, uint64_t seed, cudaStream_t st) {
+                               float p_drop, cudaStream_t st) {
   const int d = cfg.d_model, H = cfg.n_heads, dh = d / H, ks = cfg.kernel_size, n_mel = cfg.n_mel_channels, L = cfg.n_blocks;
   const int T1 = (Tin - 1) / 2, T2 = (T1 - 1) / 2, F1 = (n_mel - 1) / 2, F2 = (F1 - 1) / 2, T1p = T1 + (T1 & 1);
   CFM_REQUIRE(Tin >= 7 && T2 >= 1 && F2 >= 1, "input too short for two stride-2 3x3 convolutions");
   const int64_t M = static_cast<int64_t>(B) * T2, M2 = M * F2;
   const int R = 2 * T2 - 1;
-  TC c{st, num_sms, &ws, p_drop, seed};
+  TC c{st, num_sms, &ws, p_drop, train.seed_dev};
   TrainState& t = train;
   const bool run = !ws.measuring();
   t.tape = TrainTape{};
   TrainTape& tp = t.tape;
-  tp.B = B; tp.Tin = Tin; tp.T2 = T2; tp.p = p_drop; tp.seed = seed; tp.mel = mel;
+  tp.B = B; tp.Tin = Tin; tp.T2 = T2; tp.p = p_drop; tp.mel = mel;
   // ---- tape (lives until the backward) ----
   TAKE(out1, TA, static_cast<int64_t>(B) * T1p * F1 * d);
   TAKE(h2, TA, M2 * d);
@@ -306,7 +316,7 @@ int Module::train_forward_impl(const float* mel, const int64_t* len_in, float* y
                    EPI_BIAS_RELU, nullptr, 0.f, &g));
   CFM_TRY(gemm_any(c, static_cast<const TA*>(h2), F2 * d, WSel<TA>::w(t.lin), t.lin.b, x0, d, static_cast<int>(M), d, F2 * d, EPI_BIAS_F32,
                    nullptr, 0.f));
-  CFM_TRY(drop_inplace(x0, M * d, make_drop(p_drop, seed, SITE_INPUT), st));
+  CFM_TRY(drop_inplace(x0, M * d, make_drop(p_drop, t.seed_dev, SITE_INPUT), st));
   if (len_in != nullptr) CFM_TRY(lengths_and_mask(len_in, len_out ? len_out : lens, kp, B, T2, true, false, st));
   CFM_TRY(rel_pos_table<TA>(t.div_term, static_cast<TA*>(pe), T2, d, st));
 
@@ -388,7 +398,7 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
   Workspace ws;
   ws.init(ws_base, static_cast<size_t>(ws_bytes), false);
   ws.take(tp.end_of_tape);
-  TC c{st, num_sms, &ws, tp.p, tp.seed};
+  TC c{st, num_sms, &ws, tp.p, train.seed_dev};
   TAKE(dx, float, M * d);                 // gradient of the residual stream (persists across calls: first allocation)
   TAKE(f32a, float, M * 4 * d);
   TAKE(f32b, float, M * d);
@@ -466,7 +476,7 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
   TAKE(dout1, float, static_cast<int64_t>(B) * T1p * F1 * d);
   const TA* h2 = static_cast<const TA*>(tp.h2);
   const TA* out1 = static_cast<const TA*>(tp.out1);
-  CFM_TRY(cast_scale_drop<TA>(dx, dxl, M * d, 1.f, make_drop(tp.p, tp.seed, SITE_INPUT), st));
+  CFM_TRY(cast_scale_drop<TA>(dx, dxl, M * d, 1.f, make_drop(tp.p, t.seed_dev, SITE_INPUT), st));
   // Encoder.linear on the channels-last flatten: gradient in the packed column order, then scattered to the parameter's
   {
     const int K = F2 * d;
@@ -507,8 +517,8 @@ int64_t Module::train_workspace_bytes(int B, int Tin) {
   if (!train.bound) { set_error("call cfm_train_bind first"); return -1; }
   Workspace ws;
   ws.init(nullptr, 0, true);
-  int s = bf16_mode ? train_forward_impl<bf16>(nullptr, reinterpret_cast<const int64_t*>(8), nullptr, nullptr, B, Tin, ws, 0.f, 0, nullptr)
-                    : train_forward_impl<float>(nullptr, reinterpret_cast<const int64_t*>(8), nullptr, nullptr, B, Tin, ws, 0.f, 0, nullptr);
+  int s = bf16_mode ? train_forward_impl<bf16>(nullptr, reinterpret_cast<const int64_t*>(8), nullptr, nullptr, B, Tin, ws, 0.f, nullptr)
+                    : train_forward_impl<float>(nullptr, reinterpret_cast<const int64_t*>(8), nullptr, nullptr, B, Tin, ws, 0.f, nullptr);
   if (s != 0) return -1;
   const size_t tape = train.tape.end_of_tape, fwd_peak = ws.peak();
   // backward scratch (the larger of the block phase and the front-end phase), sized generously from the shapes
@@ -525,21 +535,129 @@ int64_t Module::train_workspace_bytes(int B, int Tin) {
   return static_cast<int64_t>((fwd_peak > bwd ? fwd_peak : bwd) + 4096);
 }
 
+// ---- CUDA graphs of the step's launch sequences -------------------------------------------------------------------
+// The training step is ~2 500 small launches and the host cannot issue them as fast as the GPU retires them.  Every
+// argument of those launches is a function of (pointers, shapes, dropout rate) - the dropout seed lives in device memory -
+// so a sequence seen twice with the same key is captured (on a private stream: the caller's may be the legacy default
+// stream, which cannot capture) and replayed from then on with one cudaGraphLaunch on the caller's stream.
+namespace {
+__global__ void set_seed_kernel(uint32_t* dst, uint32_t lo, uint32_t hi) {
+  dst[0] = lo;
+  dst[1] = hi;
+}
+uint64_t key_ptr(const void* p) { return static_cast<uint64_t>(reinterpret_cast<uintptr_t>(p)); }
+}  // namespace
+
+void Module::train_drop_graphs() {
+  for (TrainGraph& g : train.graphs)
+    if (g.exec != nullptr) cudaGraphExecDestroy(g.exec);
+  train.graphs.clear();
+}
+
+template <class Body>
+static int train_graphed(Module& m, const uint64_t (&key)[10], bool is_forward, cudaStream_t st, Body&& body) {
+  TrainState& t = m.train;
+  if (!t.graphs_on) {
+    ++t.n_direct;
+    return body(st);
+  }
+  TrainGraph* g = nullptr;
+  for (TrainGraph& c : t.graphs)
+    if (std::memcmp(c.key, key, sizeof(key)) == 0) {
+      g = &c;
+      break;
+    }
+  if (g != nullptr && g->exec != nullptr) {
+    if (is_forward) t.tape = g->tape;
+    CFM_CUDA_OK(cudaGraphLaunch(g->exec, st));
+    ++t.n_replayed;
+    return 0;
+  }
+  if (g == nullptr) {                                            // first sighting: run directly (also sets kernel attributes)
+    if (t.graphs.size() < 512) {
+      TrainGraph n;
+      std::memcpy(n.key, key, sizeof(key));
+      n.seen = 1;
+      t.graphs.push_back(n);
+    }
+    ++t.n_direct;
+    return body(st);
+  }
+  if (g->dead) {
+    ++t.n_direct;
+    return body(st);
+  }
+  if (t.cap_stream == nullptr) CFM_CUDA_OK(cudaStreamCreateWithFlags(&t.cap_stream, cudaStreamNonBlocking));
+  if (cudaStreamBeginCapture(t.cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    g->dead = true;
+    ++t.n_failed;
+    return body(st);
+  }
+  const int s = body(t.cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(t.cap_stream, &graph);
+  if (s != 0 || e != cudaSuccess || graph == nullptr) {
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g->dead = true;
+    ++t.n_failed;
+    return s != 0 ? s : body(st);
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess || exec == nullptr) {
+    cudaGetLastError();
+    g->dead = true;
+    ++t.n_failed;
+    return body(st);
+  }
+  g->exec = exec;
+  ++t.n_captured;
+  if (is_forward) g->tape = t.tape;
+  CFM_CUDA_OK(cudaGraphLaunch(g->exec, st));
+  return 0;
+}
+
+static int train_graphed_refresh(Module& m, cudaStream_t st) {
+  const uint64_t key[10] = {3};
+  return train_graphed(m, key, false, st, [&](cudaStream_t s) { return train_refresh_body(m, s); });
+}
+
 int Module::train_forward(const float* mel, const int64_t* len_in, float* y, int64_t* len_out, int B, int Tin, void* wsp, int64_t ws_bytes,
                           float p_drop, uint64_t seed, cudaStream_t st) {
   CFM_REQUIRE(train.bound, "call cfm_train_bind first");
   CFM_REQUIRE(mel != nullptr && y != nullptr && wsp != nullptr && B > 0, "bad training-forward arguments");
   CFM_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout rate must be in [0, 1)");
-  Workspace ws;
-  ws.init(wsp, static_cast<size_t>(ws_bytes), false);
-  return bf16_mode ? train_forward_impl<bf16>(mel, len_in, y, len_out, B, Tin, ws, p_drop, seed, st)
-                   : train_forward_impl<float>(mel, len_in, y, len_out, B, Tin, ws, p_drop, seed, st);
+  set_seed_kernel<<<1, 1, 0, st>>>(train.seed_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  CFM_CUDA_OK(cudaGetLastError());
+  uint32_t pbits;
+  std::memcpy(&pbits, &p_drop, 4);
+  const uint64_t key[10] = {1, key_ptr(mel), key_ptr(len_in), key_ptr(y), key_ptr(len_out), key_ptr(wsp), static_cast<uint64_t>(ws_bytes),
+                            static_cast<uint64_t>(B), static_cast<uint64_t>(Tin), pbits};
+  return train_graphed(*this, key, true, st, [&](cudaStream_t s) {
+    Workspace ws;
+    ws.init(wsp, static_cast<size_t>(ws_bytes), false);
+    return bf16_mode ? train_forward_impl<bf16>(mel, len_in, y, len_out, B, Tin, ws, p_drop, s)
+                     : train_forward_impl<float>(mel, len_in, y, len_out, B, Tin, ws, p_drop, s);
+  });
 }
 
 int Module::train_backward(const float* dy, int block_hi, int block_lo, bool front, void* wsp, int64_t ws_bytes, cudaStream_t st) {
   CFM_REQUIRE(train.bound, "call cfm_train_bind first");
-  return bf16_mode ? train_backward_impl<bf16>(dy, block_hi, block_lo, front, wsp, ws_bytes, st)
-                   : train_backward_impl<float>(dy, block_hi, block_lo, front, wsp, ws_bytes, st);
+  const TrainTape& tp = train.tape;
+  CFM_REQUIRE(tp.valid, "cfm_encoder_train_backward needs the tape of a preceding cfm_encoder_train_forward");
+  uint32_t pbits;
+  std::memcpy(&pbits, &tp.p, 4);
+  // the tape's layout is a function of (workspace, B, Tin, lengths given); mel is read again by conv_1's weight gradient
+  const uint64_t key[10] = {2, key_ptr(dy), key_ptr(wsp), static_cast<uint64_t>(ws_bytes), key_ptr(tp.mel),
+                            (static_cast<uint64_t>(tp.B) << 32) | static_cast<uint64_t>(tp.Tin), tp.kp != nullptr ? 1u : 0u, pbits,
+                            (static_cast<uint64_t>(block_hi) << 32) | static_cast<uint64_t>(block_lo), front ? 1u : 0u};
+  return train_graphed(*this, key, false, st, [&](cudaStream_t s) {
+    return bf16_mode ? train_backward_impl<bf16>(dy, block_hi, block_lo, front, wsp, ws_bytes, s)
+                     : train_backward_impl<float>(dy, block_hi, block_lo, front, wsp, ws_bytes, s);
+  });
 }
 
 }  // namespace cfm

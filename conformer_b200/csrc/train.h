@@ -6,27 +6,31 @@ namespace cfm {
 
 // nn.Dropout as a stateless hash: element i of dropout site `site` is kept with probability 1 - p and scaled by
 // 1 / (1 - p); the same (seed, site, i) gives the same decision in the forward and in the backward pass.
+// Stateless dropout: keep/drop of element i of dropout site `site` is a hash of (seed, site, i), so the backward
+// regenerates the forward's mask instead of storing it.  The seed is read from DEVICE memory (two 32-bit words written by
+// cfm_encoder_train_forward before the step's kernels): kernel arguments then do not change from step to step, which is
+// what lets a whole training forward / block backward replay as a CUDA graph.
 struct Drop {
   float p = 0.f, inv_keep = 1.f;
-  uint32_t seed_lo = 0, seed_hi = 0, site = 0;
+  const uint32_t* seed = nullptr;       // device: {lo, hi}
+  uint32_t site = 0;
   // one 32-bit hash per PAIR of elements, 16 bits each (kernels handle 4 consecutive elements per thread, so the hash
   // of a pair is computed once)
-  __host__ __device__ __forceinline__ float factor(int64_t i) const {
+  __device__ __forceinline__ float factor(int64_t i) const {
     if (p <= 0.f) return 1.f;
     const uint64_t j = static_cast<uint64_t>(i) >> 1;
-    uint32_t h = seed_lo ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(j >> 32) * 0x85EBCA6Bu);
+    uint32_t h = __ldg(seed) ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(j >> 32) * 0x85EBCA6Bu);
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-    h ^= seed_hi; h *= 0x9E3779B1u; h ^= h >> 15;
+    h ^= __ldg(seed + 1); h *= 0x9E3779B1u; h ^= h >> 15;
     const uint32_t u = (i & 1) ? (h >> 16) : (h & 0xFFFFu);
     return (static_cast<float>(u) * (1.0f / 65536.0f)) >= p ? inv_keep : 0.f;
   }
 };
-inline Drop make_drop(float p, uint64_t seed, uint32_t site) {
+inline Drop make_drop(float p, const uint32_t* seed_dev, uint32_t site) {
   Drop d;
   d.p = p;
   d.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  d.seed_lo = static_cast<uint32_t>(seed);
-  d.seed_hi = static_cast<uint32_t>(seed >> 32);
+  d.seed = seed_dev;
   d.site = site;
   return d;
 }

@@ -33,6 +33,7 @@ class TrainState:
         self.workspace: Optional[torch.Tensor] = None
         self.seed = 0x5EED
         self.step = 0
+        self.graphs = True               # replay the step's launch sequences as CUDA graphs (cfm_train_set_graphs)
         self.on_block_done: Optional[Callable[[int, int, int], None]] = None      # (block index or -1 for the front-end, lo, hi)
         self.params = [(n, p) for n, p in enc.named_parameters() if p.requires_grad]
         sizes = [p.numel() for _, p in self.params]
@@ -89,10 +90,24 @@ class TrainState:
             for (name, _), v in zip(self.params, self.views):
                 check(lib().cfm_module_set_grad(h, name.encode(), v.data_ptr(), v.numel()))
             check(lib().cfm_train_bind(h, compute))
+            check(lib().cfm_train_set_graphs(h, 1 if self.graphs else 0))
         except Exception:
             lib().cfm_module_destroy(h)
             raise
         self.handle, self.key, self.compute = h, key, compute
+
+    def set_graphs(self, enable: bool) -> None:
+        """CUDA-graph replay of the forward / per-block backward / weight refresh (on by default)."""
+        self.graphs = bool(enable)
+        if self.handle is not None:
+            check(lib().cfm_train_set_graphs(self.handle, 1 if self.graphs else 0))
+
+    def graph_stats(self) -> dict:
+        """{'direct', 'captured', 'replayed', 'failed'} call counts of the native handle (cfm_train_graph_stats)."""
+        out = (C.c_int64 * 4)()
+        if self.handle is not None:
+            check(lib().cfm_train_graph_stats(self.handle, out))
+        return dict(zip(("direct", "captured", "replayed", "failed"), (int(v) for v in out)))
 
     def __del__(self):
         try:
@@ -149,13 +164,20 @@ class _EncoderTrainFn(torch.autograd.Function):
         return None, None, None, None, None
 
 
-def encoder_train_forward(enc, x: torch.Tensor, lengths: Optional[torch.Tensor]):
-    """Encoder.forward in training mode (called by modules.Encoder.forward)."""
-    dev = x.device
+def encoder_train_state(enc, device=None) -> TrainState:
+    """The native training state of an Encoder on `device` (default: where its parameters are), created on first use."""
+    dev = torch.device(device) if device is not None else next(enc.parameters()).device
     st = enc._train_state
     if st is None or st.device != dev:
         st = TrainState(enc, dev)
         object.__setattr__(enc, "_train_state", st)
+    return st
+
+
+def encoder_train_forward(enc, x: torch.Tensor, lengths: Optional[torch.Tensor]):
+    """Encoder.forward in training mode (called by modules.Encoder.forward)."""
+    dev = x.device
+    st = encoder_train_state(enc, dev)
     compute = enc._compute()
     with _on_device(dev):
         st.bind(enc, compute)

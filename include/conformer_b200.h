@@ -204,6 +204,15 @@ CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_clas
 CFM_API int cfm_module_set_grad(cfm_module_t m, const char* name, float* grad, int64_t numel);
 CFM_API int cfm_train_bind(cfm_module_t m, int compute);
 CFM_API int cfm_train_refresh(cfm_module_t m, void* stream);
+/* CUDA graphs of the training step (default: on).  A training forward, a block range of the backward or the weight
+ * refresh that is called a second time with the same arguments (pointers, shapes, dropout rate) is captured and from
+ * then on replayed with one graph launch on the caller's stream; the dropout seed is passed through device memory, so
+ * it may change from step to step.  Any other argument that changes makes that call launch directly (and is remembered
+ * in turn).  cfm_train_bind discards all graphs.  Buffers named in a captured call (input, lengths, output, workspace,
+ * output gradient) must stay allocated while the handle may replay it. */
+CFM_API int cfm_train_set_graphs(cfm_module_t m, int32_t enable);
+/* out4 = {calls launched directly, sequences captured, graph replays, captures that failed (those keys stay direct)} */
+CFM_API int cfm_train_graph_stats(cfm_module_t m, int64_t* out4);
 /* One buffer holds the tape (activations kept for the backward) followed by scratch. */
 CFM_API int64_t cfm_encoder_train_workspace_bytes(cfm_module_t m, int32_t batch, int32_t Tin);
 /* Encoder.forward(x, lengths) in TRAINING mode: dropout with rate dropout_p at every nn.Dropout of the path (stateless
