@@ -710,13 +710,15 @@ def main():
         lo_hosts = [lo_host] + [torch.empty_like(lo_host).pin_memory() for _ in range(n_slots - 1)]
         e2e_count = [0]
 
-        def make_e2e_step(xh):
+        def make_e2e_step(xh, yhs=None):
+            yhs = y_hosts if yhs is None else yhs
+
             def step():
                 k = e2e_count[0]
                 e2e_count[0] += 1
                 st = b.streams[k % n_dev_streams]
                 with torch.cuda.stream(st):
-                    enc.forward_host_pipelined(xh, b.lengths_host, y_hosts[k % n_slots], lo_hosts[k % n_slots], k % n_slots,
+                    enc.forward_host_pipelined(xh, b.lengths_host, yhs[k % n_slots], lo_hosts[k % n_slots], k % n_slots,
                                                copy_in, copy_out)
                 return copy_out                       # a step is complete when its result has landed on the host
             return step
@@ -727,13 +729,22 @@ def main():
             step_e2e()
         torch.cuda.synchronize()
         ms_e2e, ms_e2e_median = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_e2e)
-        ms_e2e_fp32in = None
+        ms_e2e_fp32in = ms_e2e_bf16out = None
         if bf16_in:
             step_f32 = make_e2e_step(b.x_host)
             for _ in range(n_slots):
                 step_f32()
             torch.cuda.synchronize()
             ms_e2e_fp32in, _ = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_f32)
+            # informational: the result also crossing PCIe as bf16 (a caller option of cfm_encoder_forward_host_io; the
+            # headline keeps the reference's fp32 result).  Shows how much of e2e is the host link at N GPUs.
+            y16 = [torch.empty(y_host.shape, dtype=torch.bfloat16).pin_memory() for _ in range(n_slots)]
+            step_16 = make_e2e_step(x_e2e, y16)
+            for _ in range(2 * n_slots):
+                step_16()
+            torch.cuda.synchronize()
+            ms_e2e_bf16out, _ = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_16)
+            del y16
         clocks = sampler.stop() if rank == 0 else None       # sampled across the timed regions above
         # profiled pass (per-launch CUDA events on the launching stream), not part of the headline
         prof_steps = min(args.steps, 5)
@@ -806,7 +817,8 @@ def main():
                 "ms_per_step_median": ms_e2e_median, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "pcie_gbs_per_rank": {"h2d": h2d / (ms_e2e * 1e-3) / 1e9, "d2h": d2h / (ms_e2e * 1e-3) / 1e9},
                 "host_dtypes": {"mel": "bf16" if bf16_in else "f32", "result": "f32"},
-                "fp32_mel_ms_per_step": ms_e2e_fp32in, "serial_ms_per_step": ms_e2e_serial,
+                "fp32_mel_ms_per_step": ms_e2e_fp32in, "bf16_result_ms_per_step": ms_e2e_bf16out,
+                "serial_ms_per_step": ms_e2e_serial,
                 "api": "cfm_encoder_forward_host_io (Encoder.forward_host_pipelined): pinned host mel -> device -> forward -> "
                        f"host; {n_slots} in-flight slots over {n_dev_streams} compute streams, copies on a copy-in and a "
                        "copy-out stream ordered by the library's per-slot events; serial_ms_per_step is the same call "

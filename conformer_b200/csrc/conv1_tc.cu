@@ -68,7 +68,8 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   // zero the A stages once: the producers only ever rewrite the two 16-byte chunks that hold k = 0..15
   for (int i = threadIdx.x; i < A_STAGES * A_BYTES / 16; i += NUM_THREADS)
     reinterpret_cast<uint4*>(a_s)[i] = make_uint4(0u, 0u, 0u, 0u);
-  if (threadIdx.x < C) bias_s[threadIdx.x] = p.bias[threadIdx.x];
+  const int slab = blockIdx.y;                                  // 256 output channels per slab (Conformer-L: two)
+  if (threadIdx.x < C) bias_s[threadIdx.x] = p.bias[slab * C + threadIdx.x];
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -80,7 +81,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
     const int pt = (warp == 0 ? 0 : 32) + lane;
     if (pt == 0) {
       mbar_expect_tx(w_bar, W_BYTES);
-      tma_load_2d(w_s, &tmW, w_bar, 0, 0);
+      tma_load_2d(w_s, &tmW, w_bar, 0, slab * C);
     }
     const int64_t rows_per_b = static_cast<int64_t>(p.T1p) * p.F1;
     uint32_t it = 0;
@@ -177,7 +178,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
       named_bar_sync(2, NUM_EPI_THREADS);
       if (tid_e == 0) {
 #pragma unroll
-        for (int blk = 0; blk < C / 64; ++blk) tma_store_2d(&tmOut, cb + blk * CBLK_BYTES, blk * 64, tile * BM);
+        for (int blk = 0; blk < C / 64; ++blk) tma_store_2d(&tmOut, cb + blk * CBLK_BYTES, slab * C + blk * 64, tile * BM);
         bulk_commit();
       }
     }
@@ -200,7 +201,7 @@ __global__ void pack_conv1_weight_kernel(const float* __restrict__ w, bf16* __re
 
 }  // namespace
 
-bool conv1_tc_supported(int Cn) { return Cn == C; }
+bool conv1_tc_supported(int Cn) { return Cn >= C && Cn % C == 0; }
 
 int pack_conv1_weight(const float* w, bf16* out, int Cn, cudaStream_t stream) {
   pack_conv1_weight_kernel<<<(Cn * 64 + 255) / 256, 256, 0, stream>>>(w, out, Cn);
@@ -211,20 +212,21 @@ int pack_conv1_weight(const float* w, bf16* out, int Cn, cudaStream_t stream) {
 int subsample_conv1_tc(const float* mel, const bf16* w_packed, const float* bias, bf16* out, int B, int n_mel, int Tin, int T1,
                        int T1p, int F1, int Cn, int num_sms, cudaStream_t stream) {
   CFM_TRY(tc_init());
-  CFM_REQUIRE(Cn == C, "tensor-core conv1 is specialised for 256 channels");
+  CFM_REQUIRE(Cn >= C && Cn % C == 0, "tensor-core conv1 works on slabs of 256 channels");
+  const int slabs = Cn / C;
   CFM_REQUIRE(B > 0 && T1 > 0 && F1 > 0, "input too short for the subsampling convs");
   const int64_t M = static_cast<int64_t>(B) * T1p * F1;
   CFM_REQUIRE(M < (1LL << 31) - BM, "conv1 output has too many rows");
   CUtensorMap tmW, tmOut;
   {
-    cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(C)};
+    cuuint64_t dims[2] = {64, static_cast<cuuint64_t>(Cn)};
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {64, C};
     CFM_TRY(encode_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dims, strides, box, "conv1 W"));
   }
   {
-    cuuint64_t dims[2] = {static_cast<cuuint64_t>(C), static_cast<cuuint64_t>(M)};
-    cuuint64_t strides[1] = {static_cast<cuuint64_t>(C) * 2};
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(Cn), static_cast<cuuint64_t>(M)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(Cn) * 2};
     cuuint32_t box[2] = {64, BM};
     CFM_TRY(encode_tmap(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, dims, strides, box, "conv1 out"));
   }
@@ -232,7 +234,8 @@ int subsample_conv1_tc(const float* mel, const bf16* w_packed, const float* bias
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(conv1_tc_kernel), SMEM_BYTES));
   const int tiles = static_cast<int>(ceil_div(M, BM));
   Conv1Params p{mel, bias, n_mel, Tin, T1, T1p, F1, M, tiles};
-  const int grid = tiles < num_sms ? tiles : num_sms;
+  const int per_slab = num_sms / slabs > 0 ? num_sms / slabs : 1;
+  dim3 grid(static_cast<unsigned>(tiles < per_slab ? tiles : per_slab), static_cast<unsigned>(slabs));
   conv1_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW, tmOut, p);
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
