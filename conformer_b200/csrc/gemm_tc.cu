@@ -34,20 +34,24 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 
 constexpr bool epi_out_f32(int epi) { return epi == EPI_BIAS_RES || epi == EPI_BIAS_F32; }
 
-template <int BLOCK_N, int EPI> struct Cfg {
+template <int BLOCK_N, int EPI, bool PAIR = false> struct Cfg {
   static constexpr bool OUT_F32 = epi_out_f32(EPI);
   static constexpr bool GLU = (EPI == EPI_BIAS_GLU);
   static constexpr int OUT_N = GLU ? BLOCK_N / 2 : BLOCK_N;    // output columns per tile
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2 / (PAIR ? 2 : 1);   // a CTA of a pair holds half the rows of B
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int CBLK_COLS = OUT_F32 ? 32 : 64;          // columns per staging block
-  static constexpr int NUM_CBLK = OUT_N / CBLK_COLS;
+  // a 256-wide fp32 tile (128 KB) is staged in two passes of 4 blocks: pass p carries columns 64 g + 32 p .. +31 of every
+  // 64-column warp group g
+  static constexpr bool F32_WIDE = OUT_F32 && BLOCK_N == 256;
+  static constexpr int PASSES = F32_WIDE ? 2 : 1;
+  static constexpr int NUM_CBLK = F32_WIDE ? 4 : OUT_N / CBLK_COLS;
   static constexpr int CBUF_BYTES = NUM_CBLK * CBLK_BYTES;
   // bf16 128-wide tiles can afford two staging buffers, so a TMA store drains while the next tile is written
   static constexpr int CBUF_COUNT = (!OUT_F32 && OUT_N == 128) ? 2 : 1;
   static constexpr int AUX_BYTES = 1024 /*alignment slack*/ + 256 /*barriers*/ + BLOCK_N * 4 /*bias*/;
   static constexpr int STAGES_FIT = (SMEM_LIMIT - CBUF_COUNT * CBUF_BYTES - AUX_BYTES) / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_FIT > 6 ? 6 : STAGES_FIT;
+  static constexpr int STAGES = STAGES_FIT > (PAIR ? 8 : 6) ? (PAIR ? 8 : 6) : STAGES_FIT;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;                // two accumulator stages
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CBUF_COUNT * CBUF_BYTES + AUX_BYTES;
   static_assert(STAGES >= 2, "not enough shared memory for a pipeline");
@@ -56,6 +60,7 @@ template <int BLOCK_N, int EPI> struct Cfg {
 struct GemmParams {
   int M, N, K;
   int num_m_tiles, num_n_tiles, num_kb;
+  int num_m_pairs;                     // PAIR: 256-row tiles
   int k_splits, kb_per_split;          // split-K (reduce-add epilogue only): tile = (split, m_tile, n_tile)
   const float* bias;
   float res_scale;
@@ -72,7 +77,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define TRACE(slot)                                                                         \
   do {                                                                                      \
-    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(tile / gridDim.x) * 8 + (slot)] = gtime(); \
+    if (p.trace != nullptr && blockIdx.x == 0 && lane == 0) p.trace[(tile / ncta) * 8 + (slot)] = gtime(); \
   } while (0)
 
 // TF32: A and W are fp32 in memory and multiplied as TF32 (kind::tf32, K = 8 per MMA, 32 elements per 128-byte row);
@@ -83,14 +88,22 @@ __device__ __forceinline__ unsigned long long gtime() {
 // contraction runs over the rows).  Both operands are then MN-major: a stage holds [64 k-rows][64 mn] slabs of 8 KB
 // (128-byte rows, one swizzle atom along MN), consecutive slabs = consecutive 64-wide MN atoms (descriptor LBO = 8 KB,
 // SBO = 1 KB = 8 k-rows), and one K = 16 MMA step advances the start address by 16 rows = 2 KB.
-template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false, bool SPLITK = false, bool TN = false>
+// PAIR: the kernel runs on CTA pairs (cluster of 2, tcgen05 cta_group::2).  A pair owns a 256 x BLOCK_N tile: each CTA
+// loads its own 128 rows of A and HALF the rows of the W tile, the pair's leader issues M = 256 MMAs for both SMs, every
+// CTA drains its own 128 accumulator rows.  Per 64-wide K block a CTA then moves 16 + BLOCK_N/16 KB through its
+// shared-memory port twice (TMA fill + MMA read) instead of 16 + BLOCK_N/8 KB: with BLOCK_N = 256 that is 125 B/clk
+// against the 128 B/clk port - the single-CTA form needs 188 B/clk and tops out at ~70 % of the tensor pipe on long
+// contractions.  Barriers the issuing warp waits on live in the leader (the peer's TMA loads and epilogue warps reach
+// them through cluster addresses); MMA completions are multicast to both CTAs.
+template <int BLOCK_N, int EPI, bool CONV, bool TF32 = false, bool SPLITK = false, bool TN = false, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, GemmParams p) {
   constexpr bool OUT_F32 = epi_out_f32(EPI);
   constexpr bool GLU = (EPI == EPI_BIAS_GLU);
   static_assert(!GLU || BLOCK_N == 256, "the GLU epilogue pairs two 32-column chunks per warp");
-  using C_ = Cfg<BLOCK_N, EPI>;
+  static_assert(!PAIR || (!TF32 && !SPLITK && !TN), "CTA pairs: plain bf16 GEMM and the implicit-GEMM convolution");
+  using C_ = Cfg<BLOCK_N, EPI, PAIR>;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -104,8 +117,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = p.num_m_tiles * p.num_n_tiles * (SPLITK ? p.k_splits : 1);
+  const int num_tiles = PAIR ? p.num_m_pairs * p.num_n_tiles : p.num_m_tiles * p.num_n_tiles * (SPLITK ? p.k_splits : 1);
   constexpr int BK = TF32 ? BLOCK_K / 2 : BLOCK_K;         // elements per 128-byte operand row
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = the pair's leader
+  const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -119,23 +135,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
+      mbar_init(&tempty_bar[s], PAIR ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
     }
     mbar_init(res_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);               // whole TMEM: the CTA owns the SM, base is 0
+  if (warp == 2) {                                         // whole TMEM: the CTA owns the SM, base is 0
+    if constexpr (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();                  // both CTAs' barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = cta; tile < num_tiles; tile += ncta) {
       const int mn = SPLITK ? tile % (p.num_m_tiles * p.num_n_tiles) : tile, ks = SPLITK ? tile / (p.num_m_tiles * p.num_n_tiles) : 0;
-      const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
+      const int m_tile = PAIR ? 2 * (mn / p.num_n_tiles) + static_cast<int>(rank) : mn / p.num_n_tiles;
+      const int n_tile = mn - (mn / p.num_n_tiles) * p.num_n_tiles;
       const int kb0 = SPLITK ? ks * p.kb_per_split : 0, kb1 = SPLITK ? min(p.num_kb, kb0 + p.kb_per_split) : p.num_kb;
       int cb = 0, cf = 0, ct = 0;
       if (CONV) {
@@ -152,6 +173,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
           uint8_t* sa = smem + s * C_::STAGE_BYTES;
           uint8_t* sb = sa + A_STAGE_BYTES;
+          if constexpr (PAIR) {
+            // own rows of A, own half of the W tile; every byte of both CTAs completes on the leader's barrier
+            const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C_::STAGE_BYTES);
+            if (CONV) {
+              const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
+              const int kw = tap / 3, kh = tap - kw * 3;
+              tma_load_5d_pair(sa, &tmA, bar, c0, 2 * cf + kh, kw & 1, ct * BLOCK_M + (kw >> 1), cb);
+            } else {
+              tma_load_2d_pair(sa, &tmA, bar, kb * BK, m_tile * BLOCK_M);
+            }
+            tma_load_2d_pair(sb, &tmB, bar, kb * BK, n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+          } else {
           mbar_expect_tx(&full_bar[s], C_::STAGE_BYTES);
           if (CONV) {
             const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * BLOCK_K;
@@ -170,16 +204,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_tile * BLOCK_N);
           }
+          }
         }
         __syncwarp();
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (PAIR: the leader's, for both SMs)
     constexpr uint32_t idesc = TF32 ? umma_idesc_tf32(BLOCK_M, BLOCK_N)
-                                    : (TN ? (umma_idesc_bf16(BLOCK_M, BLOCK_N) | (1u << 15) | (1u << 16)) : umma_idesc_bf16(BLOCK_M, BLOCK_N));
+                                    : (TN ? (umma_idesc_bf16(BLOCK_M, BLOCK_N) | (1u << 15) | (1u << 16))
+                                          : umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, BLOCK_N));
     uint32_t it = 0, acc_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++acc_it) {
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&tempty_bar[as], aph ^ 1);                     // epilogue has drained this accumulator
       tc_fence_after();
@@ -203,10 +239,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {         // one MMA covers 32 bytes of K (K-major) or 16 k-rows = 2 KB (MN-major)
             if (TN) tc_mma_f16_lo(d_tmem, sa + k * (2048 >> 4), sb + k * (2048 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else if (TF32) tc_mma_tf32_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
+            else if (PAIR) tc_mma_f16_lo_pair(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
             else tc_mma_f16_lo(d_tmem, sa + k * (UMMA_K * 2 >> 4), sb + k * (UMMA_K * 2 >> 4), idesc, ((kb - kb0) | k) != 0 ? 1u : 0u);
           }
+          if constexpr (PAIR) {
+            tc_commit_pair(&empty_bar[s]);                     // both CTAs' slots are free once these MMAs retire
+            if (kb == kb1 - 1) tc_commit_pair(&tfull_bar[as]);
+          } else {
           tc_commit(&empty_bar[s]);                            // smem slot free once these MMAs retire
           if (kb == kb1 - 1) tc_commit(&tfull_bar[as]);        // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -225,9 +267,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t row_off = row * 128;
     const int sw = row & 7;
     uint32_t acc_it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++acc_it) {
+    const uint32_t tempty_remote[2] = {PAIR ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u, PAIR ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
+    for (int tile = cta; tile < num_tiles; tile += ncta, ++acc_it) {
       const int mn = SPLITK ? tile % (p.num_m_tiles * p.num_n_tiles) : tile, ks = SPLITK ? tile / (p.num_m_tiles * p.num_n_tiles) : 0;
-      const int m_tile = mn / p.num_n_tiles, n_tile = mn - m_tile * p.num_n_tiles;
+      const int m_tile = PAIR ? 2 * (mn / p.num_n_tiles) + static_cast<int>(rank) : mn / p.num_n_tiles;
+      const int n_tile = mn - (mn / p.num_n_tiles) * p.num_n_tiles;
       const int n0 = n_tile * BLOCK_N;                        // first GEMM column of the tile
       const int o0 = n_tile * C_::OUT_N;                      // first OUTPUT column of the tile
       const int out_n = GLU ? (p.N >> 1) : p.N;
@@ -250,7 +294,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);              // accumulator stage may be overwritten
+      if (lane == 0) {                                          // accumulator stage may be overwritten
+        if constexpr (PAIR) mbar_arrive_cluster(tempty_remote[as]);
+        else mbar_arrive(&tempty_bar[as]);
+      }
       if (GLU) {
         // this warp's 64 GEMM columns are 32 value columns followed by their 32 gate columns
         const int gc = cgrp * COLS_PER_WARP;                   // GEMM column (in tile) of the value half
@@ -275,7 +322,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
 #pragma unroll
+      for (int pass = 0; pass < C_::PASSES; ++pass) {
+      if (pass > 0) {                                          // the first pass has left the staging buffer
+        if (leader) bulk_wait_read0();
+        named_bar_sync(1, NUM_EPI_THREADS);
+      }
+#pragma unroll
       for (int ch = 0; ch < (GLU ? 0 : NCH); ++ch) {
+        if (C_::F32_WIDE && ch != pass) continue;
         const int col_in_tile = cgrp * COLS_PER_WARP + ch * 32;
         if (n0 + col_in_tile >= p.N) continue;
         float v[32];
@@ -296,8 +350,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (OUT_F32) {
-          // 32 fp32 columns = one full 128-byte row of staging block (col_in_tile / 32)
-          uint8_t* blk = cb + (col_in_tile >> 5) * CBLK_BYTES + row_off;
+          // 32 fp32 columns = one full 128-byte row of a staging block
+          uint8_t* blk = cb + (C_::F32_WIDE ? cgrp : (col_in_tile >> 5)) * CBLK_BYTES + row_off;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4* dst = reinterpret_cast<float4*>(blk + ((j ^ sw) << 4));
@@ -324,7 +378,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       named_bar_sync(1, NUM_EPI_THREADS);
       if (leader) {
         for (int blk = 0; blk < C_::NUM_CBLK; ++blk) {
-          const int col = o0 + blk * C_::CBLK_COLS;
+          const int col = C_::F32_WIDE ? o0 + blk * 64 + pass * 32 : o0 + blk * C_::CBLK_COLS;
           if (col >= out_n) continue;
           if (CONV) {
             const int ct = m_tile % p.TCH, cf = (m_tile / p.TCH) % p.F2, cbi = m_tile / (p.TCH * p.F2);
@@ -337,15 +391,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         bulk_commit();
       }
+      }
       if (warp == 4) TRACE(7);
     }
     if (leader) bulk_wait0();                                   // all output tiles have left shared memory
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();                  // the peer's shared memory and barriers stay valid until both are done
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -379,13 +436,31 @@ int encode_conv_5d(CUtensorMap* tm, const void* base, const ConvGeom& g) {
   return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, "conv A");
 }
 
-template <int BLOCK_N, int EPI, bool CONV, bool SPLITK = false>
+template <int BLOCK_N, int EPI, bool CONV, bool SPLITK = false, bool PAIR = false>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, int num_sms,
            cudaStream_t stream) {
-  using C_ = Cfg<BLOCK_N, EPI>;
-  auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV, false, SPLITK>;
+  using C_ = Cfg<BLOCK_N, EPI, PAIR>;
+  auto kern = gemm_tc_kernel<BLOCK_N, EPI, CONV, false, SPLITK, false, PAIR>;
   static std::atomic<uint64_t> attr_done{0};        // one per template instantiation
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
+  if (PAIR) {
+    const int tiles = p.num_m_pairs * p.num_n_tiles;
+    const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C_::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
+    return 0;
+  }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
@@ -393,15 +468,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   return 0;
 }
 
-template <int BLOCK_N, bool CONV>
+template <int BLOCK_N, bool CONV, bool PAIR>
 int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p, Epilogue epi,
                int num_sms, cudaStream_t stream) {
   switch (epi) {
-    case EPI_BIAS: return launch<BLOCK_N, EPI_BIAS, CONV>(tmA, tmB, tmC, p, num_sms, stream);
-    case EPI_BIAS_SWISH: return launch<BLOCK_N, EPI_BIAS_SWISH, CONV>(tmA, tmB, tmC, p, num_sms, stream);
-    case EPI_BIAS_RELU: return launch<BLOCK_N, EPI_BIAS_RELU, CONV>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS: return launch<BLOCK_N, EPI_BIAS, CONV, false, PAIR>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS_SWISH: return launch<BLOCK_N, EPI_BIAS_SWISH, CONV, false, PAIR>(tmA, tmB, tmC, p, num_sms, stream);
+    case EPI_BIAS_RELU: return launch<BLOCK_N, EPI_BIAS_RELU, CONV, false, PAIR>(tmA, tmB, tmC, p, num_sms, stream);
     case EPI_BIAS_GLU:
-      if (BLOCK_N == 256 && !CONV) return launch<256, EPI_BIAS_GLU, false>(tmA, tmB, tmC, p, num_sms, stream);
+      if (BLOCK_N == 256 && !CONV) return launch<256, EPI_BIAS_GLU, false, false, PAIR>(tmA, tmB, tmC, p, num_sms, stream);
       break;
     default: break;
   }
@@ -409,8 +484,16 @@ int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap
   return 1;
 }
 int launch_epi_f32(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                   Epilogue epi, int num_sms, cudaStream_t stream) {
+                   Epilogue epi, bool pair, bool wide, int num_sms, cudaStream_t stream) {
   if (epi == EPI_BIAS_RES && p.k_splits > 1) return launch<128, EPI_BIAS_RES, false, true>(tmA, tmB, tmC, p, num_sms, stream);
+  if (pair && wide) {
+    if (epi == EPI_BIAS_RES) return launch<256, EPI_BIAS_RES, false, false, true>(tmA, tmB, tmC, p, num_sms, stream);
+    return launch<256, EPI_BIAS_F32, false, false, true>(tmA, tmB, tmC, p, num_sms, stream);
+  }
+  if (pair) {
+    if (epi == EPI_BIAS_RES) return launch<128, EPI_BIAS_RES, false, false, true>(tmA, tmB, tmC, p, num_sms, stream);
+    return launch<128, EPI_BIAS_F32, false, false, true>(tmA, tmB, tmC, p, num_sms, stream);
+  }
   if (epi == EPI_BIAS_RES) return launch<128, EPI_BIAS_RES, false>(tmA, tmB, tmC, p, num_sms, stream);
   return launch<128, EPI_BIAS_F32, false>(tmA, tmB, tmC, p, num_sms, stream);
 }
@@ -598,11 +681,13 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
     const int64_t tiles = static_cast<int64_t>(p.num_m_tiles) * ceil_div(N, bn);
     return ceil_div(tiles, num_sms) * bn;
   };
-  const bool use256 = epi == EPI_BIAS_GLU || (!out_f32 && (N > 128) && (cost(256) <= cost(128)));
+  // CTA pairs (cta_group::2) for the long contractions: the single-CTA main loop is bound by the shared-memory port
+  // (see the kernel's header); GEMMs with K < 512 are bound by their epilogue and stay as they are
+  const bool pair_ok = !(epi == EPI_BIAS_RES && split_k) && p.num_kb >= 8 && p.num_m_tiles >= 2 && num_sms >= 2;
+  const bool use256 = epi == EPI_BIAS_GLU || ((!out_f32 || pair_ok) && (N > 128) && (cost(256) <= cost(128)));
   const int bn = use256 ? 256 : 128;
   p.num_n_tiles = static_cast<int>(ceil_div(N, bn));
-  CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
-                         static_cast<uint32_t>(bn), "W"));
+  p.num_m_pairs = (p.num_m_tiles + 1) / 2;
   if (epi == EPI_BIAS_RES && split_k) {
     // few output tiles and a long contraction (the weight-gradient GEMMs of the training step): split K over the idle SMs;
     // every split reduce-adds its partial product into C, the bias enters with split 0
@@ -616,12 +701,22 @@ int gemm_bf16_tc(const bf16* A, int lda, const bf16* W, const float* bias, void*
       }
     }
   }
-  if (out_f32) return launch_epi_f32(tmA, tmB, tmC, p, epi, num_sms, stream);
-  if (conv != nullptr)
-    return use256 ? launch_epi<256, true>(tmA, tmB, tmC, p, epi, num_sms, stream)
-                  : launch_epi<128, true>(tmA, tmB, tmC, p, epi, num_sms, stream);
-  return use256 ? launch_epi<256, false>(tmA, tmB, tmC, p, epi, num_sms, stream)
-                : launch_epi<128, false>(tmA, tmB, tmC, p, epi, num_sms, stream);
+  const bool pair = pair_ok;
+  CFM_TRY(encode_2d_bf16(&tmB, W, static_cast<uint64_t>(K), static_cast<uint64_t>(N), static_cast<uint64_t>(K), BLOCK_K,
+                         static_cast<uint32_t>(pair ? bn / 2 : bn), "W"));
+  if (out_f32) return launch_epi_f32(tmA, tmB, tmC, p, epi, pair, use256, num_sms, stream);
+  if (conv != nullptr) {
+    if (pair)
+      return use256 ? launch_epi<256, true, true>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                    : launch_epi<128, true, true>(tmA, tmB, tmC, p, epi, num_sms, stream);
+    return use256 ? launch_epi<256, true, false>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                  : launch_epi<128, true, false>(tmA, tmB, tmC, p, epi, num_sms, stream);
+  }
+  if (pair)
+    return use256 ? launch_epi<256, false, true>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                  : launch_epi<128, false, true>(tmA, tmB, tmC, p, epi, num_sms, stream);
+  return use256 ? launch_epi<256, false, false>(tmA, tmB, tmC, p, epi, num_sms, stream)
+                : launch_epi<128, false, false>(tmA, tmB, tmC, p, epi, num_sms, stream);
 }
 
 }  // namespace cfm
