@@ -11,7 +11,7 @@ import subprocess
 import sys
 
 LIB = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "conformer_b200", "lib", "libconformer_b200.so")
-KEYS = ["UTCHMMA", "UTCMMA_OTHER", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "HMMA", "FFMA", "FFMA2", "MUFU", "SHFL", "ATOM/RED"]
+KEYS = ["UTCHMMA", "UTCHMMA.2CTA", "UTCMMA_OTHER", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "HMMA", "FFMA", "FFMA2", "MUFU", "SHFL", "ATOM/RED"]
 
 
 def main():
@@ -36,6 +36,8 @@ def main():
         c["total"] += 1
         if base == "UTCHMMA":
             c["UTCHMMA"] += 1
+            if ".2CTA" in op:
+                c["UTCHMMA.2CTA"] += 1                          # tcgen05.mma.cta_group::2 (issued for a CTA pair)
         elif base.startswith("UTC") and "MMA" in base:
             c["UTCMMA_OTHER"] += 1
         elif base in ("LDTM", "STTM", "UTMALDG", "UTMASTG", "UTMAREDG", "HMMA", "FFMA", "FFMA2", "MUFU", "SHFL"):
