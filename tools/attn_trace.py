@@ -22,7 +22,6 @@ m = m.cuda().eval().set_compute("bf16")
 x = torch.randn(B, T, d, device="cuda")
 pos = torch.randn(1, 2 * T - 1, d, device="cuda")
 POS = None if os.environ.get('ATTN_POS', 'none') == 'none' else pos
-lib().cfm_set_attention_kernel(1)
 for _ in range(3):
     m(x, x, x, POS, None)
 trace = torch.zeros(128, dtype=torch.int64, device="cuda")
