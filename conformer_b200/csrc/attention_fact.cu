@@ -307,13 +307,12 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
       const uint8_t* crow = rot_s + grp * Q_BYTES + row * 128;          // cos(i w_k), k = 64*grp .. +63
       const uint8_t* srow = rot_s + (2 + grp) * Q_BYTES + row * 128;    // sin(i w_k)
       const float* pc = p.pos_const + h * D;
-      // 16 frequencies at a time; the accumulator columns of chunk cc+1 are in flight while chunk cc is rotated
-      uint32_t ar[2][16], br[2][16];
-      tmem_ld_32x16(tlane + TM_AB + grp * 64, ar[0]);
-      tmem_ld_32x16(tlane + TM_AB + NF + grp * 64, br[0]);
 #pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int k0 = grp * 64 + cc * 16, cur = cc & 1;
+      for (int cc = 0; cc < 4; ++cc) {                   // 16 frequencies at a time
+        const int k0 = grp * 64 + cc * 16;
+        uint32_t ar[16], br[16];
+        tmem_ld_32x16(tlane + TM_AB + k0, ar);
+        tmem_ld_32x16(tlane + TM_AB + NF + k0, br);
         const uint4 c0 = *reinterpret_cast<const uint4*>(crow + (((2 * cc) ^ sw) << 4));
         const uint4 c1 = *reinterpret_cast<const uint4*>(crow + (((2 * cc + 1) ^ sw) << 4));
         const uint4 s0 = *reinterpret_cast<const uint4*>(srow + (((2 * cc) ^ sw) << 4));
@@ -328,19 +327,14 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
           ka[4 * e] = va.x; ka[4 * e + 1] = va.y; ka[4 * e + 2] = va.z; ka[4 * e + 3] = va.w;
           kb2[4 * e] = vb.x; kb2[4 * e + 1] = vb.y; kb2[4 * e + 2] = vb.z; kb2[4 * e + 3] = vb.w;
         }
-        tmem_ld_wait_for16(ar[cur]);
-        tmem_ld_wait_for16(br[cur]);
-        if (cc + 1 < 4) {
-          tmem_ld_32x16(tlane + TM_AB + k0 + 16, ar[cur ^ 1]);
-          tmem_ld_32x16(tlane + TM_AB + NF + k0 + 16, br[cur ^ 1]);
-        }
+        tmem_ld_wait();
         uint32_t oa[8], ob[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float2 cs = __half22float2(*reinterpret_cast<const __half2*>(&cw[e]));
           const float2 sn = __half22float2(*reinterpret_cast<const __half2*>(&sw8[e]));
-          const float a0 = __uint_as_float(ar[cur][2 * e]) + ka[2 * e], a1 = __uint_as_float(ar[cur][2 * e + 1]) + ka[2 * e + 1];
-          const float b0 = __uint_as_float(br[cur][2 * e]) + kb2[2 * e], b1 = __uint_as_float(br[cur][2 * e + 1]) + kb2[2 * e + 1];
+          const float a0 = __uint_as_float(ar[2 * e]) + ka[2 * e], a1 = __uint_as_float(ar[2 * e + 1]) + ka[2 * e + 1];
+          const float b0 = __uint_as_float(br[2 * e]) + kb2[2 * e], b1 = __uint_as_float(br[2 * e + 1]) + kb2[2 * e + 1];
           oa[e] = pack_bf16x2(a0 * sn.x + b0 * cs.x, a1 * sn.y + b1 * cs.y);
           ob[e] = pack_bf16x2(b0 * sn.x - a0 * cs.x, b1 * sn.y - a1 * cs.y);
         }
