@@ -21,6 +21,8 @@ Printed JSON (rank 0, one line):
                        on this GPU under torch.autocast(bf16) at the same batch: the cuBLAS/cuDNN bar
   configs              the other BASELINE configs (C1 fp32, C3, C5) at their own shape: ms_per_step, RTFx, dominant kernel
   strong               strong scaling: the named batch split over the N ranks
+  next_rows            (N = 1) the rows either side of the encoder: log-mel front-end and CTC head + greedy
+                       decode at the shapes they have around this batch, next to the same computation in eager PyTorch
   cpu_baseline         the reference's CPU path on this box's host cores, bounded sample
   --impl reference     times that CPU path alone, same metric/config.
 """
@@ -282,6 +284,75 @@ def gpu_eager_baseline(cfg, batch, t_in, len_mode, dev, steps=5, warmup=2, seed=
     out["what"] = (("reference Encoder from baseline/_ref" if kind == "reference" else "oracle port of the reference Encoder")
                    + f", eager PyTorch {torch.__version__} on this GPU, batch {batch} x {t_in} frames, median of {steps} "
                    "CUDA-event-timed forwards after warm-up")
+    return out
+
+
+def _time_ms(fn, steps=10, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def next_rows_bench(cb, dev, batch=64, seconds=15.0):
+    """SURVEY.md 8f rows either side of the encoder, at the shapes they have around the C2 batch (informational, rank 0 at
+    N = 1): the log-mel front-end on 64 x 15 s of 16 kHz audio and the CTC head (LSTM 256 -> 640, vocabulary 370, greedy
+    decode) on the encoder's 64 x 374 x 256 output, each next to the same computation in eager PyTorch on this GPU."""
+    out = {}
+    try:
+        fe = cb.LogMelFrontEnd()
+        wav = torch.randn(batch, int(seconds * 16000), device=dev) * 0.1
+        ms = _time_ms(lambda: fe.mel_spectrogram(wav))
+        win = torch.hann_window(400, periodic=True, device=dev)
+        fb = fe.fb.to(dev)
+
+        def eager():
+            spec = torch.stft(wav, 400, 160, 400, win, center=True, pad_mode="reflect", return_complex=True).abs() ** 2
+            return torch.log(torch.clamp(torch.matmul(fb.T, spec), min=1e-5))
+
+        out["logmel_frontend"] = {"ms_per_batch": ms, "value": batch * seconds / (ms * 1e-3), "unit": "audio-s/s",
+                                  "eager_torch_ms": _time_ms(eager), "what": f"{batch} x {seconds:g} s waveforms -> log-mel "
+                                  "(cfm_logmel_forward: 3xTF32 tcgen05 DFT + filterbank GEMMs); eager = torch.stft (cuFFT) + matmul"}
+        del wav
+    except Exception as e:  # noqa: BLE001 - informational
+        out["logmel_frontend"] = {"error": str(e)[:200]}
+    try:
+        from conformer_b200.synth import synth_decoder_state_dict
+        d, V, H, T = 256, VOCAB, 640, 374
+        sd = {k[len("decoder."):]: v for k, v in synth_decoder_state_dict(d, V, hidden=H, seed=3).items()}
+        dec = cb.Decoder(V, d, H, 1)
+        dec.load_state_dict(sd, strict=True)
+        dec = dec.to(dev).eval()
+        x = torch.randn(batch, T, d, device=dev)
+        lengths = torch.full((batch,), T, dtype=torch.long, device=dev)
+        row = {}
+        for mode in ("fp32", "bf16"):
+            dec.set_compute(mode)
+            row[mode + "_ms"] = _time_ms(lambda: cb.greedy_ctc_decode(dec(x, lengths)))
+        ref = None
+        if os.path.isdir(os.path.join(REF_DIR, "model")):
+            if REF_DIR not in sys.path:
+                sys.path.insert(0, REF_DIR)
+            from model.modules.decoder import Decoder as RefDecoder
+            ref = RefDecoder(V, d, H, 1)
+            ref.load_state_dict(sd)
+            ref = ref.to(dev).eval()
+            row["eager_reference_ms"] = _time_ms(lambda: ref(x, lengths).argmax(-1))
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                row["eager_reference_bf16_autocast_ms"] = _time_ms(lambda: ref(x, lengths).argmax(-1))
+        row["what"] = (f"CTC head on {batch} x {T} x {d}: LSTM({d} -> {H}) + Swish + BatchNorm + Linear({H} -> {V}) + greedy decode "
+                       "(cfm_decoder_forward + cfm_ctc_greedy_decode); eager = the reference Decoder (cuDNN LSTM) + argmax")
+        out["ctc_head"] = row
+    except Exception as e:  # noqa: BLE001 - informational
+        out["ctc_head"] = {"error": str(e)[:200]}
     return out
 
 
@@ -773,7 +844,7 @@ def main():
 
     # the other BASELINE configs at their own shape, and the eager-PyTorch bar, on rank 0's GPU after the headline numbers
     # (every rank runs them so the barriers match; only rank 0 reports)
-    configs, eager = {}, None
+    configs, eager, next_rows = {}, None, None
     if not args.no_extras and args.config == "C2":
         del b
         torch.cuda.empty_cache()
@@ -784,6 +855,8 @@ def main():
                 configs[name] = {"error": str(e)[:300]}
         if rank == 0:
             eager = gpu_eager_baseline(cfg, batch, t_in, len_mode, dev)
+            if world == 1:
+                next_rows = next_rows_bench(cb, dev)
 
     if dist is not None:
         dist.barrier()
@@ -841,6 +914,8 @@ def main():
         bf = eager.get("bf16_autocast", {})
         if "ms_per_step" in bf:
             eager["speedup_vs_bf16_autocast"] = {"single_stream": bf["ms_per_step"] / ours, "two_streams": bf["ms_per_step"] / ms_dev}
+    if next_rows is not None:
+        line["next_rows"] = next_rows
     if not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_reference_rtfx(cfg, t_in, len_mode)
     print(json.dumps(line), flush=True)

@@ -201,6 +201,12 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, const v
                ::"l"(tm), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// non-tensor bulk copy global -> shared (contiguous bytes, multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }

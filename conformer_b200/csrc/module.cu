@@ -180,8 +180,19 @@ struct Packer {
       const float* bhh = param("lstm.bias_hh" + sfx, 4LL * H);
       float* bsum = alloc_f32(4LL * H);
       if (!status && add_vec(bih, bhh, bsum, 4 * H, stream)) status = 2;
-      finish_linear(w.layers[l].ih, wih, bsum, 4 * H, in);
       w.layers[l].w_hh = vec("lstm.weight_hh" + sfx, 4LL * H * H);
+      if (bf16_mode && lstm_tc_supported(H)) {
+        // tensor-core recurrence: gate rows of W_ih, the bias and W_hh in the row order of lstm_tc.cu
+        float* wih_p = alloc_f32(4LL * H * in);
+        float* bsum_p = alloc_f32(4LL * H);
+        w.layers[l].w_hh16p = alloc_bf16(4LL * H * H);
+        if (!status && (lstm_pack_rows_f32(wih, wih_p, H, in, stream) || lstm_pack_rows_f32(bsum, bsum_p, H, 1, stream) ||
+                        lstm_pack_rows_bf16(w.layers[l].w_hh, w.layers[l].w_hh16p, H, H, stream)))
+          status = 2;
+        finish_linear(w.layers[l].ih, wih_p, bsum_p, 4 * H, in);
+        continue;
+      }
+      finish_linear(w.layers[l].ih, wih, bsum, 4 * H, in);
     }
     const float* lw = param("linear.weight", static_cast<int64_t>(V) * H);
     const float* lb = param("linear.bias", V);
@@ -215,7 +226,9 @@ size_t arena_bytes_for(const Module& m) {
   for (const auto& kv : m.params) total += static_cast<size_t>(kv.second.numel);
   // fp32 copy + bf16 copy + per-tensor 256-byte alignment slack + the fused pos_proj copy
   const size_t d = m.cfg.d_model;
-  return total * 6 + (m.params.size() * 2 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 32 + (1 << 16);
+  // (the CTC head keeps a second, row-packed copy of its LSTM matrices for the tensor-core recurrence)
+  const size_t per_elem = m.kind == CFM_KIND_DECODER ? 14 : 6;
+  return total * per_elem + (m.params.size() * 4 + 64) * 256 + static_cast<size_t>(m.cfg.n_blocks + 1) * d * d * 32 + (1 << 16);
 }
 
 }  // namespace
@@ -678,26 +691,40 @@ int Module::forward_impl(Ctx& c, int op, const float* x, const float* pos, const
       TA* seq_b = ws_take<TA>(c, M * Hd);
       float* hst = ws_take<float>(c, 2LL * B * Hd);
       float* cst = ws_take<float>(c, static_cast<int64_t>(B) * Hd);
+      uint8_t* tcs = ws_take<uint8_t>(c, static_cast<int64_t>(lstm_tc_scratch_bytes(Hd)));
+      WS_CHECK(tcs);
       float* lg = ws_take<float>(c, M * dec.Vp);
       WS_CHECK(xin); WS_CHECK(seq_a); WS_CHECK(seq_b); WS_CHECK(hst); WS_CHECK(cst); WS_CHECK(lg);
       if (c.ws.measuring()) return 0;
       const TA* cur = reinterpret_cast<const TA*>(x);
+      const int L = static_cast<int>(dec.layers.size());
+      // tensor-core recurrence (bf16 mode, hidden size a multiple of 64): the whole head runs TIME-MAJOR ([T, B, .]), see lstm_tc.cu
+      const bool tm = sizeof(TA) == 2 && L > 0 && dec.layers[0].w_hh16p != nullptr;
       if (sizeof(TA) == 2) {
-        KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(seq_a), M * d, c.stream));
+        if (tm) KRUN(KC_MISC, 0, 6.0 * M * d, lstm_to_time_major(x, reinterpret_cast<bf16*>(seq_a), B, T, d, c.stream));
+        else KRUN(KC_MISC, 0, 6.0 * M * d, cast_f32_to_bf16(x, reinterpret_cast<bf16*>(seq_a), M * d, c.stream));
         cur = seq_a;
       }
-      const int L = static_cast<int>(dec.layers.size());
       for (int l = 0; l < L; ++l) {
         const int in = l == 0 ? d : Hd;
         CFM_TRY(Dispatch<TA>::gemm(c, cur, in, dec.layers[l].ih, xin, 4 * Hd, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
         TA* dst = (cur == seq_b) ? seq_a : seq_b;
-        KRUN(KC_MISC, 8.0 * M * Hd * Hd, 4.0 * M * 5 * Hd,
-             lstm_layer_forward<TA>(xin, dec.layers[l].w_hh, len_in, hst, cst, dst, B, T, Hd, l == L - 1, c.num_sms, c.stream));
+        if (tm) {
+          KRUN(KC_MISC, 8.0 * M * Hd * Hd, 4.0 * M * 5 * Hd,
+               lstm_layer_forward_tc<TA>(xin, dec.layers[l].w_hh16p, len_in, tcs, dst, B, T, Hd, l == L - 1, c.num_sms, c.stream));
+        } else {
+          KRUN(KC_MISC, 8.0 * M * Hd * Hd, 4.0 * M * 5 * Hd,
+               lstm_layer_forward<TA>(xin, dec.layers[l].w_hh, len_in, hst, cst, dst, B, T, Hd, l == L - 1, c.num_sms, c.stream));
+        }
         cur = dst;
       }
       CFM_TRY(Dispatch<TA>::gemm(c, cur, Hd, dec.out, lg, dec.Vp, static_cast<int>(M), EPI_BIAS_F32, nullptr, 0.f, nullptr));
-      CFM_CUDA_OK(cudaMemcpy2DAsync(y, static_cast<size_t>(dec.V) * 4, lg, static_cast<size_t>(dec.Vp) * 4,
-                                    static_cast<size_t>(dec.V) * 4, static_cast<size_t>(M), cudaMemcpyDeviceToDevice, c.stream));
+      if (tm) {
+        KRUN(KC_MISC, 0, 8.0 * M * dec.V, lstm_logits_from_time_major(lg, y, B, T, dec.V, dec.Vp, c.stream));
+      } else {
+        CFM_CUDA_OK(cudaMemcpy2DAsync(y, static_cast<size_t>(dec.V) * 4, lg, static_cast<size_t>(dec.Vp) * 4,
+                                      static_cast<size_t>(dec.V) * 4, static_cast<size_t>(M), cudaMemcpyDeviceToDevice, c.stream));
+      }
       return 0;
     }
     case CFM_KIND_ENCODER: {

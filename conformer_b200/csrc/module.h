@@ -114,7 +114,11 @@ struct FrontW {
   Linear conv2;
 };
 
-struct LstmLayerW { Linear ih; const float* w_hh = nullptr; };   // ih: [4H, in] with bias b_ih + b_hh
+struct LstmLayerW {
+  Linear ih;                         // [4H, in] with bias b_ih + b_hh (tensor-core recurrence: rows in its packed order)
+  const float* w_hh = nullptr;       // [4H, H] fp32, nn.LSTM row order (CUDA-core recurrence)
+  bf16* w_hh16p = nullptr;           // [4H, H] bf16, packed row order (lstm_tc.cu); null: CUDA-core recurrence
+};
 struct DecW {
   std::vector<LstmLayerW> layers;
   Linear out;                        // vocabulary projection with the eval-mode BatchNorm folded in, rows padded to a multiple of 8

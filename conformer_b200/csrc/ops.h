@@ -78,6 +78,17 @@ bool conv_module_fused_supported(int d, int ksize);
 template <typename TOut>
 int lstm_layer_forward(const float* xin, const float* w_hh, const int64_t* lengths, float* h_state, float* c_state, TOut* out,
                        int B, int T, int H, bool last_layer, int num_sms, cudaStream_t stream);
+// tensor-core recurrence (lstm_tc.cu, bf16 mode): W_ih / W_hh rows in the packed order, see lstm_tc.cu
+bool lstm_tc_supported(int H);
+int lstm_pack_rows_f32(const float* src, float* dst, int H, int K, cudaStream_t stream);
+int lstm_pack_rows_bf16(const float* src, bf16* dst, int H, int K, cudaStream_t stream);
+size_t lstm_tc_scratch_bytes(int H);
+// xin_tm / out_tm are TIME-MAJOR: [T, B, 4H] and [T, B, H]
+template <typename TOut>
+int lstm_layer_forward_tc(const float* xin_tm, const bf16* w_hh_packed, const int64_t* lengths, void* scratch, TOut* out_tm, int B, int T,
+                          int H, bool last_layer, int num_sms, cudaStream_t stream);
+int lstm_to_time_major(const float* x, bf16* y, int B, int T, int d, cudaStream_t stream);
+int lstm_logits_from_time_major(const float* lg, float* y, int B, int T, int V, int Vp, cudaStream_t stream);
 int fold_bn_linear(const float* w, const float* b, const float* gamma, const float* beta, const float* mean, const float* var,
                    float eps, float* w_out /*[Vp,H]*/, float* b_out /*[Vp]*/, int V, int Vp, int H, cudaStream_t stream);
 int add_vec(const float* a, const float* b, float* o, int n, cudaStream_t stream);

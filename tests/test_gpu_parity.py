@@ -820,3 +820,37 @@ def test_decoder_head_large_vs_oracle_and_timing(B, T, H):
     torch.cuda.synchronize()
     print(f"decoder head B={B} T={T} H={H}: ours (whole head) {ev[0].elapsed_time(ev[1]):.3f} ms, cuDNN LSTM alone "
           f"{ev[2].elapsed_time(ev[3]):.3f} ms, max abs err vs oracle {err:.2e}")
+
+
+@pytest.mark.parametrize("B,T,H,L", [(64, 374, 640, 1), (7, 50, 128, 2), (100, 33, 192, 1), (16, 120, 640, 1)])
+def test_decoder_head_bf16_tensor_core_recurrence_vs_oracle(B, T, H, L):
+    """bf16 mode with a hidden size that is a multiple of 64 runs the recurrence on tcgen05 (lstm_tc.cu: W_hh slice
+    resident in shared memory, one MMA group per time step, grid barrier between steps): against the oracle's fp32 time
+    loop.  Batches that are not a multiple of 16, batches above 64 (independent slices), two layers, variable lengths."""
+    d, V = 256, 370
+    sd = sub(synth_decoder_state_dict(d, V, hidden=H, seed=90 + B), "decoder.")
+    if L == 2:
+        g = torch.Generator().manual_seed(5)
+        bound = 1.0 / H ** 0.5
+        sd["lstm.weight_ih_l1"] = (torch.rand(4 * H, H, generator=g) * 2 - 1) * bound
+        sd["lstm.weight_hh_l1"] = (torch.rand(4 * H, H, generator=g) * 2 - 1) * bound
+        sd["lstm.bias_ih_l1"] = (torch.rand(4 * H, generator=g) * 2 - 1) * bound
+        sd["lstm.bias_hh_l1"] = (torch.rand(4 * H, generator=g) * 2 - 1) * bound
+    dec = cb.Decoder(V, d, H, L)
+    dec.load_state_dict(sd, strict=True)
+    dec = dec.to(DEV).eval().set_compute("bf16")
+    g = torch.Generator().manual_seed(B * 7 + T)
+    x = torch.randn(B, T, d, generator=g).to(DEV)
+    lengths = synth_lengths(B, T).to(DEV)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    want = O.decoder_head({"decoder." + k: v.to(DEV) for k, v in sd.items()}, x, lengths)
+    got = dec(x, lengths)
+    got2 = dec(x, lengths)
+    assert torch.equal(got, got2)
+    rel = ((got - want).norm() / want.norm()).item()
+    print(f"tensor-core LSTM head B={B} T={T} H={H} L={L}: rel err vs fp32 oracle {rel:.2e}")
+    assert rel < 2e-2, rel
+    nolen = dec(x, None)
+    want_nolen = O.decoder_head({"decoder." + k: v.to(DEV) for k, v in sd.items()}, x, None)
+    assert ((nolen - want_nolen).norm() / want_nolen.norm()).item() < 2e-2
