@@ -2,7 +2,7 @@
 //
 // The recurrence is sequential in time: per step  gates[4H, B] = W_hh[4H, H] . h_{t-1}[B, H]^T + xin_t  and then the cell
 // update.  The CUDA-core kernel (decoder.cu, kept for the fp32 parity mode) spends 29 us per step at the head's size
-// (B = 64, H = 640), cuDNN's LSTM 12-15 us, this kernel 5.9 us.  A CTA owns 16 hidden units = 64 gate rows and keeps its
+// (B = 64, H = 640), cuDNN's LSTM 12-15 us, this kernel 5.5 us.  A CTA owns 16 hidden units = 64 gate rows and keeps its
 // [64 x H] bf16 slice of W_hh in SHARED MEMORY for the whole sequence (80 KB at H = 640: loaded once by TMA), next to a
 // buffer for the WHOLE h_{t-1} (80 KB at B = 64).  A step is
 //   grid barrier (h_{t-1} of all CTAs is in L2; polled with relaxed loads, one acquire fence afterwards)
@@ -14,11 +14,12 @@
 //      in flight during the copies and MMAs; its columns are packed in the same row order, so a warp reads 128 contiguous
 //      bytes per batch row)
 //   -> the four gates of a unit sit in four lanes of one warp (row order below): a 4 x 4 transpose over those lanes (two
-//      shuffle stages, branch-free selects) hands every lane the i, f, g, o values of ITS cells (unit, batch columns
-//      b = 4 j + gate index); cell state c and h stay in registers for the whole sequence
-//   -> h_t (bf16) into the ping-pong image the next step's copies read, the layer output (swish(h) for the last layer),
-//      one GPU-scope fence, arrive on the grid barrier.
-// Measured step (tools/lstm_trace.py): copies 1.8 us, MMAs done at 2.8, cells 2.6, publish 0.6.  Three things each cost
+//      shuffle stages run over all cells at once, branch-free selects) hands every lane the i, f, g, o values of ITS cells
+//      (unit, batch columns b = 4 j + gate index); cell state c and h stay in registers for the whole sequence
+//   -> h_t (bf16) and the layer output (swish(h) for the last layer) are staged in shared memory as [batch row][16 units]
+//      and leave as 16-byte stores: h_t into the ping-pong image the next step's copies read; one GPU-scope fence, arrive
+//      on the grid barrier.
+// Measured step (tools/lstm_trace.py): copies 1.8 us, MMAs done at 2.8, cells 0.8, publish 0.9.  Three things each cost
 // more than the arithmetic before they were found: selects written as ?: on a lane-dependent index compile to divergent
 // branches (a cell then took 0.67 us instead of 0.16); polling the barrier with ld.acquire invalidates the SM's L1 on
 // every poll; loads the compiler is free to sink end up behind the accumulator wait.
@@ -82,6 +83,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, LstmTcParams p) {
   uint64_t* w_bar = full_bar + 16;
   uint64_t* d_full = w_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+  bf16* st_h = reinterpret_cast<bf16*>(reinterpret_cast<uint8_t*>(full_bar) + 256);        // [64][16] staging of h_t
+  TOut* st_o = reinterpret_cast<TOut*>(reinterpret_cast<uint8_t*>(st_h) + LT_NMAX * LT_UNITS * 2);   // [64][16] staging of the output
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta = blockIdx.x, ncta = gridDim.x;
@@ -197,43 +200,62 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, LstmTcParams p) {
         }
       }
       tc_fence_before();
-      // h_t goes out as the swizzled image: element (b, k) of k-block k / 64 at b * 128 + ((k % 64 / 8) ^ (b & 7)) * 16 + k % 8 * 2
-      uint8_t* h_next = reinterpret_cast<uint8_t*>(p.hbuf) + (static_cast<size_t>((t + 1) & 1) * KB + (unit >> 6)) * NPAD * 128 + (unit & 7) * 2;
-      const int kchunk = (unit & 63) >> 3;
+      // ---- gates: 4 x 4 transpose over the four lanes that hold the gates of one unit (lane bits 3 and 4 = gate index);
+      //      afterwards this lane holds i, f, g, o of batch column 4 j + g_me.  Stage by stage over all cells, so that the
+      //      shuffles of different cells overlap.
+      const bool b0 = (g_me & 1) != 0, b1 = (g_me & 2) != 0;
+      float ga[LT_NMAX / 4][4];
 #pragma unroll
-      for (int j = 0; j < LT_NMAX / 4; ++j) {
-        if (j >= ncell) break;
-        // 4 x 4 transpose over the four lanes that hold the gates of one unit (lane bits 3 and 4 = gate index): afterwards
-        // this lane holds i, f, g, o of batch column 4 j + g_me
-        const bool b0 = (g_me & 1) != 0, b1 = (g_me & 2) != 0;
+      for (int j = 0; j < LT_NMAX / 4; ++j) {                     // stage A (partner: gate ^ 1): keep columns b0 and b0 + 2
         const float a0 = __uint_as_float(r[4 * j + 0]) + xv[4 * j + 0], a1 = __uint_as_float(r[4 * j + 1]) + xv[4 * j + 1];
         const float a2 = __uint_as_float(r[4 * j + 2]) + xv[4 * j + 2], a3 = __uint_as_float(r[4 * j + 3]) + xv[4 * j + 3];
-        // stage A (partner: gate ^ 1): keep columns b0 and b0 + 2, send the other two
         const float rA0 = __shfl_xor_sync(0xffffffffu, selp(b0, a0, a1), 8), rA1 = __shfl_xor_sync(0xffffffffu, selp(b0, a2, a3), 8);
         const float kA0 = selp(b0, a1, a0), kA1 = selp(b0, a3, a2);
-        const float lo_e = selp(b0, rA0, kA0), lo_o = selp(b0, kA0, rA0);      // column b0, gates 2 b1 and 2 b1 + 1
-        const float hi_e = selp(b0, rA1, kA1), hi_o = selp(b0, kA1, rA1);      // column b0 + 2
-        // stage B (partner: gate ^ 2): keep column b0 + 2 b1, send the other
+        ga[j][0] = selp(b0, rA0, kA0); ga[j][1] = selp(b0, kA0, rA0);    // column b0: gates 2 b1, 2 b1 + 1
+        ga[j][2] = selp(b0, rA1, kA1); ga[j][3] = selp(b0, kA1, rA1);    // column b0 + 2
+      }
+#pragma unroll
+      for (int j = 0; j < LT_NMAX / 4; ++j) {                     // stage B (partner: gate ^ 2): keep column b0 + 2 b1
+        const float lo_e = ga[j][0], lo_o = ga[j][1], hi_e = ga[j][2], hi_o = ga[j][3];
         const float rB_e = __shfl_xor_sync(0xffffffffu, selp(b1, lo_e, hi_e), 16), rB_o = __shfl_xor_sync(0xffffffffu, selp(b1, lo_o, hi_o), 16);
         const float kB_e = selp(b1, hi_e, lo_e), kB_o = selp(b1, hi_o, lo_o);
-        const float gi = selp(b1, rB_e, kB_e), gf = selp(b1, rB_o, kB_o), gg = selp(b1, kB_e, rB_e), go = selp(b1, kB_o, rB_o);
+        ga[j][0] = selp(b1, rB_e, kB_e); ga[j][1] = selp(b1, rB_o, kB_o); ga[j][2] = selp(b1, kB_e, rB_e); ga[j][3] = selp(b1, kB_o, rB_o);
+      }
+      // ---- cells; h_t and the layer output are staged in shared memory as [batch row][16 units] and leave as 16-byte stores
+#pragma unroll
+      for (int j = 0; j < LT_NMAX / 4; ++j) {
         const int b = 4 * j + g_me;
         const bool live = t < len[j];
         float tg, tc;
-        asm("tanh.approx.f32 %0, %1;" : "=f"(tg) : "f"(gg));
-        const float c = sigmoid_tanh(gf) * c_reg[j] + sigmoid_tanh(gi) * tg;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tg) : "f"(ga[j][2]));
+        const float c = sigmoid_tanh(ga[j][1]) * c_reg[j] + sigmoid_tanh(ga[j][0]) * tg;
         asm("tanh.approx.f32 %0, %1;" : "=f"(tc) : "f"(c));
-        const float hn = selp(live, sigmoid_tanh(go) * tc, h_reg[j]);
+        const float hn = selp(live, sigmoid_tanh(ga[j][3]) * tc, h_reg[j]);
         c_reg[j] = selp(live, c, c_reg[j]);
         h_reg[j] = hn;
-        if (b < B) {
-          *reinterpret_cast<bf16*>(h_next + b * 128 + ((kchunk ^ (b & 7)) << 4)) = __float2bfloat16_rn(hn);
-          const float o = selp(live, p.last_layer ? swish_tanh(hn) : hn, 0.f);
-          out[(static_cast<int64_t>(t) * p.Btot + b) * H + unit] = from_f32<TOut>(o);
-        }
+        st_h[b * LT_UNITS + q * 8 + u8] = __float2bfloat16_rn(hn);
+        st_o[b * LT_UNITS + q * 8 + u8] = from_f32<TOut>(selp(live, p.last_layer ? swish_tanh(hn) : hn, 0.f));
       }
       if (warp == 0) LTRACE(6);
-      named_bar_sync(1, 64);                                    // every cell thread's stores are ordered before thread 0 ...
+      named_bar_sync(1, 64);
+      {
+        // thread = batch row: its 16 units are two 16-byte chunks of the swizzled image (element (b, k) of k-block k / 64 at
+        // b * 128 + ((k % 64 / 8) ^ (b & 7)) * 16 + k % 8 * 2) and 16 contiguous outputs
+        const int bb = threadIdx.x;
+        if (bb < B) {
+          const int k0 = cta * LT_UNITS;
+          uint8_t* img = reinterpret_cast<uint8_t*>(p.hbuf) + (static_cast<size_t>((t + 1) & 1) * KB + (k0 >> 6)) * NPAD * 128 + bb * 128;
+          const uint4* src = reinterpret_cast<const uint4*>(st_h + bb * LT_UNITS);
+          const int kc = (k0 & 63) >> 3;
+          *reinterpret_cast<uint4*>(img + (((kc) ^ (bb & 7)) << 4)) = src[0];
+          *reinterpret_cast<uint4*>(img + (((kc + 1) ^ (bb & 7)) << 4)) = src[1];
+          const uint4* so = reinterpret_cast<const uint4*>(st_o + bb * LT_UNITS);
+          uint4* dst = reinterpret_cast<uint4*>(out + (static_cast<int64_t>(t) * p.Btot + bb) * H + k0);
+#pragma unroll
+          for (int i = 0; i < static_cast<int>(LT_UNITS * sizeof(TOut) / 16); ++i) dst[i] = so[i];
+        }
+      }
+      named_bar_sync(1, 64);                                    // every thread's stores are ordered before thread 0 ...
       if (threadIdx.x == 0) {
         __threadfence();                                        // ... whose cumulative GPU-scope fence publishes them
         atomicAdd(p.bar, 1u);
@@ -298,7 +320,7 @@ int lstm_logits_from_time_major(const float* lg, float* y, int B, int T, int V, 
 extern unsigned long long* g_gemm_trace;
 
 bool lstm_tc_supported(int H) {
-  return H % 64 == 0 && H / 64 <= 16 && static_cast<size_t>(H / 64) * (LT_ROWS + LT_NMAX) * 128 + LT_ROWS * 128 + 2048 <= 227 * 1024;
+  return H % 64 == 0 && H / 64 <= 16 && static_cast<size_t>(H / 64) * (LT_ROWS + LT_NMAX) * 128 + LT_ROWS * 128 + 2048 + LT_NMAX * LT_UNITS * 6 <= 227 * 1024;
 }
 
 int lstm_pack_rows_f32(const float* src, float* dst, int H, int K, cudaStream_t stream) {
@@ -323,7 +345,7 @@ int lstm_layer_forward_tc(const float* xin_tm, const bf16* w_hh_packed, const in
   CFM_REQUIRE(B > 0 && T > 0 && lstm_tc_supported(H), "tensor-core LSTM: hidden size must be a multiple of 64 (up to 1024)");
   CFM_REQUIRE(H / LT_UNITS <= num_sms, "tensor-core LSTM keeps 16 hidden units per SM");
   const int KB = H / LT_KB;
-  const int smem = 1024 + KB * (LT_ROWS + LT_NMAX) * 128 + LT_ROWS * 128 + 256;
+  const int smem = 1024 + KB * (LT_ROWS + LT_NMAX) * 128 + LT_ROWS * 128 + 256 + LT_NMAX * LT_UNITS * 6;
   auto kern = lstm_tc_kernel<TOut>;
   static std::atomic<uint64_t> attr_done{0};
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), smem));
