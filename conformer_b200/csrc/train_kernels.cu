@@ -239,6 +239,102 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
   }
 }
 
+// d = 256 * G: lane owns 8 contiguous columns of every 256-column group (two 16-byte accesses), nothing is predicated.
+template <int G>
+__global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                         const float* __restrict__ gamma, float* dx, int accumulate,
+                                                         float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
+                                                         int rows_per_warp) {
+  constexpr int d = 256 * G, NV = 8 * G;
+  __shared__ float red[2 * d];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float gam[NV], gsum[NV], bsum[NV];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(gamma + g * 256 + lane * 8)), b = __ldg(reinterpret_cast<const float4*>(gamma + g * 256 + lane * 8) + 1);
+    gam[8 * g + 0] = a.x; gam[8 * g + 1] = a.y; gam[8 * g + 2] = a.z; gam[8 * g + 3] = a.w;
+    gam[8 * g + 4] = b.x; gam[8 * g + 5] = b.y; gam[8 * g + 6] = b.z; gam[8 * g + 7] = b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < NV; ++i) gsum[i] = bsum[i] = 0.f;
+  const int64_t r0 = (static_cast<int64_t>(blockIdx.x) * nwarps + warp) * rows_per_warp;
+  for (int rr = 0; rr < rows_per_warp; ++rr) {
+    const int64_t row = r0 + rr;
+    if (row >= rows) break;
+    float xv[NV], dv[NV];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float4* xp = reinterpret_cast<const float4*>(x + row * d + g * 256 + lane * 8);
+      const float4* dp = reinterpret_cast<const float4*>(dy + row * d + g * 256 + lane * 8);
+      const float4 a = xp[0], b = xp[1], c = dp[0], e = dp[1];
+      xv[8 * g + 0] = a.x; xv[8 * g + 1] = a.y; xv[8 * g + 2] = a.z; xv[8 * g + 3] = a.w;
+      xv[8 * g + 4] = b.x; xv[8 * g + 5] = b.y; xv[8 * g + 6] = b.z; xv[8 * g + 7] = b.w;
+      dv[8 * g + 0] = c.x; dv[8 * g + 1] = c.y; dv[8 * g + 2] = c.z; dv[8 * g + 3] = c.w;
+      dv[8 * g + 4] = e.x; dv[8 * g + 5] = e.y; dv[8 * g + 6] = e.z; dv[8 * g + 7] = e.w;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += xv[i];
+    const float mean = warp_sum(s) * (1.0f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xv[i] -= mean;
+      q += xv[i] * xv[i];
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + 1e-5f);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      xv[i] *= rstd;                                            // xhat
+      const float gy = dv[i] * gam[i];
+      s1 += gy;
+      s2 += gy * xv[i];
+      gsum[i] += dv[i] * xv[i];
+      bsum[i] += dv[i];
+      dv[i] = gy;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {                          // both sums in one butterfly
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    s1 *= (1.0f / d);
+    s2 *= (1.0f / d);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float4* op = reinterpret_cast<float4*>(dx + row * d + g * 256 + lane * 8);
+      float4 a, b;
+      a.x = rstd * (dv[8 * g + 0] - s1 - xv[8 * g + 0] * s2); a.y = rstd * (dv[8 * g + 1] - s1 - xv[8 * g + 1] * s2);
+      a.z = rstd * (dv[8 * g + 2] - s1 - xv[8 * g + 2] * s2); a.w = rstd * (dv[8 * g + 3] - s1 - xv[8 * g + 3] * s2);
+      b.x = rstd * (dv[8 * g + 4] - s1 - xv[8 * g + 4] * s2); b.y = rstd * (dv[8 * g + 5] - s1 - xv[8 * g + 5] * s2);
+      b.z = rstd * (dv[8 * g + 6] - s1 - xv[8 * g + 6] * s2); b.w = rstd * (dv[8 * g + 7] - s1 - xv[8 * g + 7] * s2);
+      if (accumulate) {
+        const float4 pa = op[0], pb = op[1];
+        a.x += pa.x; a.y += pa.y; a.z += pa.z; a.w += pa.w;
+        b.x += pb.x; b.y += pb.y; b.z += pb.z; b.w += pb.w;
+      }
+      op[0] = a;
+      op[1] = b;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&red[g * 256 + lane * 8 + e], gsum[8 * g + e]);
+      atomicAdd(&red[d + g * 256 + lane * 8 + e], bsum[8 * g + e]);
+    }
+  __syncthreads();
+  for (int i = threadIdx.x * 4; i < 2 * d; i += blockDim.x * 4) {
+    float* dst = i < d ? dgamma + i : dbeta + (i - d);
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(red[i]), "f"(red[i + 1]), "f"(red[i + 2]), "f"(red[i + 3])
+                 : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------- depthwise conv
 // z[b,t,c] = bias[c] + sum_j w[c,j] g[b,t+j-half,c]   (Conv1d groups = channels, zero padding at the tensor edges,
 // convolution.py:15,26); weights in the module's own layout [c][k].  FLIP = true computes the input gradient
@@ -631,6 +727,16 @@ int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool 
   int rpw = static_cast<int>((rows + 296 * warps - 1) / (296 * warps));
   if (rpw < 2) rpw = 2;
   const unsigned grid = nblk(rows, rpw * warps);
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
+                         reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
+  if (aligned && d == 256) {
+    ln_bwd_vec_kernel<1><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw);
+    LAUNCH_OK();
+  }
+  if (aligned && d == 512) {
+    ln_bwd_vec_kernel<2><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw);
+    LAUNCH_OK();
+  }
   const size_t smem = static_cast<size_t>(2) * d * 4;
   const int nv = (d + 31) / 32;
   if (nv <= 8) ln_bwd_kernel<8><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
