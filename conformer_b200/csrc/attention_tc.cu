@@ -246,6 +246,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
     const uint32_t t_ps = tlane + TM_PS + 32 * grp + 32 * (3 - w);     // 64-column window holding their positional scores
     const uint32_t t_o = tlane + TM_O + 32 * grp;                      // the half of the O row this thread rescales
     uint8_t* prow = p_s + row * 128;
+    const DropK dk = p.dr.load();                  // TRAIN: dropout seed in registers
     float m_ref = -CUDART_INF_F, l_part = 0.f;
 
     for (int j = 0; j < ntiles; ++j) {
@@ -326,7 +327,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
           psum += p0 + p1;
           if (TRAIN) {
             const int64_t e0 = (static_cast<int64_t>(b * p.H + h) * Tn + qi) * Tn + j * BKV + 32 * grp + c4 * 8 + 2 * e;
-            o[e] = pack_bf16x2(p0 * p.dr.factor(e0), p1 * p.dr.factor(e0 + 1));
+            o[e] = pack_bf16x2(p0 * dk.factor(e0), p1 * dk.factor(e0 + 1));
           } else {
             o[e] = pack_bf16x2(p0, p1);
           }

@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(AttnArgs p, TA* __res
 #pragma unroll
     for (int c = 0; c < 4; ++c) o[a][c] = 0.f;
   }
+  const DropK dk = p.dr.load();
   for (int j0 = 0; j0 < Tn; j0 += TK) {
     __syncthreads();
     load_rows<TA>(Kt, qkv + d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(AttnArgs p, TA* __res
         const float pv = dead[e] ? 0.f : __expf(s[a][e] - mn);
         rs += pv;
         const int j = j0 + tj + 16 * e;
-        const float f = p.dr.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
+        const float f = dk.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
         Ps[(ti + 16 * a) * LDS_ + tj + 16 * e] = pv * f;
       }
       l[a] = l[a] * corr + group16_sum(rs);
@@ -282,6 +283,7 @@ __global__ void attn_delta_kernel(const float* __restrict__ dctx, const TA* __re
 // shared by the two backward kernels: P (undropped), Pd = f P and ds (scaled) of this thread's 4 x 4 entries
 __device__ __forceinline__ void bwd_entries(const AttnArgs& p, const float (&s)[4][4], const float (&dpd)[4][4], const float* lse_s,
                                             const float* D_s, int b, int h, int i0, int j0, int ti, int tj, float* Ps, float* DSs) {
+  const DropK dk = p.dr.load();
   const int Tn = p.Tn;
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -293,7 +295,7 @@ __device__ __forceinline__ void bwd_entries(const AttnArgs& p, const float (&s)[
       float pd = 0.f, ds = 0.f;
       if (!dead && i < Tn) {
         const float pv = __expf(s[a][e] - lse_s[il]);
-        const float f = p.dr.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
+        const float f = dk.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
         pd = pv * f;
         ds = pv * (f * dpd[a][e] - D_s[il]) * p.scale;
       }

@@ -105,6 +105,7 @@ __device__ __forceinline__ void mma_abt(const bf16* A, int lda, const bf16* Bm, 
 __device__ __forceinline__ void scores_and_grads(const MmaArgs& p, const bf16* Qc, const bf16* Qp, const bf16* dO, const bf16* Kt, const bf16* Vt,
                                                  const bf16* Pw, float* Ss, float* Us, float* DPs, const float* lse_s, const float* D_s,
                                                  bf16* Pd_b, bf16* dS_b, bf16* dSu_b, int b, int h, int i0, int j0) {
+  const DropK dk = p.dr.load();
   const int warp = threadIdx.x >> 5;
   const int rb = warp >> 1;
 #pragma unroll
@@ -133,7 +134,7 @@ __device__ __forceinline__ void scores_and_grads(const MmaArgs& p, const bf16* Q
       if (!dead) {
         const float s = p.scale * (Ss[il * LDF + jl] + Us[il * LDUF + jl - il + (TQ - 1)]);
         const float pv = __expf(s - lse);
-        const float f = p.dr.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
+        const float f = dk.factor((static_cast<int64_t>(b * p.H + h) * Tn + i) * Tn + j);
         pd = pv * f;
         ds = pv * (f * DPs[il * LDF + jl] - Dv) * p.scale;
       }

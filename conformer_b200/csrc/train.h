@@ -10,20 +10,33 @@ namespace cfm {
 // regenerates the forward's mask instead of storing it.  The seed is read from DEVICE memory (two 32-bit words written by
 // cfm_encoder_train_forward before the step's kernels): kernel arguments then do not change from step to step, which is
 // what lets a whole training forward / block backward replay as a CUDA graph.
-struct Drop {
+struct DropK {                          // kernel-side: the seed in registers (Drop::load, once per thread)
   float p = 0.f, inv_keep = 1.f;
-  const uint32_t* seed = nullptr;       // device: {lo, hi}
-  uint32_t site = 0;
+  uint32_t lo = 0, hi = 0, site = 0;
   // one 32-bit hash per PAIR of elements, 16 bits each (kernels handle 4 consecutive elements per thread, so the hash
   // of a pair is computed once)
   __device__ __forceinline__ float factor(int64_t i) const {
     if (p <= 0.f) return 1.f;
     const uint64_t j = static_cast<uint64_t>(i) >> 1;
-    uint32_t h = __ldg(seed) ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(j >> 32) * 0x85EBCA6Bu);
+    uint32_t h = lo ^ (site * 0x9E3779B9u) ^ static_cast<uint32_t>(j) ^ (static_cast<uint32_t>(j >> 32) * 0x85EBCA6Bu);
     h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-    h ^= __ldg(seed + 1); h *= 0x9E3779B1u; h ^= h >> 15;
+    h ^= hi; h *= 0x9E3779B1u; h ^= h >> 15;
     const uint32_t u = (i & 1) ? (h >> 16) : (h & 0xFFFFu);
     return (static_cast<float>(u) * (1.0f / 65536.0f)) >= p ? inv_keep : 0.f;
+  }
+};
+struct Drop {                           // kernel argument
+  float p = 0.f, inv_keep = 1.f;
+  const uint32_t* seed = nullptr;       // device: {lo, hi}
+  uint32_t site = 0;
+  __device__ __forceinline__ DropK load() const {
+    DropK k;
+    k.p = p; k.inv_keep = inv_keep; k.site = site;
+    if (p > 0.f) {
+      k.lo = __ldg(seed);
+      k.hi = __ldg(seed + 1);
+    }
+    return k;
   }
 };
 inline Drop make_drop(float p, const uint32_t* seed_dev, uint32_t site) {

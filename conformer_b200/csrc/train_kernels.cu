@@ -49,8 +49,9 @@ __global__ void cast_scale_drop_kernel(const float* __restrict__ in, TOut* __res
   if (i >= n) return;
   float v[4];
   ld4(in + i, v);
+  const DropK dk = dr.load();
 #pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] *= scale * dr.factor(i + e);
+  for (int e = 0; e < 4; ++e) v[e] *= scale * dk.factor(i + e);
   st4(out + i, v);
 }
 // bf16 activations: the result is rounded to bf16, so the one-MUFU forms (tanh.approx, error ~5e-4) are exact enough;
@@ -69,8 +70,9 @@ __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict_
   if (i >= n) return;
   float v[4];
   ld4(hp + i, v);
+  const DropK dk = dr.load();
 #pragma unroll
-  for (int e = 0; e < 4; ++e) v[e] = swish_act<TA>(v[e]) * dr.factor(i + e);
+  for (int e = 0; e < 4; ++e) v[e] = swish_act<TA>(v[e]) * dk.factor(i + e);
   st4(out + i, v);
 }
 template <typename TA>
@@ -80,10 +82,11 @@ __global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __
   float x[4], g[4];
   ld4(hp + i, x);
   ld4(dh + i, g);
+  const DropK dk = dr.load();
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const float s = sigmoid_act<TA>(x[e]);
-    g[e] *= dr.factor(i + e) * (s + x[e] * s * (1.f - s));
+    g[e] *= dk.factor(i + e) * (s + x[e] * s * (1.f - s));
   }
   st4(out + i, g);
 }
@@ -94,13 +97,14 @@ __global__ void residual_drop_add_kernel(const float* __restrict__ x, const floa
   float a[4], b[4];
   ld4(x + i, a);
   ld4(t + i, b);
+  const DropK dk = dr.load();
 #pragma unroll
-  for (int e = 0; e < 4; ++e) a[e] += scale * dr.factor(i + e) * b[e];
+  for (int e = 0; e < 4; ++e) a[e] += scale * dk.factor(i + e) * b[e];
   st4(out + i, a);
 }
 __global__ void drop_inplace_kernel(float* __restrict__ x, int64_t n, Drop dr) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) x[i] *= dr.factor(i);
+  if (i < n) x[i] *= dr.load().factor(i);
 }
 template <typename TA>
 __global__ void glu_fwd_kernel(const TA* __restrict__ u, TA* __restrict__ g, int64_t rows, int d) {
