@@ -198,7 +198,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
     D_s[i] = ok ? p.D[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
   }
   for (int i = threadIdx.x; i < WINR * LDF; i += THREADS) Wacc[i] = 0.f;
-  for (int i = threadIdx.x; i < 2 * DHP; i += THREADS) red[i] = 0.f;
   // dQ accumulators: warp -> row block rb = warp / 2, column blocks (warp & 1) * 2 + {0, 1}; content and positional parts
   FragC dqc[2], dqp[2];
 #pragma unroll
@@ -285,20 +284,19 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
       for (int c = 0; c < 16; c += 2) {
         const float a0 = Ss[il * LDF + c0 + c], a1 = Ss[il * LDF + c0 + c + 1];
         const float b0 = DPs[il * LDF + c0 + c], b1 = DPs[il * LDF + c0 + c + 1];
-        if (c0 + c < dh) {
-          *reinterpret_cast<uint32_t*>(dst + c0 + c) = pack_bf16x2(a0 + b0, a1 + b1);
-          atomicAdd(&red[c0 + c], a0);
-          atomicAdd(&red[c0 + c + 1], a1);
-          atomicAdd(&red[DHP + c0 + c], b0);
-          atomicAdd(&red[DHP + c0 + c + 1], b1);
-        }
+        if (c0 + c < dh) *reinterpret_cast<uint32_t*>(dst + c0 + c) = pack_bf16x2(a0 + b0, a1 + b1);
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < dh; c += THREADS) {
-    atomicAdd(du + h * dh + c, red[c]);
-    atomicAdd(dv + h * dh + c, red[DHP + c]);
+  // column sums over the valid rows: one thread per column (64 threads adding into one shared address made the
+  // compare-and-swap loop of the shared-memory float atomic spin for a tenth of the kernel)
+  if (threadIdx.x < 2 * DHP) {
+    const int c = threadIdx.x % DHP;
+    const float* src = threadIdx.x < DHP ? Ss : DPs;
+    const int nrow = min(TQ, Tn - i0);
+    float acc = 0.f;
+    for (int r = 0; r < nrow; ++r) acc += src[r * LDF + c];
+    if (c < dh) atomicAdd((threadIdx.x < DHP ? du : dv) + h * dh + c, acc);
   }
 }
 
