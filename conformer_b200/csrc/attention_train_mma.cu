@@ -85,6 +85,87 @@ __device__ __forceinline__ void load_tile_f32(bf16* dst, const float* src, int64
   }
 }
 
+// The tiles of one loop iteration in ONE pass: every global load is issued before the first shared-memory store, so the
+// iteration pays one memory latency instead of one per tile (the per-tile loaders above made the load wait of each
+// tile the top stall of both kernels).
+__device__ __forceinline__ uint4 add_bias8(uint4 o, const float* add, int c8) {
+  uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+    w[e] = pack_bf16x2(__uint_as_float(w[e] << 16) + add[c8 + 2 * e], __uint_as_float(w[e] & 0xffff0000u) + add[c8 + 2 * e + 1]);
+  return o;
+}
+// query side, per key tile: K, V rows j0 .. j0+63 and the 128-row window of the projected table starting at row r0
+__device__ __forceinline__ void load_key_tiles(bf16* Kt, bf16* Vt, bf16* Pw, const bf16* kbase, const bf16* vbase, int64_t stride, int j0,
+                                               int Tn, const bf16* pp, int64_t ppstride, int r0, int R, int dh) {
+  static_assert(TK * (DHP / 8) == 2 * THREADS && WINR * (DHP / 8) == 4 * THREADS, "loader shape");
+  uint4 k[2], v[2], w[4];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8, row = j0 + r;
+    k[it] = v[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (row < Tn && c8 < dh) {
+      k[it] = *reinterpret_cast<const uint4*>(kbase + static_cast<int64_t>(row) * stride + c8);
+      v[it] = *reinterpret_cast<const uint4*>(vbase + static_cast<int64_t>(row) * stride + c8);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8, row = r0 + r;
+    w[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (row >= 0 && row < R && c8 < dh) w[it] = *reinterpret_cast<const uint4*>(pp + static_cast<int64_t>(row) * ppstride + c8);
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8;
+    *reinterpret_cast<uint4*>(Kt + r * LDB + c8) = k[it];
+    *reinterpret_cast<uint4*>(Vt + r * LDB + c8) = v[it];
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8;
+    *reinterpret_cast<uint4*>(Pw + r * LDB + c8) = w[it];
+  }
+}
+// key side, per query tile: q rows i0 .. i0+63 (+ u -> Qc, + v -> Qp), dctx rows (fp32 -> bf16) and the window of the table
+__device__ __forceinline__ void load_query_tiles(bf16* Qc, bf16* Qp, bf16* dO, bf16* Pw, const bf16* qbase, int64_t stride, const float* u,
+                                                 const float* vb, const float* dctx, int64_t dstride, int i0, int Tn, const bf16* pp,
+                                                 int64_t ppstride, int r0, int R, int dh) {
+  uint4 q[2], w[4];
+  float4 g[2][2];
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8, row = i0 + r;
+    q[it] = make_uint4(0u, 0u, 0u, 0u);
+    g[it][0] = g[it][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < Tn && c8 < dh) {
+      q[it] = *reinterpret_cast<const uint4*>(qbase + static_cast<int64_t>(row) * stride + c8);
+      g[it][0] = *reinterpret_cast<const float4*>(dctx + static_cast<int64_t>(row) * dstride + c8);
+      g[it][1] = *reinterpret_cast<const float4*>(dctx + static_cast<int64_t>(row) * dstride + c8 + 4);
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8, row = r0 + r;
+    w[it] = make_uint4(0u, 0u, 0u, 0u);
+    if (row >= 0 && row < R && c8 < dh) w[it] = *reinterpret_cast<const uint4*>(pp + static_cast<int64_t>(row) * ppstride + c8);
+  }
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8, row = i0 + r;
+    const bool ok = row < Tn && c8 < dh;                          // rows past T stay zero (no bias either), as load_tile does
+    *reinterpret_cast<uint4*>(Qc + r * LDB + c8) = ok ? add_bias8(q[it], u, c8) : q[it];
+    *reinterpret_cast<uint4*>(Qp + r * LDB + c8) = ok ? add_bias8(q[it], vb, c8) : q[it];
+    *reinterpret_cast<uint4*>(dO + r * LDB + c8) = make_uint4(pack_bf16x2(g[it][0].x, g[it][0].y), pack_bf16x2(g[it][0].z, g[it][0].w),
+                                                              pack_bf16x2(g[it][1].x, g[it][1].y), pack_bf16x2(g[it][1].z, g[it][1].w));
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * THREADS, r = idx >> 3, c8 = (idx & 7) * 8;
+    *reinterpret_cast<uint4*>(Pw + r * LDB + c8) = w[it];
+  }
+}
+
 // C[16 rb .. , 16 cb ..] = A[rows 16 rb][K] . B^T, A row-major (pitch lda), B stored [n][k] (pitch ldb): K = 64
 __device__ __forceinline__ void mma_abt(const bf16* A, int lda, const bf16* Bm, int ldb, int rb, int cb, float* out, int ldo) {
   FragC c;
@@ -209,9 +290,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
   for (int j0 = 0; j0 < Tn; j0 += TK) {
     __syncthreads();
     const int r0 = (Tn - 1) + j0 - i0 - (TQ - 1);
-    load_tile(Kt, qkv + d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
-    load_tile(Vt, qkv + 2 * d, 3 * d, j0, 0, Tn, TK, dh, nullptr);
-    load_tile(Pw, pp, d, r0, 0, 2 * Tn - 1, WINR, dh, nullptr);
+    load_key_tiles(Kt, Vt, Pw, qkv + d, qkv + 2 * d, 3 * d, j0, Tn, pp, d, r0, 2 * Tn - 1, dh);
     __syncthreads();
     scores_and_grads(p, Qc, Qp, dO, Kt, Vt, Pw, Ss, Us, DPs, lse_s, D_s, nullptr, dS_b, dSu_b, b, h, i0, j0);
     // dQc += ds K   (A = ds [i][j], B[k = j][n = d] = K[j][d]);   dQp += dsu Pw   (K = 128 window rows)
@@ -331,10 +410,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, 
   }
   for (int i0 = 0; i0 < Tn; i0 += TQ) {
     __syncthreads();
-    load_tile(Qc, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.u + h * dh);
-    load_tile(Qp, qkv, 3 * d, i0, 0, Tn, TQ, dh, p.v + h * dh);
-    load_tile_f32(dO, p.dctx + static_cast<int64_t>(b) * Tn * d + h * dh, d, i0, Tn, TQ, dh);
-    load_tile(Pw, pp, d, (Tn - 1) + j0 - i0 - (TQ - 1), 0, 2 * Tn - 1, WINR, dh, nullptr);
+    load_query_tiles(Qc, Qp, dO, Pw, qkv, 3 * d, p.u + h * dh, p.v + h * dh, p.dctx + static_cast<int64_t>(b) * Tn * d + h * dh, d, i0, Tn,
+                     pp, d, (Tn - 1) + j0 - i0 - (TQ - 1), 2 * Tn - 1, dh);
     for (int i = threadIdx.x; i < TQ; i += THREADS) {
       const bool ok = i0 + i < Tn;
       lse_s[i] = ok ? p.lse[(static_cast<int64_t>(b) * p.H + h) * Tn + i0 + i] : 0.f;
