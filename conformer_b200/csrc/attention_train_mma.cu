@@ -14,18 +14,17 @@
 //   key-side kernel, one CTA = 64 keys, loop over query tiles: the same S / U / dP / element-wise stage, then
 //     dV += Pd^T dO,  dK += ds^T Qc
 //
-// This is the interim tensor-core form (the nvcuda::wmma interface, i.e. the warp-level MMA path): it takes the backward
-// from the fp32 FMA pipe to the tensor pipe with fragments the compiler lays out; a tcgen05 version with the
-// accumulators in tensor memory is the next step.  The fp32 gradient-parity mode keeps the
-// CUDA-core kernels of attention_train.cu.
-#include <mma.h>
-
+// This is the interim tensor-core form: warp-level mma.sync.m16n8k16 with ldmatrix operand loads (the HMMA path).  It
+// takes the backward from the fp32 FMA pipe to the tensor pipe; a tcgen05 version with the accumulators in tensor memory
+// is the next step.  Profile-guided history of the two kernels at C4 (14.2 -> 9.0 ms per step):
+// one thread per column for the du / dv sums instead of contended shared-memory float atomics (compare-and-swap loops),
+// all tiles of an iteration loaded in one pass (one memory latency instead of one per tile), ldmatrix + mma.sync instead
+// of nvcuda::wmma (whose loads compiled to generic 32-bit loads).  The fp32 gradient-parity mode keeps the CUDA-core
+// kernels of attention_train.cu.
 #include "train.h"
 
 namespace cfm {
 namespace {
-
-using namespace nvcuda;
 
 constexpr int TQ = 64, TK = 64, DHP = 64, WINR = 128;             // 127 window rows used, 128 stored
 constexpr int LDB = DHP + 8;                                       // bf16 operand tiles: 72 elements = 144 B per row
@@ -48,11 +47,66 @@ struct MmaArgs {
   Drop dr;
 };
 
-typedef wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::row_major> FragA;
-typedef wmma::fragment<wmma::matrix_a, 16, 16, 16, __nv_bfloat16, wmma::col_major> FragAT;
-typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::row_major> FragB;     // B[k][n] stored [k][n]
-typedef wmma::fragment<wmma::matrix_b, 16, 16, 16, __nv_bfloat16, wmma::col_major> FragBT;    // B[k][n] stored [n][k]
-typedef wmma::fragment<wmma::accumulator, 16, 16, 16, float> FragC;
+// 16 x 16 x 16 tile products as two mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with ldmatrix operand loads.  (The
+// nvcuda::wmma loads this file started with compiled to 32-bit GENERIC loads plus MOVM transposes - 528 LD.E for 144 HMMA in
+// the query-side kernel, a quarter of its stall samples; one ldmatrix.x4 replaces sixteen of them.)
+struct FragA { uint32_t r[4]; };                 // A[16 m][16 k]
+struct FragB { uint32_t r[4]; };                 // B[16 k][16 n]: r[0], r[1] = columns 0-7; r[2], r[3] = columns 8-15
+struct FragC { float c[8]; };                    // C[16][16]: c[0..3] = columns 0-7 (rows g, g+8), c[4..7] = columns 8-15
+__device__ __forceinline__ void frag_zero(FragC& c) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c.c[i] = 0.f;
+}
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+// A row-major: p = &A[m0][k0], pitch ld (elements)
+__device__ __forceinline__ void ld_a(FragA& a, const bf16* p, int ld) {
+  const int l = threadIdx.x & 31;
+  ldsm4(a.r, p + ((l & 7) + 8 * ((l >> 3) & 1)) * ld + 8 * (l >> 4));
+}
+// A stored transposed: element A[m][k] at p[k * ld + m], p = &smem[k0][m0]
+__device__ __forceinline__ void ld_a_t(FragA& a, const bf16* p, int ld) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm4_t(a.r, p + ((l & 7) + 8 * (mi >> 1)) * ld + 8 * (mi & 1));
+}
+// B stored [n][k] (k contiguous): p = &smem[n0][k0]
+__device__ __forceinline__ void ld_b_nk(FragB& b, const bf16* p, int ld) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm4(b.r, p + ((l & 7) + 8 * (mi >> 1)) * ld + 8 * (mi & 1));
+}
+// B stored [k][n] (n contiguous): p = &smem[k0][n0]
+__device__ __forceinline__ void ld_b_kn(FragB& b, const bf16* p, int ld) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm4_t(b.r, p + ((l & 7) + 8 * (mi & 1)) * ld + 8 * (mi >> 1));
+}
+__device__ __forceinline__ void frag_mma(FragC& c, const FragA& a, const FragB& b) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c.c[0]), "+f"(c.c[1]), "+f"(c.c[2]), "+f"(c.c[3])
+               : "r"(a.r[0]), "r"(a.r[1]), "r"(a.r[2]), "r"(a.r[3]), "r"(b.r[0]), "r"(b.r[1]));
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c.c[4]), "+f"(c.c[5]), "+f"(c.c[6]), "+f"(c.c[7])
+               : "r"(a.r[0]), "r"(a.r[1]), "r"(a.r[2]), "r"(a.r[3]), "r"(b.r[2]), "r"(b.r[3]));
+}
+// C <-> fp32 row-major shared memory: p = &out[m0][n0]
+__device__ __forceinline__ void frag_store(float* p, int ld, const FragC& c) {
+  const int l = threadIdx.x & 31, g = l >> 2, t = l & 3;
+  *reinterpret_cast<float2*>(p + g * ld + 2 * t) = make_float2(c.c[0], c.c[1]);
+  *reinterpret_cast<float2*>(p + (g + 8) * ld + 2 * t) = make_float2(c.c[2], c.c[3]);
+  *reinterpret_cast<float2*>(p + g * ld + 8 + 2 * t) = make_float2(c.c[4], c.c[5]);
+  *reinterpret_cast<float2*>(p + (g + 8) * ld + 8 + 2 * t) = make_float2(c.c[6], c.c[7]);
+}
+__device__ __forceinline__ void frag_load(FragC& c, const float* p, int ld) {
+  const int l = threadIdx.x & 31, g = l >> 2, t = l & 3;
+  const float2 v0 = *reinterpret_cast<const float2*>(p + g * ld + 2 * t), v1 = *reinterpret_cast<const float2*>(p + (g + 8) * ld + 2 * t);
+  const float2 v2 = *reinterpret_cast<const float2*>(p + g * ld + 8 + 2 * t), v3 = *reinterpret_cast<const float2*>(p + (g + 8) * ld + 8 + 2 * t);
+  c.c[0] = v0.x; c.c[1] = v0.y; c.c[2] = v1.x; c.c[3] = v1.y; c.c[4] = v2.x; c.c[5] = v2.y; c.c[6] = v3.x; c.c[7] = v3.y;
+}
 
 // dst[r][c] (bf16, pitch LDB) = src[(row0 + r) * stride + c] (+ add[c]) for row0 + r in [lo, hi), zeros elsewhere / c >= dh
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t stride, int row0, int lo, int hi, int rows, int dh,
@@ -169,16 +223,16 @@ __device__ __forceinline__ void load_query_tiles(bf16* Qc, bf16* Qp, bf16* dO, b
 // C[16 rb .. , 16 cb ..] = A[rows 16 rb][K] . B^T, A row-major (pitch lda), B stored [n][k] (pitch ldb): K = 64
 __device__ __forceinline__ void mma_abt(const bf16* A, int lda, const bf16* Bm, int ldb, int rb, int cb, float* out, int ldo) {
   FragC c;
-  wmma::fill_fragment(c, 0.f);
+  frag_zero(c);
 #pragma unroll
   for (int k = 0; k < DHP; k += 16) {
     FragA a;
-    FragBT b;
-    wmma::load_matrix_sync(a, A + rb * 16 * lda + k, lda);
-    wmma::load_matrix_sync(b, Bm + cb * 16 * ldb + k, ldb);
-    wmma::mma_sync(c, a, b, c);
+    FragB b;
+    ld_a(a, A + rb * 16 * lda + k, lda);
+    ld_b_nk(b, Bm + cb * 16 * ldb + k, ldb);
+    frag_mma(c, a, b);
   }
-  wmma::store_matrix_sync(out + rb * 16 * ldo + cb * 16, c, ldo, wmma::mem_row_major);
+  frag_store(out + rb * 16 * ldo + cb * 16, ldo, c);
 }
 
 // the shared first half of both kernels: S, U, dP on the tensor cores, then the per-entry stage.
@@ -283,8 +337,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
   FragC dqc[2], dqp[2];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
-    wmma::fill_fragment(dqc[e], 0.f);
-    wmma::fill_fragment(dqp[e], 0.f);
+    frag_zero(dqc[e]);
+    frag_zero(dqp[e]);
   }
   const int rb = warp >> 1;
   for (int j0 = 0; j0 < Tn; j0 += TK) {
@@ -301,33 +355,33 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
       for (int k = 0; k < TK; k += 16) {
         FragA a;
         FragB bm;
-        wmma::load_matrix_sync(a, dS_b + rb * 16 * LDB + k, LDB);
-        wmma::load_matrix_sync(bm, Kt + k * LDB + cb * 16, LDB);
-        wmma::mma_sync(dqc[e], a, bm, dqc[e]);
+        ld_a(a, dS_b + rb * 16 * LDB + k, LDB);
+        ld_b_kn(bm, Kt + k * LDB + cb * 16, LDB);
+        frag_mma(dqc[e], a, bm);
       }
 #pragma unroll
       for (int k = 0; k < WINR; k += 16) {
         FragA a;
         FragB bm;
-        wmma::load_matrix_sync(a, dSu_b + rb * 16 * LDU + k, LDU);
-        wmma::load_matrix_sync(bm, Pw + k * LDB + cb * 16, LDB);
-        wmma::mma_sync(dqp[e], a, bm, dqp[e]);
+        ld_a(a, dSu_b + rb * 16 * LDU + k, LDU);
+        ld_b_kn(bm, Pw + k * LDB + cb * 16, LDB);
+        frag_mma(dqp[e], a, bm);
       }
     }
     // dPw[w][d] += sum_i dsu[i][w] Qp[i][d]: warp = 16 window rows, all four column blocks; accumulator lives in shared memory
 #pragma unroll
     for (int cb = 0; cb < 4; ++cb) {
       FragC c;
-      wmma::load_matrix_sync(c, Wacc + warp * 16 * LDF + cb * 16, LDF, wmma::mem_row_major);
+      frag_load(c, Wacc + warp * 16 * LDF + cb * 16, LDF);
 #pragma unroll
       for (int k = 0; k < TQ; k += 16) {
-        FragAT a;                                                  // A[m = w][k = i] stored at dsu[i][w]
+        FragA a;                                                   // A[m = w][k = i] stored at dsu[i][w]
         FragB bm;
-        wmma::load_matrix_sync(a, dSu_b + k * LDU + warp * 16, LDU);
-        wmma::load_matrix_sync(bm, Qp + k * LDB + cb * 16, LDB);
-        wmma::mma_sync(c, a, bm, c);
+        ld_a_t(a, dSu_b + k * LDU + warp * 16, LDU);
+        ld_b_kn(bm, Qp + k * LDB + cb * 16, LDB);
+        frag_mma(c, a, bm);
       }
-      wmma::store_matrix_sync(Wacc + warp * 16 * LDF + cb * 16, c, LDF, wmma::mem_row_major);
+      frag_store(Wacc + warp * 16 * LDF + cb * 16, LDF, c);
     }
     __syncthreads();
     // window rows < 64 are complete: add them to the table gradient; rows >= 64 become rows - 64 of the next window
@@ -351,8 +405,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int cb = (warp & 1) * 2 + e;
-    wmma::store_matrix_sync(Ss + rb * 16 * LDF + cb * 16, dqc[e], LDF, wmma::mem_row_major);
-    wmma::store_matrix_sync(DPs + rb * 16 * LDF + cb * 16, dqp[e], LDF, wmma::mem_row_major);
+    frag_store(Ss + rb * 16 * LDF + cb * 16, LDF, dqc[e]);
+    frag_store(DPs + rb * 16 * LDF + cb * 16, LDF, dqp[e]);
   }
   __syncthreads();
   {
@@ -405,8 +459,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, 
   FragC dvv[2], dk[2];                                             // rows = keys 16 rb .., column blocks (warp & 1) * 2 + {0, 1}
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
-    wmma::fill_fragment(dvv[e], 0.f);
-    wmma::fill_fragment(dk[e], 0.f);
+    frag_zero(dvv[e]);
+    frag_zero(dk[e]);
   }
   for (int i0 = 0; i0 < Tn; i0 += TQ) {
     __syncthreads();
@@ -425,14 +479,14 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, 
       const int cb = (warp & 1) * 2 + e;
 #pragma unroll
       for (int k = 0; k < TQ; k += 16) {
-        FragAT a;
+        FragA a;
         FragB bm;
-        wmma::load_matrix_sync(a, Pd_b + k * LDB + rb * 16, LDB);
-        wmma::load_matrix_sync(bm, dO + k * LDB + cb * 16, LDB);
-        wmma::mma_sync(dvv[e], a, bm, dvv[e]);
-        wmma::load_matrix_sync(a, dS_b + k * LDB + rb * 16, LDB);
-        wmma::load_matrix_sync(bm, Qc + k * LDB + cb * 16, LDB);
-        wmma::mma_sync(dk[e], a, bm, dk[e]);
+        ld_a_t(a, Pd_b + k * LDB + rb * 16, LDB);
+        ld_b_kn(bm, dO + k * LDB + cb * 16, LDB);
+        frag_mma(dvv[e], a, bm);
+        ld_a_t(a, dS_b + k * LDB + rb * 16, LDB);
+        ld_b_kn(bm, Qc + k * LDB + cb * 16, LDB);
+        frag_mma(dk[e], a, bm);
       }
     }
   }
@@ -440,8 +494,8 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, 
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     const int cb = (warp & 1) * 2 + e;
-    wmma::store_matrix_sync(Ss + rb * 16 * LDF + cb * 16, dk[e], LDF, wmma::mem_row_major);
-    wmma::store_matrix_sync(DPs + rb * 16 * LDF + cb * 16, dvv[e], LDF, wmma::mem_row_major);
+    frag_store(Ss + rb * 16 * LDF + cb * 16, LDF, dk[e]);
+    frag_store(DPs + rb * 16 * LDF + cb * 16, LDF, dvv[e]);
   }
   __syncthreads();
   const int jl = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16, j = j0 + jl;
