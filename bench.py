@@ -16,7 +16,8 @@ Printed JSON (rank 0, one line):
   e2e                  the same through the host-buffer entry point (cfm_encoder_forward_host_io): pinned HOST mel in,
                        HOST result out, H2D/D2H copies inside the timed region
   roofline             the dominant single kernel, timed per launch with CUDA events on the launching stream in a
-                       separate profiled pass of the same steps; `kernels` lists all classes
+                       separate profiled pass of the same steps; `kernels` lists all classes; `roofline_second` is the
+                       runner-up (at C2 the fused FFN and the attention kernel are within 2 % of each other)
   gpu_eager_baseline   the reference's own modules (baseline/_ref when it travelled, else the oracle port) run EAGERLY
                        on this GPU under torch.autocast(bf16) at the same batch: the cuBLAS/cuDNN bar
   configs              the other BASELINE configs (C1 fp32, C3, C5) at their own shape: ms_per_step, RTFx, dominant kernel
@@ -467,11 +468,13 @@ def kernel_table(prof, prof_steps, peaks):
     return kernels
 
 
-def dominant_roofline(kernels, peaks):
+def dominant_roofline(kernels, peaks, rank=0):
     """The roofline block describes ONE kernel (so does its ncu traffic figure): the most expensive class that is a single
-    kernel function; "gemm_tcgen05" aggregates several GEMM shapes and stays in `kernels`."""
+    kernel function; "gemm_tcgen05" aggregates several GEMM shapes and stays in `kernels`.  rank = 1: the runner-up (at C2
+    the fused FFN and the attention kernel are within 2 % of each other, so which one is "dominant" changes from run to run)."""
     single = [n for n in kernels if n in SINGLE_KERNEL_CLASSES]
-    dom_name = max(single or kernels, key=lambda n: kernels[n]["ms_per_step"])
+    order = sorted(single or kernels, key=lambda n: -kernels[n]["ms_per_step"])
+    dom_name = order[min(rank, len(order) - 1)]
     dom = kernels[dom_name]
     if "tflops" in dom and dom_name in TENSOR_CLASSES:
         roof = {"kernel": dom_name, "bound": "tensor", "achieved": dom["tflops"], "peak": peaks["tensor"],
@@ -902,6 +905,7 @@ def main():
         "algorithmic_tflops": flops / (ms_dev * 1e-3) / 1e12,
         "tensor_frac_whole_step": flops / (ms_dev * 1e-3) / 1e12 / peaks["tensor"],
         "roofline": roof,
+        "roofline_second": dominant_roofline(kernels, peaks, rank=1),
         "kernels": kernels,
     }
     if strong is not None:
