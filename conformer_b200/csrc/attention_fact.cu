@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmE,
                           const __grid_constant__ CUtensorMap tmWp, const __grid_constant__ CUtensorMap tmRot, FactParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* q_s = smem;                                 // Qs tile as TMA delivers it
   uint8_t* rot_s = q_s + Q_BYTES;                      // rotation factors, laid out like a [128 x 256] K-major operand
   uint8_t* kp_ring = rot_s + ROT_BYTES;                // NS x (K | E)

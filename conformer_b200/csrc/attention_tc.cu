@@ -81,7 +81,7 @@ template <bool TRAIN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmPos, AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* qu_s = smem;
   uint8_t* qv_s = qu_s + Q_BYTES;
   uint8_t* kp_ring = qv_s + Q_BYTES;                   // 2 x (K | window)

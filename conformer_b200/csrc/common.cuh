@@ -99,6 +99,12 @@ __device__ __forceinline__ float warp_max(float v) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// 1024-byte alignment of the dynamic shared memory base (128B-swizzled TMA tiles).  The offset is ADDED to the shared
+// pointer: rounding through an integer and casting back hides the address space from the compiler, and every C++
+// access to the buffers then compiles to a generic LD.E / ST.E with 64-bit address arithmetic instead of LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* raw) {
+  return raw + ((1024u - (smem_u32(raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -34,7 +34,7 @@ struct Conv1Params {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmOut, Conv1Params p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* w_s = smem;
   uint8_t* a_s = w_s + W_BYTES;
   uint8_t* cbuf = a_s + A_STAGES * A_BYTES;

@@ -79,7 +79,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* xs = smem;
   uint8_t* gs = xs + XS_BYTES;
   uint8_t* ring = gs + GS_BYTES_AL;
@@ -291,7 +291,23 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
     }
     CTRACE(6);
 
-    // ---- final epilogue: out = res + acc2 + b2, staged fp32, 3-D TMA store (frames past T are clipped)
+    // ---- final epilogue: out = res + acc2 + b2, staged fp32 (frames past T are skipped)
+    // The residual rows of this warp's frames (frame o = cw + 8 i; lane = columns 4 lane .. +3 and 128 + 4 lane .. +3, so
+    // a warp reads 512 contiguous bytes per instruction from shared and global memory alike) are requested BEFORE the
+    // wait on pw2: their latency hides behind the MMAs and the staging pass.
+    constexpr int EP_ROWS = TO / NUM_CW, EP_EARLY = 8;             // the last rows are requested after the staging pass
+    float4 r0[EP_ROWS], r1[EP_ROWS];                               // (its 32 TMEM registers and these do not fit together)
+    auto load_res = [&](int i) {
+      const int t = t_out0 + cw + i * NUM_CW;
+      r0[i] = r1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.res != nullptr && t < Tn) {
+        const float4* rr = reinterpret_cast<const float4*>(p.res + (static_cast<int64_t>(b) * Tn + t) * D);
+        r0[i] = rr[lane];
+        r1[i] = rr[lane + 32];
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < EP_EARLY; ++i) load_res(i);
     mbar_wait(acc2_full, 0);
     tc_fence_after();
     CTRACE(7);
@@ -312,46 +328,42 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
     }
     tc_fence_before();
     CTRACE(8);
+#pragma unroll
+    for (int i = EP_EARLY; i < EP_ROWS; ++i) load_res(i);
     named_bar_sync(1, NUM_CT);
-    // second pass, coalesced: one warp = one frame, lane = 8 consecutive channels
+    // second pass, coalesced: one warp = one frame
     {
-      const float4 b2a = __ldg(reinterpret_cast<const float4*>(p.b2) + 2 * lane);
-      const float4 b2b = __ldg(reinterpret_cast<const float4*>(p.b2) + 2 * lane + 1);
+      const float4 b2a = __ldg(reinterpret_cast<const float4*>(p.b2) + lane);
+      const float4 b2b = __ldg(reinterpret_cast<const float4*>(p.b2) + lane + 32);
       float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, ba = ga, bb = ga;
       if (p.a_out != nullptr) {
-        ga = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + 2 * lane); gb = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + 2 * lane + 1);
-        ba = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + 2 * lane); bb = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + 2 * lane + 1);
+        ga = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + lane); gb = __ldg(reinterpret_cast<const float4*>(p.ln2_g) + lane + 32);
+        ba = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + lane); bb = __ldg(reinterpret_cast<const float4*>(p.ln2_b) + lane + 32);
       }
-#pragma unroll 4
-      for (int o = cw; o < TO; o += NUM_CW) {
-        const int t = t_out0 + o;
-        if (t >= Tn) break;
-        const float4* srow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(stage_out) + o * OUT_LD) + 2 * lane;
-        float4 v0 = srow[0], v1 = srow[1];
-        const int64_t goff = (static_cast<int64_t>(b) * Tn + t) * D;
-        if (p.res != nullptr) {
-          const float4* rr = reinterpret_cast<const float4*>(p.res + goff) + 2 * lane;
-          const float4 r0 = rr[0], r1 = rr[1];
-          v0.x += r0.x; v0.y += r0.y; v0.z += r0.z; v0.w += r0.w;
-          v1.x += r1.x; v1.y += r1.y; v1.z += r1.z; v1.w += r1.w;
-        }
-        v0.x += b2a.x; v0.y += b2a.y; v0.z += b2a.z; v0.w += b2a.w;
-        v1.x += b2b.x; v1.y += b2b.y; v1.z += b2b.z; v1.w += b2b.w;
-        float4* orow = reinterpret_cast<float4*>(p.out + goff) + 2 * lane;
-        orow[0] = v0;
-        orow[1] = v1;
-        if (p.a_out != nullptr) {                                  // the whole frame is in this warp: LayerNorm it
-          const float mean = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w)) * (1.0f / D);
-          v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
-          v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
-          const float rstd = rsqrtf(warp_sum((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w) +
-                                             (v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w)) * (1.0f / D) + 1e-5f);
-          uint4 o4;
-          o4.x = pack_bf16x2(v0.x * rstd * ga.x + ba.x, v0.y * rstd * ga.y + ba.y);
-          o4.y = pack_bf16x2(v0.z * rstd * ga.z + ba.z, v0.w * rstd * ga.w + ba.w);
-          o4.z = pack_bf16x2(v1.x * rstd * gb.x + bb.x, v1.y * rstd * gb.y + bb.y);
-          o4.w = pack_bf16x2(v1.z * rstd * gb.z + bb.z, v1.w * rstd * gb.w + bb.w);
-          reinterpret_cast<uint4*>(p.a_out + goff)[lane] = o4;
+#pragma unroll
+      for (int i = 0; i < EP_ROWS; ++i) {
+        const int o = cw + i * NUM_CW, t = t_out0 + o;
+        if (t < Tn) {
+          const float4* srow = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(stage_out) + o * OUT_LD);
+          float4 v0 = srow[lane], v1 = srow[lane + 32];
+          const int64_t goff = (static_cast<int64_t>(b) * Tn + t) * D;
+          v0.x = (v0.x + r0[i].x) + b2a.x; v0.y = (v0.y + r0[i].y) + b2a.y; v0.z = (v0.z + r0[i].z) + b2a.z; v0.w = (v0.w + r0[i].w) + b2a.w;
+          v1.x = (v1.x + r1[i].x) + b2b.x; v1.y = (v1.y + r1[i].y) + b2b.y; v1.z = (v1.z + r1[i].z) + b2b.z; v1.w = (v1.w + r1[i].w) + b2b.w;
+          float4* orow = reinterpret_cast<float4*>(p.out + goff);
+          orow[lane] = v0;
+          orow[lane + 32] = v1;
+          if (p.a_out != nullptr) {                                // the whole frame is in this warp: LayerNorm it
+            const float mean = warp_sum((v0.x + v0.y) + (v0.z + v0.w) + (v1.x + v1.y) + (v1.z + v1.w)) * (1.0f / D);
+            v0.x -= mean; v0.y -= mean; v0.z -= mean; v0.w -= mean;
+            v1.x -= mean; v1.y -= mean; v1.z -= mean; v1.w -= mean;
+            const float rstd = rsqrtf(warp_sum((v0.x * v0.x + v0.y * v0.y) + (v0.z * v0.z + v0.w * v0.w) +
+                                               (v1.x * v1.x + v1.y * v1.y) + (v1.z * v1.z + v1.w * v1.w)) * (1.0f / D) + 1e-5f);
+            uint2* arow = reinterpret_cast<uint2*>(p.a_out + goff);
+            arow[lane] = make_uint2(pack_bf16x2(v0.x * rstd * ga.x + ba.x, v0.y * rstd * ga.y + ba.y),
+                                    pack_bf16x2(v0.z * rstd * ga.z + ba.z, v0.w * rstd * ga.w + ba.w));
+            arow[lane + 32] = make_uint2(pack_bf16x2(v1.x * rstd * gb.x + bb.x, v1.y * rstd * gb.y + bb.y),
+                                         pack_bf16x2(v1.z * rstd * gb.z + bb.z, v1.w * rstd * gb.w + bb.w));
+          }
         }
       }
     }

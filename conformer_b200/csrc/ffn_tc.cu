@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA, FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* xs = smem;
   uint8_t* stage_out = xs + XS_BYTES;
   uint8_t* ring = stage_out + OUT_BYTES;

@@ -106,7 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using C_ = Cfg<BLOCK_N, EPI, PAIR>;
   constexpr int STAGES = C_::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* cbuf = smem + STAGES * C_::STAGE_BYTES;
   float* bias_s = reinterpret_cast<float*>(cbuf + C_::CBUF_COUNT * C_::CBUF_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);

@@ -75,7 +75,7 @@ template <typename TOut>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmW, LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   const int KB = p.H / LT_KB;
   uint8_t* w_s = smem;                                        // KB blocks of [64 rows x 64 k] bf16 (8 KB each)
   uint8_t* h_s = w_s + KB * (LT_ROWS * 128);                  // KB blocks of [NPAD rows x 64 k] (<= 8 KB each): all of h_{t-1}
