@@ -277,8 +277,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int out_n = GLU ? (p.N >> 1) : p.N;
       const uint32_t as = acc_it & 1, aph = (acc_it >> 1) & 1;
       uint8_t* cb = cbuf + (C_::CBUF_COUNT == 2 ? (acc_it & 1) * C_::CBUF_BYTES : 0);
-      // the staging buffer must have been drained by the TMA store that last used it
-      if (leader) {
+      // The staging buffer must have been drained by the TMA store that last used it.  Single-pass epilogues wait for
+      // that only after the accumulator has been pulled and converted in registers (LATE_WAIT below): a 64 KB store
+      // takes ~1.7 us to leave shared memory, which used to sit in front of every tile's tcgen05.ld.
+      constexpr bool LATE_WAIT = !GLU && C_::PASSES == 1;
+      if (!LATE_WAIT && leader) {
         if (C_::CBUF_COUNT == 2) bulk_wait_read1(); else bulk_wait_read0();
       }
       if (tid_e < BLOCK_N) bias_s[tid_e] = (p.bias != nullptr && ks == 0 && n0 + tid_e < p.N) ? __ldg(p.bias + n0 + tid_e) : 0.f;
@@ -327,6 +330,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) bulk_wait_read0();
         named_bar_sync(1, NUM_EPI_THREADS);
       }
+      // phase A, registers only: bias, activation and scale; the results replace the accumulator bits in r
 #pragma unroll
       for (int ch = 0; ch < (GLU ? 0 : NCH); ++ch) {
         if (C_::F32_WIDE && ch != pass) continue;
@@ -349,29 +353,43 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
         }
+        if (EPI == EPI_BIAS_RES) {                             // the residual itself is added by the TMA reduction
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] *= p.res_scale;
+        }
+        if (OUT_F32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[ch][i] = __float_as_uint(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[ch][i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        }
+      }
+      if (LATE_WAIT) {
+        if (leader) {
+          if (C_::CBUF_COUNT == 2) bulk_wait_read1(); else bulk_wait_read0();
+        }
+        named_bar_sync(1, NUM_EPI_THREADS);
+      }
+      // phase B: registers -> staging blocks (128-byte rows, 16-byte chunks XOR-swizzled by the row)
+#pragma unroll
+      for (int ch = 0; ch < (GLU ? 0 : NCH); ++ch) {
+        if (C_::F32_WIDE && ch != pass) continue;
+        const int col_in_tile = cgrp * COLS_PER_WARP + ch * 32;
+        if (n0 + col_in_tile >= p.N) continue;
         if (OUT_F32) {
           // 32 fp32 columns = one full 128-byte row of a staging block
           uint8_t* blk = cb + (C_::F32_WIDE ? cgrp : (col_in_tile >> 5)) * CBLK_BYTES + row_off;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* dst = reinterpret_cast<float4*>(blk + ((j ^ sw) << 4));
-            float4 o = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
-            if (EPI == EPI_BIAS_RES) {                         // the residual itself is added by the TMA reduction
-              o.x *= p.res_scale; o.y *= p.res_scale; o.z *= p.res_scale; o.w *= p.res_scale;
-            }
-            *dst = o;
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(blk + ((j ^ sw) << 4)) = make_uint4(r[ch][j * 4], r[ch][j * 4 + 1], r[ch][j * 4 + 2], r[ch][j * 4 + 3]);
         } else {
           // 32 bf16 columns = half a 128-byte row of staging block (col_in_tile / 64)
           uint8_t* blk = cb + (col_in_tile >> 6) * CBLK_BYTES + row_off;
           const int j0 = (col_in_tile & 63) >> 3;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]); o.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-            o.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]); o.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = o;
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(blk + (((j0 + j) ^ sw) << 4)) = make_uint4(r[ch][j * 4], r[ch][j * 4 + 1], r[ch][j * 4 + 2], r[ch][j * 4 + 3]);
         }
       }
       fence_proxy_async();                                     // staging writes -> visible to the TMA engine
