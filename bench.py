@@ -552,6 +552,9 @@ def run_train_bench(args, cfg, batch, t_in, desc):
     import conformer_b200 as cb
     from conformer_b200.synth import synth_decoder_state_dict
     from conformer_b200.training import GradientAllReducer
+    if args.pdl is not None:
+        from conformer_b200._lib import lib as _cfm_lib
+        _cfm_lib().cfm_set_pdl(args.pdl)
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -707,6 +710,8 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch")
     ap.add_argument("--compute", default=None, choices=["bf16", "fp32"])
+    ap.add_argument("--pdl", type=int, default=None, choices=[0, 1],
+                    help="programmatic dependent launch of the forward kernels (cfm_set_pdl); default: library default (on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip gpu_eager_baseline, the other configs and strong scaling")
     args = ap.parse_args()
@@ -723,6 +728,9 @@ def main():
         return
 
     import conformer_b200 as cb
+    if args.pdl is not None:
+        from conformer_b200._lib import lib as _cfm_lib
+        _cfm_lib().cfm_set_pdl(args.pdl)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -47,6 +47,7 @@ SIGNATURES = {
     "cfm_module_set_grad": (C.c_int, [_p, C.c_char_p, _p, _i64]),
     "cfm_train_bind": (C.c_int, [_p, C.c_int]),
     "cfm_train_refresh": (C.c_int, [_p, _p]),
+    "cfm_set_pdl": (C.c_int, [C.c_int32]),
     "cfm_train_set_graphs": (C.c_int, [_p, C.c_int32]),
     "cfm_train_graph_stats": (C.c_int, [_p, C.POINTER(C.c_int64)]),
     "cfm_encoder_train_workspace_bytes": (_i64, [_p, _i32, _i32]),

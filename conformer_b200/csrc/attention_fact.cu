@@ -163,6 +163,7 @@ rel_attention_fact_kernel(const __grid_constant__ CUtensorMap tmQKV, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot) + p.tmem_zero;
+  pdl_wait();                                              // q|k|v exist once the projection GEMM has completed
 
   // one ring stage is filled once more than the others: its first fill is the pos_proj slice of the prologue
   auto fill_index = [](int j) { return j / NS + (j % NS == WP_STAGE ? 1 : 0); };
@@ -659,7 +660,7 @@ int rel_attention_bf16_fact(const bf16* qkv, const bf16* wpT, const bf16* e16, c
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_fact_kernel), SMEM_BYTES));
   FactParams p{pos_const, key_pad, ctx, Tn, H, 0u, g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
-  rel_attention_fact_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmE, tmWp, tmRot, p);
+  CFM_CUDA_OK(launch_pdl(rel_attention_fact_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, 1, tmQKV, tmE, tmWp, tmRot, p));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

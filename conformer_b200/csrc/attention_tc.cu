@@ -129,6 +129,7 @@ rel_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
+  pdl_wait();                                              // q|k|v exist once the projection GEMM has completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer: K + positional window
@@ -405,10 +406,10 @@ static int launch_attention_tc(const bf16* qkv, const bf16* pos, int ldp, const 
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, BQ)), static_cast<unsigned>(H), static_cast<unsigned>(B));
   if (train) {
     CFM_TRY(smem_attr_once(attr_done_t, reinterpret_cast<const void*>(rel_attention_tc_kernel<true>), SMEM_BYTES));
-    rel_attention_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
+    CFM_CUDA_OK(launch_pdl(rel_attention_tc_kernel<true>, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, 1, tmQKV, tmPos, p));
   } else {
     CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(rel_attention_tc_kernel<false>), SMEM_BYTES));
-    rel_attention_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmQKV, tmPos, p);
+    CFM_CUDA_OK(launch_pdl(rel_attention_tc_kernel<false>, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, 1, tmQKV, tmPos, p));
   }
   CFM_CUDA_OK(cudaGetLastError());
   return 0;

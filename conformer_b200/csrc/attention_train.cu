@@ -185,6 +185,7 @@ __device__ __forceinline__ float group16_sum(float v) {
 // ------------------------------------------------------------------------------------------------ forward
 template <typename TA>
 __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(AttnArgs p, TA* __restrict__ ctx, float* __restrict__ lse) {
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   constexpr int LD = Tile<TA>::LD;
   float* Ps = reinterpret_cast<float*>(sm_raw);                  // [TQ][LDS_] fp32
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(THREADS) attn_fwd_kernel(AttnArgs p, TA* __res
 // D[b,h,i] = dctx_i . ctx_i over the head's channels
 template <typename TA>
 __global__ void attn_delta_kernel(const float* __restrict__ dctx, const TA* __restrict__ ctx, float* __restrict__ D, int B, int Tn, int H, int dh) {
+  pdl_wait();
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);     // (b, i, h)
   const int lane = threadIdx.x & 31;
   if (row >= static_cast<int64_t>(B) * Tn * H) return;
@@ -311,6 +313,7 @@ template <typename TA>
 __global__ void __launch_bounds__(THREADS, 2) attn_bwd_q_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
                                                              const float* __restrict__ dctx, TA* __restrict__ dqkv, float* __restrict__ dpp,
                                                              float* __restrict__ du, float* __restrict__ dv) {
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   constexpr int LD = Tile<TA>::LD;
   float* Ps = reinterpret_cast<float*>(sm_raw);                  // fp32 score tiles and small vectors first
@@ -434,6 +437,7 @@ __global__ void __launch_bounds__(THREADS, 2) attn_bwd_q_kernel(AttnArgs p, cons
 template <typename TA>
 __global__ void __launch_bounds__(THREADS, 2) attn_bwd_kv_kernel(AttnArgs p, const float* __restrict__ lse, const float* __restrict__ D,
                                                               const float* __restrict__ dctx, TA* __restrict__ dqkv) {
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm_raw[];
   constexpr int LD = Tile<TA>::LD;
   float* Ps = reinterpret_cast<float*>(sm_raw);
@@ -507,7 +511,7 @@ int attn_train_fwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
   CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(attn_fwd_kernel<TA>), fwd_smem<TA>()));
   AttnArgs a{qkv, pp, u, v, key_pad, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
-  attn_fwd_kernel<TA><<<grid, THREADS, fwd_smem<TA>(), st>>>(a, ctx, lse);
+  CFM_CUDA_OK(launch_pdl(attn_fwd_kernel<TA>, dim3(grid), dim3(THREADS), fwd_smem<TA>(), st, 1, a, ctx, lse));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -536,14 +540,14 @@ int attn_train_bwd(const TA* qkv, const TA* pp, const float* u, const float* v, 
   CFM_TRY(smem_attr_once(done_q, reinterpret_cast<const void*>(attn_bwd_q_kernel<TA>), bwd_smem<TA>()));
   CFM_TRY(smem_attr_once(done_kv, reinterpret_cast<const void*>(attn_bwd_kv_kernel<TA>), bwd_smem<TA>()));
   const int64_t rows = static_cast<int64_t>(B) * Tn * H;
-  attn_delta_kernel<TA><<<static_cast<unsigned>(ceil_div(rows, 8)), 256, 0, st>>>(dctx, ctx, scratch, B, Tn, H, dh);
+  CFM_CUDA_OK(launch_pdl(attn_delta_kernel<TA>, dim3(static_cast<unsigned>(ceil_div(rows, 8))), dim3(256), 0, st, 1, dctx, ctx, scratch, B, Tn, H, dh));
   CFM_CUDA_OK(cudaGetLastError());
   if (bwd_on_tensor_cores(qkv, pp, u, v, key_pad, lse, dctx, dqkv, dpp, du, dv, scratch, B, Tn, H, dh, dr, st, &status)) return status;
   AttnArgs a{qkv, pp, u, v, key_pad, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
-  attn_bwd_q_kernel<TA><<<grid, THREADS, bwd_smem<TA>(), st>>>(a, lse, scratch, dctx, dqkv, dpp, du, dv);
+  CFM_CUDA_OK(launch_pdl(attn_bwd_q_kernel<TA>, dim3(grid), dim3(THREADS), bwd_smem<TA>(), st, 1, a, lse, scratch, dctx, dqkv, dpp, du, dv));
   CFM_CUDA_OK(cudaGetLastError());
-  attn_bwd_kv_kernel<TA><<<grid, THREADS, bwd_smem<TA>(), st>>>(a, lse, scratch, dctx, dqkv);
+  CFM_CUDA_OK(launch_pdl(attn_bwd_kv_kernel<TA>, dim3(grid), dim3(THREADS), bwd_smem<TA>(), st, 1, a, lse, scratch, dctx, dqkv));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -303,6 +303,7 @@ struct SmemKV {
 // ------------------------------------------------------------------------------------------------ query side
 __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, bf16* __restrict__ dqkv, float* __restrict__ dpp,
                                                                     float* __restrict__ du, float* __restrict__ dv) {
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_raw[];
   float* Ss = reinterpret_cast<float*>(sm_raw);
   float* DPs = Ss + TQ * LDF;
@@ -435,6 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) attn_bwd_q_mma_kernel(MmaArgs p, b
 
 // ------------------------------------------------------------------------------------------------ key side
 __global__ void __launch_bounds__(THREADS, 1) attn_bwd_kv_mma_kernel(MmaArgs p, bf16* __restrict__ dqkv) {
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_raw[];
   float* Ss = reinterpret_cast<float*>(sm_raw);
   float* DPs = Ss + TQ * LDF;
@@ -522,9 +524,9 @@ int attn_train_bwd_mma(const bf16* qkv, const bf16* pp, const float* u, const fl
   CFM_TRY(smem_attr_once(done_kv, reinterpret_cast<const void*>(attn_bwd_kv_mma_kernel), SmemKV::BYTES));
   MmaArgs a{qkv, pp, u, v, key_pad, lse, scratch_D, dctx, Tn, H, dh, 1.0f / sqrtf(static_cast<float>(dh)), dr};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TQ)), H, B);
-  attn_bwd_q_mma_kernel<<<grid, THREADS, SmemQ::BYTES, st>>>(a, dqkv, dpp, du, dv);
+  CFM_CUDA_OK(launch_pdl(attn_bwd_q_mma_kernel, dim3(grid), dim3(THREADS), SmemQ::BYTES, st, 1, a, dqkv, dpp, du, dv));
   CFM_CUDA_OK(cudaGetLastError());
-  attn_bwd_kv_mma_kernel<<<grid, THREADS, SmemKV::BYTES, st>>>(a, dqkv);
+  CFM_CUDA_OK(launch_pdl(attn_bwd_kv_mma_kernel, dim3(grid), dim3(THREADS), SmemKV::BYTES, st, 1, a, dqkv));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

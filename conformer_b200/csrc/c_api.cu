@@ -65,6 +65,10 @@ int cfm_train_bind(cfm_module_t m, int compute) {
   CFM_REQUIRE(m != nullptr, "null module handle");
   return m->train_bind(compute);
 }
+int cfm_set_pdl(int32_t enable) {
+  cfm::g_pdl.store(enable != 0 ? 1 : 0, std::memory_order_relaxed);
+  return 0;
+}
 int cfm_train_set_graphs(cfm_module_t m, int32_t enable) {
   if (m == nullptr) return 1;
   m->train.graphs_on = enable != 0;

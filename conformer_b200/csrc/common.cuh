@@ -52,6 +52,45 @@ static inline int smem_attr_once(std::atomic<uint64_t>& done, const void* kernel
   return 0;
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// The forward path is a chain of ~130 short kernels (10-60 us).  Launched with programmatic stream serialization, kernel
+// N+1's CTAs become resident while kernel N's last wave drains and run their set-up (barrier init, TMEM allocation,
+// descriptor prefetch) there; pdl_wait() then blocks until kernel N has completed and its memory is visible, so
+// everything after it sees exactly what a plain stream-ordered launch would.  Every kernel launched through launch_pdl
+// executes pdl_wait() in EVERY CTA before it touches global memory or exits (completion of N then implies completion
+// of everything before N), and releases its own dependents right after.  Without the launch attribute both are no-ops.
+extern std::atomic<int> g_pdl;                   // process-wide switch (cfm_set_pdl); on by default
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                     unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = cluster_x;
+    at[n].val.clusterDim.y = 1;
+    at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl.load(std::memory_order_relaxed) != 0) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ----------------------------------------------------------------------------- element access
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }

@@ -75,6 +75,7 @@ conv1_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
+  pdl_wait();
 
   if (warp == 0 || warp == 3) {
     // ------------------------------------------------------------------ A producers: 64 threads, 2 rows each per tile
@@ -236,7 +237,7 @@ int subsample_conv1_tc(const float* mel, const bf16* w_packed, const float* bias
   Conv1Params p{mel, bias, n_mel, Tin, T1, T1p, F1, M, tiles};
   const int per_slab = num_sms / slabs > 0 ? num_sms / slabs : 1;
   dim3 grid(static_cast<unsigned>(tiles < per_slab ? tiles : per_slab), static_cast<unsigned>(slabs));
-  conv1_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW, tmOut, p);
+  CFM_CUDA_OK(launch_pdl(conv1_tc_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, 1, tmW, tmOut, p));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

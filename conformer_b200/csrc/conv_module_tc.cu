@@ -116,6 +116,7 @@ conv_module_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
+  pdl_wait();                                              // x exists once the previous kernel has completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer: 8 W1p stages, 4 W2 stages
@@ -416,7 +417,7 @@ int conv_module_fused_bf16(const float* x, const float* res, float* out, const f
               "fused conv module operands must be 16-byte aligned");
   ConvParams p{x, res, ln_g, ln_b, b1p, dw_w, dw_b, b2, out, ln2_g, ln2_b, a_out, Tn, g_gemm_trace};
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, TO)), static_cast<unsigned>(B));
-  conv_module_fused_kernel<<<grid, NUM_THREADS, SMEM_BYTES, stream>>>(tmW1, tmW2, p);
+  CFM_CUDA_OK(launch_pdl(conv_module_fused_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, stream, 1, tmW1, tmW2, p));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

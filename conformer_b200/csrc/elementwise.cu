@@ -71,6 +71,7 @@ template <typename TOut, int NV, int RPW>
 __global__ void __launch_bounds__(256) layer_norm_vec_rows_kernel(const float* x, const float* __restrict__ gamma,
                                                                   const float* __restrict__ beta, TOut* y, int64_t rows) {
   constexpr int D = 128 * NV;
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(256) layer_norm_dual_kernel(const float* x, co
                                                               const float* __restrict__ g2, const float* __restrict__ b2,
                                                               bf16* __restrict__ a, int64_t rows) {
   constexpr int D = 256, RPW = 4;                                  // rows per warp: all rows' loads are in flight together
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
   if (row0 >= rows) return;
@@ -192,6 +194,7 @@ __global__ void rel_pos_table_kernel(const float* __restrict__ div_term, T* __re
 __global__ void lengths_mask_kernel(const int64_t* __restrict__ len_in, int64_t* __restrict__ len_out,
                                     uint8_t* __restrict__ key_pad, int B, int Tn, bool subsample,
                                     bool mark_valid) {
+  pdl_wait();
   const int b = blockIdx.x;
   int64_t L = len_in[b];
   if (subsample) {
@@ -293,7 +296,8 @@ int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, i
   const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) |
                          reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta)) & 15) == 0;
   if (aligned && d == 256 && rows >= 4096)
-    layer_norm_vec_rows_kernel<TOut, 2, 4><<<blocks_for(rows, 32), 256, 0, stream>>>(x, gamma, beta, y, rows);
+    CFM_CUDA_OK(launch_pdl(layer_norm_vec_rows_kernel<TOut, 2, 4>, dim3(blocks_for(rows, 32)), dim3(256), 0, stream, 1, x, gamma, beta, y,
+                           rows));
   else if (aligned && d == 256)
     layer_norm_vec_kernel<TOut, 2><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
   else if (aligned && d == 512)
@@ -312,7 +316,7 @@ int layer_norm_dual(const float* x, const float* g1, const float* b1, float* y, 
                 reinterpret_cast<uintptr_t>(g1) | reinterpret_cast<uintptr_t>(b1) | reinterpret_cast<uintptr_t>(g2) |
                 reinterpret_cast<uintptr_t>(b2)) & 15) == 0, "layer_norm_dual operands must be 16-byte aligned");
   if (rows <= 0) return 0;
-  layer_norm_dual_kernel<<<blocks_for(rows, 32), 256, 0, stream>>>(x, g1, b1, y, g2, b2, a, rows);
+  CFM_CUDA_OK(launch_pdl(layer_norm_dual_kernel, dim3(blocks_for(rows, 32)), dim3(256), 0, stream, 1, x, g1, b1, y, g2, b2, a, rows));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -333,7 +337,8 @@ template int rel_pos_table<bf16>(const float*, bf16*, int, int, cudaStream_t);
 int lengths_and_mask(const int64_t* lengths_in, int64_t* lengths_out, uint8_t* key_pad, int B, int Tn,
                      bool subsample, bool mark_valid, cudaStream_t stream) {
   CFM_REQUIRE(B > 0 && lengths_in != nullptr, "lengths_and_mask needs lengths");
-  lengths_mask_kernel<<<B, 128, 0, stream>>>(lengths_in, lengths_out, key_pad, B, Tn, subsample, mark_valid);
+  CFM_CUDA_OK(launch_pdl(lengths_mask_kernel, dim3(B), dim3(128), 0, stream, 1, lengths_in, lengths_out, key_pad, B, Tn, subsample,
+                         mark_valid));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

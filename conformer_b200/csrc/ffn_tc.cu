@@ -135,6 +135,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
   const uint32_t tm_acc2 = tmem_base + NBUF * HC;
+  pdl_wait();                                                // x / a exist once the previous kernel has completed
 
   if (warp == 0) {
     // ------------------------------------------------------------------ weight producer (each CTA: its half of every tile)
@@ -450,19 +451,8 @@ int ffn_fused_bf16(const bf16* a_pre, float* x, const bf16* W1, const float* b1,
   const int tiles = static_cast<int>(ceil_div(M, 2 * BM));
   const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
   FfnParams p{b1, b2, scale, M, tiles, g_gemm_trace};
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, ffn_fused_kernel, tmW1, tmW2, tmX, tmA, p));
+  CFM_CUDA_OK(launch_pdl(ffn_fused_kernel, dim3(static_cast<unsigned>(2 * pairs)), dim3(NUM_THREADS), SMEM_BYTES, stream, 2, tmW1,
+                         tmW2, tmX, tmA, p));
   return 0;
 }
 

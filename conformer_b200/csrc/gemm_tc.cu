@@ -149,6 +149,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_whole_sm(tmem_slot);
+  pdl_wait();                                              // set-up done; the operands exist once the previous kernel has
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -464,25 +465,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tm
   if (PAIR) {
     const int tiles = p.num_m_pairs * p.num_n_tiles;
     const int pairs = tiles < num_sms / 2 ? tiles : num_sms / 2;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(static_cast<unsigned>(2 * pairs));
-    cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = C_::SMEM_BYTES;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CFM_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, p));
+    CFM_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(2 * pairs)), dim3(NUM_THREADS), C_::SMEM_BYTES, stream, 2, tmA,
+                           tmB, tmC, p));
     return 0;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles * p.k_splits;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
-  CFM_CUDA_OK(cudaGetLastError());
+  CFM_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(NUM_THREADS), C_::SMEM_BYTES, stream, 1, tmA, tmB, tmC, p));
   return 0;
 }
 
@@ -549,6 +538,7 @@ int tc_init() {
 }
 
 unsigned long long* g_gemm_trace = nullptr;      // debug hook (cfm_debug_set_gemm_trace)
+std::atomic<int> g_pdl{1};                       // programmatic dependent launch of the forward kernels (cfm_set_pdl)
 
 int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, float* C, int ldc, int M, int N, int K, int num_sms,
                  cudaStream_t stream) {
@@ -591,14 +581,13 @@ int gemm_bf16_tn(const bf16* A, int lda, const bf16* B, int ldb, float* C, int l
     auto kern = gemm_tc_kernel<BN, EPI_BIAS_RES, false, false, true, true>;
     static std::atomic<uint64_t> done{0};
     CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
-    kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    CFM_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(NUM_THREADS), C_::SMEM_BYTES, stream, 1, tmA, tmB, tmC, p));
   } else {
     auto kern = gemm_tc_kernel<BN, EPI_BIAS_RES, false, false, false, true>;
     static std::atomic<uint64_t> done{0};
     CFM_TRY(smem_attr_once(done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
-    kern<<<grid, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
+    CFM_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(grid)), dim3(NUM_THREADS), C_::SMEM_BYTES, stream, 1, tmA, tmB, tmC, p));
   }
-  CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
@@ -642,8 +631,8 @@ int gemm_tf32_tc(const float* A, int lda, const float* W, int ldw, const float* 
   static std::atomic<uint64_t> attr_done{0};
   CFM_TRY(smem_attr_once(attr_done, reinterpret_cast<const void*>(kern), C_::SMEM_BYTES));
   const int tiles = p.num_m_tiles * p.num_n_tiles;
-  kern<<<tiles < num_sms ? tiles : num_sms, NUM_THREADS, C_::SMEM_BYTES, stream>>>(tmA, tmB, tmC, p);
-  CFM_CUDA_OK(cudaGetLastError());
+  CFM_CUDA_OK(launch_pdl(kern, dim3(static_cast<unsigned>(tiles < num_sms ? tiles : num_sms)), dim3(NUM_THREADS), C_::SMEM_BYTES,
+                         stream, 1, tmA, tmB, tmC, p));
   return 0;
 }
 

@@ -106,6 +106,7 @@ inline int conv2_wgrad(const TC& c, const float* dy2, const float* out1, float* 
 }
 
 __global__ void unpack_conv2_grad_kernel(const float* __restrict__ gp, float* __restrict__ g, int C) {
+  pdl_wait();
   // gp[n][(kw*3+kh)*C + c] -> g[n][c][kh][kw] (+=)
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= static_cast<int64_t>(C) * C * 9) return;
@@ -114,6 +115,7 @@ __global__ void unpack_conv2_grad_kernel(const float* __restrict__ gp, float* __
   g[i] += gp[static_cast<int64_t>(n) * 9 * C + static_cast<int64_t>(kw * 3 + kh) * C + cc];
 }
 __global__ void unpack_linear_grad_kernel(const float* __restrict__ gp, float* __restrict__ g, int d, int C, int F2) {
+  pdl_wait();
   // gp[n][f*C + c] -> g[n][c*F2 + f] (+=)
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t K = static_cast<int64_t>(C) * F2;
@@ -483,7 +485,7 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
     CFM_CUDA_OK(cudaMemsetAsync(gpack, 0, static_cast<size_t>(d) * K * 4, st));
     CFM_TRY(wgrad_gemm(c, static_cast<const TA*>(dxl), d, h2, K, gpack, Mi, d, K, big2, big2 + static_cast<int64_t>(d) * Mp));
     const int64_t n = static_cast<int64_t>(d) * K;
-    unpack_linear_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(gpack, t.lin.dw, d, d, F2);
+    CFM_CUDA_OK(launch_pdl(unpack_linear_grad_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1, gpack, t.lin.dw, d, d, F2));
     CFM_CUDA_OK(cudaGetLastError());
     CFM_TRY(colsum_add<TA>(dxl, d, t.lin.db, Mi, d, st));
     CFM_TRY(gemm_any(c, static_cast<const TA*>(dxl), d, WSel<TA>::wT(t.lin), nullptr, dh2f, K, Mi, K, d, EPI_BIAS_F32, nullptr, 0.f));
@@ -496,7 +498,7 @@ int Module::train_backward_impl(const float* dy, int block_hi, int block_lo, boo
     CFM_CUDA_OK(cudaMemsetAsync(gpack, 0, static_cast<size_t>(d) * 9 * d * 4, st));
     CFM_TRY(conv2_wgrad(c, dy2, out1, gpack, g, M2, M2p, big1, big2));
     const int64_t n = static_cast<int64_t>(d) * d * 9;
-    unpack_conv2_grad_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(gpack, t.conv2.dw, d);
+    CFM_CUDA_OK(launch_pdl(unpack_conv2_grad_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0, st, 1, gpack, t.conv2.dw, d));
     CFM_CUDA_OK(cudaGetLastError());
     CFM_TRY(colsum_add<TA>(dy2, d, t.conv2.db, M2i, d, st));
     // dcol = dy2 W2p  ([M2, C] x [9C, C]^T), gathered back onto conv_1's output grid through its ReLU
@@ -542,6 +544,7 @@ int64_t Module::train_workspace_bytes(int B, int Tin) {
 // stream, which cannot capture) and replayed from then on with one cudaGraphLaunch on the caller's stream.
 namespace {
 __global__ void set_seed_kernel(uint32_t* dst, uint32_t lo, uint32_t hi) {
+  pdl_wait();
   dst[0] = lo;
   dst[1] = hi;
 }
@@ -630,7 +633,7 @@ int Module::train_forward(const float* mel, const int64_t* len_in, float* y, int
   CFM_REQUIRE(train.bound, "call cfm_train_bind first");
   CFM_REQUIRE(mel != nullptr && y != nullptr && wsp != nullptr && B > 0, "bad training-forward arguments");
   CFM_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout rate must be in [0, 1)");
-  set_seed_kernel<<<1, 1, 0, st>>>(train.seed_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  CFM_CUDA_OK(launch_pdl(set_seed_kernel, dim3(1), dim3(1), 0, st, 1, train.seed_dev, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
   CFM_CUDA_OK(cudaGetLastError());
   uint32_t pbits;
   std::memcpy(&pbits, &p_drop, 4);

@@ -45,6 +45,7 @@ __device__ __forceinline__ void st4(bf16* p, const float (&v)[4]) {
 
 template <typename TOut>
 __global__ void cast_scale_drop_kernel(const float* __restrict__ in, TOut* __restrict__ out, int64_t n, float scale, Drop dr) {
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float v[4];
@@ -66,6 +67,7 @@ template <typename TA> __device__ __forceinline__ float sigmoid_act(float x) {
 }
 template <typename TA>
 __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float v[4];
@@ -77,6 +79,7 @@ __global__ void swish_drop_fwd_kernel(const TA* __restrict__ hp, TA* __restrict_
 }
 // bf16 activations, 8 per thread (16-byte accesses; n % 8 == 0)
 __global__ void swish_drop_fwd8_kernel(const bf16* __restrict__ hp, bf16* __restrict__ out, int64_t n, Drop dr) {
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   float v[8];
@@ -88,6 +91,7 @@ __global__ void swish_drop_fwd8_kernel(const bf16* __restrict__ hp, bf16* __rest
 }
 template <typename TA>
 __global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __restrict__ hp, TA* __restrict__ out, int64_t n, Drop dr) {
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float x[4], g[4];
@@ -103,6 +107,7 @@ __global__ void swish_drop_bwd_kernel(const float* __restrict__ dh, const TA* __
 }
 __global__ void residual_drop_add_kernel(const float* __restrict__ x, const float* __restrict__ t, float* __restrict__ out, int64_t n,
                                          float scale, Drop dr) {
+  pdl_wait();
   const int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i >= n) return;
   float a[4], b[4];
@@ -114,11 +119,13 @@ __global__ void residual_drop_add_kernel(const float* __restrict__ x, const floa
   st4(out + i, a);
 }
 __global__ void drop_inplace_kernel(float* __restrict__ x, int64_t n, Drop dr) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) x[i] *= dr.load().factor(i);
 }
 template <typename TA>
 __global__ void glu_fwd_kernel(const TA* __restrict__ u, TA* __restrict__ g, int64_t rows, int d) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * d) return;
   const int64_t r = i / d;
@@ -127,6 +134,7 @@ __global__ void glu_fwd_kernel(const TA* __restrict__ u, TA* __restrict__ g, int
 }
 template <typename TA>
 __global__ void glu_bwd_kernel(const float* __restrict__ dg, const TA* __restrict__ u, TA* __restrict__ du, int64_t rows, int d) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * d) return;
   const int64_t r = i / d;
@@ -137,6 +145,7 @@ __global__ void glu_bwd_kernel(const float* __restrict__ dg, const TA* __restric
 }
 template <typename TA>
 __global__ void relu_bwd_kernel(const float* __restrict__ dy, const TA* __restrict__ y, TA* __restrict__ out, int64_t n) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) out[i] = from_f32<TA>(to_f32(y[i]) > 0.f ? dy[i] : 0.f);
 }
@@ -145,6 +154,7 @@ __global__ void relu_bwd_kernel(const float* __restrict__ dy, const TA* __restri
 // contraction runs over the M rows
 template <typename T>
 __global__ void transpose_kernel(const T* __restrict__ in, int ld, T* __restrict__ out, int M, int N, int Mp) {
+  pdl_wait();
   __shared__ T tile[32][33];
   const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -162,6 +172,7 @@ __global__ void transpose_kernel(const T* __restrict__ in, int ld, T* __restrict
 // column sums: out[n] += sum_m in[m, n]   (bias gradients)
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, int M, int N, int rows_per_block) {
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -179,6 +190,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* __restrict__ d
                                                      const float* __restrict__ gamma, float* dx, int accumulate,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int d,
                                                      int rows_per_warp) {
+  pdl_wait();
   extern __shared__ float red[];                                // [2][d]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
@@ -260,6 +272,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
                                                          const float* __restrict__ gamma, float* dx, int accumulate,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows,
                                                          int rows_per_warp) {
+  pdl_wait();
   constexpr int d = 256 * G, NV = 8 * G;
   __shared__ float red[2 * d];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -358,6 +371,7 @@ __global__ void __launch_bounds__(256) ln_bwd_vec_kernel(const float* __restrict
 template <typename TIn, bool FLIP>
 __global__ void __launch_bounds__(256) dwconv_tile_kernel(const TIn* __restrict__ in, const float* __restrict__ w, const float* __restrict__ bias,
                                                           float* __restrict__ out, int Tn, int d, int ks) {
+  pdl_wait();
   constexpr int TT = 64, KMAX = 64;
   __shared__ float in_s[TT + KMAX][32];
   __shared__ float w_s[KMAX][33];
@@ -389,6 +403,7 @@ __global__ void __launch_bounds__(256) dwconv_tile_kernel(const TIn* __restrict_
 template <typename TA>
 __global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __restrict__ dz, const TA* __restrict__ g, float* __restrict__ dw,
                                                                 float* __restrict__ db, int Tn, int d, int ks) {
+  pdl_wait();
   constexpr int TT = 64, KMAX = 64;
   __shared__ float dz_s[TT][32];
   __shared__ float g_s[TT + KMAX][32];
@@ -421,6 +436,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_weight_kernel(const float* __r
 // ------------------------------------------------------------------------------------------- BatchNorm1d, training mode
 // per-channel sums over all M = B*T rows: acc[c] += sum z, acc[d + c] += sum z^2 (fp32 partials, one atomic per block)
 __global__ void bn_sums_kernel(const float* __restrict__ z, float* __restrict__ acc, int M, int d, int rows_per_block) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -438,6 +454,7 @@ __global__ void bn_sums_kernel(const float* __restrict__ z, float* __restrict__ 
 // unbiased variance and momentum 0.1
 __global__ void bn_finish_kernel(const float* __restrict__ acc, float* __restrict__ stats, float* running_mean, float* running_var,
                                  int M, int d, float momentum, float eps) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const float mean = acc[c] / M;
@@ -452,6 +469,7 @@ __global__ void bn_finish_kernel(const float* __restrict__ acc, float* __restric
 template <typename TA>
 __global__ void bn_swish_fwd_kernel(const float* __restrict__ z, const float* __restrict__ stats, const float* __restrict__ gamma,
                                     const float* __restrict__ beta, TA* __restrict__ s, int64_t M, int d) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M * d) return;
   const int c = static_cast<int>(i % d);
@@ -461,6 +479,7 @@ __global__ void bn_swish_fwd_kernel(const float* __restrict__ z, const float* __
 __global__ void bn_swish_bwd_reduce_kernel(float* ds, const float* __restrict__ z, const float* __restrict__ stats,
                                            const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ acc, int M,
                                            int d, int rows_per_block) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -482,6 +501,7 @@ __global__ void bn_swish_bwd_reduce_kernel(float* ds, const float* __restrict__ 
 __global__ void bn_bwd_apply_kernel(float* dzn, const float* __restrict__ z, const float* __restrict__ stats,
                                     const float* __restrict__ gamma, const float* __restrict__ acc, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, int M, int d, int rows_per_block) {
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= d) return;
   const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
@@ -502,6 +522,7 @@ __global__ void bn_bwd_apply_kernel(float* dzn, const float* __restrict__ z, con
 // conv_2's weight gradient (K order of pack_conv2_weight); columns m >= M2 are zero
 template <typename TA>
 __global__ void im2col_t_kernel(const TA* __restrict__ out1, TA* __restrict__ colT, ConvGeom g, int64_t M2, int64_t M2p) {
+  pdl_wait();
   __shared__ TA tile[32][33];
   const int tap = blockIdx.z, kw = tap / 3, kh = tap - kw * 3;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * 32;
@@ -526,6 +547,7 @@ __global__ void im2col_t_kernel(const TA* __restrict__ out1, TA* __restrict__ co
 // col[m][(kw*3+kh)*C + c] = out1[b][2 t2 + kw][2 f2 + kh][c], m = (b*T2 + t2)*F2 + f2: the im2col operand of conv_2's weight
 // gradient in the row-major form the TN GEMM reads in place (8 channels = 16 bytes per thread, fully coalesced)
 __global__ void im2col_rows_kernel(const bf16* __restrict__ out1, bf16* __restrict__ col, ConvGeom g, int64_t M2) {
+  pdl_wait();
   const int C8 = g.C / 8;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= M2 * 9 * C8) return;
@@ -540,6 +562,7 @@ __global__ void im2col_rows_kernel(const bf16* __restrict__ out1, bf16* __restri
 // dOut1[b,t1,f1,c] = relu'(out1) * sum over the taps that read this input of dcol[m(t2,f2)][(kw*3+kh)*C + c]
 template <typename TA>
 __global__ void col2im_relu_kernel(const TA* __restrict__ dcol, const TA* __restrict__ out1, float* __restrict__ dout1, ConvGeom g) {
+  pdl_wait();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(g.B) * g.T1p * g.F1 * g.C;
   if (i >= total) return;
@@ -568,6 +591,7 @@ template <typename TA>
 __global__ void __launch_bounds__(256) conv1_wgrad_fused_kernel(const TA* __restrict__ dcol, const TA* __restrict__ out1,
                                                                const float* __restrict__ mel, float* __restrict__ dw,
                                                                float* __restrict__ db, ConvGeom g, int n_mel, int Tin, int T1, int py) {
+  pdl_wait();
   extern __shared__ float red[];                                // [C][10]
   const int cg = g.C >> 3;                                      // groups of 8 channels
   const int c8 = threadIdx.x % cg, pl = threadIdx.x / cg;
@@ -642,6 +666,7 @@ __global__ void __launch_bounds__(256) conv1_wgrad_fused_kernel(const TA* __rest
 // block = (32 channels) x (a slab of t1 rows of one utterance)
 __global__ void conv1_wgrad_kernel(const float* __restrict__ dout1, const float* __restrict__ mel, float* __restrict__ dw, float* __restrict__ db,
                                    int n_mel, int Tin, int T1, int T1p, int F1, int C, int t_per_block) {
+  pdl_wait();
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), b = blockIdx.z;
   const int sub = threadIdx.x >> 5, nsub = blockDim.x >> 5;
   const int t0 = blockIdx.y * t_per_block, t1e = min(T1, t0 + t_per_block);
@@ -687,60 +712,60 @@ __global__ void conv1_wgrad_kernel(const float* __restrict__ dout1, const float*
 template <typename TOut>
 int cast_scale_drop(const float* in, TOut* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
   CFM_REQUIRE(n % 4 == 0, "element count must be a multiple of 4");
-  cast_scale_drop_kernel<TOut><<<nblk(n, 1024), 256, 0, st>>>(in, out, n, scale, dr);
+  CFM_CUDA_OK(launch_pdl(cast_scale_drop_kernel<TOut>, dim3(nblk(n, 1024)), dim3(256), 0, st, 1, in, out, n, scale, dr));
   LAUNCH_OK();
 }
 template <typename TA>
 int swish_drop_fwd(const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
   if constexpr (sizeof(TA) == 2) {
     if (n % 8 == 0 && ((reinterpret_cast<uintptr_t>(hp) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
-      swish_drop_fwd8_kernel<<<nblk(n, 2048), 256, 0, st>>>(reinterpret_cast<const bf16*>(hp), reinterpret_cast<bf16*>(out), n, dr);
+      CFM_CUDA_OK(launch_pdl(swish_drop_fwd8_kernel, dim3(nblk(n, 2048)), dim3(256), 0, st, 1, reinterpret_cast<const bf16*>(hp), reinterpret_cast<bf16*>(out), n, dr));
       LAUNCH_OK();
     }
   }
-  swish_drop_fwd_kernel<TA><<<nblk(n, 1024), 256, 0, st>>>(hp, out, n, dr);
+  CFM_CUDA_OK(launch_pdl(swish_drop_fwd_kernel<TA>, dim3(nblk(n, 1024)), dim3(256), 0, st, 1, hp, out, n, dr));
   LAUNCH_OK();
 }
 template <typename TA>
 int swish_drop_bwd(const float* dh, const TA* hp, TA* out, int64_t n, Drop dr, cudaStream_t st) {
-  swish_drop_bwd_kernel<TA><<<nblk(n, 1024), 256, 0, st>>>(dh, hp, out, n, dr);
+  CFM_CUDA_OK(launch_pdl(swish_drop_bwd_kernel<TA>, dim3(nblk(n, 1024)), dim3(256), 0, st, 1, dh, hp, out, n, dr));
   LAUNCH_OK();
 }
 int residual_drop_add(const float* x, const float* t, float* out, int64_t n, float scale, Drop dr, cudaStream_t st) {
-  residual_drop_add_kernel<<<nblk(n, 1024), 256, 0, st>>>(x, t, out, n, scale, dr);
+  CFM_CUDA_OK(launch_pdl(residual_drop_add_kernel, dim3(nblk(n, 1024)), dim3(256), 0, st, 1, x, t, out, n, scale, dr));
   LAUNCH_OK();
 }
 int drop_inplace(float* x, int64_t n, Drop dr, cudaStream_t st) {
   if (dr.p <= 0.f) return 0;
-  drop_inplace_kernel<<<nblk(n, 256), 256, 0, st>>>(x, n, dr);
+  CFM_CUDA_OK(launch_pdl(drop_inplace_kernel, dim3(nblk(n, 256)), dim3(256), 0, st, 1, x, n, dr));
   LAUNCH_OK();
 }
 template <typename TA>
 int glu_fwd(const TA* u, TA* g, int64_t rows, int d, cudaStream_t st) {
-  glu_fwd_kernel<TA><<<nblk(rows * d, 256), 256, 0, st>>>(u, g, rows, d);
+  CFM_CUDA_OK(launch_pdl(glu_fwd_kernel<TA>, dim3(nblk(rows * d, 256)), dim3(256), 0, st, 1, u, g, rows, d));
   LAUNCH_OK();
 }
 template <typename TA>
 int glu_bwd(const float* dg, const TA* u, TA* du, int64_t rows, int d, cudaStream_t st) {
-  glu_bwd_kernel<TA><<<nblk(rows * d, 256), 256, 0, st>>>(dg, u, du, rows, d);
+  CFM_CUDA_OK(launch_pdl(glu_bwd_kernel<TA>, dim3(nblk(rows * d, 256)), dim3(256), 0, st, 1, dg, u, du, rows, d));
   LAUNCH_OK();
 }
 template <typename TA>
 int relu_bwd(const float* dy, const TA* y, TA* out, int64_t n, cudaStream_t st) {
-  relu_bwd_kernel<TA><<<nblk(n, 256), 256, 0, st>>>(dy, y, out, n);
+  CFM_CUDA_OK(launch_pdl(relu_bwd_kernel<TA>, dim3(nblk(n, 256)), dim3(256), 0, st, 1, dy, y, out, n));
   LAUNCH_OK();
 }
 template <typename T>
 int transpose_pad(const T* in, int ld, T* out, int M, int N, int Mp, cudaStream_t st) {
   dim3 grid(nblk(Mp, 32), nblk(N, 32));
-  transpose_kernel<T><<<grid, 256, 0, st>>>(in, ld, out, M, N, Mp);
+  CFM_CUDA_OK(launch_pdl(transpose_kernel<T>, dim3(grid), dim3(256), 0, st, 1, in, ld, out, M, N, Mp));
   LAUNCH_OK();
 }
 template <typename T>
 int colsum_add(const T* in, int ld, float* out, int M, int N, cudaStream_t st) {
   const int rpb = 32;
   dim3 grid(nblk(N, 128), nblk(M, rpb));
-  colsum_kernel<T><<<grid, 128, 0, st>>>(in, ld, out, M, N, rpb);
+  CFM_CUDA_OK(launch_pdl(colsum_kernel<T>, dim3(grid), dim3(128), 0, st, 1, in, ld, out, M, N, rpb));
   LAUNCH_OK();
 }
 int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool accumulate, float* dgamma, float* dbeta, int64_t rows,
@@ -754,38 +779,38 @@ int ln_bwd(const float* dy, const float* x, const float* gamma, float* dx, bool 
   const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gamma) |
                          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dgamma) | reinterpret_cast<uintptr_t>(dbeta)) & 15) == 0;
   if (aligned && d == 256) {
-    ln_bwd_vec_kernel<1><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw);
+    CFM_CUDA_OK(launch_pdl(ln_bwd_vec_kernel<1>, dim3(grid), dim3(warps * 32), 0, st, 1, dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw));
     LAUNCH_OK();
   }
   if (aligned && d == 512) {
-    ln_bwd_vec_kernel<2><<<grid, warps * 32, 0, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw);
+    CFM_CUDA_OK(launch_pdl(ln_bwd_vec_kernel<2>, dim3(grid), dim3(warps * 32), 0, st, 1, dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, rpw));
     LAUNCH_OK();
   }
   const size_t smem = static_cast<size_t>(2) * d * 4;
   const int nv = (d + 31) / 32;
-  if (nv <= 8) ln_bwd_kernel<8><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
-  else if (nv <= 16) ln_bwd_kernel<16><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
-  else ln_bwd_kernel<32><<<grid, warps * 32, smem, st>>>(dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw);
+  if (nv <= 8) CFM_CUDA_OK(launch_pdl(ln_bwd_kernel<8>, dim3(grid), dim3(warps * 32), smem, st, 1, dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw));
+  else if (nv <= 16) CFM_CUDA_OK(launch_pdl(ln_bwd_kernel<16>, dim3(grid), dim3(warps * 32), smem, st, 1, dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw));
+  else CFM_CUDA_OK(launch_pdl(ln_bwd_kernel<32>, dim3(grid), dim3(warps * 32), smem, st, 1, dy, x, gamma, dx, accumulate ? 1 : 0, dgamma, dbeta, rows, d, rpw));
   LAUNCH_OK();
 }
 template <typename TA>
 int dwconv_fwd(const TA* g, const float* w, const float* bias, float* z, int B, int Tn, int d, int ks, cudaStream_t st) {
   CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
   dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
-  dwconv_tile_kernel<TA, false><<<grid, 256, 0, st>>>(g, w, bias, z, Tn, d, ks);
+  CFM_CUDA_OK(launch_pdl(dwconv_tile_kernel<TA, false>, dim3(grid), dim3(256), 0, st, 1, g, w, bias, z, Tn, d, ks));
   LAUNCH_OK();
 }
 int dwconv_bwd_input(const float* dz, const float* w, float* dg, int B, int Tn, int d, int ks, cudaStream_t st) {
   CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
   dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
-  dwconv_tile_kernel<float, true><<<grid, 256, 0, st>>>(dz, w, nullptr, dg, Tn, d, ks);
+  CFM_CUDA_OK(launch_pdl(dwconv_tile_kernel<float, true>, dim3(grid), dim3(256), 0, st, 1, dz, w, nullptr, dg, Tn, d, ks));
   LAUNCH_OK();
 }
 template <typename TA>
 int dwconv_bwd_weight(const float* dz, const TA* g, float* dw, float* db, int B, int Tn, int d, int ks, cudaStream_t st) {
   CFM_REQUIRE(ks <= 64, "depthwise kernel size up to 64");
   dim3 grid(nblk(d, 32), nblk(Tn, 64), B);
-  dwconv_bwd_weight_kernel<TA><<<grid, 256, 0, st>>>(dz, g, dw, db, Tn, d, ks);
+  CFM_CUDA_OK(launch_pdl(dwconv_bwd_weight_kernel<TA>, dim3(grid), dim3(256), 0, st, 1, dz, g, dw, db, Tn, d, ks));
   LAUNCH_OK();
 }
 int bn_train_stats(const float* z, float* acc2d, float* stats2d, float* running_mean, float* running_var, int M, int d, float momentum,
@@ -793,13 +818,13 @@ int bn_train_stats(const float* z, float* acc2d, float* stats2d, float* running_
   CFM_CUDA_OK(cudaMemsetAsync(acc2d, 0, static_cast<size_t>(2) * d * 4, st));
   const int rpb = 32;
   dim3 grid(nblk(d, 128), nblk(M, rpb));
-  bn_sums_kernel<<<grid, 128, 0, st>>>(z, acc2d, M, d, rpb);
-  bn_finish_kernel<<<nblk(d, 128), 128, 0, st>>>(acc2d, stats2d, running_mean, running_var, M, d, momentum, 1e-5f);
+  CFM_CUDA_OK(launch_pdl(bn_sums_kernel, dim3(grid), dim3(128), 0, st, 1, z, acc2d, M, d, rpb));
+  CFM_CUDA_OK(launch_pdl(bn_finish_kernel, dim3(nblk(d, 128)), dim3(128), 0, st, 1, acc2d, stats2d, running_mean, running_var, M, d, momentum, 1e-5f));
   LAUNCH_OK();
 }
 template <typename TA>
 int bn_swish_fwd(const float* z, const float* stats, const float* gamma, const float* beta, TA* s, int64_t M, int d, cudaStream_t st) {
-  bn_swish_fwd_kernel<TA><<<nblk(M * d, 256), 256, 0, st>>>(z, stats, gamma, beta, s, M, d);
+  CFM_CUDA_OK(launch_pdl(bn_swish_fwd_kernel<TA>, dim3(nblk(M * d, 256)), dim3(256), 0, st, 1, z, stats, gamma, beta, s, M, d));
   LAUNCH_OK();
 }
 int bn_swish_bwd(float* ds_to_dz, const float* z, const float* stats, const float* gamma, const float* beta, float* acc2d, float* dgamma,
@@ -807,33 +832,33 @@ int bn_swish_bwd(float* ds_to_dz, const float* z, const float* stats, const floa
   CFM_CUDA_OK(cudaMemsetAsync(acc2d, 0, static_cast<size_t>(2) * d * 4, st));
   const int rpb = 32;                                           // ~750 blocks at C4: enough loads in flight to reach the HBM rate
   dim3 grid(nblk(d, 128), nblk(M, rpb));
-  bn_swish_bwd_reduce_kernel<<<grid, 128, 0, st>>>(ds_to_dz, z, stats, gamma, beta, acc2d, M, d, rpb);
-  bn_bwd_apply_kernel<<<grid, 128, 0, st>>>(ds_to_dz, z, stats, gamma, acc2d, dgamma, dbeta, M, d, rpb);
+  CFM_CUDA_OK(launch_pdl(bn_swish_bwd_reduce_kernel, dim3(grid), dim3(128), 0, st, 1, ds_to_dz, z, stats, gamma, beta, acc2d, M, d, rpb));
+  CFM_CUDA_OK(launch_pdl(bn_bwd_apply_kernel, dim3(grid), dim3(128), 0, st, 1, ds_to_dz, z, stats, gamma, acc2d, dgamma, dbeta, M, d, rpb));
   LAUNCH_OK();
 }
 template <typename TA>
 int im2col_t(const TA* out1, TA* colT, const ConvGeom& g, int64_t M2, int64_t M2p, cudaStream_t st) {
   dim3 grid(nblk(M2p, 32), nblk(g.C, 32), 9);
-  im2col_t_kernel<TA><<<grid, 256, 0, st>>>(out1, colT, g, M2, M2p);
+  CFM_CUDA_OK(launch_pdl(im2col_t_kernel<TA>, dim3(grid), dim3(256), 0, st, 1, out1, colT, g, M2, M2p));
   LAUNCH_OK();
 }
 int im2col_rows(const bf16* out1, bf16* col, const ConvGeom& g, int64_t M2, cudaStream_t st) {
   CFM_REQUIRE(g.C % 8 == 0, "im2col needs channels to be a multiple of 8");
   const int64_t n = M2 * 9 * (g.C / 8);
-  im2col_rows_kernel<<<nblk(n, 256), 256, 0, st>>>(out1, col, g, M2);
+  CFM_CUDA_OK(launch_pdl(im2col_rows_kernel, dim3(nblk(n, 256)), dim3(256), 0, st, 1, out1, col, g, M2));
   LAUNCH_OK();
 }
 template <typename TA>
 int col2im_relu(const TA* dcol, const TA* out1, float* dout1, const ConvGeom& g, cudaStream_t st) {
   const int64_t total = static_cast<int64_t>(g.B) * g.T1p * g.F1 * g.C;
-  col2im_relu_kernel<TA><<<nblk(total, 256), 256, 0, st>>>(dcol, out1, dout1, g);
+  CFM_CUDA_OK(launch_pdl(col2im_relu_kernel<TA>, dim3(nblk(total, 256)), dim3(256), 0, st, 1, dcol, out1, dout1, g));
   LAUNCH_OK();
 }
 int conv1_wgrad(const float* dout1, const float* mel, float* dw, float* db, int B, int n_mel, int Tin, int T1, int T1p, int F1, int C,
                 cudaStream_t st) {
   const int tpb = 16;
   dim3 grid(nblk(C, 32), nblk(T1, tpb), B);
-  conv1_wgrad_kernel<<<grid, 256, 0, st>>>(dout1, mel, dw, db, n_mel, Tin, T1, T1p, F1, C, tpb);
+  CFM_CUDA_OK(launch_pdl(conv1_wgrad_kernel, dim3(grid), dim3(256), 0, st, 1, dout1, mel, dw, db, n_mel, Tin, T1, T1p, F1, C, tpb));
   LAUNCH_OK();
 }
 
@@ -842,7 +867,7 @@ int conv1_wgrad_fused(const TA* dcol, const TA* out1, const float* mel, float* d
                       int num_sms, cudaStream_t st) {
   CFM_REQUIRE(g.C % 8 == 0 && g.C / 8 <= 256, "fused conv_1 weight gradient needs a channel count that is a multiple of 8 (<= 2048)");
   const int cg = g.C / 8, py = 256 / cg;
-  conv1_wgrad_fused_kernel<TA><<<2 * num_sms, cg * py, static_cast<size_t>(g.C) * 10 * 4, st>>>(dcol, out1, mel, dw, db, g, n_mel, Tin, T1, py);
+  CFM_CUDA_OK(launch_pdl(conv1_wgrad_fused_kernel<TA>, dim3(2 * num_sms), dim3(cg * py), static_cast<size_t>(g.C) * 10 * 4, st, 1, dcol, out1, mel, dw, db, g, n_mel, Tin, T1, py));
   LAUNCH_OK();
 }
 

@@ -204,6 +204,11 @@ CFM_API int cfm_profile_collect(cfm_module_t m, double* out_host, int32_t n_clas
 CFM_API int cfm_module_set_grad(cfm_module_t m, const char* name, float* grad, int64_t numel);
 CFM_API int cfm_train_bind(cfm_module_t m, int compute);
 CFM_API int cfm_train_refresh(cfm_module_t m, void* stream);
+/* Programmatic dependent launch of the forward kernels (process-wide, default: on).  Each kernel of the path is launched
+ * with programmatic stream serialization: its CTAs become resident and set up (barriers, tensor memory, descriptors)
+ * while the previous kernel's last wave drains, then wait (griddepcontrol.wait) until that kernel has completed and its
+ * memory is visible before they touch any operand.  Results are identical to plain stream order; 0 turns it off. */
+CFM_API int cfm_set_pdl(int32_t enable);
 /* CUDA graphs of the training step (default: on).  A training forward, a block range of the backward or the weight
  * refresh that is called a second time with the same arguments (pointers, shapes, dropout rate) is captured and from
  * then on replayed with one graph launch on the caller's stream; the dropout seed is passed through device memory, so
