@@ -199,6 +199,47 @@ def test_module_built_under_inference_mode():
     assert torch.equal(y, y2)
 
 
+@pytest.mark.parametrize("cfg,B,Tin", [(CONFORMER_M, 8, 1501), (CONFORMER_L, 4, 801)])
+def test_programmatic_dependent_launch_matches_stream_order(cfg, B, Tin):
+    """cfm_set_pdl: with programmatic dependent launch every kernel's CTAs start while the previous kernel drains and wait
+    (griddepcontrol.wait) before touching an operand - the forward must give what plain stream order gives, on one stream
+    and on two streams running concurrently.  (Not bit-compared: the fused FFN's split tiles reduce-add into x in an
+    order that varies from run to run, a few fp32 ulps; a kernel that started on stale operands is off by O(1).)"""
+    from conformer_b200._lib import lib
+    enc = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+    enc.load_state_dict(synth_encoder_state_dict(cfg, 3))
+    enc = enc.to(DEV).eval().set_compute("bf16")
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, Tin, cfg.n_mel_channels, generator=g).to(DEV)
+    lengths = torch.tensor([Tin - 37 * i for i in range(B)], dtype=torch.int64, device=DEV)
+    try:
+        lib().cfm_set_pdl(0)
+        with torch.inference_mode():
+            y0, l0 = enc(x, lengths)
+        torch.cuda.synchronize()
+        tol = 1e-4 * (1.0 + float(y0.abs().max()))
+        lib().cfm_set_pdl(1)
+        with torch.inference_mode():
+            for _ in range(3):
+                y1, l1 = enc(x, lengths)
+                assert torch.equal(l0, l1)
+                assert float((y1 - y0).abs().max()) <= tol, float((y1 - y0).abs().max())
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            enc2 = cb.Encoder(cfg.n_mel_channels, cfg.n_blocks, cfg.d_model, cfg.n_heads, cfg.kernel_size)
+            enc2.load_state_dict(synth_encoder_state_dict(cfg, 3))
+            enc2 = enc2.to(DEV).eval().set_compute("bf16")
+            torch.cuda.synchronize()
+            outs = []
+            for it in range(4):
+                with torch.cuda.stream(s1 if it % 2 == 0 else s2):
+                    outs.append((enc if it % 2 == 0 else enc2)(x, lengths)[0])
+            torch.cuda.synchronize()
+            for y in outs:
+                assert float((y - y0).abs().max()) <= tol, float((y - y0).abs().max())
+    finally:
+        lib().cfm_set_pdl(1)
+
+
 @pytest.mark.timeout(600)
 @pytest.mark.parametrize("name,cfg,B,Tin,full", [("C2-M", CONFORMER_M, 64, 1501, True), ("C3-L", CONFORMER_L, 32, 2001, False),
                                                  ("C5-M", CONFORMER_M, 16, 6001, True), ("C2-M-varlen", CONFORMER_M, 8, 1501, False)])
