@@ -210,7 +210,7 @@ def test_programmatic_dependent_launch_matches_stream_order(cfg, B, Tin):
     enc.load_state_dict(synth_encoder_state_dict(cfg, 3))
     enc = enc.to(DEV).eval().set_compute("bf16")
     g = torch.Generator().manual_seed(11)
-    x = torch.randn(B, Tin, cfg.n_mel_channels, generator=g).to(DEV)
+    x = torch.randn(B, cfg.n_mel_channels, Tin, generator=g).to(DEV)
     lengths = torch.tensor([Tin - 37 * i for i in range(B)], dtype=torch.int64, device=DEV)
     try:
         lib().cfm_set_pdl(0)
