@@ -499,6 +499,20 @@ def dominant_roofline(kernels, peaks, rank=0):
     return roof
 
 
+_PDL_AUTO = True          # no --pdl flag: programmatic dependent launch on for single-stream legs, off for multi-stream legs
+
+
+def pdl_for(multi_stream):
+    """Programmatic dependent launch (cfm_set_pdl) lets a kernel's CTAs become resident while the previous kernel of ITS
+    stream drains.  On one stream that hides launch ramps (C2: 4.37 -> 4.06 ms per step); with two streams alternating,
+    those parked CTAs hold SMs the other stream's kernels would have used (C3: 7.9 -> 8.4 ms), so a throughput-oriented
+    caller turns it off.  bench.py does what such a caller would: off for the multi-stream legs, on for the
+    single-stream and graph-replay legs - unless --pdl fixes it."""
+    if _PDL_AUTO:
+        from conformer_b200._lib import lib as _cfm_lib
+        _cfm_lib().cfm_set_pdl(0 if multi_stream else 1)
+
+
 def side_config(cb, name, dev, rank, dist, world, steps, peaks):
     """One of the other BASELINE configs at its own shape: device-resident two-stream time, single-stream time, dominant
     kernel.  Fewer steps than the headline; same timing rules."""
@@ -509,8 +523,11 @@ def side_config(cb, name, dev, rank, dist, world, steps, peaks):
             b.step()
         for _ in range(2 * b.n_streams):
             b.step_rotating()
+        pdl_for(False)
         ms_serial = b.timed_serial(b.step, steps)
+        pdl_for(b.n_streams > 1)
         ms, med = b.timed_rotating(steps)
+        pdl_for(False)
         prof = b.profile(min(steps, 3))
     kernels = kernel_table(prof, min(steps, 3), peaks)
     flops = encoder_flops(batch, t_in, cfg.d_model, cfg.n_blocks, cfg.n_mel_channels, cfg.kernel_size)
@@ -728,9 +745,11 @@ def main():
         return
 
     import conformer_b200 as cb
+    global _PDL_AUTO
     if args.pdl is not None:
         from conformer_b200._lib import lib as _cfm_lib
         _cfm_lib().cfm_set_pdl(args.pdl)
+        _PDL_AUTO = False
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -768,8 +787,11 @@ def main():
             step_e2e_serial()
         if rank == 0:
             sampler.begin_timed()
+        pdl_for(False)
         ms_dev_serial = b.timed_serial(b.step, args.steps)
+        pdl_for(n_dev_streams > 1)
         ms_dev, ms_dev_median = b.timed_rotating(args.steps)
+        pdl_for(False)
         launches = enc.last_launch_count
         # informational: the same forward replayed from a CUDA graph on one stream (Encoder.capture)
         ms_graph_serial = None
@@ -810,6 +832,7 @@ def main():
         for _ in range(2 * n_slots):
             step_e2e()
         torch.cuda.synchronize()
+        pdl_for(n_dev_streams > 1)
         ms_e2e, ms_e2e_median = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_e2e)
         ms_e2e_fp32in = ms_e2e_bf16out = None
         if bf16_in:
@@ -827,6 +850,7 @@ def main():
             torch.cuda.synchronize()
             ms_e2e_bf16out, _ = b.timed_rotating(args.steps, extra_streams=(copy_in, copy_out), fn=step_16)
             del y16
+        pdl_for(False)
         clocks = sampler.stop() if rank == 0 else None       # sampled across the timed regions above
         # profiled pass (per-launch CUDA events on the launching stream), not part of the headline
         prof_steps = min(args.steps, 5)
@@ -845,7 +869,9 @@ def main():
                     sb.step()
                 for _ in range(2 * sb.n_streams):
                     sb.step_rotating()
+                pdl_for(sb.n_streams > 1)
                 ms_s, med_s = sb.timed_rotating(args.steps)
+                pdl_for(False)
                 total_secs = audio_seconds(make_lengths(len_mode, batch, t_in), batch, t_in)
                 strong = {"per_rank_batches": strong_scaling_batches(batch, world), "ms_per_step": ms_s,
                           "ms_per_step_median": med_s, "value": total_secs / (ms_s * 1e-3), "unit": "audio-s/s",
@@ -895,6 +921,9 @@ def main():
                    "issue": f"steps rotate over {n_dev_streams} CUDA streams per GPU (independent batches overlap at kernel "
                             "boundaries); serial_ms_per_step is the single-stream time; ms_per_step = total / steps, "
                             "ms_per_step_median = median interval between consecutive step completions",
+                   "pdl": ("programmatic dependent launch (cfm_set_pdl): off for the multi-stream legs (value, e2e, configs.*.ms_per_step), "
+                           "on for the single-stream and graph-replay legs - what a caller tuning for throughput / latency sets")
+                          if _PDL_AUTO else f"programmatic dependent launch fixed by --pdl {args.pdl}",
                    "l2": "no flush needed: one step streams ~1.3 GB of activations (conv1 output alone 958 MB) "
                          "through the 126 MB L2"},
         "e2e": {"value": whole_job_rtfx(world, secs_per_step, ms_e2e), "unit": "audio-s/s", "ms_per_step": ms_e2e,

@@ -64,7 +64,9 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
-template <typename... KArgs, typename... Args>
+// PDL = false: a plain stream-ordered launch (the fp32 parity path: its kernels are short and many, and measured slower
+// with programmatic launches - C1 5.47 -> 5.99 ms under graph replay).
+template <bool PDL = true, typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                                      unsigned cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -81,7 +83,7 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     at[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (g_pdl.load(std::memory_order_relaxed) != 0) {
+  if (PDL && g_pdl.load(std::memory_order_relaxed) != 0) {
     at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) dwconv_bf16_kernel(const bf16* __restrict
                                                           const float* __restrict__ bias, bf16* __restrict__ y, int Tn,
                                                           int d) {
   constexpr int HALF = (KS - 1) / 2, ROWS = DV_TT + KS - 1;
+  pdl_wait();
   __shared__ __align__(16) float gs[ROWS * DV_CH];
   __shared__ __align__(16) float ws[KS * DV_CH];
   const int b = blockIdx.z, c0 = blockIdx.y * DV_CH, t0 = blockIdx.x * DV_TT;
@@ -288,7 +289,7 @@ int dwconv_bn_swish_bf16(const bf16* g, const float* w, const float* bias, bf16*
                          cudaStream_t stream) {
   CFM_REQUIRE(d % DV_CH == 0 && ksize == 31, "fast depthwise path needs channels % 64 == 0 and kernel size 31");
   dim3 grid(static_cast<unsigned>(ceil_div(Tn, DV_TT)), static_cast<unsigned>(d / DV_CH), static_cast<unsigned>(B));
-  dwconv_bf16_kernel<31><<<grid, 256, 0, stream>>>(g, w, bias, y, Tn, d);
+  CFM_CUDA_OK(launch_pdl(dwconv_bf16_kernel<31>, grid, dim3(256), 0, stream, 1, g, w, bias, y, Tn, d));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }

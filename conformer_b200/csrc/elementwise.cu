@@ -9,6 +9,7 @@ namespace {
 template <typename TOut>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const float* x, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, TOut* y, int64_t rows, int d) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -31,6 +32,7 @@ __global__ void __launch_bounds__(256) layer_norm_kernel(const float* x, const f
 template <typename TOut, int NV>
 __global__ void __launch_bounds__(256) layer_norm_vec_kernel(const float* x, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, TOut* y, int64_t rows) {
+  pdl_wait();
   constexpr int D = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -299,13 +301,16 @@ int layer_norm(const float* x, const float* gamma, const float* beta, TOut* y, i
     CFM_CUDA_OK(launch_pdl(layer_norm_vec_rows_kernel<TOut, 2, 4>, dim3(blocks_for(rows, 32)), dim3(256), 0, stream, 1, x, gamma, beta, y,
                            rows));
   else if (aligned && d == 256)
-    layer_norm_vec_kernel<TOut, 2><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+    CFM_CUDA_OK(launch_pdl<sizeof(TOut) == 2>(layer_norm_vec_kernel<TOut, 2>, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, 1, x, gamma, beta,
+                                             y, rows));
   else if (aligned && d == 512)
-    layer_norm_vec_kernel<TOut, 4><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+    CFM_CUDA_OK(launch_pdl<sizeof(TOut) == 2>(layer_norm_vec_kernel<TOut, 4>, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, 1, x, gamma, beta,
+                                             y, rows));
   else if (aligned && d == 128)
-    layer_norm_vec_kernel<TOut, 1><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows);
+    CFM_CUDA_OK(launch_pdl<sizeof(TOut) == 2>(layer_norm_vec_kernel<TOut, 1>, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, 1, x, gamma, beta,
+                                             y, rows));
   else
-    layer_norm_kernel<TOut><<<blocks_for(rows, 8), 256, 0, stream>>>(x, gamma, beta, y, rows, d);
+    CFM_CUDA_OK(launch_pdl<sizeof(TOut) == 2>(layer_norm_kernel<TOut>, dim3(blocks_for(rows, 8)), dim3(256), 0, stream, 1, x, gamma, beta, y, rows, d));
   CFM_CUDA_OK(cudaGetLastError());
   return 0;
 }
