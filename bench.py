@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: Conformer-M encoder forward, audio-seconds per second (RTFx).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C1|C2|C3|C4|C5] [--pdl 0|1]
 
 One "step" = one encoder forward over one synthetic batch of the named workload (BASELINE.json
 configs[1] = "C2": Conformer-M, d=256, 16 blocks, 4 heads, bf16, 64 x 15 s of 80-mel log-fbank,
@@ -25,6 +25,9 @@ Printed JSON (rank 0, one line):
   next_rows            (N = 1) the rows either side of the encoder: log-mel front-end and CTC head + greedy
                        decode at the shapes they have around this batch, next to the same computation in eager PyTorch
   cpu_baseline         the reference's CPU path on this box's host cores, bounded sample
+  config.pdl           programmatic dependent launch (cfm_set_pdl): without --pdl the multi-stream legs (value, e2e,
+                       configs.*.ms_per_step) run with it off and the single-stream / graph-replay legs with it on - what a
+                       caller tuning for throughput resp. latency would set
   --impl reference     times that CPU path alone, same metric/config.
 """
 from __future__ import annotations

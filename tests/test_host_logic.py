@@ -135,3 +135,13 @@ def test_reference_written_checkpoint_loads_and_round_trips(tmp_path):
         bad = dict(ck.strip_ddp_prefix(raw["model"]))
         bad["encoder.extra"] = torch.zeros(1)
         ck.load_model(bad, fresh)
+
+
+def test_launch_mode_switch_needs_no_device():
+    """cfm_set_pdl only records how the next kernels are launched (programmatic dependent launch on / off): callable
+    on a box without a GPU, any non-zero value means on."""
+    from conformer_b200._lib import lib
+    assert lib().cfm_set_pdl(0) == 0
+    assert lib().cfm_set_pdl(7) == 0
+    cb.set_pdl(False)
+    cb.set_pdl(True)
