@@ -65,3 +65,20 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(_lib.NativeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def test_ctypes_argument_counts_match_the_header():
+    """Signature drift between include/conformer_b200.h and the ctypes table is an ABI bug no compiler sees: every
+    declaration's parameter count (and whether it returns a 64-bit value) must match its binding."""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    decls = re.findall(r"CFM_API\s+([\w\s\*]+?)\b(cfm_\w+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(decls) == len(header_symbols())
+    for ret, name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else len([p for p in params.split(",") if p.strip()])
+        restype, argtypes = _lib.SIGNATURES[name]
+        assert n == len(argtypes), f"{name}: header has {n} parameters, ctypes table {len(argtypes)}"
+        if "int64_t" in ret:
+            assert restype is C.c_int64, f"{name} returns int64_t in the header"
+        if "char" in ret:
+            assert restype is C.c_char_p, f"{name} returns a string in the header"
